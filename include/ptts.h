@@ -1,0 +1,152 @@
+/*
+ * ptts.h -- C ABI of libptts_b200.so: pocket-tts streaming generation on NVIDIA B200 (sm_100a).
+ *
+ * The reference (jishnuvenugopal/pocket-tts-mlx) has no FFI: its hot path is Python over the MLX
+ * tensor runtime.  This header is the boundary a host runtime binds instead of MLX for that path;
+ * every entry point names the reference code it replaces (paths relative to
+ * /root/reference/pocket_tts_mlx/).  The Python facade `pocket_tts_mlx_b200.TTSModel` binds it with
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative ptts_status; ptts_last_error() gives the
+ *     thread-local message of the last failure;
+ *   - all pointers are HOST pointers to plain arrays whose lifetime spans the call; the library owns
+ *     every device allocation;
+ *   - one ptts_ctx per GPU; a ctx (and the objects made from it) must be used by one thread at a
+ *     time; different ctxs may be used concurrently from different threads or processes;
+ *   - there is no CPU fallback: without a CUDA device ptts_ctx_create fails with PTTS_ERR_CUDA.
+ */
+#ifndef PTTS_H_
+#define PTTS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTTS_ABI_VERSION 1
+
+typedef enum {
+  PTTS_OK = 0,
+  PTTS_ERR_INVALID = -1,   /* bad argument / shape / unknown name */
+  PTTS_ERR_CUDA = -2,      /* CUDA runtime or driver failure (includes "no device") */
+  PTTS_ERR_STATE = -3,     /* call order violated (e.g. step before prefill) */
+  PTTS_ERR_NOMEM = -4,     /* KV page pool or device memory exhausted */
+  PTTS_ERR_MISSING = -5    /* a required checkpoint tensor was never loaded */
+} ptts_status;
+
+typedef enum { PTTS_BF16 = 0, PTTS_FP32 = 1 } ptts_precision;
+typedef enum { PTTS_DT_F32 = 0, PTTS_DT_BF16 = 1, PTTS_DT_F16 = 2 } ptts_dtype;
+
+/* Model geometry + sampling knobs.  Field meanings follow config/b6369a24.yaml and the kwargs of
+ * TTSModel.load_model (models/tts_model.py:202-221). */
+typedef struct {
+  /* FlowLM backbone (models/flow_lm.py, modules/mimi_transformer.py:104-114) */
+  int32_t d_model, n_heads, n_layers, ffn_dim, n_bins, latent_dim;
+  float max_period;
+  /* flow head (modules/mlp.py:122-168) */
+  int32_t flow_dim, flow_depth;
+  /* Mimi decoder transformer (modules/mimi_transformer.py:123-171) */
+  int32_t mimi_d, mimi_heads, mimi_layers, mimi_ffn, mimi_context;
+  float mimi_max_period;
+  /* SEANet decoder (modules/seanet.py:111-170) */
+  int32_t seanet_dim, n_filters, n_ratios, ratios[8];
+  int32_t kernel_size, res_kernel_size, last_kernel_size, compress;
+  int32_t upsample_stride;          /* 16: encoder frame rate / frame rate (models/mimi.py:48-52) */
+  /* sampling (default_parameters.py:3-10) */
+  float temp;
+  int32_t lsd_decode_steps;
+  float noise_clamp;                /* < 0 or NaN: no clamp */
+  float eos_threshold;
+  /* runtime */
+  int32_t precision;                /* ptts_precision: storage of weights + KV cache */
+  int64_t kv_pool_tokens;           /* capacity of the paged FlowLM KV pool, in tokens */
+  int32_t max_batch;                /* largest batch a ptts_batch may hold */
+  int32_t reserved[8];
+} ptts_config;
+
+typedef struct ptts_ctx ptts_ctx;
+typedef struct ptts_batch ptts_batch;
+
+int32_t ptts_abi_version(void);
+const char* ptts_last_error(void);
+int32_t ptts_device_count(void);       /* 0 when no CUDA device/driver is usable */
+
+/* ---- context + weights --------------------------------------------------------------------
+ * Replaces TTSModel._from_pydantic_config_with_weights (models/tts_model.py:96-200): module tree
+ * construction, the safetensors key walk and the conv weight transposes (:175-186). */
+int32_t ptts_ctx_create(int32_t device, const ptts_config* cfg, ptts_ctx** out);
+void ptts_ctx_destroy(ptts_ctx* ctx);
+/* One checkpoint tensor in CHECKPOINT (PyTorch) layout under its checkpoint key, e.g.
+ * "flow_lm.transformer.layers.0.self_attn.in_proj.weight".  Unknown names are ignored (return 1),
+ * like the reference's skipped keys (:171-173,190-192). */
+int32_t ptts_load_weight(ptts_ctx* ctx, const char* name, int32_t dtype, int32_t ndim,
+                         const int64_t* shape, const void* data);
+/* Re-pack (conv taps -> GEMM K axis, transposed convs -> polyphase), fold constants (time
+ * embeddings of the LSD schedule, modules/mlp.py:53-74), convert to the storage precision, upload. */
+int32_t ptts_finalize_weights(ptts_ctx* ctx);
+
+/* ---- voice prompt -------------------------------------------------------------------------
+ * Replaces get_state_for_audio_prompt's prefill (models/tts_model.py:510-518): runs cond
+ * [n_frames, d_model] through the backbone and keeps the KV pages as an immutable prefix that any
+ * number of sequences share.  Returns the voice id (>= 0). */
+int32_t ptts_voice_create(ptts_ctx* ctx, const float* cond, int32_t n_frames);
+int32_t ptts_voice_destroy(ptts_ctx* ctx, int32_t voice_id);
+int32_t ptts_voice_length(ptts_ctx* ctx, int32_t voice_id);
+
+/* ---- a batch of sequences generated in lock-step -------------------------------------------
+ * Replaces the state plumbing of _generate_audio_stream_short_text (models/tts_model.py:372-384):
+ * state copy, _expand_kv_cache, init_states(mimi), with per-sequence lengths instead of the
+ * reference's single batch-1 `current_end`.  max_len[b] = voice + text + frames upper bound. */
+int32_t ptts_batch_create(ptts_ctx* ctx, int32_t n_seq, const int32_t* voice_ids,
+                          const int32_t* max_len, ptts_batch** out);
+void ptts_batch_destroy(ptts_batch* batch);
+/* Text prefill (tts_model.py:388-391): ids of sequence b are ids[offsets[b]..offsets[b+1]). */
+int32_t ptts_batch_prefill_text(ptts_batch* batch, const int32_t* ids, const int32_t* offsets);
+/* _warmup_mimi_decoder (tts_model.py:464-476): n_frames zero latents decoded and discarded. */
+int32_t ptts_batch_warmup_mimi(ptts_batch* batch, int32_t n_frames);
+/* One frame for every sequence = one replay of the per-frame CUDA graph (tts_model.py:404-426):
+ * FlowLM step over the KV cache -> EOS logit -> flow head (all LSD steps) -> Mimi decode.
+ *   noise      [n_seq, lsd_steps?1:1, latent_dim] raw N(0,1) draws (scaled by sqrt(temp) and clamped
+ *              on the device, models/flow_lm.py:103-109), or NULL to use the device Philox stream;
+ *   out_latent [n_seq, latent_dim] or NULL;  out_eos_logit [n_seq] or NULL;
+ *   out_audio  [n_seq, 1920] or NULL (NULL also skips the device->host copy, not the decode). */
+int32_t ptts_batch_step(ptts_batch* batch, const float* noise, float* out_latent,
+                        float* out_eos_logit, float* out_audio);
+/* Teacher forcing for parity tests: overwrite the latent that the next step feeds back. */
+int32_t ptts_batch_set_prev_latent(ptts_batch* batch, const float* latent);
+/* Same step without the host round trip: results stay on the device (used by bench `value`). */
+int32_t ptts_batch_step_device(ptts_batch* batch);
+int32_t ptts_batch_seed(ptts_batch* batch, uint64_t seed);
+int32_t ptts_batch_lengths(ptts_batch* batch, int32_t* out_len);
+
+/* Mimi decode only (models/mimi.py:70-75 driven frame by frame as in tts_model.py:415-419):
+ * latents [n_seq, n_frames, latent_dim] -> audio [n_seq, n_frames*1920], continuing the batch's
+ * Mimi streaming state.  audio may be NULL (device-resident timing). */
+int32_t ptts_batch_mimi_decode(ptts_batch* batch, const float* latents, int32_t n_frames, float* audio);
+
+/* ---- timing + introspection -------------------------------------------------------------- */
+int32_t ptts_sync(ptts_ctx* ctx);
+/* CUDA events on the library's own stream: begin/end bracket a region, elapsed in milliseconds. */
+int32_t ptts_timer_begin(ptts_ctx* ctx);
+int32_t ptts_timer_end(ptts_ctx* ctx, float* elapsed_ms);
+/* Kernel launches issued by this library since the counter was last reset (graph replays count
+ * their kernel nodes). */
+int64_t ptts_launch_count(ptts_ctx* ctx, int32_t reset);
+/* Per-stage timing of one eager (non-graph) frame for profiling: names are returned as a single
+ * ';'-separated string valid until the next call; ms has room for `cap` entries. */
+int32_t ptts_batch_profile_step(ptts_batch* batch, float* ms, int32_t cap, const char** names);
+/* Write an L2-sized scratch buffer (flushes L2 between timed iterations). */
+int32_t ptts_flush_l2(ptts_ctx* ctx);
+/* Stand-alone entry to the multi-tap linear operator, for kernel-level parity tests:
+ * Y[b,t,n] = sum_{j<taps} sum_c A[b,t+j,c] * W[n, j*C+c] (+bias[n]); path 0 auto, 1 SIMT tile,
+ * 2 small-M GEMV, 3 tcgen05 (bf16 storage only). */
+int32_t ptts_debug_linear(ptts_ctx* ctx, int32_t path, int32_t n_b, int32_t n_t, int32_t taps,
+                          int32_t c_in, int32_t n_out, const float* a, const float* w,
+                          const float* bias, float* y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTTS_H_ */

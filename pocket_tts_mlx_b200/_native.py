@@ -1,0 +1,307 @@
+"""ctypes binding of libptts_b200.so (include/ptts.h).  No torch, no CPU fallback: if the shared
+library is missing or no CUDA device is usable the calls raise."""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libptts_b200.so"
+
+PTTS_BF16, PTTS_FP32 = 0, 1
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2
+
+EXPORTED = [
+    "ptts_abi_version", "ptts_last_error", "ptts_device_count", "ptts_ctx_create", "ptts_ctx_destroy",
+    "ptts_load_weight", "ptts_finalize_weights", "ptts_voice_create", "ptts_voice_destroy",
+    "ptts_voice_length", "ptts_batch_create", "ptts_batch_destroy", "ptts_batch_prefill_text",
+    "ptts_batch_warmup_mimi", "ptts_batch_step", "ptts_batch_set_prev_latent", "ptts_batch_step_device",
+    "ptts_batch_seed", "ptts_batch_lengths", "ptts_batch_mimi_decode", "ptts_sync", "ptts_timer_begin",
+    "ptts_timer_end", "ptts_launch_count", "ptts_batch_profile_step", "ptts_flush_l2", "ptts_debug_linear",
+]
+
+
+class PttsError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libptts_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("d_model", C.c_int32), ("n_heads", C.c_int32), ("n_layers", C.c_int32), ("ffn_dim", C.c_int32),
+        ("n_bins", C.c_int32), ("latent_dim", C.c_int32), ("max_period", C.c_float),
+        ("flow_dim", C.c_int32), ("flow_depth", C.c_int32),
+        ("mimi_d", C.c_int32), ("mimi_heads", C.c_int32), ("mimi_layers", C.c_int32), ("mimi_ffn", C.c_int32),
+        ("mimi_context", C.c_int32), ("mimi_max_period", C.c_float),
+        ("seanet_dim", C.c_int32), ("n_filters", C.c_int32), ("n_ratios", C.c_int32), ("ratios", C.c_int32 * 8),
+        ("kernel_size", C.c_int32), ("res_kernel_size", C.c_int32), ("last_kernel_size", C.c_int32),
+        ("compress", C.c_int32), ("upsample_stride", C.c_int32),
+        ("temp", C.c_float), ("lsd_decode_steps", C.c_int32), ("noise_clamp", C.c_float),
+        ("eos_threshold", C.c_float),
+        ("precision", C.c_int32), ("kv_pool_tokens", C.c_int64), ("max_batch", C.c_int32),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m pocket_tts_mlx_b200.build_native` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(str(LIB_PATH))
+    vp, i32, f32p, i32p = C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    sig = {
+        "ptts_abi_version": (i32, []),
+        "ptts_last_error": (C.c_char_p, []),
+        "ptts_device_count": (i32, []),
+        "ptts_ctx_create": (i32, [i32, C.POINTER(Config), C.POINTER(vp)]),
+        "ptts_ctx_destroy": (None, [vp]),
+        "ptts_load_weight": (i32, [vp, C.c_char_p, i32, i32, C.POINTER(C.c_int64), vp]),
+        "ptts_finalize_weights": (i32, [vp]),
+        "ptts_voice_create": (i32, [vp, f32p, i32]),
+        "ptts_voice_destroy": (i32, [vp, i32]),
+        "ptts_voice_length": (i32, [vp, i32]),
+        "ptts_batch_create": (i32, [vp, i32, i32p, i32p, C.POINTER(vp)]),
+        "ptts_batch_destroy": (None, [vp]),
+        "ptts_batch_prefill_text": (i32, [vp, i32p, i32p]),
+        "ptts_batch_warmup_mimi": (i32, [vp, i32]),
+        "ptts_batch_step": (i32, [vp, f32p, f32p, f32p, f32p]),
+        "ptts_batch_set_prev_latent": (i32, [vp, f32p]),
+        "ptts_batch_step_device": (i32, [vp]),
+        "ptts_batch_seed": (i32, [vp, C.c_uint64]),
+        "ptts_batch_lengths": (i32, [vp, i32p]),
+        "ptts_batch_mimi_decode": (i32, [vp, f32p, i32, f32p]),
+        "ptts_sync": (i32, [vp]),
+        "ptts_timer_begin": (i32, [vp]),
+        "ptts_timer_end": (i32, [vp, f32p]),
+        "ptts_launch_count": (C.c_int64, [vp, i32]),
+        "ptts_batch_profile_step": (i32, [vp, f32p, i32, C.POINTER(C.c_char_p)]),
+        "ptts_flush_l2": (i32, [vp]),
+        "ptts_debug_linear": (i32, [vp, i32, i32, i32, i32, i32, i32, f32p, f32p, f32p, f32p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        raise PttsError(rc, lib().ptts_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def device_count() -> int:
+    return int(lib().ptts_device_count())
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _fp(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def make_config(cfg, temp: float, lsd_decode_steps: int, noise_clamp: Optional[float], eos_threshold: float,
+                precision: str = "bf16", kv_pool_tokens: int = 262144, max_batch: int = 0) -> Config:
+    """pydantic Config (config.py) -> C struct."""
+    t, m, sn = cfg.flow_lm.transformer, cfg.mimi.transformer, cfg.mimi.seanet
+    c = Config()
+    c.d_model, c.n_heads, c.n_layers = t.d_model, t.num_heads, t.num_layers
+    c.ffn_dim = int(t.d_model * t.hidden_scale)
+    c.n_bins, c.latent_dim = cfg.flow_lm.lookup_table.n_bins, cfg.mimi.quantizer.dimension
+    c.max_period = float(t.max_period)
+    c.flow_dim, c.flow_depth = cfg.flow_lm.flow.dim, cfg.flow_lm.flow.depth
+    c.mimi_d, c.mimi_heads, c.mimi_layers = m.d_model, m.num_heads, m.num_layers
+    c.mimi_ffn, c.mimi_context, c.mimi_max_period = m.dim_feedforward, m.context, float(m.max_period)
+    c.seanet_dim, c.n_filters, c.n_ratios = sn.dimension, sn.n_filters, len(sn.ratios)
+    for i, r in enumerate(sn.ratios):
+        c.ratios[i] = int(r)
+    c.kernel_size, c.res_kernel_size, c.last_kernel_size = sn.kernel_size, sn.residual_kernel_size, sn.last_kernel_size
+    c.compress = sn.compress
+    hop = int(np.prod(sn.ratios))
+    c.upsample_stride = int(round(cfg.mimi.sample_rate / hop / cfg.mimi.frame_rate))
+    c.temp = float(temp)
+    c.lsd_decode_steps = int(lsd_decode_steps)
+    c.noise_clamp = -1.0 if noise_clamp is None else float(noise_clamp)
+    c.eos_threshold = float(min(max(eos_threshold, -3.0e38), 3.0e38))
+    if precision not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    c.precision = PTTS_BF16 if precision == "bf16" else PTTS_FP32
+    c.kv_pool_tokens = int(kv_pool_tokens)
+    c.max_batch = int(max_batch)
+    if m.d_model != m.input_dimension or tuple(m.output_dimensions) != (m.d_model,):
+        raise ValueError("Mimi transformer input/output projections are not supported (identity at 512/512)")
+    if sn.n_residual_layers != 1 or sn.pad_mode != "constant" or sn.channels != 1:
+        raise ValueError("only the b6369a24 SEANet decoder topology is supported")
+    return c
+
+
+class Context:
+    """One GPU: weights, KV page pool, voices."""
+
+    def __init__(self, config: Config, device: int = 0):
+        self._h = C.c_void_p()
+        self.config = config
+        check(lib().ptts_ctx_create(device, C.byref(config), C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().ptts_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_weight(self, name: str, arr: np.ndarray) -> bool:
+        a = _f32(arr)
+        shape = (C.c_int64 * max(a.ndim, 1))(*a.shape)
+        rc = check(lib().ptts_load_weight(self._h, name.encode(), DT_F32, a.ndim, shape, a.ctypes.data_as(C.c_void_p)))
+        return rc == 0
+
+    def finalize(self):
+        check(lib().ptts_finalize_weights(self._h))
+
+    def voice_create(self, cond: np.ndarray) -> int:
+        a = _f32(cond).reshape(-1, self.config.d_model)
+        return check(lib().ptts_voice_create(self._h, _fp(a), a.shape[0]))
+
+    def voice_destroy(self, vid: int):
+        check(lib().ptts_voice_destroy(self._h, vid))
+
+    def voice_length(self, vid: int) -> int:
+        return check(lib().ptts_voice_length(self._h, vid))
+
+    def sync(self):
+        check(lib().ptts_sync(self._h))
+
+    def timer_begin(self):
+        check(lib().ptts_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        check(lib().ptts_timer_end(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(lib().ptts_launch_count(self._h, 1 if reset else 0))
+
+    def flush_l2(self):
+        check(lib().ptts_flush_l2(self._h))
+
+    def debug_linear(self, a, w, bias=None, taps=1, path=0):
+        """a [nb, T+taps-1, C], w [N, taps*C] -> y [nb, T, N] through the chosen kernel path."""
+        a = _f32(a)
+        w = _f32(w)
+        nb, tp, c_in = a.shape
+        t = tp - taps + 1
+        n = w.shape[0]
+        assert w.shape[1] == taps * c_in
+        y = np.empty((nb, t, n), dtype=np.float32)
+        b = _f32(bias) if bias is not None else None
+        check(lib().ptts_debug_linear(self._h, path, nb, t, taps, c_in, n, _fp(a), _fp(w), _fp(b), _fp(y)))
+        return y
+
+
+class Batch:
+    """n_seq sequences generated in lock-step on one Context."""
+
+    def __init__(self, ctx: Context, voice_ids: Sequence[int], max_len: Sequence[int]):
+        self.ctx = ctx
+        self.n = len(voice_ids)
+        self._h = C.c_void_p()
+        v = np.ascontiguousarray(voice_ids, dtype=np.int32)
+        m = np.ascontiguousarray(max_len, dtype=np.int32)
+        check(lib().ptts_batch_create(ctx._h, self.n, _ip(v), _ip(m), C.byref(self._h)))
+        self.latent_dim = ctx.config.latent_dim
+        hop = 1
+        for i in range(ctx.config.n_ratios):
+            hop *= ctx.config.ratios[i]
+        self.frame_samples = hop * ctx.config.upsample_stride
+
+    def close(self):
+        if self._h:
+            lib().ptts_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def prefill_text(self, ids_per_seq: Sequence[Sequence[int]]):
+        assert len(ids_per_seq) == self.n
+        offs = np.zeros(self.n + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(x) for x in ids_per_seq])
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.int32) for x in ids_per_seq])
+                                    if offs[-1] else np.zeros(1, dtype=np.int32), dtype=np.int32)
+        check(lib().ptts_batch_prefill_text(self._h, _ip(flat), _ip(offs)))
+
+    def warmup_mimi(self, n_frames: int):
+        check(lib().ptts_batch_warmup_mimi(self._h, int(n_frames)))
+
+    def step(self, noise: Optional[np.ndarray] = None, want_audio: bool = True):
+        """-> (latent [n, L], eos_logit [n], audio [n, 1920] or None)."""
+        z = _f32(noise).reshape(self.n, self.latent_dim) if noise is not None else None
+        lat = np.empty((self.n, self.latent_dim), dtype=np.float32)
+        logit = np.empty((self.n,), dtype=np.float32)
+        audio = np.empty((self.n, self.frame_samples), dtype=np.float32) if want_audio else None
+        check(lib().ptts_batch_step(self._h, _fp(z), _fp(lat), _fp(logit), _fp(audio)))
+        return lat, logit, audio
+
+    def step_device(self):
+        check(lib().ptts_batch_step_device(self._h))
+
+    def set_prev_latent(self, latent: np.ndarray):
+        a = _f32(latent).reshape(self.n, self.latent_dim)
+        check(lib().ptts_batch_set_prev_latent(self._h, _fp(a)))
+
+    def seed(self, seed: int):
+        check(lib().ptts_batch_seed(self._h, C.c_uint64(seed)))
+
+    def lengths(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.int32)
+        check(lib().ptts_batch_lengths(self._h, _ip(out)))
+        return out
+
+    def mimi_decode(self, latents: np.ndarray, want_audio: bool = True):
+        a = _f32(latents).reshape(self.n, -1, self.latent_dim)
+        f = a.shape[1]
+        out = np.empty((self.n, f * self.frame_samples), dtype=np.float32) if want_audio else None
+        check(lib().ptts_batch_mimi_decode(self._h, _fp(a), f, _fp(out)))
+        return out
+
+    def profile_step(self):
+        ms = (C.c_float * 16)()
+        names = C.c_char_p()
+        n = check(lib().ptts_batch_profile_step(self._h, ms, 16, C.byref(names)))
+        return dict(zip(names.value.decode().split(";"), [float(ms[i]) for i in range(n)]))
+
+
+def max_gen_len(n_tok: int, frame_rate: float = 12.5) -> int:
+    """ceil((n_tok/3 + 2) * frame_rate), the reference's `_estimate_max_gen_len` (tts_model.py:440-444)."""
+    return math.ceil((n_tok / 3.0 + 2.0) * frame_rate)

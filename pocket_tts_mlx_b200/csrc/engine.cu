@@ -1,0 +1,1312 @@
+// libptts_b200 engine: context, weight re-packing, paged KV pool, voices, lock-step batches, per-frame
+// CUDA graphs, and the extern "C" surface declared in include/ptts.h.
+//
+// Host-side structure replaced (reference, /root/reference/pocket_tts_mlx/):
+//   models/tts_model.py:96-200   module tree + weight walk        -> Ctx::finalize (repack + upload)
+//   models/tts_model.py:484-518  voice prefill                    -> voice_create (immutable KV pages)
+//   models/tts_model.py:363-428  per-chunk state + frame loop     -> Batch (+ step graph)
+//   modules/stateful_module.py   dict-of-dicts streaming state    -> device buffers owned by Batch
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ptts.h"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+using namespace ptts;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(PTTS_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                  cudaGetErrorString(e_));                                                         \
+  } while (0)
+
+#define RET(call)                      \
+  do {                                 \
+    int r_ = (call);                   \
+    if (r_ < 0) return r_;             \
+  } while (0)
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+float h2f(uint16_t h) {   // IEEE half -> float
+  uint32_t s = (h >> 15) & 1, e = (h >> 10) & 31, m = h & 1023, u;
+  if (e == 0) {
+    if (m == 0) u = s << 31;
+    else { e = 1; while (!(m & 1024)) { m <<= 1; --e; } m &= 1023; u = (s << 31) | ((e + 112) << 23) | (m << 13); }
+  } else if (e == 31) u = (s << 31) | 0x7f800000u | (m << 13);
+  else u = (s << 31) | ((e + 112) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+struct LinW {
+  void* w = nullptr;        // [N][K] storage precision
+  __nv_bfloat16* w16 = nullptr;   // bf16 copy for the tensor-core path (== w in bf16 mode)
+  float* bias = nullptr;    // [N] fp32 or null
+  int bf16 = 0, N = 0, K = 0;
+};
+
+struct Voice {
+  int len = 0;
+  std::vector<int> pages;
+  bool alive = false;
+};
+
+struct FlowWork {
+  int cap = 0;
+  float *x = nullptr, *h = nullptr, *qkv = nullptr, *qrot = nullptr, *att = nullptr, *ff = nullptr;
+  __nv_bfloat16 *h16 = nullptr, *att16 = nullptr, *ff16 = nullptr;   // bf16 operands for the tensor-core path
+};
+
+}  // namespace
+
+struct ptts_ctx {
+  int device = 0;
+  ptts_config cfg{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool finalized = false;
+  bool bf16 = true;
+  std::unordered_map<std::string, HostTensor> host;
+  std::vector<void*> allocs;
+
+  struct FlowLayer { float *ln1w, *ln1b, *ln2w, *ln2b; LinW qkv, out, ff1, ff2; };
+  std::vector<FlowLayer> fl;
+  void* embed = nullptr;
+  float *w_in = nullptr, *bos = nullptr, *emb_std = nullptr, *emb_mean = nullptr;
+  float *outn_w = nullptr, *outn_b = nullptr, *eos_w = nullptr, *eos_b = nullptr;
+  LinW cond, ada_all, in_proj, fin;
+  std::vector<float*> cond_bias_step;
+  struct ResBlk { float *lnw, *lnb; LinW m1, m2; };
+  std::vector<ResBlk> rb;
+  int n_ada = 0;
+  float *wq = nullptr, *wu = nullptr;
+  struct MimiLayer { float *ln1w, *ln1b, *ln2w, *ln2b, *ls1, *ls2; LinW qkv, out, ff1, ff2; };
+  std::vector<MimiLayer> ml;
+  LinW conv0;
+  struct Stage { LinW ct, r3, r1; int stride, c_in, c_out, hidden; };
+  std::vector<Stage> stages;
+  float *fin_w = nullptr, *fin_b = nullptr;
+  int fin_taps = 0, fin_c = 0;
+  float *freqs_flow = nullptr, *freqs_mimi = nullptr;
+
+  void* pool = nullptr;
+  long long n_pages = 0, page_stride = 0, layer_stride = 0;
+  std::vector<int> free_pages;
+  std::vector<Voice> voices;
+  FlowWork prefill_work;
+  void* l2_scratch = nullptr;
+  size_t l2_bytes = 0;
+  std::string prof_names;
+
+  int dalloc(void** p, size_t bytes) {
+    CU(cudaMalloc(p, bytes ? bytes : 16));
+    allocs.push_back(*p);
+    return 0;
+  }
+};
+
+namespace {
+
+using Ctx = ptts_ctx;
+
+// ---- weight staging ---------------------------------------------------------------------------------------
+const HostTensor* find(Ctx& c, const std::string& name) {
+  auto it = c.host.find(name);
+  return it == c.host.end() ? nullptr : &it->second;
+}
+
+int need(Ctx& c, const std::string& name, std::initializer_list<int64_t> shape, const HostTensor** out) {
+  const HostTensor* t = find(c, name);
+  if (!t) return fail(PTTS_ERR_MISSING, "checkpoint tensor '%s' was not loaded", name.c_str());
+  std::vector<int64_t> want(shape);
+  if (t->shape != want) {
+    std::string got, exp;
+    for (auto s : t->shape) got += std::to_string(s) + ",";
+    for (auto s : want) exp += std::to_string(s) + ",";
+    return fail(PTTS_ERR_INVALID, "tensor '%s' has shape [%s] but [%s] is required", name.c_str(), got.c_str(),
+                exp.c_str());
+  }
+  *out = t;
+  return 0;
+}
+
+int upload_f32(Ctx& c, const float* src, size_t n, float** dst) {
+  RET(c.dalloc((void**)dst, n * sizeof(float)));
+  CU(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int upload_vec(Ctx& c, const std::string& name, int64_t n, float** dst) {
+  const HostTensor* t;
+  RET(need(c, name, {n}, &t));
+  return upload_f32(c, t->data.data(), (size_t)n, dst);
+}
+
+// matrix [N][K] in storage precision (+ bf16 copy when storage is fp32 is NOT made: fp32 mode is SIMT-only)
+int upload_mat(Ctx& c, const std::vector<float>& w, int N, int K, LinW* out) {
+  out->N = N; out->K = K; out->bf16 = c.bf16 ? 1 : 0;
+  if (c.bf16) {
+    std::vector<uint16_t> h((size_t)N * K);
+    for (size_t i = 0; i < h.size(); ++i) h[i] = f2bf(w[i]);
+    RET(c.dalloc(&out->w, h.size() * 2));
+    CU(cudaMemcpy(out->w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    out->w16 = (__nv_bfloat16*)out->w;
+  } else {
+    RET(c.dalloc(&out->w, w.size() * 4));
+    CU(cudaMemcpy(out->w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int load_linear(Ctx& c, const std::string& prefix, int N, int K, bool bias, LinW* out) {
+  const HostTensor* t;
+  RET(need(c, prefix + ".weight", {N, K}, &t));
+  RET(upload_mat(c, t->data, N, K, out));
+  if (bias) RET(upload_vec(c, prefix + ".bias", N, &out->bias));
+  return 0;
+}
+
+// Conv1d checkpoint weight (out,in,k) -> [out][j*in + c]
+int load_conv(Ctx& c, const std::string& prefix, int c_out, int c_in, int k, LinW* out) {
+  const HostTensor* t;
+  RET(need(c, prefix + ".weight", {c_out, c_in, k}, &t));
+  std::vector<float> w((size_t)c_out * k * c_in);
+  for (int o = 0; o < c_out; ++o)
+    for (int ci = 0; ci < c_in; ++ci)
+      for (int j = 0; j < k; ++j)
+        w[((size_t)o * k + j) * c_in + ci] = t->data[((size_t)o * c_in + ci) * k + j];
+  RET(upload_mat(c, w, c_out, k * c_in, out));
+  return upload_vec(c, prefix + ".bias", c_out, &out->bias);
+}
+
+// ConvTranspose1d checkpoint weight (in,out,2s), stride s -> polyphase [r*out+co][tap*in + ci]:
+// tap 0 multiplies the previous input column (kernel index r+s), tap 1 the current one (kernel index r).
+int load_convtr(Ctx& c, const std::string& prefix, int c_in, int c_out, int s, LinW* out) {
+  const HostTensor *t, *b;
+  RET(need(c, prefix + ".weight", {c_in, c_out, 2 * s}, &t));
+  RET(need(c, prefix + ".bias", {c_out}, &b));
+  const int N = s * c_out, K = 2 * c_in;
+  std::vector<float> w((size_t)N * K);
+  for (int r = 0; r < s; ++r)
+    for (int co = 0; co < c_out; ++co)
+      for (int ci = 0; ci < c_in; ++ci) {
+        const size_t n = (size_t)r * c_out + co;
+        w[n * K + ci] = t->data[((size_t)ci * c_out + co) * 2 * s + r + s];
+        w[n * K + c_in + ci] = t->data[((size_t)ci * c_out + co) * 2 * s + r];
+      }
+  RET(upload_mat(c, w, N, K, out));
+  std::vector<float> bias((size_t)N);
+  for (int r = 0; r < s; ++r)
+    for (int co = 0; co < c_out; ++co) bias[(size_t)r * c_out + co] = b->data[co];
+  return upload_f32(c, bias.data(), bias.size(), &out->bias);
+}
+
+// time-embedding constant of one LSD step: (emb(s,0)+emb(t,1))/2, modules/mlp.py:53-74,161-163
+int time_embedding(Ctx& c, int j, double tau, std::vector<double>* out) {
+  const int fd = c.cfg.flow_dim;
+  const std::string p = "flow_lm.flow_net.time_embed." + std::to_string(j) + ".mlp";
+  const HostTensor *w1, *b1, *w2, *b2, *al;
+  RET(need(c, p + ".0.weight", {fd, 256}, &w1));
+  RET(need(c, p + ".0.bias", {fd}, &b1));
+  RET(need(c, p + ".2.weight", {fd, fd}, &w2));
+  RET(need(c, p + ".2.bias", {fd}, &b2));
+  RET(need(c, p + ".3.alpha", {fd}, &al));
+  std::vector<double> e(256), z1(fd), z2(fd);
+  for (int i = 0; i < 128; ++i) {
+    const double f = (double)(float)std::exp(-std::log(10000.0) * i / 128.0);
+    const double arg = (double)(float)((float)tau * (float)f);
+    e[i] = std::cos(arg);
+    e[128 + i] = std::sin(arg);
+  }
+  for (int o = 0; o < fd; ++o) {
+    double a = b1->data[o];
+    for (int i = 0; i < 256; ++i) a += (double)w1->data[(size_t)o * 256 + i] * e[i];
+    z1[o] = a / (1.0 + std::exp(-a));
+  }
+  double mean = 0;
+  for (int o = 0; o < fd; ++o) {
+    double a = b2->data[o];
+    for (int i = 0; i < fd; ++i) a += (double)w2->data[(size_t)o * fd + i] * z1[i];
+    z2[o] = a;
+    mean += a;
+  }
+  mean /= fd;
+  double var = 0;
+  for (int o = 0; o < fd; ++o) var += (z2[o] - mean) * (z2[o] - mean);
+  var /= (fd - 1);
+  out->resize(fd);
+  for (int o = 0; o < fd; ++o) (*out)[o] = z2[o] * ((double)al->data[o] / std::sqrt(1e-5 + var));
+  return 0;
+}
+
+int finalize(Ctx& c) {
+  const ptts_config& g = c.cfg;
+  const int D = g.d_model, FF = g.ffn_dim, L = g.latent_dim, fd = g.flow_dim;
+  // FlowLM
+  c.fl.resize(g.n_layers);
+  for (int i = 0; i < g.n_layers; ++i) {
+    const std::string p = "flow_lm.transformer.layers." + std::to_string(i);
+    auto& l = c.fl[i];
+    RET(upload_vec(c, p + ".norm1.weight", D, &l.ln1w));
+    RET(upload_vec(c, p + ".norm1.bias", D, &l.ln1b));
+    RET(upload_vec(c, p + ".norm2.weight", D, &l.ln2w));
+    RET(upload_vec(c, p + ".norm2.bias", D, &l.ln2b));
+    RET(load_linear(c, p + ".self_attn.in_proj", 3 * D, D, false, &l.qkv));
+    RET(load_linear(c, p + ".self_attn.out_proj", D, D, false, &l.out));
+    RET(load_linear(c, p + ".linear1", FF, D, false, &l.ff1));
+    RET(load_linear(c, p + ".linear2", D, FF, false, &l.ff2));
+  }
+  {
+    const HostTensor* t;
+    RET(need(c, "flow_lm.conditioner.embed.weight", {g.n_bins + 1, D}, &t));
+    LinW tmp;
+    RET(upload_mat(c, t->data, g.n_bins + 1, D, &tmp));
+    c.embed = tmp.w;
+    RET(need(c, "flow_lm.input_linear.weight", {D, L}, &t));
+    RET(upload_f32(c, t->data.data(), t->data.size(), &c.w_in));
+  }
+  RET(upload_vec(c, "flow_lm.bos_emb", L, &c.bos));
+  RET(upload_vec(c, "flow_lm.emb_std", L, &c.emb_std));
+  RET(upload_vec(c, "flow_lm.emb_mean", L, &c.emb_mean));
+  RET(upload_vec(c, "flow_lm.out_norm.weight", D, &c.outn_w));
+  RET(upload_vec(c, "flow_lm.out_norm.bias", D, &c.outn_b));
+  {
+    const HostTensor* t;
+    RET(need(c, "flow_lm.out_eos.weight", {1, D}, &t));
+    RET(upload_f32(c, t->data.data(), D, &c.eos_w));
+    RET(upload_vec(c, "flow_lm.out_eos.bias", 1, &c.eos_b));
+  }
+  // flow head
+  const std::string fp = "flow_lm.flow_net";
+  RET(load_linear(c, fp + ".cond_embed", fd, D, true, &c.cond));
+  RET(load_linear(c, fp + ".input_proj", fd, L, true, &c.in_proj));
+  RET(load_linear(c, fp + ".final_layer.linear", L, fd, true, &c.fin));
+  c.rb.resize(g.flow_depth);
+  c.n_ada = g.flow_depth * 3 * fd + 2 * fd;
+  std::vector<float> ada_w((size_t)c.n_ada * fd), ada_b((size_t)c.n_ada);
+  for (int i = 0; i < g.flow_depth; ++i) {
+    const std::string p = fp + ".res_blocks." + std::to_string(i);
+    RET(upload_vec(c, p + ".in_ln.weight", fd, &c.rb[i].lnw));
+    RET(upload_vec(c, p + ".in_ln.bias", fd, &c.rb[i].lnb));
+    RET(load_linear(c, p + ".mlp.0", fd, fd, true, &c.rb[i].m1));
+    RET(load_linear(c, p + ".mlp.2", fd, fd, true, &c.rb[i].m2));
+    const HostTensor *w, *b;
+    RET(need(c, p + ".adaLN_modulation.1.weight", {3 * fd, fd}, &w));
+    RET(need(c, p + ".adaLN_modulation.1.bias", {3 * fd}, &b));
+    memcpy(&ada_w[(size_t)i * 3 * fd * fd], w->data.data(), w->data.size() * 4);
+    memcpy(&ada_b[(size_t)i * 3 * fd], b->data.data(), b->data.size() * 4);
+  }
+  {
+    const HostTensor *w, *b;
+    RET(need(c, fp + ".final_layer.adaLN_modulation.1.weight", {2 * fd, fd}, &w));
+    RET(need(c, fp + ".final_layer.adaLN_modulation.1.bias", {2 * fd}, &b));
+    memcpy(&ada_w[(size_t)g.flow_depth * 3 * fd * fd], w->data.data(), w->data.size() * 4);
+    memcpy(&ada_b[(size_t)g.flow_depth * 3 * fd], b->data.data(), b->data.size() * 4);
+    RET(upload_mat(c, ada_w, c.n_ada, fd, &c.ada_all));
+    RET(upload_f32(c, ada_b.data(), ada_b.size(), &c.ada_all.bias));
+  }
+  {
+    const HostTensor* cb;
+    RET(need(c, fp + ".cond_embed.bias", {fd}, &cb));
+    const int n = g.lsd_decode_steps;
+    c.cond_bias_step.resize(n);
+    for (int i = 0; i < n; ++i) {
+      std::vector<double> e0, e1;
+      RET(time_embedding(c, 0, (double)i / n, &e0));
+      RET(time_embedding(c, 1, (double)(i + 1) / n, &e1));
+      std::vector<float> bias(fd);
+      for (int o = 0; o < fd; ++o) bias[o] = (float)((e0[o] + e1[o]) * 0.5 + cb->data[o]);
+      RET(upload_f32(c, bias.data(), fd, &c.cond_bias_step[i]));
+    }
+  }
+  // Mimi
+  const int MD = g.mimi_d, SD = g.seanet_dim, S = g.upsample_stride;
+  {
+    const HostTensor* t;
+    RET(need(c, "mimi.quantizer.output_proj.weight", {SD, L, 1}, &t));
+    RET(upload_f32(c, t->data.data(), t->data.size(), &c.wq));
+    RET(need(c, "mimi.upsample.convtr.convtr.weight", {SD, 1, 2 * S}, &t));
+    RET(upload_f32(c, t->data.data(), t->data.size(), &c.wu));
+  }
+  c.ml.resize(g.mimi_layers);
+  for (int i = 0; i < g.mimi_layers; ++i) {
+    const std::string p = "mimi.decoder_transformer.transformer.layers." + std::to_string(i);
+    auto& l = c.ml[i];
+    RET(upload_vec(c, p + ".norm1.weight", MD, &l.ln1w));
+    RET(upload_vec(c, p + ".norm1.bias", MD, &l.ln1b));
+    RET(upload_vec(c, p + ".norm2.weight", MD, &l.ln2w));
+    RET(upload_vec(c, p + ".norm2.bias", MD, &l.ln2b));
+    RET(upload_vec(c, p + ".layer_scale_1.scale", MD, &l.ls1));
+    RET(upload_vec(c, p + ".layer_scale_2.scale", MD, &l.ls2));
+    RET(load_linear(c, p + ".self_attn.in_proj", 3 * MD, MD, false, &l.qkv));
+    RET(load_linear(c, p + ".self_attn.out_proj", MD, MD, false, &l.out));
+    RET(load_linear(c, p + ".linear1", g.mimi_ffn, MD, false, &l.ff1));
+    RET(load_linear(c, p + ".linear2", MD, g.mimi_ffn, false, &l.ff2));
+  }
+  // SEANet decoder: model.0 conv, then per ratio [ELU, convtr, resblock], then [ELU, conv]
+  int mult = 1 << g.n_ratios, idx = 0;
+  RET(load_conv(c, "mimi.decoder.model.0.conv", mult * g.n_filters, SD, g.kernel_size, &c.conv0));
+  idx = 1;
+  c.stages.resize(g.n_ratios);
+  for (int r = 0; r < g.n_ratios; ++r) {
+    auto& st = c.stages[r];
+    st.stride = g.ratios[r];
+    st.c_in = mult * g.n_filters;
+    st.c_out = st.c_in / 2;
+    st.hidden = st.c_out / g.compress;
+    idx += 1;
+    RET(load_convtr(c, "mimi.decoder.model." + std::to_string(idx) + ".convtr", st.c_in, st.c_out, st.stride, &st.ct));
+    idx += 1;
+    const std::string rp = "mimi.decoder.model." + std::to_string(idx) + ".block.";
+    RET(load_conv(c, rp + "1.conv", st.hidden, st.c_out, g.res_kernel_size, &st.r3));
+    RET(load_conv(c, rp + "3.conv", st.c_out, st.hidden, 1, &st.r1));
+    idx += 1;
+    mult /= 2;
+  }
+  idx += 1;
+  {
+    const HostTensor *t, *b;
+    const std::string p = "mimi.decoder.model." + std::to_string(idx) + ".conv";
+    RET(need(c, p + ".weight", {1, g.n_filters, g.last_kernel_size}, &t));
+    RET(need(c, p + ".bias", {1}, &b));
+    c.fin_taps = g.last_kernel_size;
+    c.fin_c = g.n_filters;
+    std::vector<float> w((size_t)c.fin_taps * c.fin_c);
+    for (int ci = 0; ci < c.fin_c; ++ci)
+      for (int j = 0; j < c.fin_taps; ++j) w[(size_t)j * c.fin_c + ci] = t->data[(size_t)ci * c.fin_taps + j];
+    RET(upload_f32(c, w.data(), w.size(), &c.fin_w));
+    RET(upload_f32(c, b->data.data(), 1, &c.fin_b));
+  }
+  // RoPE frequency tables exactly as modules/rope.py:17-18 computes them (fp32 exp of an fp32 product)
+  auto freqs = [&](float period, float** dst) -> int {
+    float f[32];
+    const float scale = (float)(-std::log((double)period) * 2.0 / kHeadDim);
+    for (int i = 0; i < 32; ++i) f[i] = expf((float)i * scale);
+    return upload_f32(c, f, 32, dst);
+  };
+  RET(freqs(g.max_period, &c.freqs_flow));
+  RET(freqs(g.mimi_max_period, &c.freqs_mimi));
+  // KV pool
+  c.page_stride = 2LL * g.n_heads * kPageTokens * kHeadDim;
+  c.n_pages = (g.kv_pool_tokens + kPageTokens - 1) / kPageTokens;
+  c.layer_stride = c.n_pages * c.page_stride;
+  const size_t esz = c.bf16 ? 2 : 4;
+  RET(c.dalloc(&c.pool, (size_t)g.n_layers * c.layer_stride * esz));
+  c.free_pages.resize(c.n_pages);
+  for (long long i = 0; i < c.n_pages; ++i) c.free_pages[i] = (int)(c.n_pages - 1 - i);
+  c.host.clear();
+  c.finalized = true;
+  return 0;
+}
+
+// ---- operator dispatch -----------------------------------------------------------------------------------
+void run_linear(Ctx& c, const LinW& w, LinearParams p) {
+  p.W = w.w; p.w_bf16 = w.bf16; p.N = w.N;
+  if (!p.bias) p.bias = w.bias;
+  if (p.out_scale == 0.f) p.out_scale = 1.f;
+  if (linear_gemv_supported(p)) launch_linear_gemv(p, c.stream);
+  else launch_linear_tile(p, c.stream);
+}
+
+LinearParams rows_linear(const float* A, int M, int C, float* Y, int N) {
+  LinearParams p{};
+  p.A = A; p.a_bs = 0; p.a_rs = C; p.nb = 1; p.T = M; p.taps = 1; p.C = C;
+  p.Y = Y; p.y_bs = 0; p.y_rs = N;
+  p.out_scale = 1.f;
+  return p;
+}
+
+void rows_norm(Ctx& c, const float* X, int M, int C, const float* w, const float* b, float eps, float* Y,
+               const float* scale = nullptr, const float* shift = nullptr, long long mod_rs = 0) {
+  NormParams n{};
+  n.X = X; n.x_bs = 0; n.x_rs = C; n.nb = 1; n.T = M; n.C = C;
+  n.w = w; n.b = b; n.eps = eps; n.scale = scale; n.shift = shift; n.mod_rs = mod_rs;
+  n.Y = Y; n.y_bs = 0; n.y_rs = C;
+  launch_layernorm(n, c.stream);
+}
+
+int alloc_flow_work(Ctx& c, FlowWork& w, int M) {
+  if (M <= w.cap) return 0;
+  const int D = c.cfg.d_model;
+  float** ptrs[] = {&w.x, &w.h, &w.qkv, &w.qrot, &w.att, &w.ff};
+  const size_t widths[] = {(size_t)D, (size_t)D, (size_t)3 * D, (size_t)D, (size_t)D, (size_t)c.cfg.ffn_dim};
+  for (int i = 0; i < 6; ++i) {
+    if (*ptrs[i]) CU(cudaFree(*ptrs[i]));
+    CU(cudaMalloc((void**)ptrs[i], (size_t)M * widths[i] * sizeof(float)));
+  }
+  w.cap = M;
+  return 0;
+}
+
+void free_flow_work(FlowWork& w) {
+  float* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff};
+  for (float* p : ptrs) if (p) cudaFree(p);
+  w = FlowWork{};
+}
+
+// the 6 pre-LN layers over M rows that sit at (row_seq, row_pos) of their sequences
+void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_pos, const int* page_table,
+                 int max_pages) {
+  const int D = c.cfg.d_model, FF = c.cfg.ffn_dim;
+  for (int i = 0; i < c.cfg.n_layers; ++i) {
+    auto& l = c.fl[i];
+    rows_norm(c, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, w.h);
+    run_linear(c, l.qkv, rows_linear(w.h, M, D, w.qkv, 3 * D));
+    FlowAttnParams a{};
+    a.qkv = w.qkv; a.q_rot = w.qrot; a.out = w.att;
+    a.pool = c.pool; a.kv_bf16 = c.bf16; a.layer_stride = c.layer_stride; a.page_stride = c.page_stride;
+    a.layer = i; a.row_seq = row_seq; a.row_pos = row_pos; a.page_table = page_table; a.max_pages = max_pages;
+    a.M = M; a.H = c.cfg.n_heads; a.freqs = c.freqs_flow;
+    launch_flow_rope_append(a, c.stream);
+    launch_flow_attention(a, c.stream);
+    LinearParams o = rows_linear(w.att, M, D, w.x, D);
+    o.res = w.x; o.res_bs = 0; o.res_rs = D;
+    run_linear(c, l.out, o);
+    rows_norm(c, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, w.h);
+    LinearParams f1 = rows_linear(w.h, M, D, w.ff, FF);
+    f1.act = ACT_GELU;
+    run_linear(c, l.ff1, f1);
+    LinearParams f2 = rows_linear(w.ff, M, FF, w.x, D);
+    f2.res = w.x; f2.res_bs = 0; f2.res_rs = D;
+    run_linear(c, l.ff2, f2);
+  }
+}
+
+int take_pages(Ctx& c, int n, std::vector<int>* out) {
+  if ((int)c.free_pages.size() < n)
+    return fail(PTTS_ERR_NOMEM, "KV page pool exhausted: need %d pages, %zu free (kv_pool_tokens=%lld)", n,
+                c.free_pages.size(), (long long)c.cfg.kv_pool_tokens);
+  for (int i = 0; i < n; ++i) {
+    out->push_back(c.free_pages.back());
+    c.free_pages.pop_back();
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ---- batch -----------------------------------------------------------------------------------------------
+struct ptts_batch {
+  Ctx* ctx = nullptr;
+  int B = 0, max_pages = 0;
+  std::vector<int> h_len, voice_ids, max_len, owned_pages;
+  std::vector<void*> allocs;
+  bool prefilled = false;
+  unsigned long long seed = 0x5eed5eedULL;
+  int *d_page_table = nullptr, *d_len = nullptr, *d_bos = nullptr, *d_mimi_off = nullptr, *d_frame_idx = nullptr;
+  unsigned long long* d_counter = nullptr;
+  FlowWork fw;
+  // head
+  float *d_noise = nullptr, *d_x = nullptr, *d_latent = nullptr, *d_c = nullptr, *d_logit = nullptr;
+  float *d_sy = nullptr, *d_ada = nullptr, *d_x1 = nullptr, *d_hh = nullptr, *d_u = nullptr, *d_v = nullptr;
+  float* d_zero_lat = nullptr;
+  // mimi
+  float *d_zprev = nullptr, *d_c0 = nullptr, *d_mh = nullptr, *d_mqkv = nullptr, *d_mqrot = nullptr;
+  float *d_matt = nullptr, *d_mff = nullptr, *d_audio = nullptr, *d_fin = nullptr;
+  struct StageBuf { float *ct_in, *r_in, *hid; int T_in, T_out; };
+  std::vector<StageBuf> sb;
+  void* ring = nullptr;
+  long long ring_layer_stride = 0, ring_kv_stride = 0;
+  ShiftEntry* d_shift = nullptr;
+  int n_shift = 0;
+  int T0 = 0;           // steps per frame at the SEANet input (upsample stride)
+  int frame_samples = 0;
+  // pinned staging
+  float *h_noise = nullptr, *h_latent = nullptr, *h_logit = nullptr, *h_audio = nullptr;
+  // graphs: index = host_noise*2 + copy_out
+  cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long step_graph_launches[4] = {0, 0, 0, 0};
+  std::map<int, std::pair<cudaGraphExec_t, long long>> mimi_graphs;   // keyed by n_frames
+  float *d_lat_all = nullptr, *d_audio_all = nullptr;
+  long long lat_all_cap = 0;
+
+  int dalloc(void** p, size_t bytes) {
+    CU(cudaMalloc(p, bytes ? bytes : 16));
+    allocs.push_back(*p);
+    return 0;
+  }
+};
+
+namespace {
+
+using Batch = ptts_batch;
+
+// one Mimi frame for every sequence: latent [B][L] -> audio [B][frame_samples]
+void mimi_frame(Batch& bt, const float* latent) {
+  Ctx& c = *bt.ctx;
+  const ptts_config& g = c.cfg;
+  const int B = bt.B, T = bt.T0, MD = g.mimi_d, SD = g.seanet_dim;
+  const int k0 = g.kernel_size;
+  const long long c0_bs = (long long)(T + k0 - 1) * SD;
+  float* x = bt.d_c0 + (long long)(k0 - 1) * SD;     // residual stream lives in conv0's input rows
+  launch_quant_upsample(latent, c.emb_std, c.emb_mean, c.wq, c.wu, bt.d_zprev, x, c0_bs, B, g.latent_dim, SD,
+                        g.upsample_stride, c.stream);
+  for (int i = 0; i < g.mimi_layers; ++i) {
+    auto& l = c.ml[i];
+    NormParams n{};
+    n.X = x; n.x_bs = c0_bs; n.x_rs = MD; n.nb = B; n.T = T; n.C = MD;
+    n.w = l.ln1w; n.b = l.ln1b; n.eps = 1e-5f;
+    n.Y = bt.d_mh; n.y_bs = (long long)T * MD; n.y_rs = MD;
+    launch_layernorm(n, c.stream);
+    LinearParams q{};
+    q.A = bt.d_mh; q.a_bs = (long long)T * MD; q.a_rs = MD; q.nb = B; q.T = T; q.taps = 1; q.C = MD;
+    q.Y = bt.d_mqkv; q.y_bs = (long long)T * 3 * MD; q.y_rs = 3 * MD; q.out_scale = 1.f;
+    run_linear(c, l.qkv, q);
+    MimiAttnParams a{};
+    a.qkv = bt.d_mqkv; a.q_rot = bt.d_mqrot; a.out = bt.d_matt;
+    a.ring = bt.ring; a.kv_bf16 = c.bf16; a.layer_stride = bt.ring_layer_stride; a.kv_stride = bt.ring_kv_stride;
+    a.layer = i; a.offset = bt.d_mimi_off; a.B = B; a.T = T; a.H = g.mimi_heads; a.context = g.mimi_context;
+    a.freqs = c.freqs_mimi;
+    launch_mimi_rope_ring(a, c.stream);
+    launch_mimi_attention(a, c.stream);
+    LinearParams o{};
+    o.A = bt.d_matt; o.a_bs = (long long)T * MD; o.a_rs = MD; o.nb = B; o.T = T; o.taps = 1; o.C = MD;
+    o.col_scale = l.ls1; o.res = x; o.res_bs = c0_bs; o.res_rs = MD;
+    o.Y = x; o.y_bs = c0_bs; o.y_rs = MD; o.out_scale = 1.f;
+    run_linear(c, l.out, o);
+    n.w = l.ln2w; n.b = l.ln2b;
+    launch_layernorm(n, c.stream);
+    LinearParams f1 = q;
+    f1.Y = bt.d_mff; f1.y_bs = (long long)T * g.mimi_ffn; f1.y_rs = g.mimi_ffn; f1.act = ACT_GELU;
+    run_linear(c, l.ff1, f1);
+    LinearParams f2 = o;
+    f2.A = bt.d_mff; f2.a_bs = (long long)T * g.mimi_ffn; f2.a_rs = g.mimi_ffn; f2.C = g.mimi_ffn;
+    f2.col_scale = l.ls2;
+    run_linear(c, l.ff2, f2);
+  }
+  // SEANet: conv0 -> [ELU, convtr, resblock] x n -> ELU -> last conv
+  {
+    LinearParams p{};
+    p.A = bt.d_c0; p.a_bs = c0_bs; p.a_rs = SD; p.nb = B; p.T = T; p.taps = k0; p.C = SD;
+    auto& s0 = bt.sb[0];
+    const int c1 = c.stages[0].c_in;
+    p.Y = s0.ct_in + c1; p.y_bs = (long long)(T + 1) * c1; p.y_rs = c1; p.out_scale = 1.f;
+    run_linear(c, c.conv0, p);
+  }
+  for (size_t r = 0; r < c.stages.size(); ++r) {
+    auto& st = c.stages[r];
+    auto& b = bt.sb[r];
+    const int rk = g.res_kernel_size;
+    const long long r_bs = (long long)(b.T_out + rk - 1) * st.c_out;
+    {  // ELU -> transposed conv as a 2-tap GEMM with N = stride*c_out; rows land time-major in r_in
+      LinearParams p{};
+      p.A = b.ct_in; p.a_bs = (long long)(b.T_in + 1) * st.c_in; p.a_rs = st.c_in;
+      p.nb = B; p.T = b.T_in; p.taps = 2; p.C = st.c_in; p.a_pro = ACT_ELU;
+      p.Y = b.r_in + (long long)(rk - 1) * st.c_out; p.y_bs = r_bs; p.y_rs = (long long)st.stride * st.c_out;
+      p.out_scale = 1.f;
+      run_linear(c, st.ct, p);
+    }
+    {  // resblock: x + conv_k1(ELU(conv_k3(ELU(x))))
+      LinearParams p{};
+      p.A = b.r_in; p.a_bs = r_bs; p.a_rs = st.c_out; p.nb = B; p.T = b.T_out; p.taps = rk; p.C = st.c_out;
+      p.a_pro = ACT_ELU;
+      p.Y = b.hid; p.y_bs = (long long)b.T_out * st.hidden; p.y_rs = st.hidden; p.out_scale = 1.f;
+      run_linear(c, st.r3, p);
+      LinearParams q{};
+      q.A = b.hid; q.a_bs = (long long)b.T_out * st.hidden; q.a_rs = st.hidden; q.nb = B; q.T = b.T_out;
+      q.taps = 1; q.C = st.hidden; q.a_pro = ACT_ELU;
+      q.res = b.r_in + (long long)(rk - 1) * st.c_out; q.res_bs = r_bs; q.res_rs = st.c_out;
+      q.out_scale = 1.f;
+      if (r + 1 < c.stages.size()) {
+        auto& nb = bt.sb[r + 1];
+        q.Y = nb.ct_in + st.c_out; q.y_bs = (long long)(b.T_out + 1) * st.c_out; q.y_rs = st.c_out;
+      } else {
+        q.Y = bt.d_fin + (long long)(c.fin_taps - 1) * st.c_out;
+        q.y_bs = (long long)(b.T_out + c.fin_taps - 1) * st.c_out; q.y_rs = st.c_out;
+      }
+      run_linear(c, st.r1, q);
+    }
+  }
+  launch_final_conv(bt.d_fin, (long long)(bt.frame_samples + c.fin_taps - 1) * c.fin_c, c.fin_w, c.fin_b, bt.d_audio,
+                    bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream);
+  launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream);
+}
+
+// FlowLM decode step + EOS + flow head; leaves the new latent in d_latent
+void flow_step(Batch& bt, bool host_noise) {
+  Ctx& c = *bt.ctx;
+  const ptts_config& g = c.cfg;
+  const int B = bt.B, D = g.d_model, L = g.latent_dim, fd = g.flow_dim;
+  launch_input_rows(c.w_in, c.bos, bt.d_latent, bt.d_bos, bt.fw.x, B, D, L, c.stream);
+  flow_layers(c, bt.fw, B, nullptr, bt.d_len, bt.d_page_table, bt.max_pages);
+  launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.d_logit, B, D, c.stream);
+  launch_noise_prep(bt.d_noise, bt.d_x, B * L, sqrtf(g.temp), (g.noise_clamp >= 0.f) ? g.noise_clamp : -1.f,
+                    host_noise ? 0 : 1, bt.seed, bt.d_counter, c.stream);
+  const int n = g.lsd_decode_steps;
+  for (int i = 0; i < n; ++i) {
+    LinearParams ce = rows_linear(bt.d_c, B, D, bt.d_sy, fd);
+    ce.bias = c.cond_bias_step[i];
+    ce.act = ACT_SILU;
+    run_linear(c, c.cond, ce);                                     // silu(t_emb + cond_embed(c))
+    run_linear(c, c.ada_all, rows_linear(bt.d_sy, B, fd, bt.d_ada, c.n_ada));   // every AdaLN modulation at once
+    run_linear(c, c.in_proj, rows_linear(bt.d_x, B, L, bt.d_x1, fd));
+    for (int r = 0; r < g.flow_depth; ++r) {
+      const float* ada = bt.d_ada + (long long)r * 3 * fd;
+      rows_norm(c, bt.d_x1, B, fd, c.rb[r].lnw, c.rb[r].lnb, 1e-6f, bt.d_hh, ada + fd, ada, c.n_ada);
+      LinearParams m1 = rows_linear(bt.d_hh, B, fd, bt.d_u, fd);
+      m1.act = ACT_SILU;
+      run_linear(c, c.rb[r].m1, m1);
+      LinearParams m2 = rows_linear(bt.d_u, B, fd, bt.d_x1, fd);
+      m2.row_gate = ada + 2 * fd; m2.gate_bs = 0; m2.gate_rs = c.n_ada;
+      m2.res = bt.d_x1; m2.res_bs = 0; m2.res_rs = fd;
+      run_linear(c, c.rb[r].m2, m2);
+    }
+    const float* adaf = bt.d_ada + (long long)g.flow_depth * 3 * fd;
+    rows_norm(c, bt.d_x1, B, fd, nullptr, nullptr, 1e-6f, bt.d_hh, adaf + fd, adaf, c.n_ada);
+    LinearParams fo = rows_linear(bt.d_hh, B, fd, bt.d_x, L);     // x += v / n
+    fo.out_scale = 1.0f / (float)n;
+    fo.res = bt.d_x; fo.res_bs = 0; fo.res_rs = L;
+    run_linear(c, c.fin, fo);
+  }
+  cudaMemcpyAsync(bt.d_latent, bt.d_x, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, c.stream);
+}
+
+void full_step(Batch& bt, bool host_noise, bool copy_out) {
+  Ctx& c = *bt.ctx;
+  const int B = bt.B, L = c.cfg.latent_dim;
+  if (host_noise)
+    cudaMemcpyAsync(bt.d_noise, bt.h_noise, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
+  flow_step(bt, host_noise);
+  mimi_frame(bt, bt.d_latent);
+  launch_advance(bt.d_len, bt.d_bos, bt.d_mimi_off, bt.d_counter, B, 1, bt.T0, c.stream);
+  if (copy_out) {
+    cudaMemcpyAsync(bt.h_latent, bt.d_latent, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpyAsync(bt.h_logit, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpyAsync(bt.h_audio, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost,
+                    c.stream);
+  }
+}
+
+int ensure_step_graph(Batch& bt, bool host_noise, bool copy_out) {
+  const int idx = (host_noise ? 2 : 0) + (copy_out ? 1 : 0);
+  if (bt.step_graph[idx]) return 0;
+  Ctx& c = *bt.ctx;
+  const long long before = g_launches;
+  cudaGraph_t graph;
+  CU(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed));
+  full_step(bt, host_noise, copy_out);
+  CU(cudaStreamEndCapture(c.stream, &graph));
+  bt.step_graph_launches[idx] = g_launches - before;
+  g_launches = before;
+  CU(cudaGraphInstantiate(&bt.step_graph[idx], graph, 0));
+  CU(cudaGraphDestroy(graph));
+  return 0;
+}
+
+int run_step(Batch& bt, bool host_noise, bool copy_out) {
+  RET(ensure_step_graph(bt, host_noise, copy_out));
+  const int idx = (host_noise ? 2 : 0) + (copy_out ? 1 : 0);
+  CU(cudaGraphLaunch(bt.step_graph[idx], bt.ctx->stream));
+  g_launches += bt.step_graph_launches[idx];
+  for (auto& l : bt.h_len) l += 1;
+  return 0;
+}
+
+int check_step_ready(Batch& bt) {
+  if (!bt.prefilled) return fail(PTTS_ERR_STATE, "ptts_batch_step called before ptts_batch_prefill_text");
+  for (int b = 0; b < bt.B; ++b)
+    if (bt.h_len[b] + 1 > bt.max_len[b])
+      return fail(PTTS_ERR_STATE, "sequence %d would exceed its max_len %d", b, bt.max_len[b]);
+  return 0;
+}
+
+}  // namespace
+
+// ============================================================ extern "C" ====================================
+extern "C" {
+
+int32_t ptts_abi_version(void) { return PTTS_ABI_VERSION; }
+const char* ptts_last_error(void) { return g_err.c_str(); }
+
+int32_t ptts_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int32_t ptts_ctx_create(int32_t device, const ptts_config* cfg, ptts_ctx** out) {
+  if (!cfg || !out) return fail(PTTS_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+    return fail(PTTS_ERR_CUDA, "no CUDA device is available; libptts_b200 has no CPU fallback");
+  if (device < 0 || device >= n) return fail(PTTS_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  if (cfg->d_model != cfg->n_heads * kHeadDim || cfg->mimi_d != cfg->mimi_heads * kHeadDim)
+    return fail(PTTS_ERR_INVALID, "kernels are specialised for 64-wide attention heads");
+  if (cfg->d_model > 1024 || cfg->mimi_d > 1024 || cfg->flow_dim > 1024)
+    return fail(PTTS_ERR_INVALID, "row-norm kernels support widths up to 1024");
+  if (cfg->n_ratios < 1 || cfg->n_ratios > 8 || cfg->lsd_decode_steps < 1 || cfg->latent_dim % 8 ||
+      cfg->kv_pool_tokens < kPageTokens || cfg->upsample_stride > 16)
+    return fail(PTTS_ERR_INVALID, "unsupported configuration");
+  if (cfg->n_heads * 32 > 1024) return fail(PTTS_ERR_INVALID, "too many heads");
+  CU(cudaSetDevice(device));
+  auto c = std::make_unique<ptts_ctx>();
+  c->device = device;
+  c->cfg = *cfg;
+  c->bf16 = cfg->precision == PTTS_BF16;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  gemm_tc_init();
+  *out = c.release();
+  return 0;
+}
+
+void ptts_ctx_destroy(ptts_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_flow_work(c->prefill_work);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->l2_scratch) cudaFree(c->l2_scratch);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int32_t ptts_load_weight(ptts_ctx* c, const char* name, int32_t dtype, int32_t ndim, const int64_t* shape,
+                         const void* data) {
+  if (!c || !name || !shape || !data) return fail(PTTS_ERR_INVALID, "null argument");
+  if (c->finalized) return fail(PTTS_ERR_STATE, "weights already finalized");
+  const std::string nm(name);
+  if (nm.rfind("flow_lm.", 0) != 0 && nm.rfind("mimi.", 0) != 0) return 1;
+  if (nm.rfind("mimi.encoder", 0) == 0 || nm.rfind("mimi.downsample", 0) == 0) return 1;   // voice cloning: out of scope
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t n = t.numel();
+  t.data.resize((size_t)n);
+  if (dtype == PTTS_DT_F32) memcpy(t.data.data(), data, (size_t)n * 4);
+  else if (dtype == PTTS_DT_BF16) for (int64_t i = 0; i < n; ++i) t.data[i] = bf2f(((const uint16_t*)data)[i]);
+  else if (dtype == PTTS_DT_F16) for (int64_t i = 0; i < n; ++i) t.data[i] = h2f(((const uint16_t*)data)[i]);
+  else return fail(PTTS_ERR_INVALID, "unsupported dtype %d for '%s'", dtype, name);
+  c->host[nm] = std::move(t);
+  return 0;
+}
+
+int32_t ptts_finalize_weights(ptts_ctx* c) {
+  if (!c) return fail(PTTS_ERR_INVALID, "null ctx");
+  if (c->finalized) return fail(PTTS_ERR_STATE, "weights already finalized");
+  CU(cudaSetDevice(c->device));
+  return finalize(*c);
+}
+
+int32_t ptts_voice_create(ptts_ctx* c, const float* cond, int32_t n_frames) {
+  if (!c || !cond || n_frames <= 0) return fail(PTTS_ERR_INVALID, "bad voice prompt");
+  if (!c->finalized) return fail(PTTS_ERR_STATE, "finalize weights first");
+  CU(cudaSetDevice(c->device));
+  const int D = c->cfg.d_model;
+  Voice v;
+  v.len = n_frames;
+  const int np = (n_frames + kPageTokens - 1) / kPageTokens;
+  RET(take_pages(*c, np, &v.pages));
+  RET(alloc_flow_work(*c, c->prefill_work, n_frames));
+  std::vector<int> seq(n_frames, 0), pos(n_frames);
+  for (int i = 0; i < n_frames; ++i) pos[i] = i;
+  int *d_seq, *d_pos, *d_pt;
+  CU(cudaMalloc(&d_seq, n_frames * 4));
+  CU(cudaMalloc(&d_pos, n_frames * 4));
+  CU(cudaMalloc(&d_pt, np * 4));
+  CU(cudaMemcpyAsync(d_seq, seq.data(), n_frames * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_pos, pos.data(), n_frames * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_pt, v.pages.data(), np * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->prefill_work.x, cond, (size_t)n_frames * D * 4, cudaMemcpyHostToDevice, c->stream));
+  flow_layers(*c, c->prefill_work, n_frames, d_seq, d_pos, d_pt, np);
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  cudaFree(d_seq); cudaFree(d_pos); cudaFree(d_pt);
+  v.alive = true;
+  for (size_t i = 0; i < c->voices.size(); ++i)
+    if (!c->voices[i].alive && c->voices[i].pages.empty()) {
+      c->voices[i] = std::move(v);
+      return (int32_t)i;
+    }
+  c->voices.push_back(std::move(v));
+  return (int32_t)c->voices.size() - 1;
+}
+
+int32_t ptts_voice_destroy(ptts_ctx* c, int32_t id) {
+  if (!c || id < 0 || id >= (int)c->voices.size() || !c->voices[id].alive)
+    return fail(PTTS_ERR_INVALID, "unknown voice id %d", id);
+  for (int p : c->voices[id].pages) c->free_pages.push_back(p);
+  c->voices[id] = Voice{};
+  return 0;
+}
+
+int32_t ptts_voice_length(ptts_ctx* c, int32_t id) {
+  if (!c || id < 0 || id >= (int)c->voices.size() || !c->voices[id].alive)
+    return fail(PTTS_ERR_INVALID, "unknown voice id %d", id);
+  return c->voices[id].len;
+}
+
+static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, const int32_t* max_len,
+                             std::unique_ptr<ptts_batch>& bt);
+
+int32_t ptts_batch_create(ptts_ctx* c, int32_t B, const int32_t* voice_ids, const int32_t* max_len,
+                          ptts_batch** out) {
+  if (!c || !voice_ids || !max_len || !out || B <= 0) return fail(PTTS_ERR_INVALID, "bad batch arguments");
+  *out = nullptr;
+  std::unique_ptr<ptts_batch> bt;
+  const int r = batch_create_impl(c, B, voice_ids, max_len, bt);
+  if (r < 0) {
+    const std::string keep = g_err;
+    if (bt) ptts_batch_destroy(bt.release());
+    g_err = keep;
+    return r;
+  }
+  *out = bt.release();
+  return 0;
+}
+
+static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, const int32_t* max_len,
+                             std::unique_ptr<ptts_batch>& bt) {
+  if (!c->finalized) return fail(PTTS_ERR_STATE, "finalize weights first");
+  if (c->cfg.max_batch > 0 && B > c->cfg.max_batch) return fail(PTTS_ERR_INVALID, "batch %d exceeds max_batch", B);
+  CU(cudaSetDevice(c->device));
+  const ptts_config& g = c->cfg;
+  bt = std::make_unique<ptts_batch>();
+  bt->ctx = c;
+  bt->B = B;
+  bt->voice_ids.assign(voice_ids, voice_ids + B);
+  bt->max_len.assign(max_len, max_len + B);
+  bt->h_len.resize(B);
+  int maxp = 1;
+  for (int b = 0; b < B; ++b) {
+    const int v = voice_ids[b];
+    if (v < 0 || v >= (int)c->voices.size() || !c->voices[v].alive) return fail(PTTS_ERR_INVALID, "unknown voice id %d", v);
+    if (max_len[b] < c->voices[v].len) return fail(PTTS_ERR_INVALID, "max_len[%d] shorter than the voice prefix", b);
+    maxp = std::max(maxp, (max_len[b] + kPageTokens - 1) / kPageTokens);
+    bt->h_len[b] = c->voices[v].len;
+  }
+  bt->max_pages = maxp;
+  // page tables: full prefix pages are shared with the voice; its partial tail page is copied
+  std::vector<int> pt((size_t)B * maxp, 0), src, dst;
+  for (int b = 0; b < B; ++b) {
+    const Voice& v = c->voices[voice_ids[b]];
+    const int full = v.len / kPageTokens;
+    const int need_pages = (max_len[b] + kPageTokens - 1) / kPageTokens;
+    for (int i = 0; i < full; ++i) pt[(size_t)b * maxp + i] = v.pages[i];
+    std::vector<int> mine;
+    RET(take_pages(*c, need_pages - full, &mine));
+    for (int i = full; i < need_pages; ++i) pt[(size_t)b * maxp + i] = mine[i - full];
+    bt->owned_pages.insert(bt->owned_pages.end(), mine.begin(), mine.end());
+    if (v.len % kPageTokens) {
+      src.push_back(v.pages[full]);
+      dst.push_back(mine[0]);
+    }
+  }
+  Batch& t = *bt;
+  RET(t.dalloc((void**)&t.d_page_table, pt.size() * 4));
+  CU(cudaMemcpyAsync(t.d_page_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  if (!src.empty()) {
+    int *d_src, *d_dst;
+    RET(t.dalloc((void**)&d_src, src.size() * 4));
+    RET(t.dalloc((void**)&d_dst, dst.size() * 4));
+    CU(cudaMemcpyAsync(d_src, src.data(), src.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_dst, dst.data(), dst.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_copy_pages(c->pool, c->bf16, c->layer_stride, c->page_stride, g.n_layers, d_src, d_dst, (int)src.size(),
+                      c->stream);
+  }
+  RET(t.dalloc((void**)&t.d_len, B * 4));
+  RET(t.dalloc((void**)&t.d_bos, B * 4));
+  RET(t.dalloc((void**)&t.d_mimi_off, B * 4));
+  RET(t.dalloc((void**)&t.d_frame_idx, 4));
+  RET(t.dalloc((void**)&t.d_counter, 8));
+  CU(cudaMemcpyAsync(t.d_len, t.h_len.data(), B * 4, cudaMemcpyHostToDevice, c->stream));
+  launch_fill_u32((unsigned*)t.d_bos, 1u, B, c->stream);
+  CU(cudaMemsetAsync(t.d_mimi_off, 0, B * 4, c->stream));
+  CU(cudaMemsetAsync(t.d_frame_idx, 0, 4, c->stream));
+  CU(cudaMemsetAsync(t.d_counter, 0, 8, c->stream));
+  RET(alloc_flow_work(*c, t.fw, B));
+  const int D = g.d_model, L = g.latent_dim, fd = g.flow_dim;
+  auto fz = [&](float** p, size_t n) -> int {
+    RET(t.dalloc((void**)p, n * 4));
+    CU(cudaMemsetAsync(*p, 0, n * 4, c->stream));
+    return 0;
+  };
+  RET(fz(&t.d_noise, (size_t)B * L));
+  RET(fz(&t.d_x, (size_t)B * L));
+  RET(fz(&t.d_latent, (size_t)B * L));
+  RET(fz(&t.d_zero_lat, (size_t)B * L));
+  RET(fz(&t.d_c, (size_t)B * D));
+  RET(fz(&t.d_logit, B));
+  RET(fz(&t.d_sy, (size_t)B * fd));
+  RET(fz(&t.d_ada, (size_t)B * c->n_ada));
+  RET(fz(&t.d_x1, (size_t)B * fd));
+  RET(fz(&t.d_hh, (size_t)B * fd));
+  RET(fz(&t.d_u, (size_t)B * fd));
+  RET(fz(&t.d_v, (size_t)B * L));
+  // Mimi state + scratch.  Every conv input buffer is [B][taps-1 state rows + T rows][C], zero-initialised
+  // (= the reference's zero `previous` / `partial`, modules/conv.py:113-119,176-180).
+  const int T = g.upsample_stride, MD = g.mimi_d, SD = g.seanet_dim;
+  t.T0 = T;
+  RET(fz(&t.d_zprev, (size_t)B * SD));
+  RET(fz(&t.d_c0, (size_t)B * (T + g.kernel_size - 1) * SD));
+  RET(fz(&t.d_mh, (size_t)B * T * MD));
+  RET(fz(&t.d_mqkv, (size_t)B * T * 3 * MD));
+  RET(fz(&t.d_mqrot, (size_t)B * T * MD));
+  RET(fz(&t.d_matt, (size_t)B * T * MD));
+  RET(fz(&t.d_mff, (size_t)B * T * g.mimi_ffn));
+  std::vector<ShiftEntry> sh;
+  sh.push_back({t.d_c0, (long long)(T + g.kernel_size - 1) * SD, T, g.kernel_size - 1, SD});
+  int Tin = T;
+  t.sb.resize(g.n_ratios);
+  for (int r = 0; r < g.n_ratios; ++r) {
+    auto& st = c->stages[r];
+    auto& b = t.sb[r];
+    b.T_in = Tin;
+    b.T_out = Tin * st.stride;
+    const int rk = g.res_kernel_size;
+    RET(fz(&b.ct_in, (size_t)B * (Tin + 1) * st.c_in));
+    RET(fz(&b.r_in, (size_t)B * (b.T_out + rk - 1) * st.c_out));
+    RET(fz(&b.hid, (size_t)B * b.T_out * st.hidden));
+    sh.push_back({b.ct_in, (long long)(Tin + 1) * st.c_in, Tin, 1, st.c_in});
+    if (rk > 1) sh.push_back({b.r_in, (long long)(b.T_out + rk - 1) * st.c_out, b.T_out, rk - 1, st.c_out});
+    Tin = b.T_out;
+  }
+  t.frame_samples = Tin;
+  RET(fz(&t.d_fin, (size_t)B * (Tin + c->fin_taps - 1) * c->fin_c));
+  if (c->fin_taps > 1) sh.push_back({t.d_fin, (long long)(Tin + c->fin_taps - 1) * c->fin_c, Tin, c->fin_taps - 1, c->fin_c});
+  RET(fz(&t.d_audio, (size_t)B * Tin));
+  t.n_shift = (int)sh.size();
+  RET(t.dalloc((void**)&t.d_shift, sh.size() * sizeof(ShiftEntry)));
+  CU(cudaMemcpyAsync(t.d_shift, sh.data(), sh.size() * sizeof(ShiftEntry), cudaMemcpyHostToDevice, c->stream));
+  t.ring_kv_stride = (long long)B * g.mimi_heads * g.mimi_context * kHeadDim;
+  t.ring_layer_stride = 2 * t.ring_kv_stride;
+  const size_t ring_bytes = (size_t)g.mimi_layers * t.ring_layer_stride * (c->bf16 ? 2 : 4);
+  RET(t.dalloc(&t.ring, ring_bytes));
+  CU(cudaMemsetAsync(t.ring, 0, ring_bytes, c->stream));
+  CU(cudaMallocHost((void**)&t.h_noise, (size_t)B * L * 4));
+  CU(cudaMallocHost((void**)&t.h_latent, (size_t)B * L * 4));
+  CU(cudaMallocHost((void**)&t.h_logit, (size_t)B * 4));
+  CU(cudaMallocHost((void**)&t.h_audio, (size_t)B * Tin * 4));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+void ptts_batch_destroy(ptts_batch* bt) {
+  if (!bt) return;
+  Ctx* c = bt->ctx;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& g : bt->step_graph) if (g) cudaGraphExecDestroy(g);
+  for (auto& kv : bt->mimi_graphs) cudaGraphExecDestroy(kv.second.first);
+  free_flow_work(bt->fw);
+  for (void* p : bt->allocs) cudaFree(p);
+  if (bt->d_lat_all) cudaFree(bt->d_lat_all);
+  if (bt->d_audio_all) cudaFree(bt->d_audio_all);
+  cudaFreeHost(bt->h_noise); cudaFreeHost(bt->h_latent); cudaFreeHost(bt->h_logit); cudaFreeHost(bt->h_audio);
+  for (int p : bt->owned_pages) c->free_pages.push_back(p);
+  delete bt;
+}
+
+int32_t ptts_batch_prefill_text(ptts_batch* bt, const int32_t* ids, const int32_t* offsets) {
+  if (!bt || !ids || !offsets) return fail(PTTS_ERR_INVALID, "null argument");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  const int B = bt->B, M = offsets[B] - offsets[0];
+  if (M < 0) return fail(PTTS_ERR_INVALID, "offsets must be non-decreasing");
+  std::vector<int> seq(M), pos(M);
+  for (int b = 0; b < B; ++b) {
+    const int n = offsets[b + 1] - offsets[b];
+    if (n < 0) return fail(PTTS_ERR_INVALID, "offsets must be non-decreasing");
+    if (bt->h_len[b] + n > bt->max_len[b]) return fail(PTTS_ERR_STATE, "text of sequence %d exceeds max_len", b);
+    for (int i = 0; i < n; ++i) {
+      const int id = ids[offsets[b] + i];
+      if (id < 0 || id > c.cfg.n_bins) return fail(PTTS_ERR_INVALID, "token id %d out of range", id);
+      seq[offsets[b] - offsets[0] + i] = b;
+      pos[offsets[b] - offsets[0] + i] = bt->h_len[b] + i;
+    }
+  }
+  if (M > 0) {
+    RET(alloc_flow_work(c, c.prefill_work, M));
+    int *d_seq, *d_pos, *d_ids;
+    CU(cudaMalloc(&d_seq, M * 4));
+    CU(cudaMalloc(&d_pos, M * 4));
+    CU(cudaMalloc(&d_ids, M * 4));
+    CU(cudaMemcpyAsync(d_seq, seq.data(), M * 4, cudaMemcpyHostToDevice, c.stream));
+    CU(cudaMemcpyAsync(d_pos, pos.data(), M * 4, cudaMemcpyHostToDevice, c.stream));
+    CU(cudaMemcpyAsync(d_ids, ids + offsets[0], M * 4, cudaMemcpyHostToDevice, c.stream));
+    launch_embed_rows(c.embed, c.bf16, d_ids, c.prefill_work.x, M, c.cfg.d_model, c.stream);
+    flow_layers(c, c.prefill_work, M, d_seq, d_pos, bt->d_page_table, bt->max_pages);
+    for (int b = 0; b < B; ++b) bt->h_len[b] += offsets[b + 1] - offsets[b];
+    CU(cudaMemcpyAsync(bt->d_len, bt->h_len.data(), B * 4, cudaMemcpyHostToDevice, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    CU(cudaGetLastError());
+    cudaFree(d_seq); cudaFree(d_pos); cudaFree(d_ids);
+  }
+  bt->prefilled = true;
+  return 0;
+}
+
+int32_t ptts_batch_warmup_mimi(ptts_batch* bt, int32_t n_frames) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  for (int i = 0; i < n_frames; ++i) {
+    mimi_frame(*bt, bt->d_zero_lat);
+    launch_advance(nullptr, nullptr, bt->d_mimi_off, nullptr, bt->B, 0, bt->T0, c.stream);
+  }
+  CU(cudaStreamSynchronize(c.stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int32_t ptts_batch_step(ptts_batch* bt, const float* noise, float* out_latent, float* out_eos_logit,
+                        float* out_audio) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  RET(check_step_ready(*bt));
+  const int B = bt->B, L = c.cfg.latent_dim;
+  const bool copy_out = out_latent || out_eos_logit || out_audio;
+  if (noise) memcpy(bt->h_noise, noise, (size_t)B * L * 4);
+  RET(run_step(*bt, noise != nullptr, copy_out));
+  CU(cudaStreamSynchronize(c.stream));
+  if (out_latent) memcpy(out_latent, bt->h_latent, (size_t)B * L * 4);
+  if (out_eos_logit) memcpy(out_eos_logit, bt->h_logit, (size_t)B * 4);
+  if (out_audio) memcpy(out_audio, bt->h_audio, (size_t)B * bt->frame_samples * 4);
+  return 0;
+}
+
+int32_t ptts_batch_step_device(ptts_batch* bt) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  CU(cudaSetDevice(bt->ctx->device));
+  RET(check_step_ready(*bt));
+  return run_step(*bt, false, false);
+}
+
+int32_t ptts_batch_set_prev_latent(ptts_batch* bt, const float* latent) {
+  if (!bt || !latent) return fail(PTTS_ERR_INVALID, "null argument");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  CU(cudaMemcpyAsync(bt->d_latent, latent, (size_t)bt->B * c.cfg.latent_dim * 4, cudaMemcpyHostToDevice, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int32_t ptts_batch_seed(ptts_batch* bt, uint64_t seed) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  if (bt->seed != seed) {
+    bt->seed = seed;   // the seed is baked into the captured graphs
+    for (int i = 0; i < 2; ++i)
+      if (bt->step_graph[i]) { cudaGraphExecDestroy(bt->step_graph[i]); bt->step_graph[i] = nullptr; }
+  }
+  return 0;
+}
+
+int32_t ptts_batch_lengths(ptts_batch* bt, int32_t* out_len) {
+  if (!bt || !out_len) return fail(PTTS_ERR_INVALID, "null argument");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  CU(cudaMemcpyAsync(out_len, bt->d_len, bt->B * 4, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int32_t ptts_batch_mimi_decode(ptts_batch* bt, const float* latents, int32_t F, float* audio) {
+  if (!bt || !latents || F <= 0) return fail(PTTS_ERR_INVALID, "bad arguments");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  const int B = bt->B, L = c.cfg.latent_dim, n = bt->frame_samples;
+  if ((long long)F > bt->lat_all_cap) {
+    if (bt->d_lat_all) cudaFree(bt->d_lat_all);
+    if (bt->d_audio_all) cudaFree(bt->d_audio_all);
+    CU(cudaMalloc((void**)&bt->d_lat_all, (size_t)B * F * L * 4));
+    CU(cudaMalloc((void**)&bt->d_audio_all, (size_t)B * F * n * 4));
+    bt->lat_all_cap = F;
+    for (auto& kv : bt->mimi_graphs) cudaGraphExecDestroy(kv.second.first);
+    bt->mimi_graphs.clear();
+  }
+  CU(cudaMemcpyAsync(bt->d_lat_all, latents, (size_t)B * F * L * 4, cudaMemcpyHostToDevice, c.stream));
+  CU(cudaMemsetAsync(bt->d_frame_idx, 0, 4, c.stream));
+  auto it = bt->mimi_graphs.find(F);
+  if (it == bt->mimi_graphs.end()) {
+    const long long before = g_launches;
+    cudaGraph_t graph;
+    CU(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed));
+    launch_gather_frame(bt->d_lat_all, bt->d_x, B, F, L, bt->d_frame_idx, c.stream);
+    mimi_frame(*bt, bt->d_x);
+    launch_scatter_audio(bt->d_audio, bt->d_audio_all, B, F, n, bt->d_frame_idx, c.stream);
+    launch_advance(nullptr, nullptr, bt->d_mimi_off, nullptr, B, 0, bt->T0, c.stream);
+    launch_inc(bt->d_frame_idx, 1, c.stream);
+    CU(cudaStreamEndCapture(c.stream, &graph));
+    const long long cnt = g_launches - before;
+    g_launches = before;
+    cudaGraphExec_t exec;
+    CU(cudaGraphInstantiate(&exec, graph, 0));
+    CU(cudaGraphDestroy(graph));
+    it = bt->mimi_graphs.emplace(F, std::make_pair(exec, cnt)).first;
+  }
+  for (int f = 0; f < F; ++f) {
+    CU(cudaGraphLaunch(it->second.first, c.stream));
+    g_launches += it->second.second;
+  }
+  if (audio)
+    CU(cudaMemcpyAsync(audio, bt->d_audio_all, (size_t)B * F * n * 4, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int32_t ptts_sync(ptts_ctx* c) {
+  if (!c) return fail(PTTS_ERR_INVALID, "null ctx");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int32_t ptts_timer_begin(ptts_ctx* c) {
+  if (!c) return fail(PTTS_ERR_INVALID, "null ctx");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->ev0, c->stream));
+  return 0;
+}
+
+int32_t ptts_timer_end(ptts_ctx* c, float* ms) {
+  if (!c || !ms) return fail(PTTS_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return 0;
+}
+
+int64_t ptts_launch_count(ptts_ctx*, int32_t reset) {
+  const long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int32_t ptts_batch_profile_step(ptts_batch* bt, float* ms, int32_t cap, const char** names) {
+  if (!bt || !ms || cap < 3) return fail(PTTS_ERR_INVALID, "bad arguments");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  RET(check_step_ready(*bt));
+  cudaEvent_t ev[4];
+  for (auto& e : ev) CU(cudaEventCreate(&e));
+  CU(cudaEventRecord(ev[0], c.stream));
+  flow_step(*bt, false);
+  CU(cudaEventRecord(ev[1], c.stream));
+  mimi_frame(*bt, bt->d_latent);
+  CU(cudaEventRecord(ev[2], c.stream));
+  launch_advance(bt->d_len, bt->d_bos, bt->d_mimi_off, bt->d_counter, bt->B, 1, bt->T0, c.stream);
+  CU(cudaEventRecord(ev[3], c.stream));
+  CU(cudaEventSynchronize(ev[3]));
+  for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  for (auto& l : bt->h_len) l += 1;
+  c.prof_names = "flow_step;mimi_frame;advance";
+  if (names) *names = c.prof_names.c_str();
+  return 3;
+}
+
+int32_t ptts_flush_l2(ptts_ctx* c) {
+  if (!c) return fail(PTTS_ERR_INVALID, "null ctx");
+  CU(cudaSetDevice(c->device));
+  if (!c->l2_scratch) {
+    c->l2_bytes = 256ull << 20;
+    CU(cudaMalloc(&c->l2_scratch, c->l2_bytes));
+  }
+  launch_fill_u32((unsigned*)c->l2_scratch, 0u, (long long)(c->l2_bytes / 4), c->stream);
+  return 0;
+}
+
+int32_t ptts_debug_linear(ptts_ctx* c, int32_t path, int32_t nb, int32_t T, int32_t taps, int32_t C, int32_t N,
+                          const float* a, const float* w, const float* bias, float* y) {
+  if (!c || !a || !w || !y) return fail(PTTS_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(c->device));
+  const size_t na = (size_t)nb * (T + taps - 1) * C, nw = (size_t)N * taps * C, ny = (size_t)nb * T * N;
+  float *d_a, *d_y, *d_b = nullptr;
+  void* d_w;
+  CU(cudaMalloc((void**)&d_a, na * 4));
+  CU(cudaMalloc((void**)&d_y, ny * 4));
+  CU(cudaMemcpy(d_a, a, na * 4, cudaMemcpyHostToDevice));
+  if (c->bf16) {
+    std::vector<uint16_t> h(nw);
+    for (size_t i = 0; i < nw; ++i) h[i] = f2bf(w[i]);
+    CU(cudaMalloc(&d_w, nw * 2));
+    CU(cudaMemcpy(d_w, h.data(), nw * 2, cudaMemcpyHostToDevice));
+  } else {
+    CU(cudaMalloc(&d_w, nw * 4));
+    CU(cudaMemcpy(d_w, w, nw * 4, cudaMemcpyHostToDevice));
+  }
+  if (bias) {
+    CU(cudaMalloc((void**)&d_b, (size_t)N * 4));
+    CU(cudaMemcpy(d_b, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+  }
+  LinearParams p{};
+  p.A = d_a; p.a_bs = (long long)(T + taps - 1) * C; p.a_rs = C; p.nb = nb; p.T = T; p.taps = taps; p.C = C;
+  p.W = d_w; p.w_bf16 = c->bf16; p.N = N; p.bias = d_b; p.out_scale = 1.f;
+  p.Y = d_y; p.y_bs = (long long)T * N; p.y_rs = N;
+  int rc = 0;
+  if (path == 1) launch_linear_tile(p, c->stream);
+  else if (path == 2) {
+    if (!linear_gemv_supported(p)) rc = fail(PTTS_ERR_INVALID, "shape not supported by the GEMV path");
+    else launch_linear_gemv(p, c->stream);
+  } else if (path == 3) {
+    rc = gemm_tc_debug(p, c->bf16, c->stream);
+    if (rc < 0) rc = fail(PTTS_ERR_INVALID, "shape not supported by the tcgen05 path");
+  } else {
+    if (linear_gemv_supported(p)) launch_linear_gemv(p, c->stream);
+    else launch_linear_tile(p, c->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess && rc >= 0) e = cudaMemcpy(y, d_y, ny * 4, cudaMemcpyDeviceToHost);
+  cudaFree(d_a); cudaFree(d_y); cudaFree(d_w);
+  if (d_b) cudaFree(d_b);
+  if (rc < 0) return rc;
+  if (e != cudaSuccess) return fail(PTTS_ERR_CUDA, "debug_linear: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// Kernel-side declarations shared by the engine and the .cu translation units.
+// Everything here is device plumbing for the hot path of SURVEY.md section 8; no host-side fallbacks.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ptts {
+
+constexpr int kHeadDim = 64;      // both transformers use 64-wide heads (b6369a24.yaml)
+constexpr int kPageTokens = 32;   // FlowLM KV page: 32 tokens x H x 64
+
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_ELU = 3 };
+
+// Y[b,t,n] = epi( sum_{j<taps} sum_{c<C} pro(A[b, t+j, c]) * W[n, j*C + c] )
+//   epi(v) = res[b,t,n] + col_scale[n] * row_gate[b,t,n] * out_scale * act(v + bias[n])
+// A rows of sequence b start at A + b*a_bs, consecutive time rows are a_rs apart.  The first taps-1
+// rows of each sequence are carried streaming state (previous inputs), so a k-tap causal conv, a
+// polyphase transposed conv (taps = 2, N = stride*C_out) and a plain Linear (taps = 1) are one operator.
+struct LinearParams {
+  const float* A; long long a_bs, a_rs;
+  int nb, T, taps, C;
+  const void* W; int w_bf16;                 // [N][taps*C], bf16 or fp32 storage
+  int N;
+  const float* bias;                          // [N] or null
+  int a_pro;                                  // Act applied to A on load (ELU in front of SEANet convs)
+  int act;                                    // Act applied to the accumulator (+bias)
+  float out_scale;
+  const float* row_gate; long long gate_bs, gate_rs;   // null or [b,t,n] multiplier (AdaLN gate)
+  const float* col_scale;                     // null or [N] (LayerScale)
+  const float* res; long long res_bs, res_rs; // null or residual with Y's row indexing
+  float* Y; long long y_bs, y_rs;
+};
+
+void launch_linear_tile(const LinearParams& p, cudaStream_t s);   // any M; SIMT 64x64 tiles
+void launch_linear_gemv(const LinearParams& p, cudaStream_t s);   // M = nb*T <= 16; weight-streaming
+bool linear_gemv_supported(const LinearParams& p);
+
+// y = LN(x; w, b, eps) [* (1 + scale) + shift]; rows of width C; scale/shift are per-row vectors
+// (AdaLN modulation, modules/mlp.py:11-13,95-100) or null.
+struct NormParams {
+  const float* X; long long x_bs, x_rs;
+  int nb, T, C;
+  const float* w; const float* b; float eps;
+  const float* scale; const float* shift; long long mod_rs;   // row stride of the modulation buffer
+  float* Y; long long y_bs, y_rs;
+};
+void launch_layernorm(const NormParams& p, cudaStream_t s);
+
+// ---- FlowLM attention over the paged KV pool ------------------------------------------------------
+// Pool layout: [layer][page][k|v][head][slot(32)][64], element bf16 or fp32.
+struct FlowAttnParams {
+  const float* qkv;            // [M][3*H*64]  (q | k | v), pre-RoPE
+  float* q_rot;                // [M][H*64] scratch
+  float* out;                  // [M][H*64]
+  void* pool; int kv_bf16; long long layer_stride, page_stride;   // strides in elements
+  int layer;
+  const int* row_seq;          // [M] sequence of each row, or null => row m belongs to sequence m
+  const int* row_pos;          // [M] absolute position of each row (decode: the sequence length)
+  const int* page_table; int max_pages;   // [n_seq][max_pages]
+  int M, H;
+  const float* freqs;          // [32] RoPE frequencies (fp32, computed like modules/rope.py:17-18)
+};
+void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s);
+void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s);
+
+// ---- Mimi ring-buffer attention --------------------------------------------------------------------
+// Ring layout: [layer][k|v][seq][head][slot(context)][64].
+struct MimiAttnParams {
+  const float* qkv;            // [B*T][3*H*64]
+  float* q_rot;                // [B*T][H*64]
+  float* out;                  // [B*T][H*64]
+  void* ring; int kv_bf16; long long layer_stride, kv_stride;
+  int layer;
+  const int* offset;           // [B] absolute position of this chunk's first step (= end_offset)
+  int B, T, H, context;
+  const float* freqs;
+};
+void launch_mimi_rope_ring(const MimiAttnParams& p, cudaStream_t s);
+void launch_mimi_attention(const MimiAttnParams& p, cudaStream_t s);
+
+// ---- small fused ops --------------------------------------------------------------------------------
+// x[b] = W_in (bos_flag[b] ? bos : prev[b])            (models/flow_lm.py:93-94)
+void launch_input_rows(const float* w_in, const float* bos, const float* prev, const int* bos_flag,
+                       float* x, int B, int D, int L, cudaStream_t s);
+// rows[m] = table[ids[m]]                               (conditioners/text.py:43-45)
+void launch_embed_rows(const void* table, int table_bf16, const int* ids, float* rows, int M, int D,
+                       cudaStream_t s);
+// c = LN(x[row_of[b]]); logit = w_eos . c + b_eos      (models/flow_lm.py:120,100)
+void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w, const float* ln_b,
+                           const float* w_eos, const float* b_eos, float* c, float* logit, int B, int D,
+                           cudaStream_t s);
+// x0 = clip(sqrt(temp) * z); z from the host buffer or a Philox4x32-10 + Box-Muller stream
+void launch_noise_prep(const float* z, float* x0, int n, float std, float clamp, int use_philox,
+                       unsigned long long seed, const unsigned long long* counter, cudaStream_t s);
+// z = Wq (lat*std + mean); up[b,t,c] = wu[c,t] z[c] + wu[c,S+t] zprev[b,c]; zprev = z
+void launch_quant_upsample(const float* lat, const float* emb_std, const float* emb_mean, const float* wq,
+                           const float* wu, float* zprev, float* out, long long out_bs, int B, int L, int C,
+                           int S, cudaStream_t s);
+// audio[b,t] = bias + sum_{j<taps} sum_c elu(x~[b,t+j,c]) w[j*C+c]      (SEANet last conv, N = 1)
+void launch_final_conv(const float* x, long long x_bs, const float* w, const float* bias, float* audio,
+                       long long audio_bs, int B, int T, int C, int taps, cudaStream_t s);
+// carried conv state: move the last `rows` time rows of each sequence's buffer to its front
+struct ShiftEntry { float* buf; long long bs; int T, rows, C; };
+void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s);
+// seq_len += inc_len; bos_flag = 0; mimi_offset += inc_mimi; philox counter += 1
+void launch_advance(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter, int B,
+                    int inc_len, int inc_mimi, cudaStream_t s);
+// y = a * x + y   (Euler update x += v / n)
+void launch_axpy(const float* x, float* y, float a, int n, cudaStream_t s);
+void launch_copy_pages(void* pool, int kv_bf16, long long layer_stride, long long page_stride, int n_layers,
+                       const int* src_pages, const int* dst_pages, int n_pairs, cudaStream_t s);
+void launch_fill_u32(unsigned int* dst, unsigned int v, long long n, cudaStream_t s);
+void launch_gather_frame(const float* lat_all, float* lat, int B, int F, int L, const int* frame_idx,
+                         cudaStream_t s);
+void launch_scatter_audio(const float* audio, float* audio_all, int B, int F, int n, const int* frame_idx,
+                          cudaStream_t s);
+void launch_inc(int* v, int inc, cudaStream_t s);
+
+// launch accounting (ptts_launch_count)
+extern long long g_launches;
+
+// ---- device helpers ----------------------------------------------------------------------------------
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    case ACT_SILU: return v / (1.0f + __expf(-v));
+    case ACT_ELU: return v > 0.0f ? v : expm1f(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void epilogue_store(const LinearParams& p, int b, int t, int n, float v) {
+  if (p.bias) v += p.bias[n];
+  v = act_apply(v, p.act) * p.out_scale;
+  if (p.row_gate) v *= p.row_gate[b * p.gate_bs + t * p.gate_rs + n];
+  if (p.col_scale) v *= p.col_scale[n];
+  if (p.res) v += p.res[b * p.res_bs + t * p.res_rs + n];
+  p.Y[b * p.y_bs + t * p.y_rs + n] = v;
+}
+
+}  // namespace ptts

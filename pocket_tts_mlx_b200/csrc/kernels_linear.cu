@@ -1,0 +1,250 @@
+// Multi-tap linear operator, CUDA-core paths.
+//   * linear_tile_kernel : 64x64x16 register-tiled SIMT GEMM for any M (fp32 mode, odd shapes, and the
+//                          reference point the tcgen05 path is checked against).
+//   * linear_gemv_kernel : M <= 16 rows (batch-1 decode, 16-step Mimi chunk): every weight byte is read
+//                          exactly once with 16-byte loads; HBM-bound by construction.
+// Replaces mx.matmul / nn.Linear / nn.Conv1d / mx.conv_transpose1d call sites listed in SURVEY.md 2.3.
+#include "kernels.cuh"
+
+namespace ptts {
+
+long long g_launches = 0;
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <typename WT>
+__device__ __forceinline__ void load_w4(const WT* w, float (&out)[4]);
+template <>
+__device__ __forceinline__ void load_w4<float>(const float* w, float (&out)[4]) {
+  float4 v = *reinterpret_cast<const float4*>(w);
+  out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void load_w4<__nv_bfloat16>(const __nv_bfloat16* w, float (&out)[4]) {
+  uint2 v = *reinterpret_cast<const uint2*>(w);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&v.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  out[0] = fa.x; out[1] = fa.y; out[2] = fb.x; out[3] = fb.y;
+}
+
+// grid (ceil(N/64), ceil(M/64)); 256 threads, each a 4x4 micro-tile.  K = taps*C, C % 16 == 0.
+template <typename WT>
+__global__ void __launch_bounds__(256) linear_tile_kernel(const LinearParams p) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Ws[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int M = p.nb * p.T, K = p.taps * p.C;
+  const WT* W = reinterpret_cast<const WT*>(p.W);
+
+  // loader mapping: 64 rows x 4 k-quads
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int am = m0 + lr;
+  const bool a_ok = am < M;
+  const int ab = a_ok ? am / p.T : 0, at = a_ok ? am % p.T : 0;
+  const float* a_row = p.A + ab * p.a_bs + at * p.a_rs;
+  const int wn = n0 + lr;
+  const bool w_ok = wn < p.N;
+  const WT* w_row = W + (long long)(w_ok ? wn : 0) * K;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    const int kk = k0 + lk;
+    const int tap = kk / p.C, c = kk - tap * p.C;
+    float av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a_ok) {
+      float4 v = *reinterpret_cast<const float4*>(a_row + tap * p.a_rs + c);
+      av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+      if (p.a_pro != ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = act_apply(av[i], p.a_pro);
+      }
+    }
+    float wv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (w_ok) load_w4<WT>(w_row + kk, wv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[lk + i][lr] = av[i];
+      Ws[lk + i][lr] = wv[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 w4 = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int b = m / p.T, t = m % p.T;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < p.N) epilogue_store(p, b, t, n, acc[i][j]);
+    }
+  }
+}
+
+// ---- small-M weight-streaming path -------------------------------------------------------------------
+// grid = ceil(N / 8); 128 threads = 4 warps x 2 output rows each.  The (T+taps-1) x C input rows of every
+// sequence are staged in shared memory once (prologue activation applied); each lane then streams
+// 16-byte weight vectors and keeps MT accumulators per output row.
+template <typename WT> struct WVec;
+template <> struct WVec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      o[2 * i] = f.x; o[2 * i + 1] = f.y;
+    }
+  }
+};
+template <> struct WVec<float> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const float* p, float (&o)[8]) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+};
+
+template <typename WT, int MT>
+__global__ void __launch_bounds__(128) linear_gemv_kernel(const LinearParams p) {
+  extern __shared__ __align__(16) float xs[];   // [nb][T+taps-1][C]
+  const int rows_per_seq = p.T + p.taps - 1;
+  const int C = p.C, K = p.taps * p.C;
+  const int M = p.nb * p.T;
+  {
+    const int c4 = C >> 2;
+    const int total = p.nb * rows_per_seq * c4;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int q = i % c4, r = (i / c4) % rows_per_seq, b = i / (c4 * rows_per_seq);
+      float4 v = *reinterpret_cast<const float4*>(p.A + b * p.a_bs + r * p.a_rs + q * 4);
+      if (p.a_pro != ACT_NONE) {
+        v.x = act_apply(v.x, p.a_pro); v.y = act_apply(v.y, p.a_pro);
+        v.z = act_apply(v.z, p.a_pro); v.w = act_apply(v.w, p.a_pro);
+      }
+      *reinterpret_cast<float4*>(xs + ((long long)(b * rows_per_seq + r)) * C + q * 4) = v;
+    }
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_base = blockIdx.x * 8 + warp * 2;
+  const WT* W = reinterpret_cast<const WT*>(p.W);
+  float acc[2][MT];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[r][m] = 0.f;
+
+  const bool ok0 = n_base < p.N, ok1 = n_base + 1 < p.N;
+  const WT* w0 = W + (long long)(ok0 ? n_base : 0) * K;
+  const WT* w1 = W + (long long)(ok1 ? n_base + 1 : 0) * K;
+
+  for (int k = lane * 8; k < K; k += 256) {
+    float wa[8], wb[8];
+    WVec<WT>::load(w0 + k, wa);
+    WVec<WT>::load(w1 + k, wb);
+    const int tap = k / C, c = k - tap * C;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < M) {
+        const int b = m / p.T, t = m - b * p.T;
+        const float* xr = xs + ((long long)(b * rows_per_seq + t + tap)) * C + c;
+        float4 x0 = *reinterpret_cast<const float4*>(xr);
+        float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
+        const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[0][m] = fmaf(wa[i], x[i], acc[0][m]);
+          acc[1][m] = fmaf(wb[i], x[i], acc[1][m]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[r][m] = warp_sum(acc[r][m]);
+
+  // lanes 0..2*MT-1 each finish one (row, m) output
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (lane == r * MT + m && m < M) {
+        const int n = n_base + r;
+        if (n < p.N) {
+          const int b = m / p.T, t = m - b * p.T;
+          epilogue_store(p, b, t, n, acc[r][m]);
+        }
+      }
+    }
+  }
+}
+
+template <typename WT>
+void launch_gemv_t(const LinearParams& p, cudaStream_t s) {
+  const int M = p.nb * p.T;
+  const size_t smem = (size_t)p.nb * (p.T + p.taps - 1) * p.C * sizeof(float);
+  dim3 grid((p.N + 7) / 8), block(128);
+#define PTTS_GEMV(MT)                                                                                   \
+  do {                                                                                                  \
+    auto kfn = linear_gemv_kernel<WT, MT>;                                                              \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    kfn<<<grid, block, smem, s>>>(p);                                                                   \
+  } while (0)
+  if (M <= 1) PTTS_GEMV(1);
+  else if (M <= 2) PTTS_GEMV(2);
+  else if (M <= 4) PTTS_GEMV(4);
+  else if (M <= 8) PTTS_GEMV(8);
+  else PTTS_GEMV(16);
+#undef PTTS_GEMV
+}
+
+}  // namespace
+
+bool linear_gemv_supported(const LinearParams& p) {
+  const int M = p.nb * p.T;
+  const size_t smem = (size_t)p.nb * (p.T + p.taps - 1) * p.C * sizeof(float);
+  return M <= 16 && (p.C % 8) == 0 && smem <= 160 * 1024;
+}
+
+void launch_linear_tile(const LinearParams& p, cudaStream_t s) {
+  const int M = p.nb * p.T;
+  dim3 grid((p.N + BN - 1) / BN, (M + BM - 1) / BM), block(256);
+  if (p.w_bf16) linear_tile_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(p);
+  else linear_tile_kernel<float><<<grid, block, 0, s>>>(p);
+  ++g_launches;
+}
+
+void launch_linear_gemv(const LinearParams& p, cudaStream_t s) {
+  if (p.w_bf16) launch_gemv_t<__nv_bfloat16>(p, s);
+  else launch_gemv_t<float>(p, s);
+  ++g_launches;
+}
+
+}  // namespace ptts

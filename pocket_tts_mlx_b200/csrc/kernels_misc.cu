@@ -1,0 +1,363 @@
+// Row-wise normalisation and the small fused ops around the GEMMs (LayerNorm,
+// Embedding, NaN->BOS, noise, quantizer + upsample, last SEANet conv, carried conv state).
+#include "kernels.cuh"
+
+namespace ptts {
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+// one CTA (128 threads) per row; two-pass mean / biased variance exactly as LayerNorm is defined
+__global__ void __launch_bounds__(128) layernorm_kernel(const NormParams p) {
+  __shared__ float red[32];
+  const int m = blockIdx.x;
+  const int b = m / p.T, t = m % p.T;
+  const float* x = p.X + b * p.x_bs + t * p.x_rs;
+  float* y = p.Y + b * p.y_bs + t * p.y_rs;
+  const int C = p.C;
+  float v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 128;
+    v[i] = c < C ? x[c] : 0.f;
+    s += v[i];
+  }
+  const float mean = block_sum(s, red) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 128;
+    const float d = c < C ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float var = block_sum(q, red) / (float)C;
+  const float rstd = 1.0f / sqrtf(var + p.eps);
+  const float* sc = p.scale ? p.scale + (long long)m * p.mod_rs : nullptr;
+  const float* sh = p.shift ? p.shift + (long long)m * p.mod_rs : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 128;
+    if (c < C) {
+      float o = (v[i] - mean) * rstd;
+      if (p.w) o = o * p.w[c] + p.b[c];
+      if (sc) o = o * (1.0f + sc[c]) + sh[c];
+      y[c] = o;
+    }
+  }
+}
+
+__global__ void input_rows_kernel(const float* __restrict__ w_in, const float* __restrict__ bos,
+                                  const float* __restrict__ prev, const int* __restrict__ bos_flag,
+                                  float* __restrict__ x, int D, int L) {
+  extern __shared__ float lat[];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) lat[i] = bos_flag[b] ? bos[i] : prev[b * L + i];
+  __syncthreads();
+  for (int n = threadIdx.x; n < D; n += blockDim.x) {
+    const float* w = w_in + (long long)n * L;
+    float a = 0.f;
+    for (int i = 0; i < L; ++i) a = fmaf(w[i], lat[i], a);
+    x[(long long)b * D + n] = a;
+  }
+}
+
+template <typename WT>
+__global__ void embed_rows_kernel(const WT* __restrict__ table, const int* __restrict__ ids,
+                                  float* __restrict__ rows, int D) {
+  const int m = blockIdx.x;
+  const WT* src = table + (long long)ids[m] * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) rows[(long long)m * D + c] = (float)src[c];
+}
+
+__global__ void __launch_bounds__(128) final_norm_eos_kernel(const float* __restrict__ x,
+                                                             const int* __restrict__ row_of,
+                                                             const float* __restrict__ ln_w,
+                                                             const float* __restrict__ ln_b,
+                                                             const float* __restrict__ w_eos,
+                                                             const float* __restrict__ b_eos,
+                                                             float* __restrict__ cout,
+                                                             float* __restrict__ logit, int D) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* xr = x + (long long)(row_of ? row_of[b] : b) * D;
+  float v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 128;
+    v[i] = c < D ? xr[c] : 0.f;
+    s += v[i];
+  }
+  const float mean = block_sum(s, red) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 128;
+    const float d = c < D ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = 1.0f / sqrtf(block_sum(q, red) / (float)D + 1e-5f);
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 128;
+    if (c < D) {
+      const float o = (v[i] - mean) * rstd * ln_w[c] + ln_b[c];
+      cout[(long long)b * D + c] = o;
+      dot = fmaf(o, w_eos[c], dot);
+    }
+  }
+  dot = block_sum(dot, red);
+  if (threadIdx.x == 0) logit[b] = dot + b_eos[0];
+}
+
+// Philox4x32-10 (Salmon et al. 2011), one 128-bit block per pair of outputs is plenty here.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  constexpr unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+
+__global__ void noise_prep_kernel(const float* __restrict__ z, float* __restrict__ x0, int n, float std,
+                                  float clamp, int use_philox, unsigned long long seed,
+                                  const unsigned long long* __restrict__ counter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g;
+  if (use_philox) {
+    const unsigned long long step = counter ? *counter : 0ull;
+    uint4 r = philox4x32(make_uint4((unsigned)i, (unsigned)step, (unsigned)(step >> 32), 0u),
+                         make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const float u1 = ((r.x >> 8) + 1u) * (1.0f / 16777216.0f);   // (0,1]
+    const float u2 = (r.y >> 8) * (1.0f / 16777216.0f);
+    g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+  } else {
+    g = z[i];
+  }
+  float v = g * std;
+  if (clamp >= 0.f) v = fminf(fmaxf(v, -clamp), clamp);
+  x0[i] = v;
+}
+
+__global__ void quant_upsample_kernel(const float* __restrict__ lat, const float* __restrict__ emb_std,
+                                      const float* __restrict__ emb_mean, const float* __restrict__ wq,
+                                      const float* __restrict__ wu, float* __restrict__ zprev,
+                                      float* __restrict__ out, long long out_bs, int L, int C, int S) {
+  extern __shared__ float u[];   // normalised latent
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) u[i] = lat[b * L + i] * emb_std[i] + emb_mean[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* w = wq + (long long)c * L;
+    float z = 0.f;
+    for (int i = 0; i < L; ++i) z = fmaf(w[i], u[i], z);
+    const float zp = zprev[(long long)b * C + c];
+    zprev[(long long)b * C + c] = z;
+    const float* k = wu + (long long)c * 2 * S;
+    for (int t = 0; t < S; ++t) out[b * out_bs + (long long)t * C + c] = fmaf(k[t], z, k[S + t] * zp);
+  }
+}
+
+// 128 outputs per CTA; the (128 + taps - 1) x C input tile is staged with ELU applied, padded rows
+__global__ void __launch_bounds__(128) final_conv_kernel(const float* __restrict__ x, long long x_bs,
+                                                         const float* __restrict__ w,
+                                                         const float* __restrict__ bias,
+                                                         float* __restrict__ audio, long long audio_bs,
+                                                         int T, int C, int taps) {
+  extern __shared__ float sm[];
+  float* ws = sm;                       // [taps*C]
+  float* xs = sm + taps * C;            // [128+taps-1][C+1]
+  const int b = blockIdx.y, t0 = blockIdx.x * 128;
+  const int rows = min(128, T - t0) + taps - 1;
+  for (int i = threadIdx.x; i < taps * C; i += 128) ws[i] = w[i];
+  const float* src = x + b * x_bs + (long long)t0 * C;
+  for (int i = threadIdx.x; i < rows * C; i += 128) {
+    const int r = i / C, c = i - r * C;
+    xs[r * (C + 1) + c] = act_apply(src[i], ACT_ELU);
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= T) return;
+  float a = bias[0];
+  for (int j = 0; j < taps; ++j) {
+    const float* xr = xs + (threadIdx.x + j) * (C + 1);
+    const float* wr = ws + j * C;
+    for (int c = 0; c < C; ++c) a = fmaf(xr[c], wr[c], a);
+  }
+  audio[b * audio_bs + t] = a;
+}
+
+__global__ void state_shift_kernel(const ShiftEntry* __restrict__ entries) {
+  const ShiftEntry e = entries[blockIdx.y];
+  const int b = blockIdx.x;
+  float* base = e.buf + b * e.bs;
+  const int n = e.rows * e.C;
+  const float* src = base + (long long)e.T * e.C;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) base[i] = src[i];
+}
+
+__global__ void advance_kernel(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter,
+                               int B, int inc_len, int inc_mimi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    if (seq_len) seq_len[i] += inc_len;
+    if (bos_flag && inc_len) bos_flag[i] = 0;
+    if (mimi_offset) mimi_offset[i] += inc_mimi;
+  }
+  if (i == 0 && counter) *counter += 1ull;
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float a, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaf(a, x[i], y[i]);
+}
+
+template <typename KT>
+__global__ void copy_pages_kernel(KT* pool, long long layer_stride, long long page_stride,
+                                  const int* __restrict__ src_pages, const int* __restrict__ dst_pages) {
+  const int pair = blockIdx.x, layer = blockIdx.y;
+  const uint4* s = reinterpret_cast<const uint4*>(pool + layer * layer_stride + src_pages[pair] * page_stride);
+  uint4* d = reinterpret_cast<uint4*>(pool + layer * layer_stride + dst_pages[pair] * page_stride);
+  const int n = (int)(page_stride * sizeof(KT) / 16);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+}
+
+__global__ void fill_u32_kernel(unsigned int* dst, unsigned int v, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = v;
+}
+
+__global__ void gather_frame_kernel(const float* __restrict__ all, float* __restrict__ lat, int F, int L,
+                                    const int* __restrict__ frame_idx) {
+  const int b = blockIdx.x, f = *frame_idx;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) lat[b * L + i] = all[((long long)b * F + f) * L + i];
+}
+
+__global__ void scatter_audio_kernel(const float* __restrict__ audio, float* __restrict__ all, int F, int n,
+                                     const int* __restrict__ frame_idx) {
+  const int b = blockIdx.x, f = *frame_idx;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) all[((long long)b * F + f) * n + i] = audio[(long long)b * n + i];
+}
+
+__global__ void inc_kernel(int* v, int inc) { *v += inc; }
+
+}  // namespace
+
+void launch_layernorm(const NormParams& p, cudaStream_t s) {
+  layernorm_kernel<<<p.nb * p.T, 128, 0, s>>>(p);
+  ++g_launches;
+}
+
+void launch_input_rows(const float* w_in, const float* bos, const float* prev, const int* bos_flag, float* x,
+                       int B, int D, int L, cudaStream_t s) {
+  input_rows_kernel<<<B, 256, L * sizeof(float), s>>>(w_in, bos, prev, bos_flag, x, D, L);
+  ++g_launches;
+}
+
+void launch_embed_rows(const void* table, int table_bf16, const int* ids, float* rows, int M, int D,
+                       cudaStream_t s) {
+  if (table_bf16)
+    embed_rows_kernel<__nv_bfloat16><<<M, 256, 0, s>>>((const __nv_bfloat16*)table, ids, rows, D);
+  else
+    embed_rows_kernel<float><<<M, 256, 0, s>>>((const float*)table, ids, rows, D);
+  ++g_launches;
+}
+
+void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w, const float* ln_b,
+                           const float* w_eos, const float* b_eos, float* c, float* logit, int B, int D,
+                           cudaStream_t s) {
+  final_norm_eos_kernel<<<B, 128, 0, s>>>(x, row_of, ln_w, ln_b, w_eos, b_eos, c, logit, D);
+  ++g_launches;
+}
+
+void launch_noise_prep(const float* z, float* x0, int n, float std, float clamp, int use_philox,
+                       unsigned long long seed, const unsigned long long* counter, cudaStream_t s) {
+  noise_prep_kernel<<<(n + 255) / 256, 256, 0, s>>>(z, x0, n, std, clamp, use_philox, seed, counter);
+  ++g_launches;
+}
+
+void launch_quant_upsample(const float* lat, const float* emb_std, const float* emb_mean, const float* wq,
+                           const float* wu, float* zprev, float* out, long long out_bs, int B, int L, int C,
+                           int S, cudaStream_t s) {
+  quant_upsample_kernel<<<B, 256, L * sizeof(float), s>>>(lat, emb_std, emb_mean, wq, wu, zprev, out, out_bs,
+                                                          L, C, S);
+  ++g_launches;
+}
+
+void launch_final_conv(const float* x, long long x_bs, const float* w, const float* bias, float* audio,
+                       long long audio_bs, int B, int T, int C, int taps, cudaStream_t s) {
+  const size_t smem = (size_t)(taps * C + (128 + taps - 1) * (C + 1)) * sizeof(float);
+  dim3 grid((T + 127) / 128, B);
+  final_conv_kernel<<<grid, 128, smem, s>>>(x, x_bs, w, bias, audio, audio_bs, T, C, taps);
+  ++g_launches;
+}
+
+void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s) {
+  dim3 grid(B, n_entries);
+  state_shift_kernel<<<grid, 256, 0, s>>>(entries_dev);
+  ++g_launches;
+}
+
+void launch_advance(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter, int B,
+                    int inc_len, int inc_mimi, cudaStream_t s) {
+  advance_kernel<<<(B + 255) / 256, 256, 0, s>>>(seq_len, bos_flag, mimi_offset, counter, B, inc_len, inc_mimi);
+  ++g_launches;
+}
+
+void launch_axpy(const float* x, float* y, float a, int n, cudaStream_t s) {
+  axpy_kernel<<<(n + 255) / 256, 256, 0, s>>>(x, y, a, n);
+  ++g_launches;
+}
+
+void launch_copy_pages(void* pool, int kv_bf16, long long layer_stride, long long page_stride, int n_layers,
+                       const int* src_pages, const int* dst_pages, int n_pairs, cudaStream_t s) {
+  if (n_pairs <= 0) return;
+  dim3 grid(n_pairs, n_layers);
+  if (kv_bf16)
+    copy_pages_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)pool, layer_stride, page_stride,
+                                                          src_pages, dst_pages);
+  else
+    copy_pages_kernel<float><<<grid, 256, 0, s>>>((float*)pool, layer_stride, page_stride, src_pages, dst_pages);
+  ++g_launches;
+}
+
+void launch_fill_u32(unsigned int* dst, unsigned int v, long long n, cudaStream_t s) {
+  fill_u32_kernel<<<1184, 256, 0, s>>>(dst, v, n);
+  ++g_launches;
+}
+
+void launch_gather_frame(const float* lat_all, float* lat, int B, int F, int L, const int* frame_idx,
+                         cudaStream_t s) {
+  gather_frame_kernel<<<B, 32, 0, s>>>(lat_all, lat, F, L, frame_idx);
+  ++g_launches;
+}
+
+void launch_scatter_audio(const float* audio, float* audio_all, int B, int F, int n, const int* frame_idx,
+                          cudaStream_t s) {
+  scatter_audio_kernel<<<B, 256, 0, s>>>(audio, audio_all, F, n, frame_idx);
+  ++g_launches;
+}
+
+void launch_inc(int* v, int inc, cudaStream_t s) {
+  inc_kernel<<<1, 1, 0, s>>>(v, inc);
+  ++g_launches;
+}
+
+}  // namespace ptts

@@ -1,0 +1,303 @@
+"""`TTSModel`: the reference's public API for streaming generation, backed by libptts_b200 (CUDA, sm_100a).
+
+Drop-in surface (reference `pocket_tts_mlx/models/tts_model.py`): `load_model` (:202-221),
+`get_state_for_audio_prompt` (:484-518, predefined-voice branch), `generate_audio` (:308-334),
+`generate_audio_stream` (:336-361), properties `device` / `sample_rate` (:79-85) and the attributes
+`config, temp, lsd_decode_steps, noise_clamp, eos_threshold, has_voice_cloning` (:70-77).  Host logic kept
+in Python (sentence chunking, EOS bookkeeping, max-length estimate, trim/fade) follows :336-462; all
+arithmetic happens on the GPU through the C ABI in include/ptts.h.  There is no CPU fallback.
+
+Extensions (keyword-only, all optional): `precision`, `device_id`, `kv_pool_tokens` on `load_model`;
+`noise` / `seed` on the generate calls (injectable flow noise for parity tests);
+`generate_audio_batch` for many utterances in lock-step on one GPU.
+"""
+
+from __future__ import annotations
+
+import logging
+import time
+from pathlib import Path
+from typing import Dict, Generator, List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _native
+from .assets import resolve_asset
+from .config import Config, load_config
+from .default_parameters import (
+    DEFAULT_EOS_THRESHOLD,
+    DEFAULT_LSD_DECODE_STEPS,
+    DEFAULT_NOISE_CLAMP,
+    DEFAULT_TEMPERATURE,
+    DEFAULT_VARIANT,
+    MAX_TOKEN_PER_CHUNK,
+)
+from .safetensors_io import read_safetensors
+from .text import SentencePieceTokenizer, prepare_text_prompt, split_into_best_sentences
+
+logger = logging.getLogger(__name__)
+
+_VOICE_NAMES = ["alba", "marius", "javert", "jean", "fantine", "cosette", "eponine", "azelma"]
+PREDEFINED_VOICES = {
+    v: f"hf://kyutai/pocket-tts-without-voice-cloning/embeddings/{v}.safetensors@d4fdd22ae8c8e1cb3634e150ebeff1dab2d16df3"
+    for v in _VOICE_NAMES
+}
+
+VOICE_CLONING_UNSUPPORTED = (
+    "Voice cloning from an audio file needs the Mimi encoder, which this build does not include "
+    f"(SURVEY.md 8f-2). Use one of the predefined voices {list(PREDEFINED_VOICES)} or pass a precomputed "
+    "conditioning array to get_state_for_conditioning()."
+)
+
+
+class TTSModel:
+    _TOKENS_PER_SECOND_ESTIMATE = 3.0
+    _GEN_SECONDS_PADDING = 2.0
+    _MIMI_WARMUP_FRAMES = 1
+
+    def __init__(self, config: Config, ctx: "_native.Context", tokenizer: SentencePieceTokenizer, temp: float,
+                 lsd_decode_steps: int, noise_clamp: Optional[float], eos_threshold: float, precision: str,
+                 weights_file: Path):
+        self.config = config
+        self.temp = temp
+        self.lsd_decode_steps = lsd_decode_steps
+        self.noise_clamp = noise_clamp
+        self.eos_threshold = eos_threshold
+        self.has_voice_cloning = False
+        self.precision = precision
+        self._ctx = ctx
+        self._tokenizer = tokenizer
+        self._weights_file = Path(weights_file)
+        self._voice_cache: Dict[str, Dict] = {}
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def device(self) -> str:
+        return f"cuda:{self._ctx.device}"
+
+    @property
+    def sample_rate(self) -> int:
+        return self.config.mimi.sample_rate
+
+    @property
+    def frame_samples(self) -> int:
+        return int(self.config.mimi.sample_rate / self.config.mimi.frame_rate)
+
+    # ------------------------------------------------------------------ loading
+    @classmethod
+    def load_model(cls, config: Union[str, Path] = DEFAULT_VARIANT, temp: float = DEFAULT_TEMPERATURE,
+                   lsd_decode_steps: int = DEFAULT_LSD_DECODE_STEPS,
+                   noise_clamp: Optional[float] = DEFAULT_NOISE_CLAMP,
+                   eos_threshold: float = DEFAULT_EOS_THRESHOLD, *, precision: str = "bf16",
+                   device_id: int = 0, kv_pool_tokens: int = 262144, max_batch: int = 0) -> "TTSModel":
+        if str(config).endswith(".yaml"):
+            cfg = load_config(Path(config))
+            logger.info("Loading model from config at %s...", config)
+        else:
+            cfg = load_config(Path(__file__).parent / "config" / f"{config}.yaml")
+        if cfg.flow_lm.weights_path is not None and cfg.mimi.weights_path is None:
+            raise ValueError("If you specify flow_lm.weights_path you should specify mimi.weights_path")
+        if cfg.mimi.weights_path is not None and cfg.flow_lm.weights_path is None:
+            raise ValueError("If you specify mimi.weights_path you should specify flow_lm.weights_path")
+        if cfg.flow_lm.weights_path is not None:
+            raise ValueError("split flow_lm/mimi checkpoints are not supported by this build; use weights_path")
+        if cfg.weights_path is None:
+            raise ValueError("config has no weights_path: an uninitialised model cannot be run")
+        try:
+            weights_file = resolve_asset(cfg.weights_path)
+            if not weights_file.exists():
+                raise FileNotFoundError(str(weights_file))
+        except FileNotFoundError:
+            if cfg.weights_path_without_voice_cloning is None:
+                raise
+            weights_file = resolve_asset(cfg.weights_path_without_voice_cloning)
+        tokenizer = SentencePieceTokenizer(cfg.flow_lm.lookup_table.n_bins,
+                                           resolve_asset(cfg.flow_lm.lookup_table.tokenizer_path))
+        ccfg = _native.make_config(cfg, temp, lsd_decode_steps, noise_clamp, eos_threshold, precision,
+                                   kv_pool_tokens, max_batch)
+        ctx = _native.Context(ccfg, device_id)
+        loaded = skipped = 0
+        for key, arr in read_safetensors(weights_file).items():
+            if arr.dtype.kind != "f":
+                skipped += 1
+                continue
+            if ctx.load_weight(key, arr):
+                loaded += 1
+            else:
+                skipped += 1
+        ctx.finalize()
+        logger.info("Loaded %d weights, skipped %d", loaded, skipped)
+        return cls(cfg, ctx, tokenizer, temp, lsd_decode_steps, noise_clamp, eos_threshold, precision, weights_file)
+
+    # ------------------------------------------------------------------ voices
+    def _voice_file(self, name: str) -> Path:
+        import os
+        cands = []
+        if os.environ.get("POCKET_TTS_VOICES_DIR"):
+            cands.append(Path(os.environ["POCKET_TTS_VOICES_DIR"]) / f"{name}.safetensors")
+        cands.append(self._weights_file.parent / "embeddings" / f"{name}.safetensors")
+        for c in cands:
+            if c.exists():
+                return c
+        return resolve_asset(PREDEFINED_VOICES[name])
+
+    def get_state_for_conditioning(self, conditioning: np.ndarray) -> Dict:
+        """Prefill an already-projected voice conditioning [T, d_model] (or [1, T, d_model])."""
+        cond = np.asarray(conditioning, dtype=np.float32)
+        d = self.config.flow_lm.transformer.d_model
+        cond = cond.reshape(-1, d)
+        t0 = time.monotonic()
+        vid = self._ctx.voice_create(cond)
+        logger.info("Prompting audio took %d ms", int((time.monotonic() - t0) * 1000))
+        return {"voice_id": vid, "prompt_len": int(cond.shape[0])}
+
+    def get_state_for_audio_prompt(self, audio_conditioning, truncate: bool = False) -> Dict:
+        if isinstance(audio_conditioning, str) and audio_conditioning in PREDEFINED_VOICES:
+            tensors = read_safetensors(self._voice_file(audio_conditioning))
+            prompt = tensors.get("audio_prompt")
+            if prompt is None:
+                raise KeyError("audio_prompt not found in voice embedding file")
+            return self.get_state_for_conditioning(prompt)
+        if isinstance(audio_conditioning, (str, Path)):
+            if isinstance(audio_conditioning, str) and not Path(audio_conditioning).exists() \
+                    and "/" not in audio_conditioning and "." not in audio_conditioning:
+                raise ValueError(
+                    f"Predefined voice '{audio_conditioning}' not found, available voices are {list(PREDEFINED_VOICES)}.")
+            raise ValueError(VOICE_CLONING_UNSUPPORTED)
+        raise ValueError(VOICE_CLONING_UNSUPPORTED)
+
+    # ------------------------------------------------------------------ generation
+    def _estimate_max_gen_len(self, token_count: int) -> int:
+        return _native.max_gen_len(token_count, self.config.mimi.frame_rate)
+
+    def generate_audio(self, model_state: Dict, text_to_generate: str, max_tokens: int = MAX_TOKEN_PER_CHUNK,
+                       frames_after_eos: Optional[int] = None, copy_state: bool = True, trim_start_ms: int = 0,
+                       fade_in_ms: int = 0, warmup_frames: int = _MIMI_WARMUP_FRAMES, *,
+                       noise: Optional[np.ndarray] = None, seed: Optional[int] = None) -> np.ndarray:
+        chunks = list(self.generate_audio_stream(model_state, text_to_generate, max_tokens=max_tokens,
+                                                 frames_after_eos=frames_after_eos, copy_state=copy_state,
+                                                 warmup_frames=warmup_frames, noise=noise, seed=seed))
+        audio = np.concatenate(chunks, axis=0) if chunks else np.zeros(0, dtype=np.float32)
+        return postprocess_audio_start(audio, self.sample_rate, trim_start_ms, fade_in_ms)
+
+    def generate_audio_stream(self, model_state: Dict, text_to_generate: str, max_tokens: int = MAX_TOKEN_PER_CHUNK,
+                              frames_after_eos: Optional[int] = None, copy_state: bool = True,
+                              warmup_frames: int = _MIMI_WARMUP_FRAMES, *, noise: Optional[np.ndarray] = None,
+                              seed: Optional[int] = None) -> Generator[np.ndarray, None, None]:
+        chunks = split_into_best_sentences(self._tokenizer, text_to_generate, max_tokens)
+        noise_rows = None if noise is None else np.asarray(noise, dtype=np.float32).reshape(-1, self._ctx.config.latent_dim)
+        cursor = 0
+        for ci, chunk in enumerate(chunks):
+            _, guess = prepare_text_prompt(chunk)
+            effective = frames_after_eos if frames_after_eos is not None else guess + 2
+            sub_noise = None if noise_rows is None else noise_rows[cursor:]
+            used = [0]
+            yield from self._generate_chunk(model_state, chunk, effective, warmup_frames, sub_noise,
+                                            None if seed is None else seed + ci, used)
+            cursor += used[0]
+
+    def _generate_chunk(self, model_state: Dict, chunk: str, frames_after_eos: int, warmup_frames: int,
+                        noise_rows: Optional[np.ndarray], seed: Optional[int], used: List[int]):
+        tokens = self._tokenizer.encode(chunk)
+        n_tok = int(tokens.shape[0])
+        max_gen_len = self._estimate_max_gen_len(n_tok)
+        required = int(model_state["prompt_len"]) + n_tok + max_gen_len
+        batch = _native.Batch(self._ctx, [int(model_state["voice_id"])], [required])
+        try:
+            if seed is None:
+                seed = int(np.random.SeedSequence().entropy % (1 << 63))
+            batch.seed(seed)
+            batch.warmup_mimi(warmup_frames)
+            t_gen = time.monotonic()
+            batch.prefill_text([tokens])
+            used[0] = 1                                  # the reference draws (and discards) noise here
+            eos_step = None
+            produced = 0
+            for step in range(max_gen_len):
+                z = None
+                if noise_rows is not None:
+                    if used[0] >= noise_rows.shape[0]:
+                        raise ValueError("injected noise has fewer rows than generated frames")
+                    z = noise_rows[used[0]][None, :]
+                    used[0] += 1
+                _, logit, audio = batch.step(z, want_audio=True)
+                if bool(logit[0] > self.eos_threshold) and eos_step is None:
+                    eos_step = step
+                if eos_step is not None and step >= eos_step + frames_after_eos:
+                    break
+                produced += audio.shape[1]
+                yield audio[0].copy()
+            ms_audio = int(produced * 1000 / self.sample_rate)
+            ms_gen = int((time.monotonic() - t_gen) * 1000)
+            logger.info("Generated: %d ms of audio in %d ms so %.2fx faster than real-time", ms_audio, ms_gen,
+                        ms_audio / max(1, ms_gen))
+        finally:
+            batch.close()
+
+    def generate_audio_batch(self, model_states: Sequence[Dict], token_ids: Sequence[Sequence[int]],
+                             frames_after_eos: Union[int, Sequence[int]] = 3,
+                             warmup_frames: int = _MIMI_WARMUP_FRAMES, max_frames: Optional[int] = None,
+                             noise: Optional[np.ndarray] = None, seed: int = 0,
+                             return_latents: bool = False):
+        """Lock-step generation of many single-chunk utterances (token ids already prepared).
+
+        noise: optional [1 + max_frames, n, latent_dim] (row 0 is the unused text-prefill draw, as in the
+        reference).  Returns a list of 1-D float32 waveforms (and per-sequence latents when asked)."""
+        n = len(model_states)
+        fae = [frames_after_eos] * n if isinstance(frames_after_eos, int) else list(frames_after_eos)
+        n_tok = [len(t) for t in token_ids]
+        limits = [self._estimate_max_gen_len(k) for k in n_tok]
+        if max_frames is not None:
+            limits = [min(l, max_frames) for l in limits]
+        req = [int(s["prompt_len"]) + k + l for s, k, l in zip(model_states, n_tok, limits)]
+        batch = _native.Batch(self._ctx, [int(s["voice_id"]) for s in model_states], req)
+        try:
+            batch.seed(seed)
+            batch.warmup_mimi(warmup_frames)
+            batch.prefill_text(token_ids)
+            eos_step = [None] * n
+            done = [False] * n
+            audio_out: List[List[np.ndarray]] = [[] for _ in range(n)]
+            lat_out: List[List[np.ndarray]] = [[] for _ in range(n)]
+            for step in range(max(limits)):
+                z = None if noise is None else np.asarray(noise[1 + step], dtype=np.float32)
+                lat, logit, audio = batch.step(z, want_audio=True)
+                for b in range(n):
+                    if done[b]:
+                        continue
+                    if step >= limits[b]:
+                        done[b] = True
+                        continue
+                    if logit[b] > self.eos_threshold and eos_step[b] is None:
+                        eos_step[b] = step
+                    if eos_step[b] is not None and step >= eos_step[b] + fae[b]:
+                        done[b] = True
+                        continue
+                    audio_out[b].append(audio[b].copy())
+                    lat_out[b].append(lat[b].copy())
+                if all(done):
+                    break
+            waves = [np.concatenate(a) if a else np.zeros(0, dtype=np.float32) for a in audio_out]
+            if return_latents:
+                return waves, [np.array(l, dtype=np.float32).reshape(-1, self._ctx.config.latent_dim) for l in lat_out]
+            return waves
+        finally:
+            batch.close()
+
+    def close(self):
+        self._ctx.close()
+
+
+def postprocess_audio_start(audio: np.ndarray, sample_rate: int, trim_start_ms: int = 0, fade_in_ms: int = 0):
+    """Trim the first `trim_start_ms` (only if 0 < trim < len) and apply a linear fade-in whose ramp
+    includes both endpoints (reference `_postprocess_audio_start`, tts_model.py:446-462)."""
+    if trim_start_ms > 0:
+        n = int(sample_rate * trim_start_ms / 1000)
+        if 0 < n < audio.shape[0]:
+            audio = audio[n:]
+    if fade_in_ms > 0 and audio.shape[0] > 1:
+        n = min(max(0, int(sample_rate * fade_in_ms / 1000)), audio.shape[0])
+        if n > 1:
+            ramp = np.linspace(0.0, 1.0, n).astype(audio.dtype)
+            audio = np.concatenate([audio[:n] * ramp, audio[n:]], axis=0)
+    return audio
