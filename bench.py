@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): audio-seconds generated per second per B200 at batch 256, plus the
+batch-1 per-frame latency.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input = BASELINE config 4: 256 utterances
+of 60 synthetic token ids each, shared 125-frame voice prefix, Mimi warm-up frame, text prefill, then 275
+autoregressive frames (FlowLM step + flow head + Mimi decode) per utterance with EOS disabled
+(eos_threshold=+1e30) = 5632 audio-seconds.  Random-init weights of the b6369a24 architecture (seed 0).
+
+  value : device-resident (Philox noise on the device, no host copies), timed with CUDA events on the library's
+          own stream, max over ranks.
+  e2e   : the same job through the reference-facing C-ABI call ptts_batch_step with HOST buffers: noise
+          host->device and latents/EOS logits/1920-sample frames device->host inside the timed region.
+  --impl reference : the reference's algorithm on the host cores.  MLX cannot be installed in this image, so
+          this arm runs the NumPy restatement (oracle/, pinned to the reference's own Python) with all BLAS
+          threads, batch 1 (the only batch size the reference supports), on a bounded sample.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+N_SEQ, N_TOK, VOICE_FRAMES = 256, 60, 125
+FRAME_SEC = 0.08
+
+
+def _peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def _init_pg(world, rank, local):
+    if world <= 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    return dist
+
+
+def _barrier_max(dist, local, value: float) -> float:
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(local)
+
+
+def load_model(device: int, kv_pool_tokens: int):
+    from pocket_tts_mlx_b200 import TTSModel
+    from pocket_tts_mlx_b200.synthetic import default_bundle_dir, write_synthetic_bundle
+    yml = write_synthetic_bundle(default_bundle_dir(), seed=0)
+    return TTSModel.load_model(str(yml), eos_threshold=1e30, precision="bf16", device_id=device,
+                               kv_pool_tokens=kv_pool_tokens), yml
+
+
+def one_job(model, state, ids, frames, host_io: bool, rng):
+    """One step of the benchmark: create the batch, warm up Mimi, prefill text, generate `frames` frames."""
+    from pocket_tts_mlx_b200 import _native
+    n = len(ids)
+    req = [state["prompt_len"] + len(t) + frames for t in ids]
+    batch = _native.Batch(model._ctx, [state["voice_id"]] * n, req)
+    h2d = d2h = 0
+    try:
+        batch.seed(1234)
+        batch.warmup_mimi(1)
+        batch.prefill_text(ids)
+        h2d += sum(len(t) for t in ids) * 4
+        if host_io:
+            for f in range(frames):
+                z = rng.standard_normal((n, 32), dtype=np.float32)
+                lat, logit, audio = batch.step(z, want_audio=True)
+                h2d += z.nbytes
+                d2h += lat.nbytes + logit.nbytes + audio.nbytes
+        else:
+            for f in range(frames):
+                batch.step_device()
+        model._ctx.sync()
+    finally:
+        batch.close()
+    return h2d, d2h
+
+
+def latency_bs1(model, state, rng, frames=200, n_tok=42):
+    """BASELINE config 2: batch-1 streaming generation, per-frame device latency (CUDA events)."""
+    from pocket_tts_mlx_b200 import _native
+    ids = [rng.integers(0, 4000, size=n_tok).astype(np.int32)]
+    batch = _native.Batch(model._ctx, [state["voice_id"]], [state["prompt_len"] + n_tok + frames + 8])
+    batch.seed(7)
+    batch.warmup_mimi(1)
+    batch.prefill_text(ids)
+    for _ in range(5):
+        batch.step_device()
+    model._ctx.sync()
+    ms = []
+    for _ in range(frames - 5):
+        model._ctx.timer_begin()
+        batch.step_device()
+        ms.append(model._ctx.timer_end())
+    t0 = time.perf_counter()
+    e2e = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        batch.step(rng.standard_normal((1, 32), dtype=np.float32), want_audio=True)
+        e2e.append((time.perf_counter() - t0) * 1e3)
+    batch.close()
+    return {"p50_ms": float(np.percentile(ms, 50)), "p95_ms": float(np.percentile(ms, 95)),
+            "e2e_host_p50_ms": float(np.median(e2e)), "frames": len(ms), "config": "batch 1, 42 tokens, 200 frames"}
+
+
+def roofline_from_profile(model, state, ids, at_frame: int, peaks):
+    """Eager per-kernel CUDA-event profile of ONE frame in the middle of the job; the dominant kernel's
+    algorithmic bytes / flops come from the launch parameters."""
+    from pocket_tts_mlx_b200 import _native
+    n = len(ids)
+    batch = _native.Batch(model._ctx, [state["voice_id"]] * n, [state["prompt_len"] + len(t) + at_frame + 8 for t in ids])
+    batch.seed(1)
+    batch.warmup_mimi(1)
+    batch.prefill_text(ids)
+    for _ in range(at_frame):
+        batch.step_device()
+    model._ctx.sync()
+    batch.profile_step()                      # warm the eager path
+    rows = batch.profile_step()
+    batch.close()
+    total = sum(r["ms"] for r in rows)
+    # group per kernel (all call sites) to find the dominant one
+    per = {}
+    for r in rows:
+        k = r["kernel"].split(":")[0]
+        a = per.setdefault(k, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+        for f in ("ms", "launches", "flops", "bytes"):
+            a[f] += r[f]
+    top = max(per.items(), key=lambda kv: kv[1]["ms"])
+    name, a = top
+    sec = a["ms"] / 1e3
+    gbs = a["bytes"] / sec / 1e9 if sec > 0 else 0.0
+    tfs = a["flops"] / sec / 1e12 if sec > 0 else 0.0
+    t_hbm = a["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    t_tc = a["flops"] / (peaks["tf_sustained"] * 1e12)
+    if t_hbm >= t_tc:
+        roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}
+    else:
+        roof = {"bound": "tensor", "achieved": tfs, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": tfs / peaks["tf_sustained"]}
+    roof.update({"kernel": name, "share_of_frame": a["ms"] / total if total else None,
+                 "launches_per_frame": a["launches"], "avg_launch_ms": a["ms"] / max(1, a["launches"]),
+                 "traffic": None, "peak_source": peaks["source"], "frame_ms_eager": total})
+    breakdown = sorted(({"kernel": k, "ms": v["ms"], "share": v["ms"] / total} for k, v in per.items()),
+                       key=lambda r: -r["ms"])[:8]
+    return roof, breakdown, rows
+
+
+def cpu_baseline(frames: int, seed: int = 0):
+    """The oracle (NumPy restatement of the reference's path), batch 1, on this box's host cores."""
+    from oracle.ptts_oracle import Oracle
+    from pocket_tts_mlx_b200.config import load_config
+    from pocket_tts_mlx_b200.safetensors_io import read_safetensors
+    from pocket_tts_mlx_b200.synthetic import default_bundle_dir, synthetic_token_ids, write_synthetic_bundle
+    yml = write_synthetic_bundle(default_bundle_dir(), seed=0)
+    cfg = load_config(yml)
+    orc = Oracle(read_safetensors(cfg.weights_path), cfg, dtype=np.float32, eos_threshold=1e30)
+    voice = read_safetensors(Path(yml).parent / "embeddings" / "alba.safetensors")["audio_prompt"]
+    st = orc.new_flow_state()
+    orc.prefill_audio(st, voice[0])
+    ids = synthetic_token_ids(2 + seed, 1, N_TOK)[0]
+    rng = np.random.Generator(np.random.PCG64(3 + seed))
+    noise = rng.standard_normal((1 + frames, 32)).astype(np.float32)
+    t0 = time.perf_counter()
+    res = orc.generate(st, ids, noise, frames_after_eos=3, max_frames=frames)
+    dt = time.perf_counter() - t0
+    assert res["n_frames"] == frames
+    return frames * FRAME_SEC / dt, dt
+
+
+def _blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, world, rank):
+    if rank != 0:
+        return
+    frames = 25
+    for _ in range(args.warmup):
+        cpu_baseline(4)
+    t_all, audio = 0.0, 0.0
+    for k in range(args.steps):
+        _, dt = cpu_baseline(frames, seed=k)
+        t_all += dt
+        audio += frames * FRAME_SEC
+    v = audio / t_all
+    cores = _blas_threads()
+    line = {
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": v, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config 4 (256 x 60-token utterances, 125-frame voice prefix, 275 frames)",
+                   "note": "reference is batch-1 only: each step = 1 utterance x 25 frames incl. text prefill"},
+        "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} x (1 utterance, 60 tokens, {frames} frames), NumPy/OpenBLAS fp32; "
+                                   "MLX itself is not installable here"},
+        "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=275, help="frames per utterance (275 = max_gen_len of 60 tokens)")
+    ap.add_argument("--batch", type=int, default=N_SEQ)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-latency", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel frame profile (JSON) here")
+    args = ap.parse_args()
+    world, rank, local = _dist()
+    if args.impl == "reference":
+        run_reference(args, world, rank)
+        return
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dist = _init_pg(world, rank, local)
+    peaks = _peaks()
+    from pocket_tts_mlx_b200.synthetic import synthetic_token_ids
+    n_seq, frames = args.batch, args.frames
+    kv_tokens = n_seq * (VOICE_FRAMES + N_TOK + frames + 64) + 4096
+    model, _ = load_model(local, kv_tokens)
+    state = model.get_state_for_audio_prompt("alba")
+    ids = list(synthetic_token_ids(2 + rank, n_seq, N_TOK))
+    rng = np.random.Generator(np.random.PCG64(100 + rank))
+    audio_sec = n_seq * frames * FRAME_SEC
+
+    # ---- value: device-resident ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        one_job(model, state, ids, min(frames, 16), False, rng)
+    sampler = ClockSampler(local)
+    _barrier(dist, local)
+    model._ctx.sync()
+    model._ctx.launch_count(reset=True)
+    sampler.start()
+    model._ctx.timer_begin()
+    for _ in range(args.steps):
+        one_job(model, state, ids, frames, False, rng)
+    ms = model._ctx.timer_end()
+    clocks = sampler.stop()
+    launches = model._ctx.launch_count()
+    _barrier(dist, local)
+    ms = _barrier_max(dist, local, ms)
+    value = world * audio_sec * args.steps / (ms / 1e3)
+
+    # ---- e2e: host buffers through the C-ABI step call ---------------------------------------------
+    one_job(model, state, ids, min(frames, 8), True, rng)
+    _barrier(dist, local)
+    model._ctx.sync()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        a, b = one_job(model, state, ids, frames, True, rng)
+        h2d += a
+        d2h += b
+    model._ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    _barrier(dist, local)
+    e2e_s = _barrier_max(dist, local, e2e_s)
+    e2e_value = world * audio_sec * e2e_steps / e2e_s
+
+    if rank == 0:
+        roof, breakdown, rows = roofline_from_profile(model, state, ids, min(frames // 2, 137), peaks)
+        lat = None if args.skip_latency else latency_bs1(model, state, rng)
+        cpu = None
+        if not args.skip_cpu_baseline:
+            v, dt = cpu_baseline(20)
+            cpu = {"value": v, "unit": "audio-s/s", "cores": _blas_threads(), "kind": "port",
+                   "sample": "1 utterance (batch 1: the reference's only batch size), 60 tokens, text prefill + 20 "
+                             f"frames, NumPy/OpenBLAS fp32 oracle, {dt:.1f} s"}
+        line = {
+            "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"config 4: {n_seq} x {N_TOK}-token utterances, shared {VOICE_FRAMES}-frame voice prefix, "
+                                   f"{frames} frames each, random-init b6369a24 weights",
+                       "per_gpu_batch": n_seq, "frames": frames,
+                       "l2": "inputs larger than L2 (per-frame KV + activations > 126 MB)",
+                       "storage": "bf16 weights + bf16 paged KV, fp32 accumulate"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d // e2e_steps,
+                    "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps},
+            "roofline": roof, "frame_breakdown": breakdown, "cpu_baseline": cpu, "latency_bs1": lat,
+            "ms_per_frame": ms / args.steps / frames,
+        }
+        if args.profile_out:
+            Path(args.profile_out).parent.mkdir(parents=True, exist_ok=True)
+            Path(args.profile_out).write_text(json.dumps({"rows": rows, "roofline": roof}, indent=1))
+        print(json.dumps(line), flush=True)
+    _barrier(dist, local)
+    model.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -134,9 +134,10 @@ int32_t ptts_timer_end(ptts_ctx* ctx, float* elapsed_ms);
 /* Kernel launches issued by this library since the counter was last reset (graph replays count
  * their kernel nodes). */
 int64_t ptts_launch_count(ptts_ctx* ctx, int32_t reset);
-/* Per-stage timing of one eager (non-graph) frame for profiling: names are returned as a single
- * ';'-separated string valid until the next call; ms has room for `cap` entries. */
-int32_t ptts_batch_profile_step(ptts_batch* batch, float* ms, int32_t cap, const char** names);
+/* One eager (non-graph) frame with every kernel launch bracketed by CUDA events on the library's
+ * stream.  *report points at "kernel:tag,launches,ms,flops,bytes\n" lines (algorithmic flops/bytes of the
+ * launches, sorted by time) valid until the next call.  Advances the batch by one frame. */
+int32_t ptts_batch_profile_step(ptts_batch* batch, const char** report);
 /* Write an L2-sized scratch buffer (flushes L2 between timed iterations). */
 int32_t ptts_flush_l2(ptts_ctx* ctx);
 /* Stand-alone entry to the multi-tap linear operator, for kernel-level parity tests:

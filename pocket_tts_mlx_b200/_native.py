@@ -87,7 +87,7 @@ def lib() -> C.CDLL:
         "ptts_timer_begin": (i32, [vp]),
         "ptts_timer_end": (i32, [vp, f32p]),
         "ptts_launch_count": (C.c_int64, [vp, i32]),
-        "ptts_batch_profile_step": (i32, [vp, f32p, i32, C.POINTER(C.c_char_p)]),
+        "ptts_batch_profile_step": (i32, [vp, C.POINTER(C.c_char_p)]),
         "ptts_flush_l2": (i32, [vp]),
         "ptts_debug_linear": (i32, [vp, i32, i32, i32, i32, i32, i32, f32p, f32p, f32p, f32p]),
     }
@@ -296,10 +296,14 @@ class Batch:
         return out
 
     def profile_step(self):
-        ms = (C.c_float * 16)()
-        names = C.c_char_p()
-        n = check(lib().ptts_batch_profile_step(self._h, ms, 16, C.byref(names)))
-        return dict(zip(names.value.decode().split(";"), [float(ms[i]) for i in range(n)]))
+        """One eager frame with per-kernel CUDA-event timing -> list of dicts sorted by time."""
+        rep = C.c_char_p()
+        check(lib().ptts_batch_profile_step(self._h, C.byref(rep)))
+        rows = []
+        for line in rep.value.decode().strip().splitlines():
+            name, n, ms, fl, by = line.rsplit(",", 4)
+            rows.append({"kernel": name, "launches": int(n), "ms": float(ms), "flops": float(fl), "bytes": float(by)})
+        return rows
 
 
 def max_gen_len(n_tok: int, frame_rate: float = 12.5) -> int:

@@ -451,8 +451,9 @@ void run_linear(Ctx& c, const LinW& w, LinearParams p) {
   else launch_linear_tile(p, c.stream);
 }
 
-LinearParams rows_linear(const float* A, int M, int C, float* Y, int N) {
+LinearParams rows_linear(const float* A, int M, int C, float* Y, int N, const char* tag = nullptr) {
   LinearParams p{};
+  p.tag = tag;
   p.A = A; p.a_bs = 0; p.a_rs = C; p.nb = 1; p.T = M; p.taps = 1; p.C = C;
   p.Y = Y; p.y_bs = 0; p.y_rs = N;
   p.out_scale = 1.f;
@@ -489,27 +490,27 @@ void free_flow_work(FlowWork& w) {
 
 // the 6 pre-LN layers over M rows that sit at (row_seq, row_pos) of their sequences
 void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_pos, const int* page_table,
-                 int max_pages) {
+                 int max_pages, long long total_keys) {
   const int D = c.cfg.d_model, FF = c.cfg.ffn_dim;
   for (int i = 0; i < c.cfg.n_layers; ++i) {
     auto& l = c.fl[i];
     rows_norm(c, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, w.h);
-    run_linear(c, l.qkv, rows_linear(w.h, M, D, w.qkv, 3 * D));
+    run_linear(c, l.qkv, rows_linear(w.h, M, D, w.qkv, 3 * D, "flow.qkv"));
     FlowAttnParams a{};
     a.qkv = w.qkv; a.q_rot = w.qrot; a.out = w.att;
     a.pool = c.pool; a.kv_bf16 = c.bf16; a.layer_stride = c.layer_stride; a.page_stride = c.page_stride;
     a.layer = i; a.row_seq = row_seq; a.row_pos = row_pos; a.page_table = page_table; a.max_pages = max_pages;
-    a.M = M; a.H = c.cfg.n_heads; a.freqs = c.freqs_flow;
+    a.M = M; a.H = c.cfg.n_heads; a.freqs = c.freqs_flow; a.total_keys = total_keys;
     launch_flow_rope_append(a, c.stream);
     launch_flow_attention(a, c.stream);
-    LinearParams o = rows_linear(w.att, M, D, w.x, D);
+    LinearParams o = rows_linear(w.att, M, D, w.x, D, "flow.out");
     o.res = w.x; o.res_bs = 0; o.res_rs = D;
     run_linear(c, l.out, o);
     rows_norm(c, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, w.h);
-    LinearParams f1 = rows_linear(w.h, M, D, w.ff, FF);
+    LinearParams f1 = rows_linear(w.h, M, D, w.ff, FF, "flow.ff1");
     f1.act = ACT_GELU;
     run_linear(c, l.ff1, f1);
-    LinearParams f2 = rows_linear(w.ff, M, FF, w.x, D);
+    LinearParams f2 = rows_linear(w.ff, M, FF, w.x, D, "flow.ff2");
     f2.res = w.x; f2.res_bs = 0; f2.res_rs = D;
     run_linear(c, l.ff2, f2);
   }
@@ -594,6 +595,7 @@ void mimi_frame(Batch& bt, const float* latent) {
     LinearParams q{};
     q.A = bt.d_mh; q.a_bs = (long long)T * MD; q.a_rs = MD; q.nb = B; q.T = T; q.taps = 1; q.C = MD;
     q.Y = bt.d_mqkv; q.y_bs = (long long)T * 3 * MD; q.y_rs = 3 * MD; q.out_scale = 1.f;
+    q.tag = "mimi.qkv";
     run_linear(c, l.qkv, q);
     MimiAttnParams a{};
     a.qkv = bt.d_mqkv; a.q_rot = bt.d_mqrot; a.out = bt.d_matt;
@@ -606,13 +608,16 @@ void mimi_frame(Batch& bt, const float* latent) {
     o.A = bt.d_matt; o.a_bs = (long long)T * MD; o.a_rs = MD; o.nb = B; o.T = T; o.taps = 1; o.C = MD;
     o.col_scale = l.ls1; o.res = x; o.res_bs = c0_bs; o.res_rs = MD;
     o.Y = x; o.y_bs = c0_bs; o.y_rs = MD; o.out_scale = 1.f;
+    o.tag = "mimi.out";
     run_linear(c, l.out, o);
     n.w = l.ln2w; n.b = l.ln2b;
     launch_layernorm(n, c.stream);
     LinearParams f1 = q;
     f1.Y = bt.d_mff; f1.y_bs = (long long)T * g.mimi_ffn; f1.y_rs = g.mimi_ffn; f1.act = ACT_GELU;
+    f1.tag = "mimi.ff1";
     run_linear(c, l.ff1, f1);
     LinearParams f2 = o;
+    f2.tag = "mimi.ff2";
     f2.A = bt.d_mff; f2.a_bs = (long long)T * g.mimi_ffn; f2.a_rs = g.mimi_ffn; f2.C = g.mimi_ffn;
     f2.col_scale = l.ls2;
     run_linear(c, l.ff2, f2);
@@ -624,6 +629,7 @@ void mimi_frame(Batch& bt, const float* latent) {
     auto& s0 = bt.sb[0];
     const int c1 = c.stages[0].c_in;
     p.Y = s0.ct_in + c1; p.y_bs = (long long)(T + 1) * c1; p.y_rs = c1; p.out_scale = 1.f;
+    p.tag = "sn.conv0";
     run_linear(c, c.conv0, p);
   }
   for (size_t r = 0; r < c.stages.size(); ++r) {
@@ -637,6 +643,8 @@ void mimi_frame(Batch& bt, const float* latent) {
       p.nb = B; p.T = b.T_in; p.taps = 2; p.C = st.c_in; p.a_pro = ACT_ELU;
       p.Y = b.r_in + (long long)(rk - 1) * st.c_out; p.y_bs = r_bs; p.y_rs = (long long)st.stride * st.c_out;
       p.out_scale = 1.f;
+      static const char* kCt[] = {"sn.ct0", "sn.ct1", "sn.ct2", "sn.ct3", "sn.ct4", "sn.ct5", "sn.ct6", "sn.ct7"};
+      p.tag = kCt[r];
       run_linear(c, st.ct, p);
     }
     {  // resblock: x + conv_k1(ELU(conv_k3(ELU(x))))
@@ -644,6 +652,9 @@ void mimi_frame(Batch& bt, const float* latent) {
       p.A = b.r_in; p.a_bs = r_bs; p.a_rs = st.c_out; p.nb = B; p.T = b.T_out; p.taps = rk; p.C = st.c_out;
       p.a_pro = ACT_ELU;
       p.Y = b.hid; p.y_bs = (long long)b.T_out * st.hidden; p.y_rs = st.hidden; p.out_scale = 1.f;
+      static const char* kR3[] = {"sn.r3_0", "sn.r3_1", "sn.r3_2", "sn.r3_3", "sn.r3_4", "sn.r3_5", "sn.r3_6", "sn.r3_7"};
+      static const char* kR1[] = {"sn.r1_0", "sn.r1_1", "sn.r1_2", "sn.r1_3", "sn.r1_4", "sn.r1_5", "sn.r1_6", "sn.r1_7"};
+      p.tag = kR3[r];
       run_linear(c, st.r3, p);
       LinearParams q{};
       q.A = b.hid; q.a_bs = (long long)b.T_out * st.hidden; q.a_rs = st.hidden; q.nb = B; q.T = b.T_out;
@@ -657,6 +668,7 @@ void mimi_frame(Batch& bt, const float* latent) {
         q.Y = bt.d_fin + (long long)(c.fin_taps - 1) * st.c_out;
         q.y_bs = (long long)(b.T_out + c.fin_taps - 1) * st.c_out; q.y_rs = st.c_out;
       }
+      q.tag = kR1[r];
       run_linear(c, st.r1, q);
     }
   }
@@ -671,32 +683,34 @@ void flow_step(Batch& bt, bool host_noise) {
   const ptts_config& g = c.cfg;
   const int B = bt.B, D = g.d_model, L = g.latent_dim, fd = g.flow_dim;
   launch_input_rows(c.w_in, c.bos, bt.d_latent, bt.d_bos, bt.fw.x, B, D, L, c.stream);
-  flow_layers(c, bt.fw, B, nullptr, bt.d_len, bt.d_page_table, bt.max_pages);
+  long long total_keys = 0;
+  for (int l : bt.h_len) total_keys += l + 1;
+  flow_layers(c, bt.fw, B, nullptr, bt.d_len, bt.d_page_table, bt.max_pages, total_keys);
   launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.d_logit, B, D, c.stream);
   launch_noise_prep(bt.d_noise, bt.d_x, B * L, sqrtf(g.temp), (g.noise_clamp >= 0.f) ? g.noise_clamp : -1.f,
                     host_noise ? 0 : 1, bt.seed, bt.d_counter, c.stream);
   const int n = g.lsd_decode_steps;
   for (int i = 0; i < n; ++i) {
-    LinearParams ce = rows_linear(bt.d_c, B, D, bt.d_sy, fd);
+    LinearParams ce = rows_linear(bt.d_c, B, D, bt.d_sy, fd, "head.cond");
     ce.bias = c.cond_bias_step[i];
     ce.act = ACT_SILU;
     run_linear(c, c.cond, ce);                                     // silu(t_emb + cond_embed(c))
-    run_linear(c, c.ada_all, rows_linear(bt.d_sy, B, fd, bt.d_ada, c.n_ada));   // every AdaLN modulation at once
-    run_linear(c, c.in_proj, rows_linear(bt.d_x, B, L, bt.d_x1, fd));
+    run_linear(c, c.ada_all, rows_linear(bt.d_sy, B, fd, bt.d_ada, c.n_ada, "head.ada"));   // every AdaLN modulation at once
+    run_linear(c, c.in_proj, rows_linear(bt.d_x, B, L, bt.d_x1, fd, "head.in"));
     for (int r = 0; r < g.flow_depth; ++r) {
       const float* ada = bt.d_ada + (long long)r * 3 * fd;
       rows_norm(c, bt.d_x1, B, fd, c.rb[r].lnw, c.rb[r].lnb, 1e-6f, bt.d_hh, ada + fd, ada, c.n_ada);
-      LinearParams m1 = rows_linear(bt.d_hh, B, fd, bt.d_u, fd);
+      LinearParams m1 = rows_linear(bt.d_hh, B, fd, bt.d_u, fd, "head.m1");
       m1.act = ACT_SILU;
       run_linear(c, c.rb[r].m1, m1);
-      LinearParams m2 = rows_linear(bt.d_u, B, fd, bt.d_x1, fd);
+      LinearParams m2 = rows_linear(bt.d_u, B, fd, bt.d_x1, fd, "head.m2");
       m2.row_gate = ada + 2 * fd; m2.gate_bs = 0; m2.gate_rs = c.n_ada;
       m2.res = bt.d_x1; m2.res_bs = 0; m2.res_rs = fd;
       run_linear(c, c.rb[r].m2, m2);
     }
     const float* adaf = bt.d_ada + (long long)g.flow_depth * 3 * fd;
     rows_norm(c, bt.d_x1, B, fd, nullptr, nullptr, 1e-6f, bt.d_hh, adaf + fd, adaf, c.n_ada);
-    LinearParams fo = rows_linear(bt.d_hh, B, fd, bt.d_x, L);     // x += v / n
+    LinearParams fo = rows_linear(bt.d_hh, B, fd, bt.d_x, L, "head.fin");     // x += v / n
     fo.out_scale = 1.0f / (float)n;
     fo.res = bt.d_x; fo.res_bs = 0; fo.res_rs = L;
     run_linear(c, c.fin, fo);
@@ -857,7 +871,7 @@ int32_t ptts_voice_create(ptts_ctx* c, const float* cond, int32_t n_frames) {
   CU(cudaMemcpyAsync(d_pos, pos.data(), n_frames * 4, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(d_pt, v.pages.data(), np * 4, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->prefill_work.x, cond, (size_t)n_frames * D * 4, cudaMemcpyHostToDevice, c->stream));
-  flow_layers(*c, c->prefill_work, n_frames, d_seq, d_pos, d_pt, np);
+  flow_layers(*c, c->prefill_work, n_frames, d_seq, d_pos, d_pt, np, (long long)n_frames * (n_frames + 1) / 2);
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   cudaFree(d_seq); cudaFree(d_pos); cudaFree(d_pt);
@@ -1075,7 +1089,9 @@ int32_t ptts_batch_prefill_text(ptts_batch* bt, const int32_t* ids, const int32_
     CU(cudaMemcpyAsync(d_pos, pos.data(), M * 4, cudaMemcpyHostToDevice, c.stream));
     CU(cudaMemcpyAsync(d_ids, ids + offsets[0], M * 4, cudaMemcpyHostToDevice, c.stream));
     launch_embed_rows(c.embed, c.bf16, d_ids, c.prefill_work.x, M, c.cfg.d_model, c.stream);
-    flow_layers(c, c.prefill_work, M, d_seq, d_pos, bt->d_page_table, bt->max_pages);
+    long long total_keys = 0;
+    for (int i = 0; i < M; ++i) total_keys += pos[i] + 1;
+    flow_layers(c, c.prefill_work, M, d_seq, d_pos, bt->d_page_table, bt->max_pages, total_keys);
     for (int b = 0; b < B; ++b) bt->h_len[b] += offsets[b + 1] - offsets[b];
     CU(cudaMemcpyAsync(bt->d_len, bt->h_len.data(), B * 4, cudaMemcpyHostToDevice, c.stream));
     CU(cudaStreamSynchronize(c.stream));
@@ -1226,27 +1242,19 @@ int64_t ptts_launch_count(ptts_ctx*, int32_t reset) {
   return v;
 }
 
-int32_t ptts_batch_profile_step(ptts_batch* bt, float* ms, int32_t cap, const char** names) {
-  if (!bt || !ms || cap < 3) return fail(PTTS_ERR_INVALID, "bad arguments");
+int32_t ptts_batch_profile_step(ptts_batch* bt, const char** report) {
+  if (!bt || !report) return fail(PTTS_ERR_INVALID, "bad arguments");
   Ctx& c = *bt->ctx;
   CU(cudaSetDevice(c.device));
   RET(check_step_ready(*bt));
-  cudaEvent_t ev[4];
-  for (auto& e : ev) CU(cudaEventCreate(&e));
-  CU(cudaEventRecord(ev[0], c.stream));
-  flow_step(*bt, false);
-  CU(cudaEventRecord(ev[1], c.stream));
-  mimi_frame(*bt, bt->d_latent);
-  CU(cudaEventRecord(ev[2], c.stream));
-  launch_advance(bt->d_len, bt->d_bos, bt->d_mimi_off, bt->d_counter, bt->B, 1, bt->T0, c.stream);
-  CU(cudaEventRecord(ev[3], c.stream));
-  CU(cudaEventSynchronize(ev[3]));
-  for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
-  for (auto& e : ev) cudaEventDestroy(e);
+  CU(cudaStreamSynchronize(c.stream));
+  prof_start();
+  full_step(*bt, false, false);
+  CU(cudaStreamSynchronize(c.stream));
+  *report = prof_report();
+  CU(cudaGetLastError());
   for (auto& l : bt->h_len) l += 1;
-  c.prof_names = "flow_step;mimi_frame;advance";
-  if (names) *names = c.prof_names.c_str();
-  return 3;
+  return 0;
 }
 
 int32_t ptts_flush_l2(ptts_ctx* c) {

@@ -31,7 +31,16 @@ struct LinearParams {
   const float* col_scale;                     // null or [N] (LayerScale)
   const float* res; long long res_bs, res_rs; // null or residual with Y's row indexing
   float* Y; long long y_bs, y_rs;
+  const char* tag;                            // call-site label for the profiler (may be null)
 };
+
+inline double linear_flops(const LinearParams& p) { return 2.0 * p.nb * p.T * (double)p.N * p.taps * p.C; }
+inline double linear_bytes(const LinearParams& p) {
+  const double w = (double)p.N * p.taps * p.C * (p.w_bf16 ? 2 : 4);
+  const double a = (double)p.nb * (p.T + p.taps - 1) * p.C * 4;
+  const double y = (double)p.nb * p.T * p.N * 4 * (p.res ? 2 : 1);
+  return w + a + y;
+}
 
 void launch_linear_tile(const LinearParams& p, cudaStream_t s);   // any M; SIMT 64x64 tiles
 void launch_linear_gemv(const LinearParams& p, cudaStream_t s);   // M = nb*T <= 16; weight-streaming
@@ -61,6 +70,7 @@ struct FlowAttnParams {
   const int* page_table; int max_pages;   // [n_seq][max_pages]
   int M, H;
   const float* freqs;          // [32] RoPE frequencies (fp32, computed like modules/rope.py:17-18)
+  long long total_keys;        // host-side sum over rows of (row_pos+1), for the profiler's byte count
 };
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s);
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s);
@@ -118,8 +128,20 @@ void launch_scatter_audio(const float* audio, float* audio_all, int B, int F, in
                           cudaStream_t s);
 void launch_inc(int* v, int inc, cudaStream_t s);
 
-// launch accounting (ptts_launch_count)
+// launch accounting (ptts_launch_count) and the eager per-kernel profiler (ptts_batch_profile_step):
+// every launcher opens a ProfScope; when profiling is on it brackets the launch with CUDA events on the
+// launching stream and books the ALGORITHMIC flops / bytes of that launch under "kernel:tag".
 extern long long g_launches;
+extern bool g_prof_on;
+struct ProfScope {
+  int slot = -1;
+  cudaStream_t s;
+  ProfScope(const char* kernel, const char* tag, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+};
+void prof_start();
+// "name,launches,ms,flops,bytes\n" per kernel:tag, sorted by time; stops profiling
+const char* prof_report();
 
 // ---- device helpers ----------------------------------------------------------------------------------
 __device__ __forceinline__ float act_apply(float v, int act) {

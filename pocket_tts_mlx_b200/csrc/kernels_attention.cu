@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(128) mimi_attention_kernel(const MimiAttnParam
 
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s) {
   if (p.M <= 0) return;
+  ProfScope ps("flow_rope_append", nullptr, 0, (double)p.M * p.H * 64 * (3 * 4 + 4 + 2 * (p.kv_bf16 ? 2 : 4)), s);
   if (p.kv_bf16) flow_rope_append_kernel<__nv_bfloat16><<<p.M, p.H * 32, 0, s>>>(p);
   else flow_rope_append_kernel<float><<<p.M, p.H * 32, 0, s>>>(p);
   ++g_launches;
@@ -268,12 +269,15 @@ void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s) {
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
   if (p.M <= 0) return;
   dim3 grid(p.M, p.H);
+  ProfScope ps("flow_attention", nullptr, 4.0 * p.total_keys * p.H * 64,
+               2.0 * p.total_keys * p.H * 64 * (p.kv_bf16 ? 2 : 4) + 2.0 * p.M * p.H * 64 * 4, s);
   if (p.kv_bf16) flow_attention_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p);
   else flow_attention_kernel<float><<<grid, 128, 0, s>>>(p);
   ++g_launches;
 }
 
 void launch_mimi_rope_ring(const MimiAttnParams& p, cudaStream_t s) {
+  ProfScope ps("mimi_rope_ring", nullptr, 0, (double)p.B * p.T * p.H * 64 * (3 * 4 + 4 + 2 * (p.kv_bf16 ? 2 : 4)), s);
   if (p.kv_bf16) mimi_rope_ring_kernel<__nv_bfloat16><<<p.B * p.T, p.H * 32, 0, s>>>(p);
   else mimi_rope_ring_kernel<float><<<p.B * p.T, p.H * 32, 0, s>>>(p);
   ++g_launches;
@@ -281,6 +285,8 @@ void launch_mimi_rope_ring(const MimiAttnParams& p, cudaStream_t s) {
 
 void launch_mimi_attention(const MimiAttnParams& p, cudaStream_t s) {
   dim3 grid(p.B, p.H);
+  ProfScope ps("mimi_attention", nullptr, 4.0 * p.B * p.H * p.T * p.context * 64,
+               2.0 * p.B * p.H * p.context * 64 * (p.kv_bf16 ? 2 : 4) + 2.0 * p.B * p.T * p.H * 64 * 4, s);
   if (p.kv_bf16) mimi_attention_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p);
   else mimi_attention_kernel<float><<<grid, 128, 0, s>>>(p);
   ++g_launches;

@@ -236,12 +236,14 @@ bool linear_gemv_supported(const LinearParams& p) {
 void launch_linear_tile(const LinearParams& p, cudaStream_t s) {
   const int M = p.nb * p.T;
   dim3 grid((p.N + BN - 1) / BN, (M + BM - 1) / BM), block(256);
+  ProfScope ps("linear_tile", p.tag, linear_flops(p), linear_bytes(p), s);
   if (p.w_bf16) linear_tile_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(p);
   else linear_tile_kernel<float><<<grid, block, 0, s>>>(p);
   ++g_launches;
 }
 
 void launch_linear_gemv(const LinearParams& p, cudaStream_t s) {
+  ProfScope ps("linear_gemv", p.tag, linear_flops(p), linear_bytes(p), s);
   if (p.w_bf16) launch_gemv_t<__nv_bfloat16>(p, s);
   else launch_gemv_t<float>(p, s);
   ++g_launches;

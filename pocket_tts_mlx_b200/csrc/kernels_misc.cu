@@ -261,18 +261,21 @@ __global__ void inc_kernel(int* v, int inc) { *v += inc; }
 }  // namespace
 
 void launch_layernorm(const NormParams& p, cudaStream_t s) {
+  ProfScope ps("layernorm", nullptr, 0, 2.0 * p.nb * p.T * p.C * 4, s);
   layernorm_kernel<<<p.nb * p.T, 128, 0, s>>>(p);
   ++g_launches;
 }
 
 void launch_input_rows(const float* w_in, const float* bos, const float* prev, const int* bos_flag, float* x,
                        int B, int D, int L, cudaStream_t s) {
+  ProfScope ps("input_rows", nullptr, 0, (double)B * (D + L) * 4 + (double)D * L * 4, s);
   input_rows_kernel<<<B, 256, L * sizeof(float), s>>>(w_in, bos, prev, bos_flag, x, D, L);
   ++g_launches;
 }
 
 void launch_embed_rows(const void* table, int table_bf16, const int* ids, float* rows, int M, int D,
                        cudaStream_t s) {
+  ProfScope ps("embed_rows", nullptr, 0, (double)M * D * 6, s);
   if (table_bf16)
     embed_rows_kernel<__nv_bfloat16><<<M, 256, 0, s>>>((const __nv_bfloat16*)table, ids, rows, D);
   else
@@ -283,12 +286,14 @@ void launch_embed_rows(const void* table, int table_bf16, const int* ids, float*
 void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w, const float* ln_b,
                            const float* w_eos, const float* b_eos, float* c, float* logit, int B, int D,
                            cudaStream_t s) {
+  ProfScope ps("final_norm_eos", nullptr, 0, 2.0 * B * D * 4, s);
   final_norm_eos_kernel<<<B, 128, 0, s>>>(x, row_of, ln_w, ln_b, w_eos, b_eos, c, logit, D);
   ++g_launches;
 }
 
 void launch_noise_prep(const float* z, float* x0, int n, float std, float clamp, int use_philox,
                        unsigned long long seed, const unsigned long long* counter, cudaStream_t s) {
+  ProfScope ps("noise_prep", nullptr, 0, 2.0 * n * 4, s);
   noise_prep_kernel<<<(n + 255) / 256, 256, 0, s>>>(z, x0, n, std, clamp, use_philox, seed, counter);
   ++g_launches;
 }
@@ -296,6 +301,7 @@ void launch_noise_prep(const float* z, float* x0, int n, float std, float clamp,
 void launch_quant_upsample(const float* lat, const float* emb_std, const float* emb_mean, const float* wq,
                            const float* wu, float* zprev, float* out, long long out_bs, int B, int L, int C,
                            int S, cudaStream_t s) {
+  ProfScope ps("quant_upsample", nullptr, 0, (double)B * S * C * 4, s);
   quant_upsample_kernel<<<B, 256, L * sizeof(float), s>>>(lat, emb_std, emb_mean, wq, wu, zprev, out, out_bs,
                                                           L, C, S);
   ++g_launches;
@@ -303,6 +309,7 @@ void launch_quant_upsample(const float* lat, const float* emb_std, const float* 
 
 void launch_final_conv(const float* x, long long x_bs, const float* w, const float* bias, float* audio,
                        long long audio_bs, int B, int T, int C, int taps, cudaStream_t s) {
+  ProfScope ps("final_conv", nullptr, 0, (double)B * T * (C + 1) * 4, s);
   const size_t smem = (size_t)(taps * C + (128 + taps - 1) * (C + 1)) * sizeof(float);
   dim3 grid((T + 127) / 128, B);
   final_conv_kernel<<<grid, 128, smem, s>>>(x, x_bs, w, bias, audio, audio_bs, T, C, taps);
@@ -310,6 +317,7 @@ void launch_final_conv(const float* x, long long x_bs, const float* w, const flo
 }
 
 void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s) {
+  ProfScope ps("state_shift", nullptr, 0, 0, s);
   dim3 grid(B, n_entries);
   state_shift_kernel<<<grid, 256, 0, s>>>(entries_dev);
   ++g_launches;
@@ -317,11 +325,13 @@ void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cud
 
 void launch_advance(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter, int B,
                     int inc_len, int inc_mimi, cudaStream_t s) {
+  ProfScope ps("advance", nullptr, 0, 0, s);
   advance_kernel<<<(B + 255) / 256, 256, 0, s>>>(seq_len, bos_flag, mimi_offset, counter, B, inc_len, inc_mimi);
   ++g_launches;
 }
 
 void launch_axpy(const float* x, float* y, float a, int n, cudaStream_t s) {
+  ProfScope ps("axpy", nullptr, 0, 3.0 * n * 4, s);
   axpy_kernel<<<(n + 255) / 256, 256, 0, s>>>(x, y, a, n);
   ++g_launches;
 }
@@ -329,6 +339,7 @@ void launch_axpy(const float* x, float* y, float a, int n, cudaStream_t s) {
 void launch_copy_pages(void* pool, int kv_bf16, long long layer_stride, long long page_stride, int n_layers,
                        const int* src_pages, const int* dst_pages, int n_pairs, cudaStream_t s) {
   if (n_pairs <= 0) return;
+  ProfScope ps("copy_pages", nullptr, 0, 2.0 * n_pairs * n_layers * page_stride * (kv_bf16 ? 2 : 4), s);
   dim3 grid(n_pairs, n_layers);
   if (kv_bf16)
     copy_pages_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)pool, layer_stride, page_stride,
@@ -339,25 +350,89 @@ void launch_copy_pages(void* pool, int kv_bf16, long long layer_stride, long lon
 }
 
 void launch_fill_u32(unsigned int* dst, unsigned int v, long long n, cudaStream_t s) {
+  ProfScope ps("fill_u32", nullptr, 0, (double)n * 4, s);
   fill_u32_kernel<<<1184, 256, 0, s>>>(dst, v, n);
   ++g_launches;
 }
 
 void launch_gather_frame(const float* lat_all, float* lat, int B, int F, int L, const int* frame_idx,
                          cudaStream_t s) {
+  ProfScope ps("gather_frame", nullptr, 0, 0, s);
   gather_frame_kernel<<<B, 32, 0, s>>>(lat_all, lat, F, L, frame_idx);
   ++g_launches;
 }
 
 void launch_scatter_audio(const float* audio, float* audio_all, int B, int F, int n, const int* frame_idx,
                           cudaStream_t s) {
+  ProfScope ps("scatter_audio", nullptr, 0, 2.0 * B * n * 4, s);
   scatter_audio_kernel<<<B, 256, 0, s>>>(audio, audio_all, F, n, frame_idx);
   ++g_launches;
 }
 
 void launch_inc(int* v, int inc, cudaStream_t s) {
+  ProfScope ps("inc", nullptr, 0, 0, s);
   inc_kernel<<<1, 1, 0, s>>>(v, inc);
   ++g_launches;
 }
 
+}  // namespace ptts
+
+// ---- eager per-kernel profiler -------------------------------------------------------------------------
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+namespace ptts {
+bool g_prof_on = false;
+namespace {
+struct Rec { std::string name; cudaEvent_t e0, e1; double flops, bytes; };
+std::vector<Rec> g_recs;
+std::vector<cudaEvent_t> g_pool;
+std::string g_report;
+cudaEvent_t get_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+ProfScope::ProfScope(const char* kernel, const char* tag, double flops, double bytes, cudaStream_t stream) : s(stream) {
+  if (!g_prof_on) return;
+  Rec r;
+  r.name = kernel;
+  if (tag) { r.name += ":"; r.name += tag; }
+  r.e0 = get_event(); r.e1 = get_event(); r.flops = flops; r.bytes = bytes;
+  cudaEventRecord(r.e0, s);
+  slot = (int)g_recs.size();
+  g_recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_recs[slot].e1, s);
+}
+void prof_start() { g_recs.clear(); g_prof_on = true; }
+const char* prof_report() {
+  g_prof_on = false;
+  struct Agg { double ms = 0, flops = 0, bytes = 0; long n = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : g_recs) {
+    cudaEventSynchronize(r.e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    auto& a = agg[r.name];
+    a.ms += ms; a.flops += r.flops; a.bytes += r.bytes; a.n += 1;
+    g_pool.push_back(r.e0); g_pool.push_back(r.e1);
+  }
+  g_recs.clear();
+  std::vector<std::pair<std::string, Agg>> v(agg.begin(), agg.end());
+  std::sort(v.begin(), v.end(), [](auto& x, auto& y) { return x.second.ms > y.second.ms; });
+  g_report.clear();
+  char line[512];
+  for (auto& kv : v) {
+    snprintf(line, sizeof line, "%s,%ld,%.6f,%.6g,%.6g\n", kv.first.c_str(), kv.second.n, kv.second.ms,
+             kv.second.flops, kv.second.bytes);
+    g_report += line;
+  }
+  return g_report.c_str();
+}
 }  // namespace ptts
