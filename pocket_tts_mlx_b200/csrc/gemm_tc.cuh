@@ -1,9 +1,54 @@
-// tcgen05 / TMEM / TMA multi-tap GEMM (bf16 operands, fp32 accumulate) -- see gemm_tc.cu.
+// tcgen05 / TMEM / TMA multi-tap GEMM (bf16 operands, fp32 accumulation in tensor memory).
+//
+//   D[b,t,n] = sum_{j<taps} sum_{c<C} A[b, t+j, c] * W[n, j*C + c]
+//
+// A is a bf16 activation buffer [nb][T+taps-1][C] (the first taps-1 rows of every sequence are the carried
+// streaming state) described by a 3-D TMA tensor map, so tap j of a causal conv / polyphase transposed conv
+// is just the same box fetched at time coordinate t0+j; plain Linears use taps = 1.  W is [N][taps*C] bf16
+// (K-major), a 2-D tensor map.  One CTA computes a 128 x BN tile: warp 0 issues TMA into a 4-stage
+// 128B-swizzled ring, warp 1 issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM accumulator, warps 2-5 drain
+// it with tcgen05.ld and apply the fused epilogue.
 #pragma once
+#include <cuda.h>
+
 #include "kernels.cuh"
 
 namespace ptts {
+
+struct TcEpilogue {
+  const float* bias;          // [N] or null
+  int act;                    // Act on (acc + bias)
+  float out_scale;            // 0 means 1
+  const float* row_gate; long long gate_bs, gate_rs;     // [b,t,n] multiplier or null
+  const float* col_scale;     // [N] or null
+  const float* res32; long long res32_bs, res32_rs;      // fp32 residual or null
+  const __nv_bfloat16* res16; long long res16_bs, res16_rs;
+  float* y32; long long y32_bs, y32_rs;                  // fp32 output or null
+  __nv_bfloat16* y16; long long y16_bs, y16_rs; int y16_act;   // bf16 output of act2(v) or null
+  __nv_bfloat16* yraw16; long long yraw16_bs, yraw16_rs;       // bf16 copy of v or null
+};
+
+struct TcGemm {
+  CUtensorMap tm_a, tm_b;
+  int nb, T, taps, C, N;
+  int box_t, box_b;           // 128-row M tile = box_b sequences x box_t time steps
+  int bn, bk;                 // N tile (32/64/128), K chunk in elements (64 or 32)
+  TcEpilogue e;
+  const char* tag;
+  bool valid = false;
+};
+
 void gemm_tc_init();
+bool gemm_tc_available();
+// Describe one GEMM call site.  a: bf16 [nb][T+taps-1][C] with strides (a_bs, a_rs) in elements;
+// w: bf16 [N][taps*C].  Returns false when the shape is unsupported (caller keeps the SIMT path).
+bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a_rs, int nb, int T, int taps, int C,
+                  const __nv_bfloat16* w, int N, const char* tag);
+void gemm_tc_launch(const TcGemm& g, cudaStream_t s);
 // fp32-in / fp32-out debug entry used by ptts_debug_linear(path=3); returns < 0 when unsupported.
 int gemm_tc_debug(const LinearParams& p, bool bf16_storage, cudaStream_t s);
+
+// helpers used by the bf16 pipeline
+void launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t s);
+
 }  // namespace ptts

@@ -251,3 +251,33 @@ def test_api_errors(model_bf16):
     with pytest.raises(ValueError):
         model_bf16.get_state_for_audio_prompt("not_a_voice")
     assert model_bf16.sample_rate == 24000 and model_bf16.device.startswith("cuda:")
+
+
+# ---------------------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("shape", [
+    # nb, T, taps, C, N
+    (1, 256, 1, 1024, 3072),    # FlowLM qkv at batch 256 (flat rows)
+    (1, 256, 1, 4096, 1024),    # FlowLM ffn2: 64 K-iterations through the 4-stage ring
+    (1, 300, 1, 512, 512),      # ragged M (last tile partly out of bounds -> TMA zero fill)
+    (16, 16, 7, 512, 512),      # SEANet conv0: 7 taps, box = 8 sequences x 16 steps
+    (8, 16, 2, 512, 1536),      # transposed conv 512->256 stride 6 (polyphase, 2 taps)
+    (4, 96, 3, 256, 128),       # resblock k3 at T=96: box = 4 sequences x 32 steps
+    (3, 480, 2, 128, 256),      # convtr 128->64 stride 4; nb not a multiple of the box
+    (2, 1920, 3, 64, 32),       # last resblock k3: N = 32
+    (2, 1920, 1, 32, 64),       # last resblock k1: C = 32 -> 64-byte swizzle path
+])
+def test_tcgen05_gemm_matches_numpy(model_bf16, shape):
+    from pocket_tts_mlx_b200.safetensors_io import bf16_bits_to_f32, f32_to_bf16_bits
+    nb, t, taps, c, n = shape
+    rng = np.random.Generator(np.random.PCG64(hash(shape) & 0xffff))
+    a = rng.standard_normal((nb, t + taps - 1, c)).astype(np.float32)
+    w = (rng.standard_normal((n, taps * c)) / np.sqrt(taps * c)).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32)
+    y = model_bf16._ctx.debug_linear(a, w, bias, taps=taps, path=3)
+    q = lambda x: bf16_bits_to_f32(f32_to_bf16_bits(x)).reshape(x.shape).astype(np.float64)
+    aq, wq = q(a), q(w)
+    ref = np.zeros((nb, t, n), dtype=np.float64)
+    for j in range(taps):
+        ref += aq[:, j:j + t, :] @ wq[:, j * c:(j + 1) * c].T
+    ref += bias
+    assert rel_l2(y, ref) < 1e-5, rel_l2(y, ref)
