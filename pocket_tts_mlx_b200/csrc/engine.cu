@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -96,8 +97,11 @@ struct Voice {
 
 struct FlowWork {
   int cap = 0;
+  bool tc = false;            // bf16 operands + tcgen05 GEMMs (M > 16 rows in bf16 mode)
   float *x = nullptr, *h = nullptr, *qkv = nullptr, *qrot = nullptr, *att = nullptr, *ff = nullptr;
   __nv_bfloat16 *h16 = nullptr, *att16 = nullptr, *ff16 = nullptr;   // bf16 operands for the tensor-core path
+  int plan_M = 0;
+  std::vector<TcGemm> plans;  // 4 per layer: qkv, out, ff1, ff2
 };
 
 }  // namespace
@@ -109,6 +113,7 @@ struct ptts_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool finalized = false;
   bool bf16 = true;
+  bool force_simt = false;     // PTTS_FORCE_SIMT=1: keep the CUDA-core GEMMs (A/B comparisons)
   std::unordered_map<std::string, HostTensor> host;
   std::vector<void*> allocs;
 
@@ -461,37 +466,100 @@ LinearParams rows_linear(const float* A, int M, int C, float* Y, int N, const ch
 }
 
 void rows_norm(Ctx& c, const float* X, int M, int C, const float* w, const float* b, float eps, float* Y,
-               const float* scale = nullptr, const float* shift = nullptr, long long mod_rs = 0) {
+               const float* scale = nullptr, const float* shift = nullptr, long long mod_rs = 0,
+               __nv_bfloat16* Y16 = nullptr) {
   NormParams n{};
+  n.Y16 = Y16;
   n.X = X; n.x_bs = 0; n.x_rs = C; n.nb = 1; n.T = M; n.C = C;
   n.w = w; n.b = b; n.eps = eps; n.scale = scale; n.shift = shift; n.mod_rs = mod_rs;
   n.Y = Y; n.y_bs = 0; n.y_rs = C;
   launch_layernorm(n, c.stream);
 }
 
+bool want_tc(Ctx& c, int M) { return c.bf16 && gemm_tc_available() && M > 16 && !c.force_simt; }
+
+void free_flow_work(FlowWork& w) {
+  void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  w = FlowWork{};
+}
+
 int alloc_flow_work(Ctx& c, FlowWork& w, int M) {
-  if (M <= w.cap) return 0;
-  const int D = c.cfg.d_model;
-  float** ptrs[] = {&w.x, &w.h, &w.qkv, &w.qrot, &w.att, &w.ff};
-  const size_t widths[] = {(size_t)D, (size_t)D, (size_t)3 * D, (size_t)D, (size_t)D, (size_t)c.cfg.ffn_dim};
-  for (int i = 0; i < 6; ++i) {
-    if (*ptrs[i]) CU(cudaFree(*ptrs[i]));
-    CU(cudaMalloc((void**)ptrs[i], (size_t)M * widths[i] * sizeof(float)));
+  const bool tc = want_tc(c, M);
+  if (M <= w.cap && tc == w.tc) return 0;
+  free_flow_work(w);
+  const size_t D = c.cfg.d_model, FF = c.cfg.ffn_dim;
+  CU(cudaMalloc((void**)&w.x, M * D * 4));
+  CU(cudaMalloc((void**)&w.qkv, M * 3 * D * 4));
+  CU(cudaMalloc((void**)&w.qrot, M * D * 4));
+  if (tc) {
+    CU(cudaMalloc((void**)&w.h16, M * D * 2));
+    CU(cudaMalloc((void**)&w.att16, M * D * 2));
+    CU(cudaMalloc((void**)&w.ff16, M * FF * 2));
+  } else {
+    CU(cudaMalloc((void**)&w.h, M * D * 4));
+    CU(cudaMalloc((void**)&w.att, M * D * 4));
+    CU(cudaMalloc((void**)&w.ff, M * FF * 4));
   }
   w.cap = M;
+  w.tc = tc;
+  w.plan_M = 0;
   return 0;
 }
 
-void free_flow_work(FlowWork& w) {
-  float* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff};
-  for (float* p : ptrs) if (p) cudaFree(p);
-  w = FlowWork{};
+bool plan_tc(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a_rs, int nb, int T, int taps, int C,
+             const LinW& w, const char* tag) {
+  if (!w.w16 || w.K != taps * C) return false;
+  if (!gemm_tc_plan(g, a, a_bs, a_rs, nb, T, taps, C, w.w16, w.N, tag)) return false;
+  g->e.bias = w.bias;
+  return true;
+}
+
+int build_flow_plans(Ctx& c, FlowWork& w, int M) {
+  if (w.plan_M == M) return 0;
+  const int D = c.cfg.d_model, FF = c.cfg.ffn_dim;
+  w.plans.assign((size_t)c.cfg.n_layers * 4, TcGemm{});
+  for (int i = 0; i < c.cfg.n_layers; ++i) {
+    auto& l = c.fl[i];
+    TcGemm* g = &w.plans[(size_t)i * 4];
+    bool ok = plan_tc(&g[0], w.h16, 0, D, 1, M, 1, D, l.qkv, "flow.qkv") &&
+              plan_tc(&g[1], w.att16, 0, D, 1, M, 1, D, l.out, "flow.out") &&
+              plan_tc(&g[2], w.h16, 0, D, 1, M, 1, D, l.ff1, "flow.ff1") &&
+              plan_tc(&g[3], w.ff16, 0, FF, 1, M, 1, FF, l.ff2, "flow.ff2");
+    if (!ok) return fail(PTTS_ERR_CUDA, "tcgen05 plan failed for FlowLM layer %d (M=%d)", i, M);
+    g[0].e.y32 = w.qkv; g[0].e.y32_rs = 3 * D;
+    g[1].e.res32 = w.x; g[1].e.res32_rs = D; g[1].e.y32 = w.x; g[1].e.y32_rs = D;
+    g[2].e.act = ACT_GELU; g[2].e.y16 = w.ff16; g[2].e.y16_rs = FF;
+    g[3].e.res32 = w.x; g[3].e.res32_rs = D; g[3].e.y32 = w.x; g[3].e.y32_rs = D;
+  }
+  w.plan_M = M;
+  return 0;
 }
 
 // the 6 pre-LN layers over M rows that sit at (row_seq, row_pos) of their sequences
 void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_pos, const int* page_table,
                  int max_pages, long long total_keys) {
   const int D = c.cfg.d_model, FF = c.cfg.ffn_dim;
+  if (w.tc) {
+    for (int i = 0; i < c.cfg.n_layers; ++i) {
+      auto& l = c.fl[i];
+      const TcGemm* g = &w.plans[(size_t)i * 4];
+      rows_norm(c, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16);
+      gemm_tc_launch(g[0], c.stream);
+      FlowAttnParams a{};
+      a.qkv = w.qkv; a.q_rot = w.qrot; a.out16 = w.att16;
+      a.pool = c.pool; a.kv_bf16 = c.bf16; a.layer_stride = c.layer_stride; a.page_stride = c.page_stride;
+      a.layer = i; a.row_seq = row_seq; a.row_pos = row_pos; a.page_table = page_table; a.max_pages = max_pages;
+      a.M = M; a.H = c.cfg.n_heads; a.freqs = c.freqs_flow; a.total_keys = total_keys;
+      launch_flow_rope_append(a, c.stream);
+      launch_flow_attention(a, c.stream);
+      gemm_tc_launch(g[1], c.stream);
+      rows_norm(c, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16);
+      gemm_tc_launch(g[2], c.stream);
+      gemm_tc_launch(g[3], c.stream);
+    }
+    return;
+  }
   for (int i = 0; i < c.cfg.n_layers; ++i) {
     auto& l = c.fl[i];
     rows_norm(c, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, w.h);
@@ -553,6 +621,17 @@ struct ptts_batch {
   long long ring_layer_stride = 0, ring_kv_stride = 0;
   ShiftEntry* d_shift = nullptr;
   int n_shift = 0;
+  // ---- tensor-core (bf16 operand) pipeline: chosen per part by the row count (want_tc)
+  bool tc_head = false, tc_mimi = false;
+  __nv_bfloat16 *d_c16 = nullptr, *d_sy16 = nullptr, *d_hh16 = nullptr, *d_u16 = nullptr;
+  std::vector<TcGemm> g_cond, g_m1, g_m2;
+  TcGemm g_ada, g_fin;
+  float* d_xm = nullptr;
+  __nv_bfloat16 *d_mh16 = nullptr, *d_matt16 = nullptr, *d_mff16 = nullptr, *d_c0_16 = nullptr, *d_fin16 = nullptr;
+  std::vector<TcGemm> g_mimi;
+  TcGemm g_conv0;
+  struct StageBuf16 { __nv_bfloat16 *ct_in, *r_in, *xraw, *hid; int T_in, T_out; TcGemm ct, r3, r1; };
+  std::vector<StageBuf16> sb16;
   int T0 = 0;           // steps per frame at the SEANet input (upsample stride)
   int frame_samples = 0;
   // pinned staging
@@ -575,8 +654,11 @@ namespace {
 
 using Batch = ptts_batch;
 
+void mimi_frame_tc(Batch& bt, const float* latent);
+
 // one Mimi frame for every sequence: latent [B][L] -> audio [B][frame_samples]
 void mimi_frame(Batch& bt, const float* latent) {
+  if (bt.tc_mimi) return mimi_frame_tc(bt, latent);
   Ctx& c = *bt.ctx;
   const ptts_config& g = c.cfg;
   const int B = bt.B, T = bt.T0, MD = g.mimi_d, SD = g.seanet_dim;
@@ -677,6 +759,204 @@ void mimi_frame(Batch& bt, const float* latent) {
   launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream);
 }
 
+// Mimi frame on the tensor-core path: bf16 operands everywhere, every conv / transposed conv / linear is a
+// tcgen05 GEMM whose epilogue already writes the next GEMM's (ELU'd) bf16 input, incl. the carried state rows.
+void mimi_frame_tc(Batch& bt, const float* latent) {
+  Ctx& c = *bt.ctx;
+  const ptts_config& g = c.cfg;
+  const int B = bt.B, T = bt.T0, MD = g.mimi_d, SD = g.seanet_dim;
+  launch_quant_upsample(latent, c.emb_std, c.emb_mean, c.wq, c.wu, bt.d_zprev, bt.d_xm, (long long)T * SD, B,
+                        g.latent_dim, SD, g.upsample_stride, c.stream);
+  for (int i = 0; i < g.mimi_layers; ++i) {
+    auto& l = c.ml[i];
+    const TcGemm* gm = &bt.g_mimi[(size_t)i * 4];
+    NormParams n{};
+    n.X = bt.d_xm; n.x_bs = (long long)T * MD; n.x_rs = MD; n.nb = B; n.T = T; n.C = MD;
+    n.w = l.ln1w; n.b = l.ln1b; n.eps = 1e-5f;
+    n.Y16 = bt.d_mh16; n.y_bs = (long long)T * MD; n.y_rs = MD;
+    launch_layernorm(n, c.stream);
+    gemm_tc_launch(gm[0], c.stream);
+    MimiAttnParams a{};
+    a.qkv = bt.d_mqkv; a.q_rot = bt.d_mqrot; a.out16 = bt.d_matt16;
+    a.ring = bt.ring; a.kv_bf16 = c.bf16; a.layer_stride = bt.ring_layer_stride; a.kv_stride = bt.ring_kv_stride;
+    a.layer = i; a.offset = bt.d_mimi_off; a.B = B; a.T = T; a.H = g.mimi_heads; a.context = g.mimi_context;
+    a.freqs = c.freqs_mimi;
+    launch_mimi_rope_ring(a, c.stream);
+    launch_mimi_attention(a, c.stream);
+    gemm_tc_launch(gm[1], c.stream);
+    n.w = l.ln2w; n.b = l.ln2b;
+    launch_layernorm(n, c.stream);
+    gemm_tc_launch(gm[2], c.stream);
+    gemm_tc_launch(gm[3], c.stream);
+  }
+  gemm_tc_launch(bt.g_conv0, c.stream);
+  for (auto& sb : bt.sb16) {
+    gemm_tc_launch(sb.ct, c.stream);
+    gemm_tc_launch(sb.r3, c.stream);
+    gemm_tc_launch(sb.r1, c.stream);
+  }
+  launch_final_conv16(bt.d_fin16, (long long)(bt.frame_samples + c.fin_taps - 1) * c.fin_c, c.fin_w, c.fin_b,
+                      bt.d_audio, bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream);
+  launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream);
+}
+
+// flow head on the tensor-core path (M = B rows)
+void flow_head_tc(Batch& bt) {
+  Ctx& c = *bt.ctx;
+  const ptts_config& g = c.cfg;
+  const int B = bt.B, L = g.latent_dim, fd = g.flow_dim;
+  const int n = g.lsd_decode_steps;
+  for (int i = 0; i < n; ++i) {
+    gemm_tc_launch(bt.g_cond[i], c.stream);
+    gemm_tc_launch(bt.g_ada, c.stream);
+    run_linear(c, c.in_proj, rows_linear(bt.d_x, B, L, bt.d_x1, fd, "head.in"));
+    for (int r = 0; r < g.flow_depth; ++r) {
+      const float* ada = bt.d_ada + (long long)r * 3 * fd;
+      rows_norm(c, bt.d_x1, B, fd, c.rb[r].lnw, c.rb[r].lnb, 1e-6f, nullptr, ada + fd, ada, c.n_ada, bt.d_hh16);
+      gemm_tc_launch(bt.g_m1[r], c.stream);
+      gemm_tc_launch(bt.g_m2[r], c.stream);
+    }
+    const float* adaf = bt.d_ada + (long long)g.flow_depth * 3 * fd;
+    rows_norm(c, bt.d_x1, B, fd, nullptr, nullptr, 1e-6f, nullptr, adaf + fd, adaf, c.n_ada, bt.d_hh16);
+    gemm_tc_launch(bt.g_fin, c.stream);
+  }
+}
+
+int build_batch_tc(Batch& t) {
+  Ctx& c = *t.ctx;
+  const ptts_config& g = c.cfg;
+  const int B = t.B, D = g.d_model, L = g.latent_dim, fd = g.flow_dim;
+  auto bz = [&](__nv_bfloat16** p, size_t n) -> int {
+    RET(t.dalloc((void**)p, n * 2));
+    CU(cudaMemsetAsync(*p, 0, n * 2, c.stream));
+    return 0;
+  };
+  if (t.tc_head) {
+    RET(bz(&t.d_c16, (size_t)B * D));
+    RET(bz(&t.d_sy16, (size_t)B * fd));
+    RET(bz(&t.d_hh16, (size_t)B * fd));
+    RET(bz(&t.d_u16, (size_t)B * fd));
+    bool ok = true;
+    t.g_cond.assign(g.lsd_decode_steps, TcGemm{});
+    for (int i = 0; i < g.lsd_decode_steps && ok; ++i) {
+      ok = plan_tc(&t.g_cond[i], t.d_c16, 0, D, 1, B, 1, D, c.cond, "head.cond");
+      t.g_cond[i].e.bias = c.cond_bias_step[i];
+      t.g_cond[i].e.act = ACT_SILU;
+      t.g_cond[i].e.y16 = t.d_sy16; t.g_cond[i].e.y16_rs = fd;
+    }
+    ok = ok && plan_tc(&t.g_ada, t.d_sy16, 0, fd, 1, B, 1, fd, c.ada_all, "head.ada");
+    t.g_ada.e.y32 = t.d_ada; t.g_ada.e.y32_rs = c.n_ada;
+    t.g_m1.assign(g.flow_depth, TcGemm{});
+    t.g_m2.assign(g.flow_depth, TcGemm{});
+    for (int r = 0; r < g.flow_depth && ok; ++r) {
+      ok = plan_tc(&t.g_m1[r], t.d_hh16, 0, fd, 1, B, 1, fd, c.rb[r].m1, "head.m1") &&
+           plan_tc(&t.g_m2[r], t.d_u16, 0, fd, 1, B, 1, fd, c.rb[r].m2, "head.m2");
+      t.g_m1[r].e.act = ACT_SILU; t.g_m1[r].e.y16 = t.d_u16; t.g_m1[r].e.y16_rs = fd;
+      auto& e = t.g_m2[r].e;
+      e.row_gate = t.d_ada + (long long)r * 3 * fd + 2 * fd; e.gate_rs = c.n_ada;
+      e.res32 = t.d_x1; e.res32_rs = fd; e.y32 = t.d_x1; e.y32_rs = fd;
+    }
+    ok = ok && plan_tc(&t.g_fin, t.d_hh16, 0, fd, 1, B, 1, fd, c.fin, "head.fin");
+    t.g_fin.e.out_scale = 1.0f / (float)g.lsd_decode_steps;
+    t.g_fin.e.res32 = t.d_x; t.g_fin.e.res32_rs = L; t.g_fin.e.y32 = t.d_x; t.g_fin.e.y32_rs = L;
+    if (!ok) return fail(PTTS_ERR_CUDA, "tcgen05 plan failed for the flow head (B=%d)", B);
+  }
+  if (t.tc_mimi) {
+    const int T = t.T0, MD = g.mimi_d, SD = g.seanet_dim, FFm = g.mimi_ffn, k0 = g.kernel_size, rk = g.res_kernel_size;
+    RET(t.dalloc((void**)&t.d_xm, (size_t)B * T * MD * 4));
+    CU(cudaMemsetAsync(t.d_xm, 0, (size_t)B * T * MD * 4, c.stream));
+    RET(bz(&t.d_mh16, (size_t)B * T * MD));
+    RET(bz(&t.d_matt16, (size_t)B * T * MD));
+    RET(bz(&t.d_mff16, (size_t)B * T * FFm));
+    RET(bz(&t.d_c0_16, (size_t)B * (T + k0 - 1) * SD));
+    std::vector<ShiftEntry> sh;
+    sh.push_back({t.d_c0_16, (long long)(T + k0 - 1) * SD, T, k0 - 1, SD, 2});
+    bool ok = true;
+    t.g_mimi.assign((size_t)g.mimi_layers * 4, TcGemm{});
+    for (int i = 0; i < g.mimi_layers && ok; ++i) {
+      auto& l = c.ml[i];
+      TcGemm* gm = &t.g_mimi[(size_t)i * 4];
+      ok = plan_tc(&gm[0], t.d_mh16, (long long)T * MD, MD, B, T, 1, MD, l.qkv, "mimi.qkv") &&
+           plan_tc(&gm[1], t.d_matt16, (long long)T * MD, MD, B, T, 1, MD, l.out, "mimi.out") &&
+           plan_tc(&gm[2], t.d_mh16, (long long)T * MD, MD, B, T, 1, MD, l.ff1, "mimi.ff1") &&
+           plan_tc(&gm[3], t.d_mff16, (long long)T * FFm, FFm, B, T, 1, FFm, l.ff2, "mimi.ff2");
+      gm[0].e.y32 = t.d_mqkv; gm[0].e.y32_bs = (long long)T * 3 * MD; gm[0].e.y32_rs = 3 * MD;
+      for (int k : {1, 3}) {
+        auto& e = gm[k].e;
+        e.col_scale = (k == 1) ? l.ls1 : l.ls2;
+        e.res32 = t.d_xm; e.res32_bs = (long long)T * MD; e.res32_rs = MD;
+        e.y32 = t.d_xm; e.y32_bs = (long long)T * MD; e.y32_rs = MD;
+      }
+      gm[2].e.act = ACT_GELU; gm[2].e.y16 = t.d_mff16; gm[2].e.y16_bs = (long long)T * FFm; gm[2].e.y16_rs = FFm;
+      if (i == g.mimi_layers - 1) {   // the transformer output is conv0's input: bf16 copy behind the 6 state rows
+        gm[3].e.y16 = t.d_c0_16 + (long long)(k0 - 1) * SD;
+        gm[3].e.y16_bs = (long long)(T + k0 - 1) * SD; gm[3].e.y16_rs = SD; gm[3].e.y16_act = ACT_NONE;
+      }
+    }
+    t.sb16.resize(g.n_ratios);
+    int Tin = T;
+    for (int r = 0; r < g.n_ratios; ++r) {
+      auto& st = c.stages[r];
+      auto& b = t.sb16[r];
+      b.T_in = Tin; b.T_out = Tin * st.stride;
+      RET(bz(&b.ct_in, (size_t)B * (Tin + 1) * st.c_in));
+      RET(bz(&b.r_in, (size_t)B * (b.T_out + rk - 1) * st.c_out));
+      RET(bz(&b.xraw, (size_t)B * b.T_out * st.c_out));
+      RET(bz(&b.hid, (size_t)B * b.T_out * st.hidden));
+      sh.push_back({b.ct_in, (long long)(Tin + 1) * st.c_in, Tin, 1, st.c_in, 2});
+      if (rk > 1) sh.push_back({b.r_in, (long long)(b.T_out + rk - 1) * st.c_out, b.T_out, rk - 1, st.c_out, 2});
+      Tin = b.T_out;
+    }
+    RET(bz(&t.d_fin16, (size_t)B * (Tin + c.fin_taps - 1) * c.fin_c));
+    if (c.fin_taps > 1) sh.push_back({t.d_fin16, (long long)(Tin + c.fin_taps - 1) * c.fin_c, Tin, c.fin_taps - 1, c.fin_c, 2});
+    // conv0: ELU'd output lands behind the one state row of the first transposed conv
+    ok = ok && plan_tc(&t.g_conv0, t.d_c0_16, (long long)(T + k0 - 1) * SD, SD, B, T, k0, SD, c.conv0, "sn.conv0");
+    {
+      auto& e = t.g_conv0.e;
+      const int c1 = c.stages[0].c_in;
+      e.y16 = t.sb16[0].ct_in + c1; e.y16_bs = (long long)(T + 1) * c1; e.y16_rs = c1; e.y16_act = ACT_ELU;
+    }
+    static const char* kCt[] = {"sn.ct0", "sn.ct1", "sn.ct2", "sn.ct3", "sn.ct4", "sn.ct5", "sn.ct6", "sn.ct7"};
+    static const char* kR3[] = {"sn.r3_0", "sn.r3_1", "sn.r3_2", "sn.r3_3", "sn.r3_4", "sn.r3_5", "sn.r3_6", "sn.r3_7"};
+    static const char* kR1[] = {"sn.r1_0", "sn.r1_1", "sn.r1_2", "sn.r1_3", "sn.r1_4", "sn.r1_5", "sn.r1_6", "sn.r1_7"};
+    for (int r = 0; r < g.n_ratios && ok; ++r) {
+      auto& st = c.stages[r];
+      auto& b = t.sb16[r];
+      const long long r_bs = (long long)(b.T_out + rk - 1) * st.c_out;
+      ok = plan_tc(&b.ct, b.ct_in, (long long)(b.T_in + 1) * st.c_in, st.c_in, B, b.T_in, 2, st.c_in, st.ct, kCt[r]) &&
+           plan_tc(&b.r3, b.r_in, r_bs, st.c_out, B, b.T_out, rk, st.c_out, st.r3, kR3[r]) &&
+           plan_tc(&b.r1, b.hid, (long long)b.T_out * st.hidden, st.hidden, B, b.T_out, 1, st.hidden, st.r1, kR1[r]);
+      if (!ok) break;
+      {  // transposed conv: x (raw, residual) and ELU(x) (resblock input, behind its state rows)
+        auto& e = b.ct.e;
+        e.y16 = b.r_in + (long long)(rk - 1) * st.c_out; e.y16_bs = r_bs; e.y16_rs = (long long)st.stride * st.c_out;
+        e.y16_act = ACT_ELU;
+        e.yraw16 = b.xraw; e.yraw16_bs = (long long)b.T_out * st.c_out; e.yraw16_rs = (long long)st.stride * st.c_out;
+      }
+      {
+        auto& e = b.r3.e;
+        e.y16 = b.hid; e.y16_bs = (long long)b.T_out * st.hidden; e.y16_rs = st.hidden; e.y16_act = ACT_ELU;
+      }
+      {  // x + conv_k1(...): ELU'd straight into the next layer's input
+        auto& e = b.r1.e;
+        e.res16 = b.xraw; e.res16_bs = (long long)b.T_out * st.c_out; e.res16_rs = st.c_out;
+        e.y16_act = ACT_ELU;
+        if (r + 1 < g.n_ratios) {
+          e.y16 = t.sb16[r + 1].ct_in + st.c_out; e.y16_bs = (long long)(b.T_out + 1) * st.c_out; e.y16_rs = st.c_out;
+        } else {
+          e.y16 = t.d_fin16 + (long long)(c.fin_taps - 1) * st.c_out;
+          e.y16_bs = (long long)(b.T_out + c.fin_taps - 1) * st.c_out; e.y16_rs = st.c_out;
+        }
+      }
+    }
+    if (!ok) return fail(PTTS_ERR_CUDA, "tcgen05 plan failed for the Mimi decoder (B=%d)", B);
+    t.n_shift = (int)sh.size();
+    RET(t.dalloc((void**)&t.d_shift, sh.size() * sizeof(ShiftEntry)));
+    CU(cudaMemcpyAsync(t.d_shift, sh.data(), sh.size() * sizeof(ShiftEntry), cudaMemcpyHostToDevice, c.stream));
+  }
+  return 0;
+}
+
 // FlowLM decode step + EOS + flow head; leaves the new latent in d_latent
 void flow_step(Batch& bt, bool host_noise) {
   Ctx& c = *bt.ctx;
@@ -686,10 +966,16 @@ void flow_step(Batch& bt, bool host_noise) {
   long long total_keys = 0;
   for (int l : bt.h_len) total_keys += l + 1;
   flow_layers(c, bt.fw, B, nullptr, bt.d_len, bt.d_page_table, bt.max_pages, total_keys);
-  launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.d_logit, B, D, c.stream);
+  launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.tc_head ? bt.d_c16 : nullptr,
+                        bt.d_logit, B, D, c.stream);
   launch_noise_prep(bt.d_noise, bt.d_x, B * L, sqrtf(g.temp), (g.noise_clamp >= 0.f) ? g.noise_clamp : -1.f,
                     host_noise ? 0 : 1, bt.seed, bt.d_counter, c.stream);
   const int n = g.lsd_decode_steps;
+  if (bt.tc_head) {
+    flow_head_tc(bt);
+    cudaMemcpyAsync(bt.d_latent, bt.d_x, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, c.stream);
+    return;
+  }
   for (int i = 0; i < n; ++i) {
     LinearParams ce = rows_linear(bt.d_c, B, D, bt.d_sy, fd, "head.cond");
     ce.bias = c.cond_bias_step[i];
@@ -804,6 +1090,10 @@ int32_t ptts_ctx_create(int32_t device, const ptts_config* cfg, ptts_ctx** out) 
   c->device = device;
   c->cfg = *cfg;
   c->bf16 = cfg->precision == PTTS_BF16;
+  {
+    const char* fs = getenv("PTTS_FORCE_SIMT");
+    c->force_simt = fs && fs[0] == '1';
+  }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
@@ -861,6 +1151,7 @@ int32_t ptts_voice_create(ptts_ctx* c, const float* cond, int32_t n_frames) {
   const int np = (n_frames + kPageTokens - 1) / kPageTokens;
   RET(take_pages(*c, np, &v.pages));
   RET(alloc_flow_work(*c, c->prefill_work, n_frames));
+  if (c->prefill_work.tc) RET(build_flow_plans(*c, c->prefill_work, n_frames));
   std::vector<int> seq(n_frames, 0), pos(n_frames);
   for (int i = 0; i < n_frames; ++i) pos[i] = i;
   int *d_seq, *d_pos, *d_pt;
@@ -978,6 +1269,9 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
   CU(cudaMemsetAsync(t.d_frame_idx, 0, 4, c->stream));
   CU(cudaMemsetAsync(t.d_counter, 0, 8, c->stream));
   RET(alloc_flow_work(*c, t.fw, B));
+  if (t.fw.tc) RET(build_flow_plans(*c, t.fw, B));
+  t.tc_head = t.fw.tc;
+  t.tc_mimi = want_tc(*c, B * g.upsample_stride);
   const int D = g.d_model, L = g.latent_dim, fd = g.flow_dim;
   auto fz = [&](float** p, size_t n) -> int {
     RET(t.dalloc((void**)p, n * 4));
@@ -990,26 +1284,31 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
   RET(fz(&t.d_zero_lat, (size_t)B * L));
   RET(fz(&t.d_c, (size_t)B * D));
   RET(fz(&t.d_logit, B));
-  RET(fz(&t.d_sy, (size_t)B * fd));
   RET(fz(&t.d_ada, (size_t)B * c->n_ada));
   RET(fz(&t.d_x1, (size_t)B * fd));
-  RET(fz(&t.d_hh, (size_t)B * fd));
-  RET(fz(&t.d_u, (size_t)B * fd));
+  if (!t.tc_head) {
+    RET(fz(&t.d_sy, (size_t)B * fd));
+    RET(fz(&t.d_hh, (size_t)B * fd));
+    RET(fz(&t.d_u, (size_t)B * fd));
+  }
   RET(fz(&t.d_v, (size_t)B * L));
   // Mimi state + scratch.  Every conv input buffer is [B][taps-1 state rows + T rows][C], zero-initialised
   // (= the reference's zero `previous` / `partial`, modules/conv.py:113-119,176-180).
   const int T = g.upsample_stride, MD = g.mimi_d, SD = g.seanet_dim;
   t.T0 = T;
   RET(fz(&t.d_zprev, (size_t)B * SD));
-  RET(fz(&t.d_c0, (size_t)B * (T + g.kernel_size - 1) * SD));
-  RET(fz(&t.d_mh, (size_t)B * T * MD));
   RET(fz(&t.d_mqkv, (size_t)B * T * 3 * MD));
   RET(fz(&t.d_mqrot, (size_t)B * T * MD));
+  std::vector<ShiftEntry> sh;
+  int Tin = T;
+  if (t.tc_mimi) {
+    for (int r = 0; r < g.n_ratios; ++r) Tin *= c->stages[r].stride;
+  } else {
+  RET(fz(&t.d_c0, (size_t)B * (T + g.kernel_size - 1) * SD));
+  RET(fz(&t.d_mh, (size_t)B * T * MD));
   RET(fz(&t.d_matt, (size_t)B * T * MD));
   RET(fz(&t.d_mff, (size_t)B * T * g.mimi_ffn));
-  std::vector<ShiftEntry> sh;
-  sh.push_back({t.d_c0, (long long)(T + g.kernel_size - 1) * SD, T, g.kernel_size - 1, SD});
-  int Tin = T;
+  sh.push_back({t.d_c0, (long long)(T + g.kernel_size - 1) * SD, T, g.kernel_size - 1, SD, 4});
   t.sb.resize(g.n_ratios);
   for (int r = 0; r < g.n_ratios; ++r) {
     auto& st = c->stages[r];
@@ -1020,17 +1319,19 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
     RET(fz(&b.ct_in, (size_t)B * (Tin + 1) * st.c_in));
     RET(fz(&b.r_in, (size_t)B * (b.T_out + rk - 1) * st.c_out));
     RET(fz(&b.hid, (size_t)B * b.T_out * st.hidden));
-    sh.push_back({b.ct_in, (long long)(Tin + 1) * st.c_in, Tin, 1, st.c_in});
-    if (rk > 1) sh.push_back({b.r_in, (long long)(b.T_out + rk - 1) * st.c_out, b.T_out, rk - 1, st.c_out});
+    sh.push_back({b.ct_in, (long long)(Tin + 1) * st.c_in, Tin, 1, st.c_in, 4});
+    if (rk > 1) sh.push_back({b.r_in, (long long)(b.T_out + rk - 1) * st.c_out, b.T_out, rk - 1, st.c_out, 4});
     Tin = b.T_out;
   }
-  t.frame_samples = Tin;
   RET(fz(&t.d_fin, (size_t)B * (Tin + c->fin_taps - 1) * c->fin_c));
-  if (c->fin_taps > 1) sh.push_back({t.d_fin, (long long)(Tin + c->fin_taps - 1) * c->fin_c, Tin, c->fin_taps - 1, c->fin_c});
-  RET(fz(&t.d_audio, (size_t)B * Tin));
+  if (c->fin_taps > 1) sh.push_back({t.d_fin, (long long)(Tin + c->fin_taps - 1) * c->fin_c, Tin, c->fin_taps - 1, c->fin_c, 4});
   t.n_shift = (int)sh.size();
   RET(t.dalloc((void**)&t.d_shift, sh.size() * sizeof(ShiftEntry)));
   CU(cudaMemcpyAsync(t.d_shift, sh.data(), sh.size() * sizeof(ShiftEntry), cudaMemcpyHostToDevice, c->stream));
+  }
+  t.frame_samples = Tin;
+  RET(fz(&t.d_audio, (size_t)B * Tin));
+  RET(build_batch_tc(t));
   t.ring_kv_stride = (long long)B * g.mimi_heads * g.mimi_context * kHeadDim;
   t.ring_layer_stride = 2 * t.ring_kv_stride;
   const size_t ring_bytes = (size_t)g.mimi_layers * t.ring_layer_stride * (c->bf16 ? 2 : 4);
@@ -1081,6 +1382,7 @@ int32_t ptts_batch_prefill_text(ptts_batch* bt, const int32_t* ids, const int32_
   }
   if (M > 0) {
     RET(alloc_flow_work(c, c.prefill_work, M));
+    if (c.prefill_work.tc) RET(build_flow_plans(c, c.prefill_work, M));
     int *d_seq, *d_pos, *d_ids;
     CU(cudaMalloc(&d_seq, M * 4));
     CU(cudaMalloc(&d_pos, M * 4));

@@ -54,6 +54,7 @@ struct NormParams {
   const float* w; const float* b; float eps;
   const float* scale; const float* shift; long long mod_rs;   // row stride of the modulation buffer
   float* Y; long long y_bs, y_rs;
+  __nv_bfloat16* Y16;            // when set, the result is written here as bf16 (same strides) instead of Y
 };
 void launch_layernorm(const NormParams& p, cudaStream_t s);
 
@@ -63,6 +64,7 @@ struct FlowAttnParams {
   const float* qkv;            // [M][3*H*64]  (q | k | v), pre-RoPE
   float* q_rot;                // [M][H*64] scratch
   float* out;                  // [M][H*64]
+  __nv_bfloat16* out16;        // when set, bf16 output instead (A operand of the next tcgen05 GEMM)
   void* pool; int kv_bf16; long long layer_stride, page_stride;   // strides in elements
   int layer;
   const int* row_seq;          // [M] sequence of each row, or null => row m belongs to sequence m
@@ -81,6 +83,7 @@ struct MimiAttnParams {
   const float* qkv;            // [B*T][3*H*64]
   float* q_rot;                // [B*T][H*64]
   float* out;                  // [B*T][H*64]
+  __nv_bfloat16* out16;
   void* ring; int kv_bf16; long long layer_stride, kv_stride;
   int layer;
   const int* offset;           // [B] absolute position of this chunk's first step (= end_offset)
@@ -99,8 +102,8 @@ void launch_embed_rows(const void* table, int table_bf16, const int* ids, float*
                        cudaStream_t s);
 // c = LN(x[row_of[b]]); logit = w_eos . c + b_eos      (models/flow_lm.py:120,100)
 void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w, const float* ln_b,
-                           const float* w_eos, const float* b_eos, float* c, float* logit, int B, int D,
-                           cudaStream_t s);
+                           const float* w_eos, const float* b_eos, float* c, __nv_bfloat16* c16, float* logit,
+                           int B, int D, cudaStream_t s);
 // x0 = clip(sqrt(temp) * z); z from the host buffer or a Philox4x32-10 + Box-Muller stream
 void launch_noise_prep(const float* z, float* x0, int n, float std, float clamp, int use_philox,
                        unsigned long long seed, const unsigned long long* counter, cudaStream_t s);
@@ -111,8 +114,11 @@ void launch_quant_upsample(const float* lat, const float* emb_std, const float* 
 // audio[b,t] = bias + sum_{j<taps} sum_c elu(x~[b,t+j,c]) w[j*C+c]      (SEANet last conv, N = 1)
 void launch_final_conv(const float* x, long long x_bs, const float* w, const float* bias, float* audio,
                        long long audio_bs, int B, int T, int C, int taps, cudaStream_t s);
+// same with a bf16 input that already went through ELU in the producer's epilogue
+void launch_final_conv16(const __nv_bfloat16* x, long long x_bs, const float* w, const float* bias, float* audio,
+                         long long audio_bs, int B, int T, int C, int taps, cudaStream_t s);
 // carried conv state: move the last `rows` time rows of each sequence's buffer to its front
-struct ShiftEntry { float* buf; long long bs; int T, rows, C; };
+struct ShiftEntry { void* buf; long long bs; int T, rows, C, esz; };   // bs in elements, esz = bytes/element
 void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s);
 // seq_len += inc_len; bos_flag = 0; mimi_offset += inc_mimi; philox counter += 1
 void launch_advance(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter, int B,

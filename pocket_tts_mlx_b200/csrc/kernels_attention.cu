@@ -155,7 +155,9 @@ __global__ void __launch_bounds__(128) flow_attention_kernel(const FlowAttnParam
       l += sh_l[w] * c;
       a += sh_acc[w][threadIdx.x] * c;
     }
-    p.out[(long long)m * D + h * kHeadDim + threadIdx.x] = a / l;
+    const long long oi = (long long)m * D + h * kHeadDim + threadIdx.x;
+    if (p.out16) p.out16[oi] = __float2bfloat16_rn(a / l);
+    else p.out[oi] = a / l;
   }
 }
 
@@ -248,10 +250,16 @@ __global__ void __launch_bounds__(128) mimi_attention_kernel(const MimiAttnParam
     soft_merge_shfl(st[j], 16);
     const int t = warp * QW + j;
     if (lane < 8 && t < p.T) {
-      float* o = p.out + ((long long)(b * p.T + t)) * D + h * kHeadDim + sl * 8;
+      const long long oi = ((long long)(b * p.T + t)) * D + h * kHeadDim + sl * 8;
       const float inv = 1.0f / st[j].l;
+      if (p.out16) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = st[j].acc[i] * inv;
+        for (int i = 0; i < 8; i += 2)
+          *reinterpret_cast<__nv_bfloat162*>(p.out16 + oi + i) = __floats2bfloat162_rn(st[j].acc[i] * inv, st[j].acc[i + 1] * inv);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p.out[oi + i] = st[j].acc[i] * inv;
+      }
     }
   }
 }

@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const NormParams p) {
       float o = (v[i] - mean) * rstd;
       if (p.w) o = o * p.w[c] + p.b[c];
       if (sc) o = o * (1.0f + sc[c]) + sh[c];
-      y[c] = o;
+      if (p.Y16) p.Y16[b * p.y_bs + t * p.y_rs + c] = __float2bfloat16_rn(o);
+      else y[c] = o;
     }
   }
 }
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(128) final_norm_eos_kernel(const float* __rest
                                                              const float* __restrict__ w_eos,
                                                              const float* __restrict__ b_eos,
                                                              float* __restrict__ cout,
+                                                             __nv_bfloat16* __restrict__ cout16,
                                                              float* __restrict__ logit, int D) {
   __shared__ float red[32];
   const int b = blockIdx.x;
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(128) final_norm_eos_kernel(const float* __rest
     if (c < D) {
       const float o = (v[i] - mean) * rstd * ln_w[c] + ln_b[c];
       cout[(long long)b * D + c] = o;
+      if (cout16) cout16[(long long)b * D + c] = __float2bfloat16_rn(o);
       dot = fmaf(o, w_eos[c], dot);
     }
   }
@@ -175,7 +178,8 @@ __global__ void quant_upsample_kernel(const float* __restrict__ lat, const float
 }
 
 // 128 outputs per CTA; the (128 + taps - 1) x C input tile is staged with ELU applied, padded rows
-__global__ void __launch_bounds__(128) final_conv_kernel(const float* __restrict__ x, long long x_bs,
+template <typename XT, bool kElu>
+__global__ void __launch_bounds__(128) final_conv_kernel(const XT* __restrict__ x, long long x_bs,
                                                          const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          float* __restrict__ audio, long long audio_bs,
@@ -186,10 +190,11 @@ __global__ void __launch_bounds__(128) final_conv_kernel(const float* __restrict
   const int b = blockIdx.y, t0 = blockIdx.x * 128;
   const int rows = min(128, T - t0) + taps - 1;
   for (int i = threadIdx.x; i < taps * C; i += 128) ws[i] = w[i];
-  const float* src = x + b * x_bs + (long long)t0 * C;
+  const XT* src = x + b * x_bs + (long long)t0 * C;
   for (int i = threadIdx.x; i < rows * C; i += 128) {
     const int r = i / C, c = i - r * C;
-    xs[r * (C + 1) + c] = act_apply(src[i], ACT_ELU);
+    const float v = (float)src[i];
+    xs[r * (C + 1) + c] = kElu ? act_apply(v, ACT_ELU) : v;
   }
   __syncthreads();
   const int t = t0 + threadIdx.x;
@@ -206,9 +211,10 @@ __global__ void __launch_bounds__(128) final_conv_kernel(const float* __restrict
 __global__ void state_shift_kernel(const ShiftEntry* __restrict__ entries) {
   const ShiftEntry e = entries[blockIdx.y];
   const int b = blockIdx.x;
-  float* base = e.buf + b * e.bs;
-  const int n = e.rows * e.C;
-  const float* src = base + (long long)e.T * e.C;
+  // rows*C*esz is a multiple of 4 bytes for every buffer of the decoder (C >= 64)
+  unsigned* base = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(e.buf) + b * e.bs * e.esz);
+  const int n = e.rows * e.C * e.esz / 4;
+  const unsigned* src = base + (long long)e.T * e.C * e.esz / 4;
   for (int i = threadIdx.x; i < n; i += blockDim.x) base[i] = src[i];
 }
 
@@ -284,10 +290,10 @@ void launch_embed_rows(const void* table, int table_bf16, const int* ids, float*
 }
 
 void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w, const float* ln_b,
-                           const float* w_eos, const float* b_eos, float* c, float* logit, int B, int D,
-                           cudaStream_t s) {
+                           const float* w_eos, const float* b_eos, float* c, __nv_bfloat16* c16, float* logit,
+                           int B, int D, cudaStream_t s) {
   ProfScope ps("final_norm_eos", nullptr, 0, 2.0 * B * D * 4, s);
-  final_norm_eos_kernel<<<B, 128, 0, s>>>(x, row_of, ln_w, ln_b, w_eos, b_eos, c, logit, D);
+  final_norm_eos_kernel<<<B, 128, 0, s>>>(x, row_of, ln_w, ln_b, w_eos, b_eos, c, c16, logit, D);
   ++g_launches;
 }
 
@@ -312,7 +318,16 @@ void launch_final_conv(const float* x, long long x_bs, const float* w, const flo
   ProfScope ps("final_conv", nullptr, 0, (double)B * T * (C + 1) * 4, s);
   const size_t smem = (size_t)(taps * C + (128 + taps - 1) * (C + 1)) * sizeof(float);
   dim3 grid((T + 127) / 128, B);
-  final_conv_kernel<<<grid, 128, smem, s>>>(x, x_bs, w, bias, audio, audio_bs, T, C, taps);
+  final_conv_kernel<float, true><<<grid, 128, smem, s>>>(x, x_bs, w, bias, audio, audio_bs, T, C, taps);
+  ++g_launches;
+}
+
+void launch_final_conv16(const __nv_bfloat16* x, long long x_bs, const float* w, const float* bias, float* audio,
+                         long long audio_bs, int B, int T, int C, int taps, cudaStream_t s) {
+  ProfScope ps("final_conv", nullptr, 0, (double)B * T * (C / 2 + 1) * 4, s);
+  const size_t smem = (size_t)(taps * C + (128 + taps - 1) * (C + 1)) * sizeof(float);
+  dim3 grid((T + 127) / 128, B);
+  final_conv_kernel<__nv_bfloat16, false><<<grid, 128, smem, s>>>(x, x_bs, w, bias, audio, audio_bs, T, C, taps);
   ++g_launches;
 }
 

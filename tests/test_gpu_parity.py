@@ -281,3 +281,39 @@ def test_tcgen05_gemm_matches_numpy(model_bf16, shape):
         ref += aq[:, j:j + t, :] @ wq[:, j * c:(j + 1) * c].T
     ref += bias
     assert rel_l2(y, ref) < 1e-5, rel_l2(y, ref)
+
+
+# ---------------------------------------------------------------------------------------- bf16 tensor-core pipeline
+@pytest.mark.parametrize("n_seq", [2, 20])
+def test_bf16_tensor_core_batch_vs_oracle(model_bf16, cfg, weights, voices, n_seq):
+    """Batches large enough for the tcgen05 path (Mimi rows = 16 * n_seq > 16; FlowLM/head rows = n_seq > 16
+    for n_seq = 20): teacher-forced latents within 1e-2 and waveform SNR >= 30 dB against the fp32 oracle."""
+    from pocket_tts_mlx_b200 import _native
+    rng = np.random.Generator(np.random.PCG64(77 + n_seq))
+    names = ["alba", "marius"]
+    frames = 5
+    ids = [rng.integers(0, 4000, size=int(rng.integers(18, 30))).astype(np.int32) for _ in range(n_seq)]
+    noise = rng.standard_normal((1 + frames, n_seq, 32)).astype(np.float32)
+    states = [model_bf16.get_state_for_audio_prompt(names[b % 2]) for b in range(n_seq)]
+    check = [0, n_seq - 1] if n_seq > 2 else [0, 1]
+    refs = {}
+    for b in check:
+        orc, st = _oracle(weights, cfg, voices, names[b % 2], None, eos_threshold=1e30)
+        refs[b] = orc.generate(st, ids[b], noise[:, b, :], frames_after_eos=3, max_frames=frames)
+    batch = _native.Batch(model_bf16._ctx, [s["voice_id"] for s in states],
+                          [s["prompt_len"] + len(t) + frames + 2 for s, t in zip(states, ids)])
+    batch.warmup_mimi(1)
+    batch.prefill_text(ids)
+    audio = {b: [] for b in check}
+    for f in range(frames):
+        lat, logit, au = batch.step(noise[1 + f])
+        forced = lat.copy()
+        for b in check:
+            assert rel_l2(lat[b], refs[b]["latents"][f]) < 1e-2, (b, f, rel_l2(lat[b], refs[b]["latents"][f]))
+            assert abs(logit[b] - refs[b]["eos_logits"][f]) < 5e-2
+            audio[b].append(au[b].copy())
+            forced[b] = refs[b]["latents"][f]
+        batch.set_prev_latent(forced)
+    batch.close()
+    for b in check:
+        assert snr_db(np.concatenate(audio[b]), refs[b]["audio"]) > 30.0
