@@ -141,11 +141,12 @@ def load_model(device: int, kv_pool_tokens: int):
                                kv_pool_tokens=kv_pool_tokens), yml
 
 
-def one_job(model, state, ids, frames, host_io: bool, rng):
-    """One step of the benchmark: create the batch, warm up Mimi, prefill text, generate `frames` frames."""
+def one_job(model, state, ids, frames, host_io: bool, rng, cap_frames=None):
+    """One step of the benchmark: create the batch, warm up Mimi, prefill text, generate `frames` frames.
+    cap_frames sizes the KV reservation (warm-up jobs run fewer frames on the same reservation)."""
     from pocket_tts_mlx_b200 import _native
     n = len(ids)
-    req = [state["prompt_len"] + len(t) + frames for t in ids]
+    req = [state["prompt_len"] + len(t) + (cap_frames or frames) for t in ids]
     batch = _native.Batch(model._ctx, [state["voice_id"]] * n, req)
     h2d = d2h = 0
     try:
@@ -326,7 +327,7 @@ def main():
 
     # ---- value: device-resident ------------------------------------------------------------------
     for _ in range(args.warmup):
-        one_job(model, state, ids, min(frames, 16), False, rng)
+        one_job(model, state, ids, min(frames, 16), False, rng, cap_frames=frames)
     sampler = ClockSampler(local)
     _barrier(dist, local)
     model._ctx.sync()
@@ -343,7 +344,7 @@ def main():
     value = world * audio_sec * args.steps / (ms / 1e3)
 
     # ---- e2e: host buffers through the C-ABI step call ---------------------------------------------
-    one_job(model, state, ids, min(frames, 8), True, rng)
+    one_job(model, state, ids, min(frames, 8), True, rng, cap_frames=frames)
     _barrier(dist, local)
     model._ctx.sync()
     t0 = time.perf_counter()

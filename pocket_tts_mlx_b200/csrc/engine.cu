@@ -106,6 +106,7 @@ struct FlowWork {
 
 }  // namespace
 
+struct ptts_batch;
 struct ptts_ctx {
   int device = 0;
   ptts_config cfg{};
@@ -142,6 +143,7 @@ struct ptts_ctx {
   std::vector<int> free_pages;
   std::vector<Voice> voices;
   FlowWork prefill_work;
+  std::vector<ptts_batch*> parked;     // destroyed batches whose device arenas (and graphs) are recycled
   void* l2_scratch = nullptr;
   size_t l2_bytes = 0;
   std::string prof_names;
@@ -603,6 +605,8 @@ struct ptts_batch {
   int B = 0, max_pages = 0;
   std::vector<int> h_len, voice_ids, max_len, owned_pages;
   std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t>> zero_list;   // streaming state + scratch that a fresh batch starts zeroed
+  int *d_cp_src = nullptr, *d_cp_dst = nullptr;
   bool prefilled = false;
   unsigned long long seed = 0x5eed5eedULL;
   int *d_page_table = nullptr, *d_len = nullptr, *d_bos = nullptr, *d_mimi_off = nullptr, *d_frame_idx = nullptr;
@@ -828,7 +832,7 @@ int build_batch_tc(Batch& t) {
   const int B = t.B, D = g.d_model, L = g.latent_dim, fd = g.flow_dim;
   auto bz = [&](__nv_bfloat16** p, size_t n) -> int {
     RET(t.dalloc((void**)p, n * 2));
-    CU(cudaMemsetAsync(*p, 0, n * 2, c.stream));
+    t.zero_list.push_back({*p, n * 2});
     return 0;
   };
   if (t.tc_head) {
@@ -864,7 +868,7 @@ int build_batch_tc(Batch& t) {
   if (t.tc_mimi) {
     const int T = t.T0, MD = g.mimi_d, SD = g.seanet_dim, FFm = g.mimi_ffn, k0 = g.kernel_size, rk = g.res_kernel_size;
     RET(t.dalloc((void**)&t.d_xm, (size_t)B * T * MD * 4));
-    CU(cudaMemsetAsync(t.d_xm, 0, (size_t)B * T * MD * 4, c.stream));
+    t.zero_list.push_back({t.d_xm, (size_t)B * T * MD * 4});
     RET(bz(&t.d_mh16, (size_t)B * T * MD));
     RET(bz(&t.d_matt16, (size_t)B * T * MD));
     RET(bz(&t.d_mff16, (size_t)B * T * FFm));
@@ -969,7 +973,7 @@ void flow_step(Batch& bt, bool host_noise) {
   launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.tc_head ? bt.d_c16 : nullptr,
                         bt.d_logit, B, D, c.stream);
   launch_noise_prep(bt.d_noise, bt.d_x, B * L, sqrtf(g.temp), (g.noise_clamp >= 0.f) ? g.noise_clamp : -1.f,
-                    host_noise ? 0 : 1, bt.seed, bt.d_counter, c.stream);
+                    host_noise ? 0 : 1, bt.d_counter, c.stream);
   const int n = g.lsd_decode_steps;
   if (bt.tc_head) {
     flow_head_tc(bt);
@@ -1058,6 +1062,8 @@ int check_step_ready(Batch& bt) {
 // ============================================================ extern "C" ====================================
 extern "C" {
 
+static void batch_free(ptts_batch* bt);
+
 int32_t ptts_abi_version(void) { return PTTS_ABI_VERSION; }
 const char* ptts_last_error(void) { return g_err.c_str(); }
 
@@ -1106,6 +1112,8 @@ void ptts_ctx_destroy(ptts_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (ptts_batch* p : c->parked) batch_free(p);
+  c->parked.clear();
   free_flow_work(c->prefill_work);
   for (void* p : c->allocs) cudaFree(p);
   if (c->l2_scratch) cudaFree(c->l2_scratch);
@@ -1209,65 +1217,85 @@ int32_t ptts_batch_create(ptts_ctx* c, int32_t B, const int32_t* voice_ids, cons
   return 0;
 }
 
-static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, const int32_t* max_len,
-                             std::unique_ptr<ptts_batch>& bt) {
-  if (!c->finalized) return fail(PTTS_ERR_STATE, "finalize weights first");
-  if (c->cfg.max_batch > 0 && B > c->cfg.max_batch) return fail(PTTS_ERR_INVALID, "batch %d exceeds max_batch", B);
-  CU(cudaSetDevice(c->device));
-  const ptts_config& g = c->cfg;
-  bt = std::make_unique<ptts_batch>();
-  bt->ctx = c;
-  bt->B = B;
-  bt->voice_ids.assign(voice_ids, voice_ids + B);
-  bt->max_len.assign(max_len, max_len + B);
-  bt->h_len.resize(B);
-  int maxp = 1;
-  for (int b = 0; b < B; ++b) {
-    const int v = voice_ids[b];
-    if (v < 0 || v >= (int)c->voices.size() || !c->voices[v].alive) return fail(PTTS_ERR_INVALID, "unknown voice id %d", v);
-    if (max_len[b] < c->voices[v].len) return fail(PTTS_ERR_INVALID, "max_len[%d] shorter than the voice prefix", b);
-    maxp = std::max(maxp, (max_len[b] + kPageTokens - 1) / kPageTokens);
-    bt->h_len[b] = c->voices[v].len;
-  }
-  bt->max_pages = maxp;
-  // page tables: full prefix pages are shared with the voice; its partial tail page is copied
+// (re)initialise the per-utterance state of an allocated batch: page tables (full voice-prefix pages shared,
+// the partial tail page copied), lengths, BOS flags, zeroed Mimi streaming state
+static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32_t* max_len) {
+  ptts_ctx* c = t.ctx;
+  const int B = t.B, maxp = t.max_pages;
+  t.voice_ids.assign(voice_ids, voice_ids + B);
+  t.max_len.assign(max_len, max_len + B);
+  t.h_len.resize(B);
+  t.prefilled = false;
   std::vector<int> pt((size_t)B * maxp, 0), src, dst;
   for (int b = 0; b < B; ++b) {
     const Voice& v = c->voices[voice_ids[b]];
+    t.h_len[b] = v.len;
     const int full = v.len / kPageTokens;
     const int need_pages = (max_len[b] + kPageTokens - 1) / kPageTokens;
     for (int i = 0; i < full; ++i) pt[(size_t)b * maxp + i] = v.pages[i];
     std::vector<int> mine;
     RET(take_pages(*c, need_pages - full, &mine));
     for (int i = full; i < need_pages; ++i) pt[(size_t)b * maxp + i] = mine[i - full];
-    bt->owned_pages.insert(bt->owned_pages.end(), mine.begin(), mine.end());
+    t.owned_pages.insert(t.owned_pages.end(), mine.begin(), mine.end());
     if (v.len % kPageTokens) {
       src.push_back(v.pages[full]);
       dst.push_back(mine[0]);
     }
   }
-  Batch& t = *bt;
-  RET(t.dalloc((void**)&t.d_page_table, pt.size() * 4));
   CU(cudaMemcpyAsync(t.d_page_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice, c->stream));
   if (!src.empty()) {
-    int *d_src, *d_dst;
-    RET(t.dalloc((void**)&d_src, src.size() * 4));
-    RET(t.dalloc((void**)&d_dst, dst.size() * 4));
-    CU(cudaMemcpyAsync(d_src, src.data(), src.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(d_dst, dst.data(), dst.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    launch_copy_pages(c->pool, c->bf16, c->layer_stride, c->page_stride, g.n_layers, d_src, d_dst, (int)src.size(),
-                      c->stream);
+    CU(cudaMemcpyAsync(t.d_cp_src, src.data(), src.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(t.d_cp_dst, dst.data(), dst.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_copy_pages(c->pool, c->bf16, c->layer_stride, c->page_stride, c->cfg.n_layers, t.d_cp_src, t.d_cp_dst,
+                      (int)src.size(), c->stream);
   }
+  for (auto& z : t.zero_list) CU(cudaMemsetAsync(z.first, 0, z.second, c->stream));
+  CU(cudaMemcpyAsync(t.d_len, t.h_len.data(), B * 4, cudaMemcpyHostToDevice, c->stream));
+  launch_fill_u32((unsigned*)t.d_bos, 1u, B, c->stream);
+  const unsigned long long cs[2] = {0ull, t.seed};
+  CU(cudaMemcpyAsync(t.d_counter, cs, 16, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));    // pt/src/dst/cs are stack or local vectors
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, const int32_t* max_len,
+                             std::unique_ptr<ptts_batch>& bt) {
+  if (!c->finalized) return fail(PTTS_ERR_STATE, "finalize weights first");
+  if (c->cfg.max_batch > 0 && B > c->cfg.max_batch) return fail(PTTS_ERR_INVALID, "batch %d exceeds max_batch", B);
+  CU(cudaSetDevice(c->device));
+  const ptts_config& g = c->cfg;
+  int maxp = 1;
+  for (int b = 0; b < B; ++b) {
+    const int v = voice_ids[b];
+    if (v < 0 || v >= (int)c->voices.size() || !c->voices[v].alive) return fail(PTTS_ERR_INVALID, "unknown voice id %d", v);
+    if (max_len[b] < c->voices[v].len) return fail(PTTS_ERR_INVALID, "max_len[%d] shorter than the voice prefix", b);
+    maxp = std::max(maxp, (max_len[b] + kPageTokens - 1) / kPageTokens);
+  }
+  // recycle the arena (device buffers, tensor maps, captured graphs) of a destroyed batch of the same shape
+  for (size_t i = 0; i < c->parked.size(); ++i) {
+    ptts_batch* p = c->parked[i];
+    if (p->B == B && p->max_pages >= maxp) {
+      c->parked.erase(c->parked.begin() + i);
+      bt.reset(p);
+      return batch_init_state(*bt, voice_ids, max_len);
+    }
+  }
+  bt = std::make_unique<ptts_batch>();
+  bt->ctx = c;
+  bt->B = B;
+  bt->max_pages = (maxp + 7) / 8 * 8;
+  Batch& t = *bt;
+  RET(t.dalloc((void**)&t.d_page_table, (size_t)B * t.max_pages * 4));
+  RET(t.dalloc((void**)&t.d_cp_src, B * 4));
+  RET(t.dalloc((void**)&t.d_cp_dst, B * 4));
   RET(t.dalloc((void**)&t.d_len, B * 4));
   RET(t.dalloc((void**)&t.d_bos, B * 4));
   RET(t.dalloc((void**)&t.d_mimi_off, B * 4));
   RET(t.dalloc((void**)&t.d_frame_idx, 4));
-  RET(t.dalloc((void**)&t.d_counter, 8));
-  CU(cudaMemcpyAsync(t.d_len, t.h_len.data(), B * 4, cudaMemcpyHostToDevice, c->stream));
-  launch_fill_u32((unsigned*)t.d_bos, 1u, B, c->stream);
-  CU(cudaMemsetAsync(t.d_mimi_off, 0, B * 4, c->stream));
-  CU(cudaMemsetAsync(t.d_frame_idx, 0, 4, c->stream));
-  CU(cudaMemsetAsync(t.d_counter, 0, 8, c->stream));
+  RET(t.dalloc((void**)&t.d_counter, 16));
+  t.zero_list.push_back({t.d_mimi_off, (size_t)B * 4});
+  t.zero_list.push_back({t.d_frame_idx, 4});
   RET(alloc_flow_work(*c, t.fw, B));
   if (t.fw.tc) RET(build_flow_plans(*c, t.fw, B));
   t.tc_head = t.fw.tc;
@@ -1275,7 +1303,7 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
   const int D = g.d_model, L = g.latent_dim, fd = g.flow_dim;
   auto fz = [&](float** p, size_t n) -> int {
     RET(t.dalloc((void**)p, n * 4));
-    CU(cudaMemsetAsync(*p, 0, n * 4, c->stream));
+    t.zero_list.push_back({*p, n * 4});
     return 0;
   };
   RET(fz(&t.d_noise, (size_t)B * L));
@@ -1336,21 +1364,16 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
   t.ring_layer_stride = 2 * t.ring_kv_stride;
   const size_t ring_bytes = (size_t)g.mimi_layers * t.ring_layer_stride * (c->bf16 ? 2 : 4);
   RET(t.dalloc(&t.ring, ring_bytes));
-  CU(cudaMemsetAsync(t.ring, 0, ring_bytes, c->stream));
+  t.zero_list.push_back({t.ring, ring_bytes});
   CU(cudaMallocHost((void**)&t.h_noise, (size_t)B * L * 4));
   CU(cudaMallocHost((void**)&t.h_latent, (size_t)B * L * 4));
   CU(cudaMallocHost((void**)&t.h_logit, (size_t)B * 4));
   CU(cudaMallocHost((void**)&t.h_audio, (size_t)B * Tin * 4));
-  CU(cudaStreamSynchronize(c->stream));
-  CU(cudaGetLastError());
-  return 0;
+  return batch_init_state(t, voice_ids, max_len);
 }
 
-void ptts_batch_destroy(ptts_batch* bt) {
-  if (!bt) return;
+static void batch_free(ptts_batch* bt) {
   Ctx* c = bt->ctx;
-  cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
   for (auto& g : bt->step_graph) if (g) cudaGraphExecDestroy(g);
   for (auto& kv : bt->mimi_graphs) cudaGraphExecDestroy(kv.second.first);
   free_flow_work(bt->fw);
@@ -1360,6 +1383,25 @@ void ptts_batch_destroy(ptts_batch* bt) {
   cudaFreeHost(bt->h_noise); cudaFreeHost(bt->h_latent); cudaFreeHost(bt->h_logit); cudaFreeHost(bt->h_audio);
   for (int p : bt->owned_pages) c->free_pages.push_back(p);
   delete bt;
+}
+
+void ptts_batch_destroy(ptts_batch* bt) {
+  if (!bt) return;
+  Ctx* c = bt->ctx;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int p : bt->owned_pages) c->free_pages.push_back(p);
+  bt->owned_pages.clear();
+  bt->prefilled = false;
+  if (!bt->h_audio || !bt->d_counter) {   // partially constructed: cannot be recycled
+    batch_free(bt);
+    return;
+  }
+  c->parked.push_back(bt);
+  while (c->parked.size() > 3) {
+    batch_free(c->parked.front());
+    c->parked.erase(c->parked.begin());
+  }
 }
 
 int32_t ptts_batch_prefill_text(ptts_batch* bt, const int32_t* ids, const int32_t* offsets) {
@@ -1452,11 +1494,12 @@ int32_t ptts_batch_set_prev_latent(ptts_batch* bt, const float* latent) {
 
 int32_t ptts_batch_seed(ptts_batch* bt, uint64_t seed) {
   if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
-  if (bt->seed != seed) {
-    bt->seed = seed;   // the seed is baked into the captured graphs
-    for (int i = 0; i < 2; ++i)
-      if (bt->step_graph[i]) { cudaGraphExecDestroy(bt->step_graph[i]); bt->step_graph[i] = nullptr; }
-  }
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  bt->seed = seed;   // read from device memory by the noise kernel, so the captured graphs stay valid
+  const unsigned long long v = seed;
+  CU(cudaMemcpyAsync(bt->d_counter + 1, &v, 8, cudaMemcpyHostToDevice, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
   return 0;
 }
 

@@ -18,8 +18,7 @@
 namespace ptts {
 namespace {
 
-constexpr int kStages = 4;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 
 struct KArgs {
   int nb, T, taps, C, N;
@@ -101,7 +100,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN, int BK>
+// activation on 32 accumulator values with the selector hoisted out of the element loop (uniform branch)
+__device__ __forceinline__ void act32(float (&v)[32], int act) {
+  if (act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752440f));
+  } else if (act == ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
+  } else if (act == ACT_ELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.0f ? v[i] : __expf(v[i]) - 1.0f;   // output is rounded to bf16
+  }
+}
+
+template <int BN, int BK, int STAGES>
 __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                            const __grid_constant__ CUtensorMap tm_b, const KArgs g) {
   constexpr int ROW_BYTES = BK * 2;
@@ -109,10 +122,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base, sB = base + kStages * A_BYTES;
-  const uint32_t bars = sB + kStages * B_BYTES;
-  // bars: full[kStages], empty[kStages], tmem_full ; then the TMEM base address word
-  const uint32_t full0 = bars, empty0 = bars + 8 * kStages, tfull = bars + 16 * kStages, tptr = tfull + 8;
+  const uint32_t sA = base, sB = base + STAGES * A_BYTES;
+  const uint32_t bars = sB + STAGES * B_BYTES;
+  // bars: full[STAGES], empty[STAGES], tmem_full ; then the TMEM base address word
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tptr = tfull + 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
@@ -124,7 +137,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       mbar_init(full0 + 8 * i, 1);
       mbar_init(empty0 + 8 * i, 1);
     }
@@ -144,7 +157,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < iters; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1;
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
         const int tap = it / kc_per_tap, kc = it - tap * kc_per_tap;
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
@@ -156,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<BN>();
       for (int it = 0; it < iters; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1;
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
         const uint64_t da = make_desc<ROW_BYTES>(sA + s * A_BYTES);
@@ -169,8 +182,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
       tc_commit(tfull);               // accumulator complete
     }
   } else {
-    // ---- epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) ----
+    // ---- epilogue: warps 2..9; TMEM lane quadrant = warp % 4, two warps per quadrant split the columns ----
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int CHUNKS = BN / 32;
     const int r = quad * 32 + lane;                       // accumulator row within the tile
     const int b = b0 + r / g.box_t, t = t0 + r % g.box_t;
     const bool row_ok = (b < g.nb) && (t < g.T);
@@ -179,74 +194,87 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
     mbar_wait(tfull, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
+    for (int ch = half; ch < CHUNKS; ch += 2) {
+      const int cb = ch * 32;
       uint32_t raw[32];
       __syncwarp();
       tc_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb, raw);
       if (row_ok) {
-      const int n = n0 + cb;
-      float v[32];
+        const int n = n0 + cb;
+        float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x = __uint_as_float(raw[i]);
-        if (e.bias) x += __ldg(e.bias + n + i);
-        x = act_apply(x, e.act) * oscale;
-        if (e.col_scale) x *= __ldg(e.col_scale + n + i);
-        v[i] = x;
-      }
-      if (e.row_gate) {
-        const float4* gp = reinterpret_cast<const float4*>(e.row_gate + b * e.gate_bs + t * e.gate_rs + n);
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        if (e.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(e.bias + n);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 q = gp[i];
-          v[4 * i] *= q.x; v[4 * i + 1] *= q.y; v[4 * i + 2] *= q.z; v[4 * i + 3] *= q.w;
-        }
-      }
-      if (e.res32) {
-        const float4* rp = reinterpret_cast<const float4*>(e.res32 + b * e.res32_bs + t * e.res32_rs + n);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 q = rp[i];
-          v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
-        }
-      }
-      if (e.res16) {
-        const uint4* rp = reinterpret_cast<const uint4*>(e.res16 + b * e.res16_bs + t * e.res16_rs + n);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 q = rp[i];
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(h[j]);
-            v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y;
+          for (int i = 0; i < 8; ++i) {
+            const float4 q = __ldg(bp + i);
+            v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
           }
         }
-      }
-      if (e.y32) {
-        float4* yp = reinterpret_cast<float4*>(e.y32 + b * e.y32_bs + t * e.y32_rs + n);
+        act32(v, e.act);
+        if (oscale != 1.f) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) yp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      }
-      if (e.yraw16) {
-        uint4* yp = reinterpret_cast<uint4*>(e.yraw16 + b * e.yraw16_bs + t * e.yraw16_rs + n);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          yp[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                             pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-      }
-      if (e.y16) {
-        if (e.y16_act != ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], e.y16_act);
+          for (int i = 0; i < 32; ++i) v[i] *= oscale;
         }
-        uint4* yp = reinterpret_cast<uint4*>(e.y16 + b * e.y16_bs + t * e.y16_rs + n);
+        if (e.col_scale) {
+          const float4* cp = reinterpret_cast<const float4*>(e.col_scale + n);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          yp[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                             pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+          for (int i = 0; i < 8; ++i) {
+            const float4 q = __ldg(cp + i);
+            v[4 * i] *= q.x; v[4 * i + 1] *= q.y; v[4 * i + 2] *= q.z; v[4 * i + 3] *= q.w;
+          }
+        }
+        if (e.row_gate) {
+          const float4* gp = reinterpret_cast<const float4*>(e.row_gate + b * e.gate_bs + t * e.gate_rs + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 q = gp[i];
+            v[4 * i] *= q.x; v[4 * i + 1] *= q.y; v[4 * i + 2] *= q.z; v[4 * i + 3] *= q.w;
+          }
+        }
+        if (e.res32) {
+          const float4* rp = reinterpret_cast<const float4*>(e.res32 + b * e.res32_bs + t * e.res32_rs + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 q = rp[i];
+            v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+          }
+        }
+        if (e.res16) {
+          const uint4* rp = reinterpret_cast<const uint4*>(e.res16 + b * e.res16_bs + t * e.res16_rs + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 q = rp[i];
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(h[j]);
+              v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y;
+            }
+          }
+        }
+        if (e.y32) {
+          float4* yp = reinterpret_cast<float4*>(e.y32 + b * e.y32_bs + t * e.y32_rs + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) yp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        if (e.yraw16) {
+          uint4* yp = reinterpret_cast<uint4*>(e.yraw16 + b * e.yraw16_bs + t * e.yraw16_rs + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            yp[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                               pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+        }
+        if (e.y16) {
+          act32(v, e.y16_act);
+          uint4* yp = reinterpret_cast<uint4*>(e.y16 + b * e.y16_bs + t * e.y16_rs + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            yp[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                               pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+        }
       }
-      }  // row_ok
     }
   }
   tc_fence_before();
@@ -257,9 +285,9 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   }
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int STAGES>
 constexpr size_t smem_bytes() {
-  return (size_t)kStages * (128 * BK * 2 + BN * BK * 2) + 1024 + 16 * kStages + 32;
+  return (size_t)STAGES * (128 * BK * 2 + BN * BK * 2) + 1024 + 16 * STAGES + 32;
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -270,7 +298,8 @@ bool g_init_done = false;
 
 template <int BN, int BK>
 void set_attr() {
-  cudaFuncSetAttribute(gemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, BK>());
+  cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, BK, 2>());
+  cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, BK, 4>());
 }
 
 bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -367,7 +396,14 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
                        (double)g.nb * g.T * g.N * ((g.e.y32 ? 4 : 0) + (g.e.y16 ? 2 : 0) + (g.e.yraw16 ? 2 : 0) +
                                                    (g.e.res32 ? 4 : 0) + (g.e.res16 ? 2 : 0));
   ProfScope ps("gemm_tc", g.tag, flops, bytes, s);
-#define PTTS_TC(BN_, BK_) gemm_tc_kernel<BN_, BK_><<<grid, block, smem_bytes<BN_, BK_>(), s>>>(g.tm_a, g.tm_b, a)
+  // shallow K (few ring turns): 2 stages so several CTAs share an SM and one CTA's epilogue overlaps its
+  // neighbours' loads; deep K (weight streaming): 4 stages of prefetch
+  const bool deep = g.taps * (g.C / g.bk) >= 12;
+#define PTTS_TC(BN_, BK_)                                                                                   \
+  do {                                                                                                      \
+    if (deep) gemm_tc_kernel<BN_, BK_, 4><<<grid, block, smem_bytes<BN_, BK_, 4>(), s>>>(g.tm_a, g.tm_b, a); \
+    else gemm_tc_kernel<BN_, BK_, 2><<<grid, block, smem_bytes<BN_, BK_, 2>(), s>>>(g.tm_a, g.tm_b, a);      \
+  } while (0)
   if (g.bk == 64) {
     if (g.bn == 128) PTTS_TC(128, 64);
     else if (g.bn == 64) PTTS_TC(64, 64);

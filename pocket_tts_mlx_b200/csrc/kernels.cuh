@@ -106,7 +106,7 @@ void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w,
                            int B, int D, cudaStream_t s);
 // x0 = clip(sqrt(temp) * z); z from the host buffer or a Philox4x32-10 + Box-Muller stream
 void launch_noise_prep(const float* z, float* x0, int n, float std, float clamp, int use_philox,
-                       unsigned long long seed, const unsigned long long* counter, cudaStream_t s);
+                       const unsigned long long* counter, cudaStream_t s);
 // z = Wq (lat*std + mean); up[b,t,c] = wu[c,t] z[c] + wu[c,S+t] zprev[b,c]; zprev = z
 void launch_quant_upsample(const float* lat, const float* emb_std, const float* emb_mean, const float* wq,
                            const float* wu, float* zprev, float* out, long long out_bs, int B, int L, int C,

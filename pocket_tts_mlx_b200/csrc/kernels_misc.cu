@@ -138,13 +138,13 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 __global__ void noise_prep_kernel(const float* __restrict__ z, float* __restrict__ x0, int n, float std,
-                                  float clamp, int use_philox, unsigned long long seed,
+                                  float clamp, int use_philox,
                                   const unsigned long long* __restrict__ counter) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float g;
   if (use_philox) {
-    const unsigned long long step = counter ? *counter : 0ull;
+    const unsigned long long step = counter[0], seed = counter[1];   // {frame counter, seed} live on the device
     uint4 r = philox4x32(make_uint4((unsigned)i, (unsigned)step, (unsigned)(step >> 32), 0u),
                          make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
     const float u1 = ((r.x >> 8) + 1u) * (1.0f / 16777216.0f);   // (0,1]
@@ -298,9 +298,9 @@ void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w,
 }
 
 void launch_noise_prep(const float* z, float* x0, int n, float std, float clamp, int use_philox,
-                       unsigned long long seed, const unsigned long long* counter, cudaStream_t s) {
+                       const unsigned long long* counter, cudaStream_t s) {
   ProfScope ps("noise_prep", nullptr, 0, 2.0 * n * 4, s);
-  noise_prep_kernel<<<(n + 255) / 256, 256, 0, s>>>(z, x0, n, std, clamp, use_philox, seed, counter);
+  noise_prep_kernel<<<(n + 255) / 256, 256, 0, s>>>(z, x0, n, std, clamp, use_philox, counter);
   ++g_launches;
 }
 
