@@ -264,6 +264,194 @@ __global__ void __launch_bounds__(128) mimi_attention_kernel(const MimiAttnParam
   }
 }
 
+
+// ---- Mimi attention on tensor cores (bf16 ring) --------------------------------------------------------------
+// One CTA per (sequence, head); the 16-step chunk is exactly one m16 MMA tile.  Warp w owns ring slots
+// [64w, 64w+64): it stages its K/V slice in shared memory with coalesced 16-byte loads (the only HBM traffic of
+// the kernel), computes S = Q K^T and O = P V with mma.sync.m16n8k16 (ldmatrix / ldmatrix.trans operands),
+// keeps its own softmax statistics and the four partial results are merged through shared memory.  The
+// visibility rule is the reference's (modules/attention.py:88-103, 244-254).
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int kMimiLd = 72;                                   // padded smem row (bf16 elements): conflict-free ldmatrix
+constexpr int kMimiWarpSmem = 2 * 64 * kMimiLd * 2;           // bytes per warp: K + V slices
+
+__global__ void __launch_bounds__(128) mimi_attention_mma_kernel(const MimiAttnParams p) {
+  extern __shared__ __align__(16) unsigned char mimi_smem[];
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int D = p.H * kHeadDim;
+  const int cap = p.context;
+  const int e = p.offset[b];
+  const int last = e + p.T - 1;
+  const int end_index = last % cap;
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(mimi_smem + warp * kMimiWarpSmem);
+  __nv_bfloat16* Vs = Ks + 64 * kMimiLd;
+  const __nv_bfloat16* kbase = reinterpret_cast<const __nv_bfloat16*>(p.ring) + p.layer * p.layer_stride +
+                               ((long long)b * p.H + h) * cap * kHeadDim;
+  const __nv_bfloat16* vbase = kbase + p.kv_stride;
+  const int slot0 = warp * 64;
+  // ---- stage this warp's 64 slots of K and V (16-byte chunks, fully coalesced) ----
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int idx = lane + 32 * i;
+    const int row = idx >> 3, ch = idx & 7;
+    const int slot = slot0 + row;
+    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+    if (slot < cap) {
+      kv = *reinterpret_cast<const uint4*>(kbase + (long long)slot * kHeadDim + ch * 8);
+      vv = *reinterpret_cast<const uint4*>(vbase + (long long)slot * kHeadDim + ch * 8);
+    }
+    *reinterpret_cast<uint4*>(Ks + row * kMimiLd + ch * 8) = kv;
+    *reinterpret_cast<uint4*>(Vs + row * kMimiLd + ch * 8) = vv;
+  }
+  // ---- Q fragments (rows g and g+8 of the chunk), pre-scaled by 1/sqrt(64) ----
+  uint32_t qa[4][4];
+  {
+    const bool r0 = g < p.T, r1 = g + 8 < p.T;
+    const float* q0 = p.q_rot + ((long long)(b * p.T + (r0 ? g : 0))) * D + h * kHeadDim;
+    const float* q1 = p.q_rot + ((long long)(b * p.T + (r1 ? g + 8 : 0))) * D + h * kHeadDim;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int c = 16 * ks + 2 * t4;
+      const float2 a0 = *reinterpret_cast<const float2*>(q0 + c), a2 = *reinterpret_cast<const float2*>(q0 + c + 8);
+      const float2 a1 = *reinterpret_cast<const float2*>(q1 + c), a3 = *reinterpret_cast<const float2*>(q1 + c + 8);
+      qa[ks][0] = r0 ? pack2_bf16(a0.x * 0.125f, a0.y * 0.125f) : 0u;
+      qa[ks][1] = r1 ? pack2_bf16(a1.x * 0.125f, a1.y * 0.125f) : 0u;
+      qa[ks][2] = r0 ? pack2_bf16(a2.x * 0.125f, a2.y * 0.125f) : 0u;
+      qa[ks][3] = r1 ? pack2_bf16(a3.x * 0.125f, a3.y * 0.125f) : 0u;
+    }
+  }
+  __syncwarp();
+  // ---- S = Q K^T : 8 key tiles x 4 k-steps ----
+  float sc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t kb[4];
+      ldsm_x4(kb, (uint32_t)__cvta_generic_to_shared(Ks + (nt * 8 + (lane & 7)) * kMimiLd + 32 * kk + 8 * (lane >> 3)));
+      mma_bf16_16816(sc[nt], qa[2 * kk], kb[0], kb[1]);
+      mma_bf16_16816(sc[nt], qa[2 * kk + 1], kb[2], kb[3]);
+    }
+  }
+  // ---- visibility mask + per-row max over this warp's slots ----
+  const int qp0 = (g < p.T) ? e + g : -(1 << 30), qp1 = (g + 8 < p.T) ? e + g + 8 : -(1 << 30);
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int slot = slot0 + nt * 8 + 2 * t4 + j;
+      int pos_k = -1;
+      if (slot < cap) {
+        const int delta = slot - end_index;
+        pos_k = delta <= 0 ? last + delta : last + delta - cap;
+        if (slot >= e + p.T) pos_k = -1;
+      }
+      const int d0 = qp0 - pos_k, d1 = qp1 - pos_k;
+      const bool v0 = pos_k >= 0 && d0 >= 0 && d0 < cap, v1 = pos_k >= 0 && d1 >= 0 && d1 < cap;
+      if (!v0) sc[nt][j] = -INFINITY;
+      if (!v1) sc[nt][2 + j] = -INFINITY;
+      m0 = fmaxf(m0, sc[nt][j]);
+      m1 = fmaxf(m1, sc[nt][2 + j]);
+    }
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  const float mm0 = (m0 == -INFINITY) ? 0.f : m0, mm1 = (m1 == -INFINITY) ? 0.f : m1;
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t pa[4][4];                       // P as A fragments: k-step j covers slots 16j..16j+15 of the slice
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const float p00 = __expf(sc[nt][0] - mm0), p01 = __expf(sc[nt][1] - mm0);
+    const float p10 = __expf(sc[nt][2] - mm1), p11 = __expf(sc[nt][3] - mm1);
+    l0 += p00 + p01;
+    l1 += p10 + p11;
+    pa[nt >> 1][(nt & 1) * 2 + 0] = pack2_bf16(p00, p01);
+    pa[nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p10, p11);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // ---- O = P V : 8 dim tiles x 4 k-steps ----
+  float oc[8][4];
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {       // pairs of dim tiles
+      uint32_t vb[4];
+      const int mid = lane >> 3;
+      ldsm_x4_t(vb, (uint32_t)__cvta_generic_to_shared(Vs + (16 * j + 8 * (mid & 1) + (lane & 7)) * kMimiLd +
+                                                        8 * (2 * dp + (mid >> 1))));
+      mma_bf16_16816(oc[2 * dp], pa[j], vb[0], vb[1]);
+      mma_bf16_16816(oc[2 * dp + 1], pa[j], vb[2], vb[3]);
+    }
+  }
+  // ---- merge the four slices ----
+  __syncwarp();
+  float* sO = reinterpret_cast<float*>(mimi_smem + warp * kMimiWarpSmem);      // [16][64]
+  float* sM = sO + 16 * 64;                                                      // [16] max, [16] sum
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) {
+    *reinterpret_cast<float2*>(sO + g * 64 + dt * 8 + 2 * t4) = make_float2(oc[dt][0], oc[dt][1]);
+    *reinterpret_cast<float2*>(sO + (g + 8) * 64 + dt * 8 + 2 * t4) = make_float2(oc[dt][2], oc[dt][3]);
+  }
+  if (t4 == 0) {
+    sM[g] = m0; sM[g + 8] = m1;
+    sM[16 + g] = l0; sM[16 + g + 8] = l1;
+  }
+  __syncthreads();
+  {
+    const int row = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 8;      // 16 rows x 8 column groups
+    if (row < p.T) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) mx = fmaxf(mx, reinterpret_cast<const float*>(mimi_smem + w * kMimiWarpSmem)[16 * 64 + row]);
+      float l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float* base = reinterpret_cast<const float*>(mimi_smem + w * kMimiWarpSmem);
+        const float mw = base[16 * 64 + row];
+        const float cw = (mw == -INFINITY) ? 0.f : __expf(mw - mx);
+        l += base[16 * 64 + 16 + row] * cw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += base[row * 64 + c0 + i] * cw;
+      }
+      const float inv = 1.0f / l;
+      const long long oi = ((long long)(b * p.T + row)) * D + h * kHeadDim + c0;
+      if (p.out16) {
+        *reinterpret_cast<uint4*>(p.out16 + oi) =
+            make_uint4(pack2_bf16(acc[0] * inv, acc[1] * inv), pack2_bf16(acc[2] * inv, acc[3] * inv),
+                       pack2_bf16(acc[4] * inv, acc[5] * inv), pack2_bf16(acc[6] * inv, acc[7] * inv));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p.out[oi + i] = acc[i] * inv;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s) {
@@ -295,7 +483,14 @@ void launch_mimi_attention(const MimiAttnParams& p, cudaStream_t s) {
   dim3 grid(p.B, p.H);
   ProfScope ps("mimi_attention", nullptr, 4.0 * p.B * p.H * p.T * p.context * 64,
                2.0 * p.B * p.H * p.context * 64 * (p.kv_bf16 ? 2 : 4) + 2.0 * p.B * p.T * p.H * 64 * 4, s);
-  if (p.kv_bf16) mimi_attention_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p);
+  if (p.kv_bf16 && p.T <= 16 && p.context <= 256) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(mimi_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMimiWarpSmem);
+      attr_done = true;
+    }
+    mimi_attention_mma_kernel<<<grid, 128, 4 * kMimiWarpSmem, s>>>(p);
+  } else if (p.kv_bf16) mimi_attention_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p);
   else mimi_attention_kernel<float><<<grid, 128, 0, s>>>(p);
   ++g_launches;
 }
