@@ -102,6 +102,8 @@ struct FlowWork {
   __nv_bfloat16 *h16 = nullptr, *att16 = nullptr, *ff16 = nullptr;   // bf16 operands for the tensor-core path
   int plan_M = 0;
   std::vector<TcGemm> plans;  // 4 per layer: qkv, out, ff1, ff2
+  float *ws_out = nullptr, *ws_ff2 = nullptr;   // split-K partial planes [8][M][D] of out-proj / ffn2
+  int pend_n = 0;             // planes of the last ffn2 still to be added to x (consumed by the next norm)
 };
 
 }  // namespace
@@ -313,7 +315,10 @@ int finalize(Ctx& c) {
     RET(upload_mat(c, t->data, g.n_bins + 1, D, &tmp));
     c.embed = tmp.w;
     RET(need(c, "flow_lm.input_linear.weight", {D, L}, &t));
-    RET(upload_f32(c, t->data.data(), t->data.size(), &c.w_in));
+    std::vector<float> wt((size_t)D * L);                   // stored transposed [L][D] (coalesced in the kernel)
+    for (int n = 0; n < D; ++n)
+      for (int k = 0; k < L; ++k) wt[(size_t)k * D + n] = t->data[(size_t)n * L + k];
+    RET(upload_f32(c, wt.data(), wt.size(), &c.w_in));
   }
   RET(upload_vec(c, "flow_lm.bos_emb", L, &c.bos));
   RET(upload_vec(c, "flow_lm.emb_std", L, &c.emb_std));
@@ -374,9 +379,15 @@ int finalize(Ctx& c) {
   {
     const HostTensor* t;
     RET(need(c, "mimi.quantizer.output_proj.weight", {SD, L, 1}, &t));
-    RET(upload_f32(c, t->data.data(), t->data.size(), &c.wq));
+    std::vector<float> wt((size_t)SD * L);                  // [L][SD]
+    for (int ch = 0; ch < SD; ++ch)
+      for (int k = 0; k < L; ++k) wt[(size_t)k * SD + ch] = t->data[(size_t)ch * L + k];
+    RET(upload_f32(c, wt.data(), wt.size(), &c.wq));
     RET(need(c, "mimi.upsample.convtr.convtr.weight", {SD, 1, 2 * S}, &t));
-    RET(upload_f32(c, t->data.data(), t->data.size(), &c.wu));
+    std::vector<float> ut((size_t)SD * 2 * S);              // [2S][SD]
+    for (int ch = 0; ch < SD; ++ch)
+      for (int k = 0; k < 2 * S; ++k) ut[(size_t)k * SD + ch] = t->data[(size_t)ch * 2 * S + k];
+    RET(upload_f32(c, ut.data(), ut.size(), &c.wu));
   }
   c.ml.resize(g.mimi_layers);
   for (int i = 0; i < g.mimi_layers; ++i) {
@@ -469,9 +480,10 @@ LinearParams rows_linear(const float* A, int M, int C, float* Y, int N, const ch
 
 void rows_norm(Ctx& c, const float* X, int M, int C, const float* w, const float* b, float eps, float* Y,
                const float* scale = nullptr, const float* shift = nullptr, long long mod_rs = 0,
-               __nv_bfloat16* Y16 = nullptr) {
+               __nv_bfloat16* Y16 = nullptr, const float* acc = nullptr, int acc_n = 0) {
   NormParams n{};
   n.Y16 = Y16;
+  n.acc = acc; n.acc_n = acc_n; n.acc_stride = (long long)M * C;
   n.X = X; n.x_bs = 0; n.x_rs = C; n.nb = 1; n.T = M; n.C = C;
   n.w = w; n.b = b; n.eps = eps; n.scale = scale; n.shift = shift; n.mod_rs = mod_rs;
   n.Y = Y; n.y_bs = 0; n.y_rs = C;
@@ -481,7 +493,7 @@ void rows_norm(Ctx& c, const float* X, int M, int C, const float* w, const float
 bool want_tc(Ctx& c, int M) { return c.bf16 && gemm_tc_available() && M > 16 && !c.force_simt; }
 
 void free_flow_work(FlowWork& w) {
-  void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16};
+  void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16, w.ws_out, w.ws_ff2};
   for (void* p : ptrs) if (p) cudaFree(p);
   w = FlowWork{};
 }
@@ -498,6 +510,8 @@ int alloc_flow_work(Ctx& c, FlowWork& w, int M) {
     CU(cudaMalloc((void**)&w.h16, M * D * 2));
     CU(cudaMalloc((void**)&w.att16, M * D * 2));
     CU(cudaMalloc((void**)&w.ff16, M * FF * 2));
+    CU(cudaMalloc((void**)&w.ws_out, 8 * M * D * 4));
+    CU(cudaMalloc((void**)&w.ws_ff2, 8 * M * D * 4));
   } else {
     CU(cudaMalloc((void**)&w.h, M * D * 4));
     CU(cudaMalloc((void**)&w.att, M * D * 4));
@@ -510,9 +524,9 @@ int alloc_flow_work(Ctx& c, FlowWork& w, int M) {
 }
 
 bool plan_tc(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a_rs, int nb, int T, int taps, int C,
-             const LinW& w, const char* tag) {
+             const LinW& w, const char* tag, int max_splits = 1) {
   if (!w.w16 || w.K != taps * C) return false;
-  if (!gemm_tc_plan(g, a, a_bs, a_rs, nb, T, taps, C, w.w16, w.N, tag)) return false;
+  if (!gemm_tc_plan(g, a, a_bs, a_rs, nb, T, taps, C, w.w16, w.N, tag, max_splits)) return false;
   g->e.bias = w.bias;
   return true;
 }
@@ -524,15 +538,19 @@ int build_flow_plans(Ctx& c, FlowWork& w, int M) {
   for (int i = 0; i < c.cfg.n_layers; ++i) {
     auto& l = c.fl[i];
     TcGemm* g = &w.plans[(size_t)i * 4];
+    // out-proj and ffn2 only feed the residual stream, so they may run split-K: the planes are summed into x
+    // by the next LayerNorm (deterministic order) instead of an epilogue
     bool ok = plan_tc(&g[0], w.h16, 0, D, 1, M, 1, D, l.qkv, "flow.qkv") &&
-              plan_tc(&g[1], w.att16, 0, D, 1, M, 1, D, l.out, "flow.out") &&
+              plan_tc(&g[1], w.att16, 0, D, 1, M, 1, D, l.out, "flow.out", 8) &&
               plan_tc(&g[2], w.h16, 0, D, 1, M, 1, D, l.ff1, "flow.ff1") &&
-              plan_tc(&g[3], w.ff16, 0, FF, 1, M, 1, FF, l.ff2, "flow.ff2");
+              plan_tc(&g[3], w.ff16, 0, FF, 1, M, 1, FF, l.ff2, "flow.ff2", 8);
     if (!ok) return fail(PTTS_ERR_CUDA, "tcgen05 plan failed for FlowLM layer %d (M=%d)", i, M);
     g[0].e.y32 = w.qkv; g[0].e.y32_rs = 3 * D;
     g[1].e.res32 = w.x; g[1].e.res32_rs = D; g[1].e.y32 = w.x; g[1].e.y32_rs = D;
+    g[1].split_ws = w.ws_out;
     g[2].e.act = ACT_GELU; g[2].e.y16 = w.ff16; g[2].e.y16_rs = FF;
     g[3].e.res32 = w.x; g[3].e.res32_rs = D; g[3].e.y32 = w.x; g[3].e.y32_rs = D;
+    g[3].split_ws = w.ws_ff2;
   }
   w.plan_M = M;
   return 0;
@@ -543,10 +561,11 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
                  int max_pages, long long total_keys) {
   const int D = c.cfg.d_model, FF = c.cfg.ffn_dim;
   if (w.tc) {
+    int pend = 0;   // split-K planes of the previous ffn2 that the next norm must add to x
     for (int i = 0; i < c.cfg.n_layers; ++i) {
       auto& l = c.fl[i];
       const TcGemm* g = &w.plans[(size_t)i * 4];
-      rows_norm(c, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16);
+      rows_norm(c, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16, w.ws_ff2, pend);
       gemm_tc_launch(g[0], c.stream);
       FlowAttnParams a{};
       a.qkv = w.qkv; a.q_rot = w.qrot; a.out16 = w.att16;
@@ -556,12 +575,16 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       launch_flow_rope_append(a, c.stream);
       launch_flow_attention(a, c.stream);
       gemm_tc_launch(g[1], c.stream);
-      rows_norm(c, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16);
+      rows_norm(c, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16, w.ws_out,
+                g[1].splits > 1 ? g[1].splits : 0);
       gemm_tc_launch(g[2], c.stream);
       gemm_tc_launch(g[3], c.stream);
+      pend = g[3].splits > 1 ? g[3].splits : 0;
     }
+    w.pend_n = pend;
     return;
   }
+  w.pend_n = 0;
   for (int i = 0; i < c.cfg.n_layers; ++i) {
     auto& l = c.fl[i];
     rows_norm(c, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, w.h);
@@ -971,7 +994,7 @@ void flow_step(Batch& bt, bool host_noise) {
   for (int l : bt.h_len) total_keys += l + 1;
   flow_layers(c, bt.fw, B, nullptr, bt.d_len, bt.d_page_table, bt.max_pages, total_keys);
   launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.tc_head ? bt.d_c16 : nullptr,
-                        bt.d_logit, B, D, c.stream);
+                        bt.d_logit, B, D, bt.fw.ws_ff2, bt.fw.pend_n, (long long)B * D, c.stream);
   launch_noise_prep(bt.d_noise, bt.d_x, B * L, sqrtf(g.temp), (g.noise_clamp >= 0.f) ? g.noise_clamp : -1.f,
                     host_noise ? 0 : 1, bt.d_counter, c.stream);
   const int n = g.lsd_decode_steps;
@@ -1099,6 +1122,10 @@ int32_t ptts_ctx_create(int32_t device, const ptts_config* cfg, ptts_ctx** out) 
   {
     const char* fs = getenv("PTTS_FORCE_SIMT");
     c->force_simt = fs && fs[0] == '1';
+    // programmatic dependent launch measured slower on this chain (1.586 vs 1.547 ms/frame at batch 256):
+    // graph launch gaps are already ~1 us, so it stays opt-in
+    const char* np = getenv("PTTS_PDL");
+    g_pdl_on = np && np[0] == '1';
   }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&c->ev0));

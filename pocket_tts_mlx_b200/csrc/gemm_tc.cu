@@ -12,7 +12,9 @@
 #include "gemm_tc.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace ptts {
@@ -23,6 +25,9 @@ constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 struct KArgs {
   int nb, T, taps, C, N;
   int box_t, box_b, tiles_t;
+  int splits;                   // gridDim.z; split z covers k-iterations [z*ips, (z+1)*ips)
+  long long split_stride;       // elements between the partial planes of split_ws
+  float* split_ws;
   TcEpilogue e;
 };
 
@@ -120,6 +125,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   constexpr int ROW_BYTES = BK * 2;
   constexpr int A_BYTES = 128 * ROW_BYTES, B_BYTES = BN * ROW_BYTES;
   constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base, sB = base + STAGES * A_BYTES;
@@ -132,7 +138,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   const int tile_b = blockIdx.y / g.tiles_t, tile_t = blockIdx.y % g.tiles_t;
   const int b0 = tile_b * g.box_b, t0 = tile_t * g.box_t;
   const int kc_per_tap = g.C / BK;
-  const int iters = g.taps * kc_per_tap;
+  const int iters_all = g.taps * kc_per_tap;
+  const int ips = iters_all / g.splits;
+  const int it0 = blockIdx.z * ips;
+  const int iters = ips;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
@@ -153,12 +162,15 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   tc_fence_after();
   uint32_t tmem_acc;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_acc) : "r"(tptr));
+  // barriers, TMEM and descriptors are set up; everything below touches the predecessor's output
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < iters; ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
-        const int tap = it / kc_per_tap, kc = it - tap * kc_per_tap;
+        const int git = it0 + it;
+        const int tap = git / kc_per_tap, kc = git - tap * kc_per_tap;
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
         tma_load_3d(sA + s * A_BYTES, &tm_a, full0 + 8 * s, kc * BK, t0 + tap, b0);
@@ -199,7 +211,15 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
       uint32_t raw[32];
       __syncwarp();
       tc_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb, raw);
-      if (row_ok) {
+      if (row_ok && g.splits > 1) {
+        // split-K: raw fp32 partial; the consumer (LayerNorm) adds the planes to the residual stream
+        float4* yp = reinterpret_cast<float4*>(g.split_ws + blockIdx.z * g.split_stride +
+                                               ((long long)b * g.T + t) * g.N + n0 + cb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          yp[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                              __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+      } else if (row_ok) {
         const int n = n0 + cb;
         float v[32];
 #pragma unroll
@@ -296,10 +316,14 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
 EncodeFn g_encode = nullptr;
 bool g_init_done = false;
 
+template <int BN, int BK, int ST>
+void set_attr1() {
+  if (smem_bytes<BN, BK, ST>() <= 227 * 1024)
+    cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, BK, ST>());
+}
 template <int BN, int BK>
 void set_attr() {
-  cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, BK, 2>());
-  cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, BK, 4>());
+  set_attr1<BN, BK, 2>(); set_attr1<BN, BK, 4>(); set_attr1<BN, BK, 6>(); set_attr1<BN, BK, 8>();
 }
 
 bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -313,6 +337,7 @@ bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_sync();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
@@ -337,7 +362,7 @@ void gemm_tc_init() {
 bool gemm_tc_available() { return g_encode != nullptr; }
 
 bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a_rs, int nb, int T, int taps, int C,
-                  const __nv_bfloat16* w, int N, const char* tag) {
+                  const __nv_bfloat16* w, int N, const char* tag, int max_splits) {
   g->valid = false;
   if (!g_encode) return false;
   int bk = 0;
@@ -356,11 +381,35 @@ bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a
   const int tiles_t = (T + box_t - 1) / box_t;
   const int tiles_b = (nb + box_b - 1) / box_b;
   const long long m_tiles = (long long)tiles_t * tiles_b;
-  int bn = 0;
+  // Tile / split / ring-depth choice by a small cost model (microseconds).  A TMA ring turn costs ~2 us of
+  // latency, so an SM fills shared memory at min(120 GB/s, resident CTAs x stages x stage bytes / 2 us); all SMs
+  // together are limited to ~5 TB/s of L2 -> SM traffic; every tile pays a fixed prologue and an epilogue that
+  // overlaps only with co-resident CTAs.
+  const int iters = taps * (C / bk);
+  int bn = 0, best_splits = 1, best_stages = 2;
+  double best = 1e30;
   for (int cand : {128, 64, 32}) {
     if (N % cand) continue;
-    bn = cand;
-    if (m_tiles * (N / cand) >= 120) break;
+    for (int sp = 1; sp <= max_splits; sp *= 2) {
+      if (iters % sp || (sp > 1 && iters / sp < 2)) continue;
+      const int it = iters / sp;
+      const double stage_bytes = 128.0 * bk * 2 + (double)cand * bk * 2;
+      const double ctas = (double)m_tiles * (N / cand) * sp;
+      for (int st : {2, 4, 6, 8}) {
+        if (st > 2 && st > it + 1) continue;
+        if (st * stage_bytes + 2048 > 220.0 * 1024) continue;
+        int per_sm = (int)(220.0 * 1024 / (st * stage_bytes + 2048));
+        per_sm = per_sm > 4 ? 4 : per_sm;
+        const double per_sm_ctas = std::ceil(ctas / 148.0);
+        const double resident = std::min<double>(per_sm, per_sm_ctas);
+        const double rate = std::min(120e3, resident * st * stage_bytes / 2.0);          // bytes / us / SM
+        const double t_main = per_sm_ctas * it * stage_bytes / rate;
+        const double t_epi = (0.5 + 0.02 * cand) * per_sm_ctas / resident;               // exposed epilogue + prologue
+        const double t_agg = ctas * it * stage_bytes / 5e6;
+        const double t = std::max(t_main, t_agg) + t_epi + 2.0 + (sp > 1 ? 0.3 : 0.0);
+        if (t < best) { best = t; bn = cand; best_splits = sp; best_stages = st; }
+      }
+    }
   }
   if (!bn) return false;
   {
@@ -377,9 +426,14 @@ bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a
   }
   g->nb = nb; g->T = T; g->taps = taps; g->C = C; g->N = N;
   g->box_t = box_t; g->box_b = box_b; g->bn = bn; g->bk = bk;
+  g->stages = best_stages; g->splits = best_splits; g->split_ws = nullptr;
   g->e = TcEpilogue{};
   g->tag = tag;
   g->valid = true;
+  static const bool verbose = [] { const char* v = getenv("PTTS_TC_VERBOSE"); return v && v[0] == '1'; }();
+  if (verbose)
+    fprintf(stderr, "[gemm_tc] %-10s nb=%d T=%d taps=%d C=%d N=%d -> box %dx%d bn=%d bk=%d stages=%d splits=%d est=%.1fus\n",
+            tag ? tag : "?", nb, T, taps, C, N, box_b, box_t, bn, bk, best_stages, best_splits, best);
   return true;
 }
 
@@ -389,20 +443,22 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   a.box_t = g.box_t; a.box_b = g.box_b;
   a.tiles_t = (g.T + g.box_t - 1) / g.box_t;
   a.e = g.e;
+  a.splits = g.splits; a.split_ws = g.split_ws; a.split_stride = (long long)g.nb * g.T * g.N;
   const int tiles_b = (g.nb + g.box_b - 1) / g.box_b;
-  dim3 grid(g.N / g.bn, a.tiles_t * tiles_b), block(kThreads);
+  dim3 grid(g.N / g.bn, a.tiles_t * tiles_b, g.splits), block(kThreads);
   const double flops = 2.0 * g.nb * g.T * (double)g.N * g.taps * g.C;
   const double bytes = (double)g.N * g.taps * g.C * 2 + (double)g.nb * (g.T + g.taps - 1) * g.C * 2 +
                        (double)g.nb * g.T * g.N * ((g.e.y32 ? 4 : 0) + (g.e.y16 ? 2 : 0) + (g.e.yraw16 ? 2 : 0) +
                                                    (g.e.res32 ? 4 : 0) + (g.e.res16 ? 2 : 0));
   ProfScope ps("gemm_tc", g.tag, flops, bytes, s);
-  // shallow K (few ring turns): 2 stages so several CTAs share an SM and one CTA's epilogue overlaps its
-  // neighbours' loads; deep K (weight streaming): 4 stages of prefetch
-  const bool deep = g.taps * (g.C / g.bk) >= 12;
-#define PTTS_TC(BN_, BK_)                                                                                   \
-  do {                                                                                                      \
-    if (deep) gemm_tc_kernel<BN_, BK_, 4><<<grid, block, smem_bytes<BN_, BK_, 4>(), s>>>(g.tm_a, g.tm_b, a); \
-    else gemm_tc_kernel<BN_, BK_, 2><<<grid, block, smem_bytes<BN_, BK_, 2>(), s>>>(g.tm_a, g.tm_b, a);      \
+#define PTTS_TC(BN_, BK_)                                                                                       \
+  do {                                                                                                          \
+    switch (g.stages) {                                                                                         \
+      case 8: launch_k(gemm_tc_kernel<BN_, BK_, 8>, grid, block, smem_bytes<BN_, BK_, 8>(), s, g.tm_a, g.tm_b, a); break; \
+      case 6: launch_k(gemm_tc_kernel<BN_, BK_, 6>, grid, block, smem_bytes<BN_, BK_, 6>(), s, g.tm_a, g.tm_b, a); break; \
+      case 4: launch_k(gemm_tc_kernel<BN_, BK_, 4>, grid, block, smem_bytes<BN_, BK_, 4>(), s, g.tm_a, g.tm_b, a); break; \
+      default: launch_k(gemm_tc_kernel<BN_, BK_, 2>, grid, block, smem_bytes<BN_, BK_, 2>(), s, g.tm_a, g.tm_b, a); break; \
+    }                                                                                                           \
   } while (0)
   if (g.bk == 64) {
     if (g.bn == 128) PTTS_TC(128, 64);
@@ -419,7 +475,7 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
 
 void launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t s) {
   ProfScope ps("f32_to_bf16", nullptr, 0, 6.0 * n, s);
-  f32_to_bf16_kernel<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, s>>>(src, dst, n);
+  launch_k(f32_to_bf16_kernel, dim3((int)std::min<long long>((n + 255) / 256, 4096)), dim3(256), 0, s, src, dst, n);
   ++g_launches;
 }
 

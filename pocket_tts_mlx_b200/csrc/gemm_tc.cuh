@@ -33,6 +33,9 @@ struct TcGemm {
   int nb, T, taps, C, N;
   int box_t, box_b;           // 128-row M tile = box_b sequences x box_t time steps
   int bn, bk;                 // N tile (32/64/128), K chunk in elements (64 or 32)
+  int stages;                 // smem ring depth (2 or 4)
+  int splits;                 // split-K factor; > 1: raw fp32 partials go to split_ws[z][nb*T][N], epilogue skipped
+  float* split_ws;
   TcEpilogue e;
   const char* tag;
   bool valid = false;
@@ -43,7 +46,7 @@ bool gemm_tc_available();
 // Describe one GEMM call site.  a: bf16 [nb][T+taps-1][C] with strides (a_bs, a_rs) in elements;
 // w: bf16 [N][taps*C].  Returns false when the shape is unsupported (caller keeps the SIMT path).
 bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a_rs, int nb, int T, int taps, int C,
-                  const __nv_bfloat16* w, int N, const char* tag);
+                  const __nv_bfloat16* w, int N, const char* tag, int max_splits = 1);
 void gemm_tc_launch(const TcGemm& g, cudaStream_t s);
 // fp32-in / fp32-out debug entry used by ptts_debug_linear(path=3); returns < 0 when unsupported.
 int gemm_tc_debug(const LinearParams& p, bool bf16_storage, cudaStream_t s);

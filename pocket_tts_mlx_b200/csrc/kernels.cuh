@@ -55,6 +55,8 @@ struct NormParams {
   const float* scale; const float* shift; long long mod_rs;   // row stride of the modulation buffer
   float* Y; long long y_bs, y_rs;
   __nv_bfloat16* Y16;            // when set, the result is written here as bf16 (same strides) instead of Y
+  // split-K partial planes [acc_n][rows][C] of the producing GEMM: x += sum of planes (written back to X)
+  const float* acc; int acc_n; long long acc_stride;
 };
 void launch_layernorm(const NormParams& p, cudaStream_t s);
 
@@ -103,7 +105,7 @@ void launch_embed_rows(const void* table, int table_bf16, const int* ids, float*
 // c = LN(x[row_of[b]]); logit = w_eos . c + b_eos      (models/flow_lm.py:120,100)
 void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w, const float* ln_b,
                            const float* w_eos, const float* b_eos, float* c, __nv_bfloat16* c16, float* logit,
-                           int B, int D, cudaStream_t s);
+                           int B, int D, const float* acc, int acc_n, long long acc_stride, cudaStream_t s);
 // x0 = clip(sqrt(temp) * z); z from the host buffer or a Philox4x32-10 + Box-Muller stream
 void launch_noise_prep(const float* z, float* x0, int n, float std, float clamp, int use_philox,
                        const unsigned long long* counter, cudaStream_t s);
@@ -148,6 +150,27 @@ struct ProfScope {
 void prof_start();
 // "name,launches,ms,flops,bytes\n" per kernel:tag, sorted by time; stops profiling
 const char* prof_report();
+
+// ---- programmatic dependent launch -----------------------------------------------------------------------
+// Every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may be scheduled while
+// its predecessor in the stream / graph is still draining.  Kernels call pdl_trigger() first (lets THEIR
+// successor be scheduled early) and pdl_wait() before the first access to global memory that the predecessor
+// may have written (griddepcontrol.wait returns once the predecessor grid has completed and flushed).
+extern bool g_pdl_on;   // PTTS_NO_PDL=1 turns the launch attribute off (the device calls are then no-ops)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
+
+template <typename... KP, typename... Args>
+inline void launch_k(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl_on ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KP>(args)...);
+}
 
 // ---- device helpers ----------------------------------------------------------------------------------
 __device__ __forceinline__ float act_apply(float v, int act) {

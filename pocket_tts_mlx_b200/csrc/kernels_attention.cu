@@ -40,6 +40,7 @@ template <> struct KVec<float> {
 // grid = M rows, block = H*32 threads: thread (h, i) rotates pair i of head h for q and k, copies v.
 template <typename KT>
 __global__ void flow_rope_append_kernel(const FlowAttnParams p) {
+  pdl_sync();
   const int m = blockIdx.x;
   const int h = threadIdx.x >> 5, i = threadIdx.x & 31;
   const int D = p.H * kHeadDim;
@@ -102,6 +103,7 @@ __device__ __forceinline__ void soft_merge_shfl(SoftState& s, int delta) {
 // grid (M, H), block 128 = 4 warps; keys 0..pos of the row's sequence are strided over 16 lane-groups.
 template <typename KT>
 __global__ void __launch_bounds__(128) flow_attention_kernel(const FlowAttnParams p) {
+  pdl_sync();
   __shared__ float sh_m[4], sh_l[4], sh_acc[4][kHeadDim];
   const int m = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(128) flow_attention_kernel(const FlowAttnParam
 // grid = B*T rows, block = H*32
 template <typename KT>
 __global__ void mimi_rope_ring_kernel(const MimiAttnParams p) {
+  pdl_sync();
   const int m = blockIdx.x;
   const int b = m / p.T, t = m % p.T;
   const int h = threadIdx.x >> 5, i = threadIdx.x & 31;
@@ -190,6 +193,7 @@ __global__ void mimi_rope_ring_kernel(const MimiAttnParams p) {
 // grid (B, H), block 128: warp w owns queries 4w..4w+3 of the 16-step chunk (T <= 16).
 template <typename KT>
 __global__ void __launch_bounds__(128) mimi_attention_kernel(const MimiAttnParams p) {
+  pdl_sync();
   const int b = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 3, sl = lane & 7;
@@ -294,6 +298,7 @@ constexpr int kMimiLd = 72;                                   // padded smem row
 constexpr int kMimiWarpSmem = 2 * 64 * kMimiLd * 2;           // bytes per warp: K + V slices
 
 __global__ void __launch_bounds__(128) mimi_attention_mma_kernel(const MimiAttnParams p) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char mimi_smem[];
   const int b = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -457,8 +462,8 @@ __global__ void __launch_bounds__(128) mimi_attention_mma_kernel(const MimiAttnP
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s) {
   if (p.M <= 0) return;
   ProfScope ps("flow_rope_append", nullptr, 0, (double)p.M * p.H * 64 * (3 * 4 + 4 + 2 * (p.kv_bf16 ? 2 : 4)), s);
-  if (p.kv_bf16) flow_rope_append_kernel<__nv_bfloat16><<<p.M, p.H * 32, 0, s>>>(p);
-  else flow_rope_append_kernel<float><<<p.M, p.H * 32, 0, s>>>(p);
+  if (p.kv_bf16) launch_k(flow_rope_append_kernel<__nv_bfloat16>, dim3(p.M), dim3(p.H * 32), 0, s, p);
+  else launch_k(flow_rope_append_kernel<float>, dim3(p.M), dim3(p.H * 32), 0, s, p);
   ++g_launches;
 }
 
@@ -467,15 +472,15 @@ void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
   dim3 grid(p.M, p.H);
   ProfScope ps("flow_attention", nullptr, 4.0 * p.total_keys * p.H * 64,
                2.0 * p.total_keys * p.H * 64 * (p.kv_bf16 ? 2 : 4) + 2.0 * p.M * p.H * 64 * 4, s);
-  if (p.kv_bf16) flow_attention_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p);
-  else flow_attention_kernel<float><<<grid, 128, 0, s>>>(p);
+  if (p.kv_bf16) launch_k(flow_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, s, p);
+  else launch_k(flow_attention_kernel<float>, dim3(grid), dim3(128), 0, s, p);
   ++g_launches;
 }
 
 void launch_mimi_rope_ring(const MimiAttnParams& p, cudaStream_t s) {
   ProfScope ps("mimi_rope_ring", nullptr, 0, (double)p.B * p.T * p.H * 64 * (3 * 4 + 4 + 2 * (p.kv_bf16 ? 2 : 4)), s);
-  if (p.kv_bf16) mimi_rope_ring_kernel<__nv_bfloat16><<<p.B * p.T, p.H * 32, 0, s>>>(p);
-  else mimi_rope_ring_kernel<float><<<p.B * p.T, p.H * 32, 0, s>>>(p);
+  if (p.kv_bf16) launch_k(mimi_rope_ring_kernel<__nv_bfloat16>, dim3(p.B * p.T), dim3(p.H * 32), 0, s, p);
+  else launch_k(mimi_rope_ring_kernel<float>, dim3(p.B * p.T), dim3(p.H * 32), 0, s, p);
   ++g_launches;
 }
 
@@ -489,9 +494,9 @@ void launch_mimi_attention(const MimiAttnParams& p, cudaStream_t s) {
       cudaFuncSetAttribute(mimi_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMimiWarpSmem);
       attr_done = true;
     }
-    mimi_attention_mma_kernel<<<grid, 128, 4 * kMimiWarpSmem, s>>>(p);
-  } else if (p.kv_bf16) mimi_attention_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p);
-  else mimi_attention_kernel<float><<<grid, 128, 0, s>>>(p);
+    launch_k(mimi_attention_mma_kernel, dim3(grid), dim3(128), 4 * kMimiWarpSmem, s, p);
+  } else if (p.kv_bf16) launch_k(mimi_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, s, p);
+  else launch_k(mimi_attention_kernel<float>, dim3(grid), dim3(128), 0, s, p);
   ++g_launches;
 }
 

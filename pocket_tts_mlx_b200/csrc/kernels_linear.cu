@@ -9,6 +9,7 @@
 namespace ptts {
 
 long long g_launches = 0;
+bool g_pdl_on = false;
 
 namespace {
 
@@ -33,6 +34,7 @@ __device__ __forceinline__ void load_w4<__nv_bfloat16>(const __nv_bfloat16* w, f
 // grid (ceil(N/64), ceil(M/64)); 256 threads, each a 4x4 micro-tile.  K = taps*C, C % 16 == 0.
 template <typename WT>
 __global__ void __launch_bounds__(256) linear_tile_kernel(const LinearParams p) {
+  pdl_sync();
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Ws[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -132,6 +134,7 @@ template <> struct WVec<float> {
 
 template <typename WT, int MT>
 __global__ void __launch_bounds__(128) linear_gemv_kernel(const LinearParams p) {
+  pdl_sync();
   extern __shared__ __align__(16) float xs[];   // [nb][T+taps-1][C]
   const int rows_per_seq = p.T + p.taps - 1;
   const int C = p.C, K = p.taps * p.C;
@@ -215,7 +218,7 @@ void launch_gemv_t(const LinearParams& p, cudaStream_t s) {
   do {                                                                                                  \
     auto kfn = linear_gemv_kernel<WT, MT>;                                                              \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    kfn<<<grid, block, smem, s>>>(p);                                                                   \
+    launch_k(kfn, dim3(grid), dim3(block), smem, s, p);                                                                   \
   } while (0)
   if (M <= 1) PTTS_GEMV(1);
   else if (M <= 2) PTTS_GEMV(2);
@@ -237,8 +240,8 @@ void launch_linear_tile(const LinearParams& p, cudaStream_t s) {
   const int M = p.nb * p.T;
   dim3 grid((p.N + BN - 1) / BN, (M + BM - 1) / BM), block(256);
   ProfScope ps("linear_tile", p.tag, linear_flops(p), linear_bytes(p), s);
-  if (p.w_bf16) linear_tile_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(p);
-  else linear_tile_kernel<float><<<grid, block, 0, s>>>(p);
+  if (p.w_bf16) launch_k(linear_tile_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, s, p);
+  else launch_k(linear_tile_kernel<float>, dim3(grid), dim3(block), 0, s, p);
   ++g_launches;
 }
 

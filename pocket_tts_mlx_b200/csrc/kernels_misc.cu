@@ -16,65 +16,103 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-// one CTA (128 threads) per row; two-pass mean / biased variance exactly as LayerNorm is defined
-__global__ void __launch_bounds__(128) layernorm_kernel(const NormParams p) {
-  __shared__ float red[32];
-  const int m = blockIdx.x;
+// one warp per row (8 rows per CTA), row held in registers; two-pass mean / biased variance exactly as
+// LayerNorm is defined, reductions by warp shuffles only.  C <= 1024, C % 128 == 0.
+template <int VEC>   // float4 vectors per lane: C = 128 * VEC
+__global__ void __launch_bounds__(256) layernorm_kernel(const NormParams p) {
+  pdl_sync();
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= p.nb * p.T) return;
   const int b = m / p.T, t = m % p.T;
-  const float* x = p.X + b * p.x_bs + t * p.x_rs;
-  float* y = p.Y + b * p.y_bs + t * p.y_rs;
-  const int C = p.C;
-  float v[8];
+  const float4* x = reinterpret_cast<const float4*>(p.X + b * p.x_bs + t * p.x_rs);
+  float4 v[VEC];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = threadIdx.x + i * 128;
-    v[i] = c < C ? x[c] : 0.f;
-    s += v[i];
+  for (int i = 0; i < VEC; ++i) v[i] = x[lane + 32 * i];
+  if (p.acc_n > 0) {
+    float4* xw = reinterpret_cast<float4*>(const_cast<float*>(p.X) + b * p.x_bs + t * p.x_rs);
+#pragma unroll 4
+    for (int k = 0; k < p.acc_n; ++k) {
+      const float4* a = reinterpret_cast<const float4*>(p.acc + k * p.acc_stride + (long long)m * p.C);
+      float4 q[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) q[i] = a[lane + 32 * i];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { v[i].x += q[i].x; v[i].y += q[i].y; v[i].z += q[i].z; v[i].w += q[i].w; }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) xw[lane + 32 * i] = v[i];
   }
-  const float mean = block_sum(s, red) / (float)C;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / (float)p.C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = threadIdx.x + i * 128;
-    const float d = c < C ? v[i] - mean : 0.f;
-    q += d * d;
+  for (int i = 0; i < VEC; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
   }
-  const float var = block_sum(q, red) / (float)C;
-  const float rstd = 1.0f / sqrtf(var + p.eps);
-  const float* sc = p.scale ? p.scale + (long long)m * p.mod_rs : nullptr;
-  const float* sh = p.shift ? p.shift + (long long)m * p.mod_rs : nullptr;
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)p.C + p.eps);
+  const float4* sc = p.scale ? reinterpret_cast<const float4*>(p.scale + (long long)m * p.mod_rs) : nullptr;
+  const float4* sh = p.shift ? reinterpret_cast<const float4*>(p.shift + (long long)m * p.mod_rs) : nullptr;
+  const float4* w4 = reinterpret_cast<const float4*>(p.w);
+  const float4* b4 = reinterpret_cast<const float4*>(p.b);
+  const long long yo = b * p.y_bs + t * p.y_rs;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = threadIdx.x + i * 128;
-    if (c < C) {
-      float o = (v[i] - mean) * rstd;
-      if (p.w) o = o * p.w[c] + p.b[c];
-      if (sc) o = o * (1.0f + sc[c]) + sh[c];
-      if (p.Y16) p.Y16[b * p.y_bs + t * p.y_rs + c] = __float2bfloat16_rn(o);
-      else y[c] = o;
+  for (int i = 0; i < VEC; ++i) {
+    const int c4 = lane + 32 * i;
+    float4 o = make_float4(v[i].x * rstd, v[i].y * rstd, v[i].z * rstd, v[i].w * rstd);
+    if (p.w) {
+      const float4 w = w4[c4], bb = b4[c4];
+      o.x = o.x * w.x + bb.x; o.y = o.y * w.y + bb.y; o.z = o.z * w.z + bb.z; o.w = o.w * w.w + bb.w;
+    }
+    if (sc) {
+      const float4 a = sc[c4], d = sh[c4];
+      o.x = o.x * (1.0f + a.x) + d.x; o.y = o.y * (1.0f + a.y) + d.y;
+      o.z = o.z * (1.0f + a.z) + d.z; o.w = o.w * (1.0f + a.w) + d.w;
+    }
+    if (p.Y16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      *reinterpret_cast<uint2*>(p.Y16 + yo + 4 * c4) = pk;
+    } else {
+      *reinterpret_cast<float4*>(p.Y + yo + 4 * c4) = o;
     }
   }
 }
 
-__global__ void input_rows_kernel(const float* __restrict__ w_in, const float* __restrict__ bos,
-                                  const float* __restrict__ prev, const int* __restrict__ bos_flag,
-                                  float* __restrict__ x, int D, int L) {
-  extern __shared__ float lat[];
-  const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) lat[i] = bos_flag[b] ? bos[i] : prev[b * L + i];
+// w_in_t is the transposed input_linear weight [L][D] so that consecutive threads read consecutive addresses
+__global__ void __launch_bounds__(256) input_rows_kernel(const float* __restrict__ w_in_t, const float* __restrict__ bos,
+                                                         const float* __restrict__ prev, const int* __restrict__ bos_flag,
+                                                         float* __restrict__ x, int B, int D, int L) {
+  pdl_sync();
+  extern __shared__ float lat[];     // [4][L]
+  const int b0 = blockIdx.x * 4;
+  for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
+    const int r = i / L, k = i - r * L, b = b0 + r;
+    lat[i] = (b < B) ? (bos_flag[b] ? bos[k] : prev[b * L + k]) : 0.f;
+  }
   __syncthreads();
   for (int n = threadIdx.x; n < D; n += blockDim.x) {
-    const float* w = w_in + (long long)n * L;
-    float a = 0.f;
-    for (int i = 0; i < L; ++i) a = fmaf(w[i], lat[i], a);
-    x[(long long)b * D + n] = a;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < L; ++k) {
+      const float w = __ldg(w_in_t + (long long)k * D + n);
+      a0 = fmaf(w, lat[k], a0); a1 = fmaf(w, lat[L + k], a1);
+      a2 = fmaf(w, lat[2 * L + k], a2); a3 = fmaf(w, lat[3 * L + k], a3);
+    }
+    if (b0 < B) x[(long long)b0 * D + n] = a0;
+    if (b0 + 1 < B) x[(long long)(b0 + 1) * D + n] = a1;
+    if (b0 + 2 < B) x[(long long)(b0 + 2) * D + n] = a2;
+    if (b0 + 3 < B) x[(long long)(b0 + 3) * D + n] = a3;
   }
 }
 
 template <typename WT>
 __global__ void embed_rows_kernel(const WT* __restrict__ table, const int* __restrict__ ids,
                                   float* __restrict__ rows, int D) {
+  pdl_sync();
   const int m = blockIdx.x;
   const WT* src = table + (long long)ids[m] * D;
   for (int c = threadIdx.x; c < D; c += blockDim.x) rows[(long long)m * D + c] = (float)src[c];
@@ -88,16 +126,22 @@ __global__ void __launch_bounds__(128) final_norm_eos_kernel(const float* __rest
                                                              const float* __restrict__ b_eos,
                                                              float* __restrict__ cout,
                                                              __nv_bfloat16* __restrict__ cout16,
-                                                             float* __restrict__ logit, int D) {
+                                                             float* __restrict__ logit, int D,
+                                                             const float* __restrict__ acc, int acc_n,
+                                                             long long acc_stride) {
+  pdl_sync();
   __shared__ float red[32];
   const int b = blockIdx.x;
-  const float* xr = x + (long long)(row_of ? row_of[b] : b) * D;
+  const long long row = row_of ? row_of[b] : b;
+  const float* xr = x + row * D;
   float v[8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = threadIdx.x + i * 128;
     v[i] = c < D ? xr[c] : 0.f;
+    for (int k = 0; k < acc_n; ++k)
+      if (c < D) v[i] += acc[k * acc_stride + row * D + c];
     s += v[i];
   }
   const float mean = block_sum(s, red) / (float)D;
@@ -140,6 +184,7 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 __global__ void noise_prep_kernel(const float* __restrict__ z, float* __restrict__ x0, int n, float std,
                                   float clamp, int use_philox,
                                   const unsigned long long* __restrict__ counter) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float g;
@@ -158,22 +203,27 @@ __global__ void noise_prep_kernel(const float* __restrict__ z, float* __restrict
   x0[i] = v;
 }
 
-__global__ void quant_upsample_kernel(const float* __restrict__ lat, const float* __restrict__ emb_std,
-                                      const float* __restrict__ emb_mean, const float* __restrict__ wq,
-                                      const float* __restrict__ wu, float* __restrict__ zprev,
-                                      float* __restrict__ out, long long out_bs, int L, int C, int S) {
+// wq_t [L][C] and wu_t [2S][C] are stored transposed (channel fastest) for coalesced reads
+__global__ void __launch_bounds__(256) quant_upsample_kernel(const float* __restrict__ lat, const float* __restrict__ emb_std,
+                                                             const float* __restrict__ emb_mean,
+                                                             const float* __restrict__ wq_t, const float* __restrict__ wu_t,
+                                                             float* __restrict__ zprev, float* __restrict__ out,
+                                                             long long out_bs, int L, int C, int S) {
+  pdl_sync();
   extern __shared__ float u[];   // normalised latent
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < L; i += blockDim.x) u[i] = lat[b * L + i] * emb_std[i] + emb_mean[i];
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float* w = wq + (long long)c * L;
     float z = 0.f;
-    for (int i = 0; i < L; ++i) z = fmaf(w[i], u[i], z);
+#pragma unroll 8
+    for (int i = 0; i < L; ++i) z = fmaf(__ldg(wq_t + (long long)i * C + c), u[i], z);
     const float zp = zprev[(long long)b * C + c];
     zprev[(long long)b * C + c] = z;
-    const float* k = wu + (long long)c * 2 * S;
-    for (int t = 0; t < S; ++t) out[b * out_bs + (long long)t * C + c] = fmaf(k[t], z, k[S + t] * zp);
+#pragma unroll 8
+    for (int t = 0; t < S; ++t)
+      out[b * out_bs + (long long)t * C + c] =
+          fmaf(__ldg(wu_t + (long long)t * C + c), z, __ldg(wu_t + (long long)(S + t) * C + c) * zp);
   }
 }
 
@@ -184,6 +234,7 @@ __global__ void __launch_bounds__(128) final_conv_kernel(const XT* __restrict__ 
                                                          const float* __restrict__ bias,
                                                          float* __restrict__ audio, long long audio_bs,
                                                          int T, int C, int taps) {
+  pdl_sync();
   extern __shared__ float sm[];
   float* ws = sm;                       // [taps*C]
   float* xs = sm + taps * C;            // [128+taps-1][C+1]
@@ -191,10 +242,25 @@ __global__ void __launch_bounds__(128) final_conv_kernel(const XT* __restrict__ 
   const int rows = min(128, T - t0) + taps - 1;
   for (int i = threadIdx.x; i < taps * C; i += 128) ws[i] = w[i];
   const XT* src = x + b * x_bs + (long long)t0 * C;
-  for (int i = threadIdx.x; i < rows * C; i += 128) {
-    const int r = i / C, c = i - r * C;
-    const float v = (float)src[i];
-    xs[r * (C + 1) + c] = kElu ? act_apply(v, ACT_ELU) : v;
+  if constexpr (sizeof(XT) == 2) {
+    const uint4* src8 = reinterpret_cast<const uint4*>(src);     // rows are C*2 bytes, C % 8 == 0
+    for (int i = threadIdx.x; i < rows * C / 8; i += 128) {
+      const uint4 q = src8[i];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+      const int r = (i * 8) / C, c = (i * 8) - r * C;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        xs[r * (C + 1) + c + 2 * j] = kElu ? act_apply(f.x, ACT_ELU) : f.x;
+        xs[r * (C + 1) + c + 2 * j + 1] = kElu ? act_apply(f.y, ACT_ELU) : f.y;
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < rows * C; i += 128) {
+      const int r = i / C, c = i - r * C;
+      const float v = (float)src[i];
+      xs[r * (C + 1) + c] = kElu ? act_apply(v, ACT_ELU) : v;
+    }
   }
   __syncthreads();
   const int t = t0 + threadIdx.x;
@@ -203,12 +269,14 @@ __global__ void __launch_bounds__(128) final_conv_kernel(const XT* __restrict__ 
   for (int j = 0; j < taps; ++j) {
     const float* xr = xs + (threadIdx.x + j) * (C + 1);
     const float* wr = ws + j * C;
+#pragma unroll 16
     for (int c = 0; c < C; ++c) a = fmaf(xr[c], wr[c], a);
   }
   audio[b * audio_bs + t] = a;
 }
 
 __global__ void state_shift_kernel(const ShiftEntry* __restrict__ entries) {
+  pdl_sync();
   const ShiftEntry e = entries[blockIdx.y];
   const int b = blockIdx.x;
   // rows*C*esz is a multiple of 4 bytes for every buffer of the decoder (C >= 64)
@@ -220,6 +288,7 @@ __global__ void state_shift_kernel(const ShiftEntry* __restrict__ entries) {
 
 __global__ void advance_kernel(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter,
                                int B, int inc_len, int inc_mimi) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
     if (seq_len) seq_len[i] += inc_len;
@@ -230,6 +299,7 @@ __global__ void advance_kernel(int* seq_len, int* bos_flag, int* mimi_offset, un
 }
 
 __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float a, int n) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = fmaf(a, x[i], y[i]);
 }
@@ -237,6 +307,7 @@ __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, 
 template <typename KT>
 __global__ void copy_pages_kernel(KT* pool, long long layer_stride, long long page_stride,
                                   const int* __restrict__ src_pages, const int* __restrict__ dst_pages) {
+  pdl_sync();
   const int pair = blockIdx.x, layer = blockIdx.y;
   const uint4* s = reinterpret_cast<const uint4*>(pool + layer * layer_stride + src_pages[pair] * page_stride);
   uint4* d = reinterpret_cast<uint4*>(pool + layer * layer_stride + dst_pages[pair] * page_stride);
@@ -245,6 +316,7 @@ __global__ void copy_pages_kernel(KT* pool, long long layer_stride, long long pa
 }
 
 __global__ void fill_u32_kernel(unsigned int* dst, unsigned int v, long long n) {
+  pdl_sync();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] = v;
@@ -252,30 +324,41 @@ __global__ void fill_u32_kernel(unsigned int* dst, unsigned int v, long long n) 
 
 __global__ void gather_frame_kernel(const float* __restrict__ all, float* __restrict__ lat, int F, int L,
                                     const int* __restrict__ frame_idx) {
+  pdl_sync();
   const int b = blockIdx.x, f = *frame_idx;
   for (int i = threadIdx.x; i < L; i += blockDim.x) lat[b * L + i] = all[((long long)b * F + f) * L + i];
 }
 
 __global__ void scatter_audio_kernel(const float* __restrict__ audio, float* __restrict__ all, int F, int n,
                                      const int* __restrict__ frame_idx) {
+  pdl_sync();
   const int b = blockIdx.x, f = *frame_idx;
   for (int i = threadIdx.x; i < n; i += blockDim.x) all[((long long)b * F + f) * n + i] = audio[(long long)b * n + i];
 }
 
-__global__ void inc_kernel(int* v, int inc) { *v += inc; }
+__global__ void inc_kernel(int* v, int inc) {
+  pdl_sync(); *v += inc; }
 
 }  // namespace
 
 void launch_layernorm(const NormParams& p, cudaStream_t s) {
   ProfScope ps("layernorm", nullptr, 0, 2.0 * p.nb * p.T * p.C * 4, s);
-  layernorm_kernel<<<p.nb * p.T, 128, 0, s>>>(p);
+  const int rows = p.nb * p.T;
+  const int rpc = rows >= 2048 ? 8 : (rows >= 512 ? 4 : 1);     // rows per CTA: keep >= ~256 CTAs in flight
+  const int grid = (rows + rpc - 1) / rpc, block = 32 * rpc;
+  switch (p.C / 128) {
+    case 8: launch_k(layernorm_kernel<8>, dim3(grid), dim3(block), 0, s, p); break;
+    case 4: launch_k(layernorm_kernel<4>, dim3(grid), dim3(block), 0, s, p); break;
+    case 2: launch_k(layernorm_kernel<2>, dim3(grid), dim3(block), 0, s, p); break;
+    default: launch_k(layernorm_kernel<1>, dim3(grid), dim3(block), 0, s, p); break;
+  }
   ++g_launches;
 }
 
 void launch_input_rows(const float* w_in, const float* bos, const float* prev, const int* bos_flag, float* x,
                        int B, int D, int L, cudaStream_t s) {
   ProfScope ps("input_rows", nullptr, 0, (double)B * (D + L) * 4 + (double)D * L * 4, s);
-  input_rows_kernel<<<B, 256, L * sizeof(float), s>>>(w_in, bos, prev, bos_flag, x, D, L);
+  launch_k(input_rows_kernel, dim3((B + 3) / 4), dim3(256), 4 * L * sizeof(float), s, w_in, bos, prev, bos_flag, x, B, D, L);
   ++g_launches;
 }
 
@@ -283,24 +366,24 @@ void launch_embed_rows(const void* table, int table_bf16, const int* ids, float*
                        cudaStream_t s) {
   ProfScope ps("embed_rows", nullptr, 0, (double)M * D * 6, s);
   if (table_bf16)
-    embed_rows_kernel<__nv_bfloat16><<<M, 256, 0, s>>>((const __nv_bfloat16*)table, ids, rows, D);
+    launch_k(embed_rows_kernel<__nv_bfloat16>, dim3(M), dim3(256), 0, s, (const __nv_bfloat16*)table, ids, rows, D);
   else
-    embed_rows_kernel<float><<<M, 256, 0, s>>>((const float*)table, ids, rows, D);
+    launch_k(embed_rows_kernel<float>, dim3(M), dim3(256), 0, s, (const float*)table, ids, rows, D);
   ++g_launches;
 }
 
 void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w, const float* ln_b,
                            const float* w_eos, const float* b_eos, float* c, __nv_bfloat16* c16, float* logit,
-                           int B, int D, cudaStream_t s) {
+                           int B, int D, const float* acc, int acc_n, long long acc_stride, cudaStream_t s) {
   ProfScope ps("final_norm_eos", nullptr, 0, 2.0 * B * D * 4, s);
-  final_norm_eos_kernel<<<B, 128, 0, s>>>(x, row_of, ln_w, ln_b, w_eos, b_eos, c, c16, logit, D);
+  launch_k(final_norm_eos_kernel, dim3(B), dim3(128), 0, s, x, row_of, ln_w, ln_b, w_eos, b_eos, c, c16, logit, D, acc, acc_n, acc_stride);
   ++g_launches;
 }
 
 void launch_noise_prep(const float* z, float* x0, int n, float std, float clamp, int use_philox,
                        const unsigned long long* counter, cudaStream_t s) {
   ProfScope ps("noise_prep", nullptr, 0, 2.0 * n * 4, s);
-  noise_prep_kernel<<<(n + 255) / 256, 256, 0, s>>>(z, x0, n, std, clamp, use_philox, counter);
+  launch_k(noise_prep_kernel, dim3((n + 255) / 256), dim3(256), 0, s, z, x0, n, std, clamp, use_philox, counter);
   ++g_launches;
 }
 
@@ -308,7 +391,7 @@ void launch_quant_upsample(const float* lat, const float* emb_std, const float* 
                            const float* wu, float* zprev, float* out, long long out_bs, int B, int L, int C,
                            int S, cudaStream_t s) {
   ProfScope ps("quant_upsample", nullptr, 0, (double)B * S * C * 4, s);
-  quant_upsample_kernel<<<B, 256, L * sizeof(float), s>>>(lat, emb_std, emb_mean, wq, wu, zprev, out, out_bs,
+  launch_k(quant_upsample_kernel, dim3(B), dim3(256), L * sizeof(float), s, lat, emb_std, emb_mean, wq, wu, zprev, out, out_bs,
                                                           L, C, S);
   ++g_launches;
 }
@@ -318,7 +401,7 @@ void launch_final_conv(const float* x, long long x_bs, const float* w, const flo
   ProfScope ps("final_conv", nullptr, 0, (double)B * T * (C + 1) * 4, s);
   const size_t smem = (size_t)(taps * C + (128 + taps - 1) * (C + 1)) * sizeof(float);
   dim3 grid((T + 127) / 128, B);
-  final_conv_kernel<float, true><<<grid, 128, smem, s>>>(x, x_bs, w, bias, audio, audio_bs, T, C, taps);
+  launch_k(final_conv_kernel<float, true>, dim3(grid), dim3(128), smem, s, x, x_bs, w, bias, audio, audio_bs, T, C, taps);
   ++g_launches;
 }
 
@@ -327,27 +410,27 @@ void launch_final_conv16(const __nv_bfloat16* x, long long x_bs, const float* w,
   ProfScope ps("final_conv", nullptr, 0, (double)B * T * (C / 2 + 1) * 4, s);
   const size_t smem = (size_t)(taps * C + (128 + taps - 1) * (C + 1)) * sizeof(float);
   dim3 grid((T + 127) / 128, B);
-  final_conv_kernel<__nv_bfloat16, false><<<grid, 128, smem, s>>>(x, x_bs, w, bias, audio, audio_bs, T, C, taps);
+  launch_k(final_conv_kernel<__nv_bfloat16, false>, dim3(grid), dim3(128), smem, s, x, x_bs, w, bias, audio, audio_bs, T, C, taps);
   ++g_launches;
 }
 
 void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s) {
   ProfScope ps("state_shift", nullptr, 0, 0, s);
   dim3 grid(B, n_entries);
-  state_shift_kernel<<<grid, 256, 0, s>>>(entries_dev);
+  launch_k(state_shift_kernel, dim3(grid), dim3(256), 0, s, entries_dev);
   ++g_launches;
 }
 
 void launch_advance(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter, int B,
                     int inc_len, int inc_mimi, cudaStream_t s) {
   ProfScope ps("advance", nullptr, 0, 0, s);
-  advance_kernel<<<(B + 255) / 256, 256, 0, s>>>(seq_len, bos_flag, mimi_offset, counter, B, inc_len, inc_mimi);
+  launch_k(advance_kernel, dim3((B + 255) / 256), dim3(256), 0, s, seq_len, bos_flag, mimi_offset, counter, B, inc_len, inc_mimi);
   ++g_launches;
 }
 
 void launch_axpy(const float* x, float* y, float a, int n, cudaStream_t s) {
   ProfScope ps("axpy", nullptr, 0, 3.0 * n * 4, s);
-  axpy_kernel<<<(n + 255) / 256, 256, 0, s>>>(x, y, a, n);
+  launch_k(axpy_kernel, dim3((n + 255) / 256), dim3(256), 0, s, x, y, a, n);
   ++g_launches;
 }
 
@@ -357,36 +440,36 @@ void launch_copy_pages(void* pool, int kv_bf16, long long layer_stride, long lon
   ProfScope ps("copy_pages", nullptr, 0, 2.0 * n_pairs * n_layers * page_stride * (kv_bf16 ? 2 : 4), s);
   dim3 grid(n_pairs, n_layers);
   if (kv_bf16)
-    copy_pages_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)pool, layer_stride, page_stride,
+    launch_k(copy_pages_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, (__nv_bfloat16*)pool, layer_stride, page_stride,
                                                           src_pages, dst_pages);
   else
-    copy_pages_kernel<float><<<grid, 256, 0, s>>>((float*)pool, layer_stride, page_stride, src_pages, dst_pages);
+    launch_k(copy_pages_kernel<float>, dim3(grid), dim3(256), 0, s, (float*)pool, layer_stride, page_stride, src_pages, dst_pages);
   ++g_launches;
 }
 
 void launch_fill_u32(unsigned int* dst, unsigned int v, long long n, cudaStream_t s) {
   ProfScope ps("fill_u32", nullptr, 0, (double)n * 4, s);
-  fill_u32_kernel<<<1184, 256, 0, s>>>(dst, v, n);
+  launch_k(fill_u32_kernel, dim3(1184), dim3(256), 0, s, dst, v, n);
   ++g_launches;
 }
 
 void launch_gather_frame(const float* lat_all, float* lat, int B, int F, int L, const int* frame_idx,
                          cudaStream_t s) {
   ProfScope ps("gather_frame", nullptr, 0, 0, s);
-  gather_frame_kernel<<<B, 32, 0, s>>>(lat_all, lat, F, L, frame_idx);
+  launch_k(gather_frame_kernel, dim3(B), dim3(32), 0, s, lat_all, lat, F, L, frame_idx);
   ++g_launches;
 }
 
 void launch_scatter_audio(const float* audio, float* audio_all, int B, int F, int n, const int* frame_idx,
                           cudaStream_t s) {
   ProfScope ps("scatter_audio", nullptr, 0, 2.0 * B * n * 4, s);
-  scatter_audio_kernel<<<B, 256, 0, s>>>(audio, audio_all, F, n, frame_idx);
+  launch_k(scatter_audio_kernel, dim3(B), dim3(256), 0, s, audio, audio_all, F, n, frame_idx);
   ++g_launches;
 }
 
 void launch_inc(int* v, int inc, cudaStream_t s) {
   ProfScope ps("inc", nullptr, 0, 0, s);
-  inc_kernel<<<1, 1, 0, s>>>(v, inc);
+  launch_k(inc_kernel, dim3(1), dim3(1), 0, s, v, inc);
   ++g_launches;
 }
 
