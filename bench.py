@@ -36,6 +36,7 @@ sys.path.insert(0, str(REPO))
 
 N_SEQ, N_TOK, VOICE_FRAMES = 256, 60, 125
 FRAME_SEC = 0.08
+PIPELINED = os.environ.get("PTTS_BENCH_SEQUENTIAL", "0") != "1"
 
 
 def _peaks():
@@ -151,6 +152,7 @@ def one_job(model, state, ids, frames, host_io: bool, rng, cap_frames=None):
     h2d = d2h = 0
     try:
         batch.seed(1234)
+        batch.set_pipelined(PIPELINED)   # Mimi decode of frame t-1 overlaps the FlowLM step of frame t
         batch.warmup_mimi(1)
         batch.prefill_text(ids)
         h2d += sum(len(t) for t in ids) * 4
@@ -160,9 +162,13 @@ def one_job(model, state, ids, frames, host_io: bool, rng, cap_frames=None):
                 lat, logit, audio = batch.step(z, want_audio=True)
                 h2d += z.nbytes
                 d2h += lat.nbytes + logit.nbytes + audio.nbytes
+            if PIPELINED:
+                batch.flush()               # audio of the last frame (the first step returned an empty frame)
         else:
             for f in range(frames):
                 batch.step_device()
+            if PIPELINED:
+                batch.flush(want_audio=False)
         model._ctx.sync()
     finally:
         batch.close()

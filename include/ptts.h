@@ -118,6 +118,12 @@ int32_t ptts_batch_step(ptts_batch* batch, const float* noise, float* out_latent
 int32_t ptts_batch_set_prev_latent(ptts_batch* batch, const float* latent);
 /* Same step without the host round trip: results stay on the device (used by bench `value`). */
 int32_t ptts_batch_step_device(ptts_batch* batch);
+/* Throughput mode.  FlowLM step t only needs latent t-1, and so does the Mimi decode of frame t-1, so the two
+ * run as concurrent branches of one CUDA graph.  After ptts_batch_set_pipelined(batch, 1) (before the first
+ * frame) every step returns latent t and EOS logit t but the AUDIO OF FRAME t-1 (zeros at t = 0);
+ * ptts_batch_flush decodes the last frame.  Results are identical to the sequential mode, one frame later. */
+int32_t ptts_batch_set_pipelined(ptts_batch* batch, int32_t on);
+int32_t ptts_batch_flush(ptts_batch* batch, float* out_audio);
 int32_t ptts_batch_seed(ptts_batch* batch, uint64_t seed);
 int32_t ptts_batch_lengths(ptts_batch* batch, int32_t* out_len);
 
@@ -138,6 +144,10 @@ int64_t ptts_launch_count(ptts_ctx* ctx, int32_t reset);
  * stream.  *report points at "kernel:tag,launches,ms,flops,bytes\n" lines (algorithmic flops/bytes of the
  * launches, sorted by time) valid until the next call.  Advances the batch by one frame. */
 int32_t ptts_batch_profile_step(ptts_batch* batch, const char** report);
+/* In-graph timing of the frame's sections (each captured as its own CUDA graph and replayed): ms[0] FlowLM
+ * backbone, ms[1] EOS + flow head, ms[2] Mimi transformer, ms[3] SEANet decoder, ms[4] whole frame.  Perturbs
+ * the batch's streaming state (profiling only).  Returns the number of entries written. */
+int32_t ptts_batch_profile_sections(ptts_batch* batch, float* ms, int32_t cap);
 /* Write an L2-sized scratch buffer (flushes L2 between timed iterations). */
 int32_t ptts_flush_l2(ptts_ctx* ctx);
 /* Stand-alone entry to the multi-tap linear operator, for kernel-level parity tests:
@@ -146,6 +156,13 @@ int32_t ptts_flush_l2(ptts_ctx* ctx);
 int32_t ptts_debug_linear(ptts_ctx* ctx, int32_t path, int32_t n_b, int32_t n_t, int32_t taps,
                           int32_t c_in, int32_t n_out, const float* a, const float* w,
                           const float* bias, float* y);
+
+/* Kernel-level benchmark of the tcgen05 multi-tap GEMM on synthetic bf16 operands (L2 flushed between
+ * launches): median microseconds over `reps`.  force = {N tile, ring stages, split-K, persistent} or NULL for
+ * the planner's choice (returned in chosen[4]); epi = number of bf16 outputs (0: one fp32 output), +4 adds a
+ * bf16 residual read. */
+int32_t ptts_debug_gemm_bench(ptts_ctx* ctx, int32_t n_b, int32_t n_t, int32_t taps, int32_t c_in, int32_t n_out,
+                              int32_t epi, const int32_t* force, int32_t reps, float* us, int32_t* chosen);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ EXPORTED = [
     "ptts_batch_warmup_mimi", "ptts_batch_step", "ptts_batch_set_prev_latent", "ptts_batch_step_device",
     "ptts_batch_seed", "ptts_batch_lengths", "ptts_batch_mimi_decode", "ptts_sync", "ptts_timer_begin",
     "ptts_timer_end", "ptts_launch_count", "ptts_batch_profile_step", "ptts_flush_l2", "ptts_debug_linear",
+    "ptts_debug_gemm_bench", "ptts_batch_profile_sections", "ptts_batch_set_pipelined", "ptts_batch_flush",
 ]
 
 
@@ -90,6 +91,10 @@ def lib() -> C.CDLL:
         "ptts_batch_profile_step": (i32, [vp, C.POINTER(C.c_char_p)]),
         "ptts_flush_l2": (i32, [vp]),
         "ptts_debug_linear": (i32, [vp, i32, i32, i32, i32, i32, i32, f32p, f32p, f32p, f32p]),
+        "ptts_batch_profile_sections": (i32, [vp, f32p, i32]),
+        "ptts_batch_set_pipelined": (i32, [vp, i32]),
+        "ptts_batch_flush": (i32, [vp, f32p]),
+        "ptts_debug_gemm_bench": (i32, [vp, i32, i32, i32, i32, i32, i32, i32p, i32, f32p, i32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -212,6 +217,14 @@ class Context:
     def flush_l2(self):
         check(lib().ptts_flush_l2(self._h))
 
+    def gemm_bench(self, nb, t, taps, c_in, n_out, epi=0, force=None, reps=5):
+        """Median microseconds of the tcgen05 GEMM on synthetic operands -> (us, (bn, stages, splits, persist))."""
+        us = C.c_float()
+        chosen = (C.c_int32 * 4)()
+        f = (C.c_int32 * 4)(*force) if force is not None else None
+        check(lib().ptts_debug_gemm_bench(self._h, nb, t, taps, c_in, n_out, epi, f, reps, C.byref(us), chosen))
+        return float(us.value), tuple(int(x) for x in chosen)
+
     def debug_linear(self, a, w, bias=None, taps=1, path=0):
         """a [nb, T+taps-1, C], w [N, taps*C] -> y [nb, T, N] through the chosen kernel path."""
         a = _f32(a)
@@ -273,6 +286,15 @@ class Batch:
         check(lib().ptts_batch_step(self._h, _fp(z), _fp(lat), _fp(logit), _fp(audio)))
         return lat, logit, audio
 
+    def set_pipelined(self, on: bool = True):
+        """Throughput mode: step() then returns the audio of the PREVIOUS frame; flush() decodes the last one."""
+        check(lib().ptts_batch_set_pipelined(self._h, 1 if on else 0))
+
+    def flush(self, want_audio: bool = True):
+        audio = np.empty((self.n, self.frame_samples), dtype=np.float32) if want_audio else None
+        check(lib().ptts_batch_flush(self._h, _fp(audio)))
+        return audio
+
     def step_device(self):
         check(lib().ptts_batch_step_device(self._h))
 
@@ -294,6 +316,13 @@ class Batch:
         out = np.empty((self.n, f * self.frame_samples), dtype=np.float32) if want_audio else None
         check(lib().ptts_batch_mimi_decode(self._h, _fp(a), f, _fp(out)))
         return out
+
+    def profile_sections(self):
+        """In-graph milliseconds per frame section (perturbs the streaming state; profiling only)."""
+        ms = (C.c_float * 8)()
+        n = check(lib().ptts_batch_profile_sections(self._h, ms, 8))
+        names = ["flow_backbone", "eos_flow_head", "mimi_transformer", "seanet", "whole_frame"]
+        return dict(zip(names, [float(ms[i]) for i in range(n)]))
 
     def profile_step(self):
         """One eager frame with per-kernel CUDA-event timing -> list of dicts sorted by time."""

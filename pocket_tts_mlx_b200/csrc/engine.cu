@@ -112,8 +112,8 @@ struct ptts_batch;
 struct ptts_ctx {
   int device = 0;
   ptts_config cfg{};
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2 carries the Mimi branch of the pipelined frame graph
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
   bool finalized = false;
   bool bf16 = true;
   bool force_simt = false;     // PTTS_FORCE_SIMT=1: keep the CUDA-core GEMMs (A/B comparisons)
@@ -524,9 +524,9 @@ int alloc_flow_work(Ctx& c, FlowWork& w, int M) {
 }
 
 bool plan_tc(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a_rs, int nb, int T, int taps, int C,
-             const LinW& w, const char* tag, int max_splits = 1) {
+             const LinW& w, const char* tag, int max_splits = 1, int n_bf16_out = 0) {
   if (!w.w16 || w.K != taps * C) return false;
-  if (!gemm_tc_plan(g, a, a_bs, a_rs, nb, T, taps, C, w.w16, w.N, tag, max_splits)) return false;
+  if (!gemm_tc_plan(g, a, a_bs, a_rs, nb, T, taps, C, w.w16, w.N, tag, max_splits, n_bf16_out)) return false;
   g->e.bias = w.bias;
   return true;
 }
@@ -542,7 +542,7 @@ int build_flow_plans(Ctx& c, FlowWork& w, int M) {
     // by the next LayerNorm (deterministic order) instead of an epilogue
     bool ok = plan_tc(&g[0], w.h16, 0, D, 1, M, 1, D, l.qkv, "flow.qkv") &&
               plan_tc(&g[1], w.att16, 0, D, 1, M, 1, D, l.out, "flow.out", 8) &&
-              plan_tc(&g[2], w.h16, 0, D, 1, M, 1, D, l.ff1, "flow.ff1") &&
+              plan_tc(&g[2], w.h16, 0, D, 1, M, 1, D, l.ff1, "flow.ff1", 1, 1) &&
               plan_tc(&g[3], w.ff16, 0, FF, 1, M, 1, FF, l.ff2, "flow.ff2", 8);
     if (!ok) return fail(PTTS_ERR_CUDA, "tcgen05 plan failed for FlowLM layer %d (M=%d)", i, M);
     g[0].e.y32 = w.qkv; g[0].e.y32_rs = 3 * D;
@@ -551,6 +551,7 @@ int build_flow_plans(Ctx& c, FlowWork& w, int M) {
     g[2].e.act = ACT_GELU; g[2].e.y16 = w.ff16; g[2].e.y16_rs = FF;
     g[3].e.res32 = w.x; g[3].e.res32_rs = D; g[3].e.y32 = w.x; g[3].e.y32_rs = D;
     g[3].split_ws = w.ws_ff2;
+    gemm_tc_bind_outputs(&g[2]);
   }
   w.plan_M = M;
   return 0;
@@ -666,6 +667,13 @@ struct ptts_batch {
   // graphs: index = host_noise*2 + copy_out
   cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr};
   long long step_graph_launches[4] = {0, 0, 0, 0};
+  // pipelined mode: frame graph = { FlowLM step t } || { Mimi decode of latent t-1 } on two streams.
+  // Latents ping-pong between d_latent (even frames) and d_latent_b (odd frames); index = parity*2 + host_io.
+  bool pipelined = false;
+  long long frame_idx = 0;          // frames stepped since the last (re)initialisation
+  float* d_latent_b = nullptr;
+  cudaGraphExec_t pipe_graph[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long pipe_graph_launches[4] = {0, 0, 0, 0};
   std::map<int, std::pair<cudaGraphExec_t, long long>> mimi_graphs;   // keyed by n_frames
   float *d_lat_all = nullptr, *d_audio_all = nullptr;
   long long lat_all_cap = 0;
@@ -681,7 +689,7 @@ namespace {
 
 using Batch = ptts_batch;
 
-void mimi_frame_tc(Batch& bt, const float* latent);
+void mimi_frame_tc(Batch& bt, const float* latent, int part = 0);
 
 // one Mimi frame for every sequence: latent [B][L] -> audio [B][frame_samples]
 void mimi_frame(Batch& bt, const float* latent) {
@@ -788,10 +796,11 @@ void mimi_frame(Batch& bt, const float* latent) {
 
 // Mimi frame on the tensor-core path: bf16 operands everywhere, every conv / transposed conv / linear is a
 // tcgen05 GEMM whose epilogue already writes the next GEMM's (ELU'd) bf16 input, incl. the carried state rows.
-void mimi_frame_tc(Batch& bt, const float* latent) {
+void mimi_frame_tc(Batch& bt, const float* latent, int part) {   // part: 0 all, 1 transformer, 2 SEANet
   Ctx& c = *bt.ctx;
   const ptts_config& g = c.cfg;
   const int B = bt.B, T = bt.T0, MD = g.mimi_d, SD = g.seanet_dim;
+  if (part != 2) {
   launch_quant_upsample(latent, c.emb_std, c.emb_mean, c.wq, c.wu, bt.d_zprev, bt.d_xm, (long long)T * SD, B,
                         g.latent_dim, SD, g.upsample_stride, c.stream);
   for (int i = 0; i < g.mimi_layers; ++i) {
@@ -816,6 +825,8 @@ void mimi_frame_tc(Batch& bt, const float* latent) {
     gemm_tc_launch(gm[2], c.stream);
     gemm_tc_launch(gm[3], c.stream);
   }
+  }
+  if (part == 1) return;
   gemm_tc_launch(bt.g_conv0, c.stream);
   for (auto& sb : bt.sb16) {
     gemm_tc_launch(sb.ct, c.stream);
@@ -866,7 +877,7 @@ int build_batch_tc(Batch& t) {
     bool ok = true;
     t.g_cond.assign(g.lsd_decode_steps, TcGemm{});
     for (int i = 0; i < g.lsd_decode_steps && ok; ++i) {
-      ok = plan_tc(&t.g_cond[i], t.d_c16, 0, D, 1, B, 1, D, c.cond, "head.cond");
+      ok = plan_tc(&t.g_cond[i], t.d_c16, 0, D, 1, B, 1, D, c.cond, "head.cond", 1, 1);
       t.g_cond[i].e.bias = c.cond_bias_step[i];
       t.g_cond[i].e.act = ACT_SILU;
       t.g_cond[i].e.y16 = t.d_sy16; t.g_cond[i].e.y16_rs = fd;
@@ -876,7 +887,7 @@ int build_batch_tc(Batch& t) {
     t.g_m1.assign(g.flow_depth, TcGemm{});
     t.g_m2.assign(g.flow_depth, TcGemm{});
     for (int r = 0; r < g.flow_depth && ok; ++r) {
-      ok = plan_tc(&t.g_m1[r], t.d_hh16, 0, fd, 1, B, 1, fd, c.rb[r].m1, "head.m1") &&
+      ok = plan_tc(&t.g_m1[r], t.d_hh16, 0, fd, 1, B, 1, fd, c.rb[r].m1, "head.m1", 1, 1) &&
            plan_tc(&t.g_m2[r], t.d_u16, 0, fd, 1, B, 1, fd, c.rb[r].m2, "head.m2");
       t.g_m1[r].e.act = ACT_SILU; t.g_m1[r].e.y16 = t.d_u16; t.g_m1[r].e.y16_rs = fd;
       auto& e = t.g_m2[r].e;
@@ -887,6 +898,8 @@ int build_batch_tc(Batch& t) {
     t.g_fin.e.out_scale = 1.0f / (float)g.lsd_decode_steps;
     t.g_fin.e.res32 = t.d_x; t.g_fin.e.res32_rs = L; t.g_fin.e.y32 = t.d_x; t.g_fin.e.y32_rs = L;
     if (!ok) return fail(PTTS_ERR_CUDA, "tcgen05 plan failed for the flow head (B=%d)", B);
+    for (auto& gm : t.g_cond) gemm_tc_bind_outputs(&gm);
+    for (auto& gm : t.g_m1) gemm_tc_bind_outputs(&gm);
   }
   if (t.tc_mimi) {
     const int T = t.T0, MD = g.mimi_d, SD = g.seanet_dim, FFm = g.mimi_ffn, k0 = g.kernel_size, rk = g.res_kernel_size;
@@ -905,8 +918,8 @@ int build_batch_tc(Batch& t) {
       TcGemm* gm = &t.g_mimi[(size_t)i * 4];
       ok = plan_tc(&gm[0], t.d_mh16, (long long)T * MD, MD, B, T, 1, MD, l.qkv, "mimi.qkv") &&
            plan_tc(&gm[1], t.d_matt16, (long long)T * MD, MD, B, T, 1, MD, l.out, "mimi.out") &&
-           plan_tc(&gm[2], t.d_mh16, (long long)T * MD, MD, B, T, 1, MD, l.ff1, "mimi.ff1") &&
-           plan_tc(&gm[3], t.d_mff16, (long long)T * FFm, FFm, B, T, 1, FFm, l.ff2, "mimi.ff2");
+           plan_tc(&gm[2], t.d_mh16, (long long)T * MD, MD, B, T, 1, MD, l.ff1, "mimi.ff1", 1, 1) &&
+           plan_tc(&gm[3], t.d_mff16, (long long)T * FFm, FFm, B, T, 1, FFm, l.ff2, "mimi.ff2", 1, i == g.mimi_layers - 1 ? 1 : 0);
       gm[0].e.y32 = t.d_mqkv; gm[0].e.y32_bs = (long long)T * 3 * MD; gm[0].e.y32_rs = 3 * MD;
       for (int k : {1, 3}) {
         auto& e = gm[k].e;
@@ -937,7 +950,7 @@ int build_batch_tc(Batch& t) {
     RET(bz(&t.d_fin16, (size_t)B * (Tin + c.fin_taps - 1) * c.fin_c));
     if (c.fin_taps > 1) sh.push_back({t.d_fin16, (long long)(Tin + c.fin_taps - 1) * c.fin_c, Tin, c.fin_taps - 1, c.fin_c, 2});
     // conv0: ELU'd output lands behind the one state row of the first transposed conv
-    ok = ok && plan_tc(&t.g_conv0, t.d_c0_16, (long long)(T + k0 - 1) * SD, SD, B, T, k0, SD, c.conv0, "sn.conv0");
+    ok = ok && plan_tc(&t.g_conv0, t.d_c0_16, (long long)(T + k0 - 1) * SD, SD, B, T, k0, SD, c.conv0, "sn.conv0", 1, 1);
     {
       auto& e = t.g_conv0.e;
       const int c1 = c.stages[0].c_in;
@@ -950,9 +963,9 @@ int build_batch_tc(Batch& t) {
       auto& st = c.stages[r];
       auto& b = t.sb16[r];
       const long long r_bs = (long long)(b.T_out + rk - 1) * st.c_out;
-      ok = plan_tc(&b.ct, b.ct_in, (long long)(b.T_in + 1) * st.c_in, st.c_in, B, b.T_in, 2, st.c_in, st.ct, kCt[r]) &&
-           plan_tc(&b.r3, b.r_in, r_bs, st.c_out, B, b.T_out, rk, st.c_out, st.r3, kR3[r]) &&
-           plan_tc(&b.r1, b.hid, (long long)b.T_out * st.hidden, st.hidden, B, b.T_out, 1, st.hidden, st.r1, kR1[r]);
+      ok = plan_tc(&b.ct, b.ct_in, (long long)(b.T_in + 1) * st.c_in, st.c_in, B, b.T_in, 2, st.c_in, st.ct, kCt[r], 1, 2) &&
+           plan_tc(&b.r3, b.r_in, r_bs, st.c_out, B, b.T_out, rk, st.c_out, st.r3, kR3[r], 1, 1) &&
+           plan_tc(&b.r1, b.hid, (long long)b.T_out * st.hidden, st.hidden, B, b.T_out, 1, st.hidden, st.r1, kR1[r], 1, 1);
       if (!ok) break;
       {  // transposed conv: x (raw, residual) and ELU(x) (resblock input, behind its state rows)
         auto& e = b.ct.e;
@@ -977,6 +990,13 @@ int build_batch_tc(Batch& t) {
       }
     }
     if (!ok) return fail(PTTS_ERR_CUDA, "tcgen05 plan failed for the Mimi decoder (B=%d)", B);
+    for (auto& gm : t.g_mimi) gemm_tc_bind_outputs(&gm);
+    gemm_tc_bind_outputs(&t.g_conv0);
+    for (auto& b : t.sb16) {
+      gemm_tc_bind_outputs(&b.ct);
+      gemm_tc_bind_outputs(&b.r3);
+      gemm_tc_bind_outputs(&b.r1);
+    }
     t.n_shift = (int)sh.size();
     RET(t.dalloc((void**)&t.d_shift, sh.size() * sizeof(ShiftEntry)));
     CU(cudaMemcpyAsync(t.d_shift, sh.data(), sh.size() * sizeof(ShiftEntry), cudaMemcpyHostToDevice, c.stream));
@@ -985,14 +1005,20 @@ int build_batch_tc(Batch& t) {
 }
 
 // FlowLM decode step + EOS + flow head; leaves the new latent in d_latent
-void flow_step(Batch& bt, bool host_noise) {
+void flow_step(Batch& bt, bool host_noise, int part = 0, const float* lat_in = nullptr, float* lat_out = nullptr) {
+  // part: 0 all, 1 backbone, 2 EOS + flow head; lat_in / lat_out default to the single latent buffer
   Ctx& c = *bt.ctx;
+  if (!lat_in) lat_in = bt.d_latent;
+  if (!lat_out) lat_out = bt.d_latent;
   const ptts_config& g = c.cfg;
   const int B = bt.B, D = g.d_model, L = g.latent_dim, fd = g.flow_dim;
-  launch_input_rows(c.w_in, c.bos, bt.d_latent, bt.d_bos, bt.fw.x, B, D, L, c.stream);
-  long long total_keys = 0;
-  for (int l : bt.h_len) total_keys += l + 1;
-  flow_layers(c, bt.fw, B, nullptr, bt.d_len, bt.d_page_table, bt.max_pages, total_keys);
+  if (part != 2) {
+    launch_input_rows(c.w_in, c.bos, lat_in, bt.d_bos, bt.fw.x, B, D, L, c.stream);
+    long long total_keys = 0;
+    for (int l : bt.h_len) total_keys += l + 1;
+    flow_layers(c, bt.fw, B, nullptr, bt.d_len, bt.d_page_table, bt.max_pages, total_keys);
+  }
+  if (part == 1) return;
   launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.tc_head ? bt.d_c16 : nullptr,
                         bt.d_logit, B, D, bt.fw.ws_ff2, bt.fw.pend_n, (long long)B * D, c.stream);
   launch_noise_prep(bt.d_noise, bt.d_x, B * L, sqrtf(g.temp), (g.noise_clamp >= 0.f) ? g.noise_clamp : -1.f,
@@ -1000,7 +1026,7 @@ void flow_step(Batch& bt, bool host_noise) {
   const int n = g.lsd_decode_steps;
   if (bt.tc_head) {
     flow_head_tc(bt);
-    cudaMemcpyAsync(bt.d_latent, bt.d_x, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, c.stream);
+    cudaMemcpyAsync(lat_out, bt.d_x, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, c.stream);
     return;
   }
   for (int i = 0; i < n; ++i) {
@@ -1028,7 +1054,7 @@ void flow_step(Batch& bt, bool host_noise) {
     fo.res = bt.d_x; fo.res_bs = 0; fo.res_rs = L;
     run_linear(c, c.fin, fo);
   }
-  cudaMemcpyAsync(bt.d_latent, bt.d_x, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, c.stream);
+  cudaMemcpyAsync(lat_out, bt.d_x, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, c.stream);
 }
 
 void full_step(Batch& bt, bool host_noise, bool copy_out) {
@@ -1045,6 +1071,72 @@ void full_step(Batch& bt, bool host_noise, bool copy_out) {
     cudaMemcpyAsync(bt.h_audio, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost,
                     c.stream);
   }
+}
+
+// Pipelined frame t >= 1 (parity = t & 1): FlowLM step t reads latent t-1 and writes latent t on the main stream
+// while the Mimi decoder turns latent t-1 into audio on the second stream; host_io adds the noise upload and the
+// result downloads (latent t, EOS logit t, audio t-1).
+void pipelined_frame(Batch& bt, int parity, bool host_io) {
+  Ctx& c = *bt.ctx;
+  const int B = bt.B, L = c.cfg.latent_dim;
+  float* lat_cur = parity ? bt.d_latent_b : bt.d_latent;
+  float* lat_prev = parity ? bt.d_latent : bt.d_latent_b;
+  cudaStream_t main = c.stream;
+  cudaEventRecord(c.ev_fork, main);
+  cudaStreamWaitEvent(c.stream2, c.ev_fork, 0);
+  c.stream = c.stream2;                                   // every launcher below targets the Mimi branch
+  mimi_frame(bt, lat_prev);
+  launch_advance(nullptr, nullptr, bt.d_mimi_off, nullptr, B, 0, bt.T0, c.stream);
+  if (host_io)
+    cudaMemcpyAsync(bt.h_audio, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+  cudaEventRecord(c.ev_join, c.stream2);
+  c.stream = main;
+  if (host_io)
+    cudaMemcpyAsync(bt.d_noise, bt.h_noise, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
+  flow_step(bt, host_io, 0, lat_prev, lat_cur);
+  launch_advance(bt.d_len, bt.d_bos, nullptr, bt.d_counter, B, 1, 0, c.stream);
+  if (host_io) {
+    cudaMemcpyAsync(bt.h_latent, lat_cur, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpyAsync(bt.h_logit, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+  }
+  cudaStreamWaitEvent(main, c.ev_join, 0);
+}
+
+int run_pipelined_step(Batch& bt, bool host_io) {
+  Ctx& c = *bt.ctx;
+  const int B = bt.B, L = c.cfg.latent_dim;
+  if (bt.frame_idx == 0) {
+    // first frame: nothing to decode yet -> FlowLM step only (eager), writes latent 0 into the even buffer
+    if (host_io)
+      CU(cudaMemcpyAsync(bt.d_noise, bt.h_noise, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    flow_step(bt, host_io, 0, bt.d_latent, bt.d_latent);
+    launch_advance(bt.d_len, bt.d_bos, nullptr, bt.d_counter, B, 1, 0, c.stream);
+    if (host_io) {
+      CU(cudaMemcpyAsync(bt.h_latent, bt.d_latent, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+      CU(cudaMemcpyAsync(bt.h_logit, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+      CU(cudaMemsetAsync(bt.d_audio, 0, (size_t)B * bt.frame_samples * sizeof(float), c.stream));
+      CU(cudaMemcpyAsync(bt.h_audio, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+    }
+  } else {
+    const int parity = (int)(bt.frame_idx & 1);
+    const int idx = parity * 2 + (host_io ? 1 : 0);
+    if (!bt.pipe_graph[idx]) {
+      const long long before = g_launches;
+      cudaGraph_t graph;
+      CU(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed));
+      pipelined_frame(bt, parity, host_io);
+      CU(cudaStreamEndCapture(c.stream, &graph));
+      bt.pipe_graph_launches[idx] = g_launches - before;
+      g_launches = before;
+      CU(cudaGraphInstantiate(&bt.pipe_graph[idx], graph, 0));
+      CU(cudaGraphDestroy(graph));
+    }
+    CU(cudaGraphLaunch(bt.pipe_graph[idx], c.stream));
+    g_launches += bt.pipe_graph_launches[idx];
+  }
+  bt.frame_idx += 1;
+  for (auto& l : bt.h_len) l += 1;
+  return 0;
 }
 
 int ensure_step_graph(Batch& bt, bool host_noise, bool copy_out) {
@@ -1128,8 +1220,11 @@ int32_t ptts_ctx_create(int32_t device, const ptts_config* cfg, ptts_ctx** out) 
     g_pdl_on = np && np[0] == '1';
   }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
+  CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   gemm_tc_init();
   *out = c.release();
   return 0;
@@ -1146,6 +1241,9 @@ void ptts_ctx_destroy(ptts_ctx* c) {
   if (c->l2_scratch) cudaFree(c->l2_scratch);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev_fork);
+  cudaEventDestroy(c->ev_join);
+  cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1253,6 +1351,8 @@ static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32
   t.max_len.assign(max_len, max_len + B);
   t.h_len.resize(B);
   t.prefilled = false;
+  t.frame_idx = 0;
+  t.pipelined = false;
   std::vector<int> pt((size_t)B * maxp, 0), src, dst;
   for (int b = 0; b < B; ++b) {
     const Voice& v = c->voices[voice_ids[b]];
@@ -1336,6 +1436,7 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
   RET(fz(&t.d_noise, (size_t)B * L));
   RET(fz(&t.d_x, (size_t)B * L));
   RET(fz(&t.d_latent, (size_t)B * L));
+  RET(fz(&t.d_latent_b, (size_t)B * L));
   RET(fz(&t.d_zero_lat, (size_t)B * L));
   RET(fz(&t.d_c, (size_t)B * D));
   RET(fz(&t.d_logit, B));
@@ -1402,6 +1503,7 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
 static void batch_free(ptts_batch* bt) {
   Ctx* c = bt->ctx;
   for (auto& g : bt->step_graph) if (g) cudaGraphExecDestroy(g);
+  for (auto& g : bt->pipe_graph) if (g) cudaGraphExecDestroy(g);
   for (auto& kv : bt->mimi_graphs) cudaGraphExecDestroy(kv.second.first);
   free_flow_work(bt->fw);
   for (void* p : bt->allocs) cudaFree(p);
@@ -1495,7 +1597,13 @@ int32_t ptts_batch_step(ptts_batch* bt, const float* noise, float* out_latent, f
   const int B = bt->B, L = c.cfg.latent_dim;
   const bool copy_out = out_latent || out_eos_logit || out_audio;
   if (noise) memcpy(bt->h_noise, noise, (size_t)B * L * 4);
-  RET(run_step(*bt, noise != nullptr, copy_out));
+  if (bt->pipelined) {
+    if (!noise) return fail(PTTS_ERR_INVALID, "pipelined host steps take host noise (use ptts_batch_step_device otherwise)");
+    RET(run_pipelined_step(*bt, true));
+  } else {
+    RET(run_step(*bt, noise != nullptr, copy_out));
+    bt->frame_idx += 1;
+  }
   CU(cudaStreamSynchronize(c.stream));
   if (out_latent) memcpy(out_latent, bt->h_latent, (size_t)B * L * 4);
   if (out_eos_logit) memcpy(out_eos_logit, bt->h_logit, (size_t)B * 4);
@@ -1507,14 +1615,42 @@ int32_t ptts_batch_step_device(ptts_batch* bt) {
   if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
   CU(cudaSetDevice(bt->ctx->device));
   RET(check_step_ready(*bt));
+  if (bt->pipelined) return run_pipelined_step(*bt, false);
+  bt->frame_idx += 1;
   return run_step(*bt, false, false);
+}
+
+int32_t ptts_batch_set_pipelined(ptts_batch* bt, int32_t on) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  if (bt->frame_idx != 0) return fail(PTTS_ERR_STATE, "pipelining can only be switched before the first frame");
+  bt->pipelined = on != 0;
+  return 0;
+}
+
+int32_t ptts_batch_flush(ptts_batch* bt, float* out_audio) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  if (!bt->pipelined || bt->frame_idx == 0) return fail(PTTS_ERR_STATE, "nothing to flush");
+  // decode the latent of the last stepped frame (it sits in the buffer of parity (frame_idx-1)&1)
+  const float* lat = ((bt->frame_idx - 1) & 1) ? bt->d_latent_b : bt->d_latent;
+  mimi_frame(*bt, lat);
+  launch_advance(nullptr, nullptr, bt->d_mimi_off, nullptr, bt->B, 0, bt->T0, c.stream);
+  if (out_audio)
+    CU(cudaMemcpyAsync(bt->h_audio, bt->d_audio, (size_t)bt->B * bt->frame_samples * 4, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  CU(cudaGetLastError());
+  if (out_audio) memcpy(out_audio, bt->h_audio, (size_t)bt->B * bt->frame_samples * 4);
+  return 0;
 }
 
 int32_t ptts_batch_set_prev_latent(ptts_batch* bt, const float* latent) {
   if (!bt || !latent) return fail(PTTS_ERR_INVALID, "null argument");
   Ctx& c = *bt->ctx;
   CU(cudaSetDevice(c.device));
-  CU(cudaMemcpyAsync(bt->d_latent, latent, (size_t)bt->B * c.cfg.latent_dim * 4, cudaMemcpyHostToDevice, c.stream));
+  // the next FlowLM step reads the latent of frame frame_idx-1: in pipelined mode that is the ping-pong buffer
+  float* dst = (bt->pipelined && ((bt->frame_idx - 1) & 1)) ? bt->d_latent_b : bt->d_latent;
+  CU(cudaMemcpyAsync(dst, latent, (size_t)bt->B * c.cfg.latent_dim * 4, cudaMemcpyHostToDevice, c.stream));
   CU(cudaStreamSynchronize(c.stream));
   return 0;
 }
@@ -1629,6 +1765,44 @@ int32_t ptts_batch_profile_step(ptts_batch* bt, const char** report) {
   return 0;
 }
 
+int32_t ptts_batch_profile_sections(ptts_batch* bt, float* ms, int32_t cap) {
+  if (!bt || !ms || cap < 5) return fail(PTTS_ERR_INVALID, "bad arguments");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  RET(check_step_ready(*bt));
+  if (!bt->tc_mimi) return fail(PTTS_ERR_STATE, "section profile needs the tensor-core pipeline (batch >= 2, bf16)");
+  const long long before = g_launches;
+  for (int sec = 0; sec < 5; ++sec) {
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    CU(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed));
+    switch (sec) {
+      case 0: flow_step(*bt, false, 1); break;                 // FlowLM backbone (input, 6 layers)
+      case 1: flow_step(*bt, false, 2); break;                 // out-norm + EOS + flow head
+      case 2: mimi_frame_tc(*bt, bt->d_latent, 1); break;      // quantizer/upsample + Mimi transformer
+      case 3: mimi_frame_tc(*bt, bt->d_latent, 2); break;      // SEANet decoder
+      default: full_step(*bt, false, false); break;            // whole frame (advances the batch)
+    }
+    CU(cudaStreamEndCapture(c.stream, &graph));
+    CU(cudaGraphInstantiate(&exec, graph, 0));
+    CU(cudaGraphDestroy(graph));
+    const int reps = (sec == 4) ? 4 : 10;
+    for (int i = 0; i < 2; ++i) CU(cudaGraphLaunch(exec, c.stream));
+    CU(cudaEventRecord(c.ev0, c.stream));
+    for (int i = 0; i < reps; ++i) CU(cudaGraphLaunch(exec, c.stream));
+    CU(cudaEventRecord(c.ev1, c.stream));
+    CU(cudaEventSynchronize(c.ev1));
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, c.ev0, c.ev1));
+    ms[sec] = t / reps;
+    if (sec == 4) for (auto& l : bt->h_len) l += reps + 2;
+    cudaGraphExecDestroy(exec);
+  }
+  g_launches = before;
+  CU(cudaGetLastError());
+  return 5;
+}
+
 int32_t ptts_flush_l2(ptts_ctx* c) {
   if (!c) return fail(PTTS_ERR_INVALID, "null ctx");
   CU(cudaSetDevice(c->device));
@@ -1637,6 +1811,16 @@ int32_t ptts_flush_l2(ptts_ctx* c) {
     CU(cudaMalloc(&c->l2_scratch, c->l2_bytes));
   }
   launch_fill_u32((unsigned*)c->l2_scratch, 0u, (long long)(c->l2_bytes / 4), c->stream);
+  return 0;
+}
+
+int32_t ptts_debug_gemm_bench(ptts_ctx* c, int32_t nb, int32_t T, int32_t taps, int32_t C, int32_t N, int32_t epi,
+                              const int32_t* force, int32_t reps, float* us, int32_t* chosen) {
+  if (!c || !us || !chosen) return fail(PTTS_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(c->device));
+  const int r = gemm_tc_bench(nb, T, taps, C, N, epi, force, reps, us, chosen, c->stream);
+  if (r == -1) return fail(PTTS_ERR_INVALID, "configuration not supported by the tcgen05 GEMM");
+  if (r < 0) return fail(PTTS_ERR_CUDA, "gemm bench failed: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
 

@@ -24,7 +24,9 @@ constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 
 struct KArgs {
   int nb, T, taps, C, N;
-  int box_t, box_b, tiles_t;
+  int box_t, box_b, tiles_t, m_tiles;
+  int tma_store;                // bf16 outputs leave through smem + TMA bulk stores
+  int stg_tiles;                // 16 KB staging tiles behind the operand ring
   int splits;                   // gridDim.z; split z covers k-iterations [z*ips, (z+1)*ips)
   long long split_stride;       // elements between the partial planes of split_ws
   float* split_ws;
@@ -119,29 +121,44 @@ __device__ __forceinline__ void act32(float (&v)[32], int act) {
   }
 }
 
-template <int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
-                                                           const __grid_constant__ CUtensorMap tm_b, const KArgs g) {
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// Persistent, warp-specialised kernel.  grid = min(#tiles, resident CTAs); every role walks the same static
+// tile list (tile = blockIdx.x + k * gridDim.x; n-tile fastest, then m-tile, then split-K slice):
+//   warp 0   : TMA producer; its stage counter runs across tiles, so the loads of tile i+1 are in flight while
+//              tile i is still being multiplied / drained;
+//   warp 1   : tcgen05.mma issuer; two TMEM accumulator stages (tmem_full / tmem_empty mbarriers), so the MMAs
+//              of tile i+1 overlap the epilogue of tile i;
+//   warps 2-9: epilogue (TMEM lane quadrant = warp % 4, two warps per quadrant split the columns).
+template <int BN, int BK, int STAGES, int ACC>   // ACC = TMEM accumulator stages: 2 persistent, 1 one tile per CTA
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
+                                                              const __grid_constant__ CUtensorMap tm_b,
+                                                              const __grid_constant__ CUtensorMap tm_y16,
+                                                              const __grid_constant__ CUtensorMap tm_yraw16,
+                                                              const KArgs g) {
   constexpr int ROW_BYTES = BK * 2;
   constexpr int A_BYTES = 128 * ROW_BYTES, B_BYTES = BN * ROW_BYTES;
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int TMEM_COLS = ACC * BN < 32 ? 32 : ACC * BN;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base, sB = base + STAGES * A_BYTES;
-  const uint32_t bars = sB + STAGES * B_BYTES;
-  // bars: full[STAGES], empty[STAGES], tmem_full ; then the TMEM base address word
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tptr = tfull + 8;
+  // staging tiles for TMA stores: behind the ring when persistent (the producer is already refilling the ring
+  // for the next tile), on top of the idle ring when the CTA owns a single tile
+  const uint32_t stg = (ACC == 2) ? sB + STAGES * B_BYTES : base;
+  const uint32_t bars = sB + STAGES * B_BYTES + ((ACC == 2) ? (uint32_t)g.stg_tiles * 16384u : 0u);
+  // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base address word
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16,
+                 tptr = tempty0 + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int tile_b = blockIdx.y / g.tiles_t, tile_t = blockIdx.y % g.tiles_t;
-  const int b0 = tile_b * g.box_b, t0 = tile_t * g.box_t;
   const int kc_per_tap = g.C / BK;
-  const int iters_all = g.taps * kc_per_tap;
-  const int ips = iters_all / g.splits;
-  const int it0 = blockIdx.z * ips;
-  const int iters = ips;
+  const int ips = (g.taps * kc_per_tap) / g.splits;       // k-iterations per tile
+  const int n_nt = g.N / BN;
+  const int total_tiles = n_nt * g.m_tiles * g.splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
@@ -150,7 +167,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
       mbar_init(full0 + 8 * i, 1);
       mbar_init(empty0 + 8 * i, 1);
     }
-    mbar_init(tfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, 8);      // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -160,154 +180,223 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  uint32_t tmem_acc;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_acc) : "r"(tptr));
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
   // barriers, TMEM and descriptors are set up; everything below touches the predecessor's output
   pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES, ph = (it / STAGES) & 1;
-        const int git = it0 + it;
-        const int tap = git / kc_per_tap, kc = git - tap * kc_per_tap;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
-        tma_load_3d(sA + s * A_BYTES, &tm_a, full0 + 8 * s, kc * BK, t0 + tap, b0);
-        tma_load_2d(sB + s * B_BYTES, &tm_b, full0 + 8 * s, tap * g.C + kc * BK, n0);
+      uint32_t git = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % n_nt, mt = (tile / n_nt) % g.m_tiles, z = tile / (n_nt * g.m_tiles);
+        const int n0 = nt * BN;
+        const int b0 = (mt / g.tiles_t) * g.box_b, t0 = (mt % g.tiles_t) * g.box_t;
+        for (int it = 0; it < ips; ++it, ++git) {
+          const int s = git % STAGES, ph = (git / STAGES) & 1;
+          const int kit = z * ips + it;
+          const int tap = kit / kc_per_tap, kc = kit - tap * kc_per_tap;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+          tma_load_3d(sA + s * A_BYTES, &tm_a, full0 + 8 * s, kc * BK, t0 + tap, b0);
+          tma_load_2d(sB + s * B_BYTES, &tm_b, full0 + 8 * s, tap * g.C + kc * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<BN>();
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES, ph = (it / STAGES) & 1;
-        mbar_wait(full0 + 8 * s, ph);
+      uint32_t git = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t as = (ACC == 2) ? (tcount & 1) : 0, aph = (ACC == 2) ? ((tcount >> 1) & 1) : (tcount & 1);
+        mbar_wait(tempty0 + 8 * as, aph ^ 1);         // the epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint64_t da = make_desc<ROW_BYTES>(sA + s * A_BYTES);
-        const uint64_t db = make_desc<ROW_BYTES>(sB + s * B_BYTES);
+        const uint32_t tmem_acc = tmem_base + as * BN;
+        for (int it = 0; it < ips; ++it, ++git) {
+          const int s = git % STAGES, ph = (git / STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t da = make_desc<ROW_BYTES>(sA + s * A_BYTES);
+          const uint64_t db = make_desc<ROW_BYTES>(sB + s * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          tc_mma(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
-        tc_commit(empty0 + 8 * s);    // frees the stage once these MMAs have read it
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+          tc_commit(empty0 + 8 * s);    // frees the stage once these MMAs have read it
+        }
+        tc_commit(tfull0 + 8 * as);     // accumulator complete
       }
-      tc_commit(tfull);               // accumulator complete
     }
   } else {
-    // ---- epilogue: warps 2..9; TMEM lane quadrant = warp % 4, two warps per quadrant split the columns ----
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int CHUNKS = BN / 32;
-    const int r = quad * 32 + lane;                       // accumulator row within the tile
-    const int b = b0 + r / g.box_t, t = t0 + r % g.box_t;
-    const bool row_ok = (b < g.nb) && (t < g.T);
     const TcEpilogue& e = g.e;
     const float oscale = e.out_scale == 0.f ? 1.f : e.out_scale;
-    mbar_wait(tfull, 0);
-    tc_fence_after();
+    const int r = quad * 32 + lane;                       // accumulator row within the tile
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int nt = tile % n_nt, mt = (tile / n_nt) % g.m_tiles, z = tile / (n_nt * g.m_tiles);
+      const int n0 = nt * BN;
+      const int b0 = (mt / g.tiles_t) * g.box_b, t0 = (mt % g.tiles_t) * g.box_t;
+      const int b = b0 + r / g.box_t, t = t0 + r % g.box_t;
+      const bool row_ok = (b < g.nb) && (t < g.T);
+      const uint32_t as = (ACC == 2) ? (tcount & 1) : 0, aph = (ACC == 2) ? ((tcount >> 1) & 1) : (tcount & 1);
+      if (g.tma_store) {
+        // the previous tile's bulk stores must have finished reading the staging tiles before they are refilled
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+      mbar_wait(tfull0 + 8 * as, aph);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * BN + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-    for (int ch = half; ch < CHUNKS; ch += 2) {
-      const int cb = ch * 32;
-      uint32_t raw[32];
-      __syncwarp();
-      tc_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb, raw);
-      if (row_ok && g.splits > 1) {
-        // split-K: raw fp32 partial; the consumer (LayerNorm) adds the planes to the residual stream
-        float4* yp = reinterpret_cast<float4*>(g.split_ws + blockIdx.z * g.split_stride +
-                                               ((long long)b * g.T + t) * g.N + n0 + cb);
+      for (int ch = half; ch < CHUNKS; ch += 2) {
+        const int cb = ch * 32;
+        uint32_t raw[32];
+        __syncwarp();
+        tc_ld32(tmem_acc + (uint32_t)cb, raw);
+        if (row_ok && g.splits > 1) {
+          // split-K: raw fp32 partial; the consumer (LayerNorm) adds the planes to the residual stream
+          float4* yp = reinterpret_cast<float4*>(g.split_ws + z * g.split_stride + ((long long)b * g.T + t) * g.N + n0 + cb);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          yp[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
-                              __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
-      } else if (row_ok) {
-        const int n = n0 + cb;
-        float v[32];
+          for (int i = 0; i < 8; ++i)
+            yp[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                                __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+        } else if (row_ok) {
+          const int n = n0 + cb;
+          float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        if (e.bias) {
-          const float4* bp = reinterpret_cast<const float4*>(e.bias + n);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          if (e.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(e.bias + n);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 q = __ldg(bp + i);
-            v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = __ldg(bp + i);
+              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            }
           }
-        }
-        act32(v, e.act);
-        if (oscale != 1.f) {
+          act32(v, e.act);
+          if (oscale != 1.f) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= oscale;
-        }
-        if (e.col_scale) {
-          const float4* cp = reinterpret_cast<const float4*>(e.col_scale + n);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 q = __ldg(cp + i);
-            v[4 * i] *= q.x; v[4 * i + 1] *= q.y; v[4 * i + 2] *= q.z; v[4 * i + 3] *= q.w;
+            for (int i = 0; i < 32; ++i) v[i] *= oscale;
           }
-        }
-        if (e.row_gate) {
-          const float4* gp = reinterpret_cast<const float4*>(e.row_gate + b * e.gate_bs + t * e.gate_rs + n);
+          if (e.col_scale) {
+            const float4* cp = reinterpret_cast<const float4*>(e.col_scale + n);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 q = gp[i];
-            v[4 * i] *= q.x; v[4 * i + 1] *= q.y; v[4 * i + 2] *= q.z; v[4 * i + 3] *= q.w;
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = __ldg(cp + i);
+              v[4 * i] *= q.x; v[4 * i + 1] *= q.y; v[4 * i + 2] *= q.z; v[4 * i + 3] *= q.w;
+            }
           }
-        }
-        if (e.res32) {
-          const float4* rp = reinterpret_cast<const float4*>(e.res32 + b * e.res32_bs + t * e.res32_rs + n);
+          if (e.row_gate) {
+            const float4* gp = reinterpret_cast<const float4*>(e.row_gate + b * e.gate_bs + t * e.gate_rs + n);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 q = rp[i];
-            v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = gp[i];
+              v[4 * i] *= q.x; v[4 * i + 1] *= q.y; v[4 * i + 2] *= q.z; v[4 * i + 3] *= q.w;
+            }
           }
-        }
-        if (e.res16) {
-          const uint4* rp = reinterpret_cast<const uint4*>(e.res16 + b * e.res16_bs + t * e.res16_rs + n);
+          if (e.res32) {
+            const float4* rp = reinterpret_cast<const float4*>(e.res32 + b * e.res32_bs + t * e.res32_rs + n);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 q = rp[i];
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = rp[i];
+              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            }
+          }
+          if (e.res16) {
+            const uint4* rp = reinterpret_cast<const uint4*>(e.res16 + b * e.res16_bs + t * e.res16_rs + n);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(h[j]);
-              v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y;
+            for (int i = 0; i < 4; ++i) {
+              const uint4 q = rp[i];
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h[j]);
+                v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y;
+              }
+            }
+          }
+          if (e.y32) {
+            float4* yp = reinterpret_cast<float4*>(e.y32 + b * e.y32_bs + t * e.y32_rs + n);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) yp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (e.yraw16) {
+            if (g.tma_store) {
+              // staging tile of 64-column group j: [128 rows][128 B], 16-byte chunks XOR-swizzled by row % 8
+              const uint32_t tl = stg + (uint32_t)(BN / 64 + cb / 64) * 16384u + (uint32_t)r * 128u;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t chunk = (uint32_t)(((cb & 63) >> 3) + i) ^ (uint32_t)(r & 7);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tl + chunk * 16u),
+                             "r"(pack_bf16(v[8 * i], v[8 * i + 1])), "r"(pack_bf16(v[8 * i + 2], v[8 * i + 3])),
+                             "r"(pack_bf16(v[8 * i + 4], v[8 * i + 5])), "r"(pack_bf16(v[8 * i + 6], v[8 * i + 7])) : "memory");
+              }
+            } else {
+              uint4* yp = reinterpret_cast<uint4*>(e.yraw16 + b * e.yraw16_bs + t * e.yraw16_rs + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                yp[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+            }
+          }
+          if (e.y16) {
+            act32(v, e.y16_act);
+            if (g.tma_store) {
+              const uint32_t tl = stg + (uint32_t)(cb / 64) * 16384u + (uint32_t)r * 128u;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t chunk = (uint32_t)(((cb & 63) >> 3) + i) ^ (uint32_t)(r & 7);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tl + chunk * 16u),
+                             "r"(pack_bf16(v[8 * i], v[8 * i + 1])), "r"(pack_bf16(v[8 * i + 2], v[8 * i + 3])),
+                             "r"(pack_bf16(v[8 * i + 4], v[8 * i + 5])), "r"(pack_bf16(v[8 * i + 6], v[8 * i + 7])) : "memory");
+              }
+            } else {
+              uint4* yp = reinterpret_cast<uint4*>(e.y16 + b * e.y16_bs + t * e.y16_rs + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                yp[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
             }
           }
         }
-        if (e.y32) {
-          float4* yp = reinterpret_cast<float4*>(e.y32 + b * e.y32_bs + t * e.y32_rs + n);
+      }
+      // this warp is done reading the accumulator stage: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * as) : "memory");
+      if (g.tma_store) {
+        // make the generic-proxy writes visible to the async proxy, then one thread issues the bulk tensor
+        // stores; rows beyond T / nb are clipped by the tensor-map bounds
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 2 && lane == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) yp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        if (e.yraw16) {
-          uint4* yp = reinterpret_cast<uint4*>(e.yraw16 + b * e.yraw16_bs + t * e.yraw16_rs + n);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            yp[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                               pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-        }
-        if (e.y16) {
-          act32(v, e.y16_act);
-          uint4* yp = reinterpret_cast<uint4*>(e.y16 + b * e.y16_bs + t * e.y16_rs + n);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            yp[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                               pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+          for (int j = 0; j < BN / 64; ++j) {
+            if (e.y16) tma_store_3d(&tm_y16, stg + (uint32_t)j * 16384u, n0 + 64 * j, t0, b0);
+            if (e.yraw16) tma_store_3d(&tm_yraw16, stg + (uint32_t)(BN / 64 + j) * 16384u, n0 + 64 * j, t0, b0);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
+    if (g.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
 template <int BN, int BK, int STAGES>
-constexpr size_t smem_bytes() {
-  return (size_t)STAGES * (128 * BK * 2 + BN * BK * 2) + 1024 + 16 * STAGES + 32;
+constexpr size_t ring_bytes() {
+  return (size_t)STAGES * (128 * BK * 2 + BN * BK * 2);
+}
+inline size_t smem_total(int bn, int bk, int stages, int stg_tiles) {
+  return (size_t)stages * (128 * bk * 2 + bn * bk * 2) + (size_t)stg_tiles * 16384 + 1024 + 16 * stages + 64;
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -315,11 +404,14 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeFn g_encode = nullptr;
 bool g_init_done = false;
+int g_force[4] = {0, 0, 0, 0};
 
 template <int BN, int BK, int ST>
 void set_attr1() {
-  if (smem_bytes<BN, BK, ST>() <= 227 * 1024)
-    cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, BK, ST>());
+  if (ring_bytes<BN, BK, ST>() <= 200 * 1024) {
+    cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, ST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, ST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
 }
 template <int BN, int BK>
 void set_attr() {
@@ -356,13 +448,13 @@ void gemm_tc_init() {
   else
     cudaGetLastError();
   set_attr<128, 64>(); set_attr<64, 64>(); set_attr<32, 64>();
-  set_attr<128, 32>(); set_attr<64, 32>(); set_attr<32, 32>();
+  set_attr1<128, 32, 2>(); set_attr1<64, 32, 2>(); set_attr1<32, 32, 2>();
 }
 
 bool gemm_tc_available() { return g_encode != nullptr; }
 
 bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a_rs, int nb, int T, int taps, int C,
-                  const __nv_bfloat16* w, int N, const char* tag, int max_splits) {
+                  const __nv_bfloat16* w, int N, const char* tag, int max_splits, int n_bf16_out) {
   g->valid = false;
   if (!g_encode) return false;
   int bk = 0;
@@ -381,35 +473,44 @@ bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a
   const int tiles_t = (T + box_t - 1) / box_t;
   const int tiles_b = (nb + box_b - 1) / box_b;
   const long long m_tiles = (long long)tiles_t * tiles_b;
-  // Tile / split / ring-depth choice by a small cost model (microseconds).  A TMA ring turn costs ~2 us of
-  // latency, so an SM fills shared memory at min(120 GB/s, resident CTAs x stages x stage bytes / 2 us); all SMs
-  // together are limited to ~5 TB/s of L2 -> SM traffic; every tile pays a fixed prologue and an epilogue that
-  // overlaps only with co-resident CTAs.
+  // Tile / split / ring-depth / persistence rules distilled from the measured sweep in
+  // profiles/r01_gemm_tune_b256.txt (tools/gemm_tune.py, kernel-level, L2 flushed):
+  //  * persistent CTAs with the deepest ring that fits win whenever there is more than one tile per SM, even
+  //    for shallow K (the ring then prefetches across tiles);
+  //  * a weight-streaming GEMM with at most two M tiles wants many small CTAs: N tile 64 and, where the consumer
+  //    can add partial planes (out-proj / ffn2 feeding the residual stream), split-K up to ~128 CTAs.
   const int iters = taps * (C / bk);
-  int bn = 0, best_splits = 1, best_stages = 2;
-  double best = 1e30;
-  for (int cand : {128, 64, 32}) {
-    if (N % cand) continue;
-    for (int sp = 1; sp <= max_splits; sp *= 2) {
-      if (iters % sp || (sp > 1 && iters / sp < 2)) continue;
-      const int it = iters / sp;
-      const double stage_bytes = 128.0 * bk * 2 + (double)cand * bk * 2;
-      const double ctas = (double)m_tiles * (N / cand) * sp;
-      for (int st : {2, 4, 6, 8}) {
-        if (st > 2 && st > it + 1) continue;
-        if (st * stage_bytes + 2048 > 220.0 * 1024) continue;
-        int per_sm = (int)(220.0 * 1024 / (st * stage_bytes + 2048));
-        per_sm = per_sm > 4 ? 4 : per_sm;
-        const double per_sm_ctas = std::ceil(ctas / 148.0);
-        const double resident = std::min<double>(per_sm, per_sm_ctas);
-        const double rate = std::min(120e3, resident * st * stage_bytes / 2.0);          // bytes / us / SM
-        const double t_main = per_sm_ctas * it * stage_bytes / rate;
-        const double t_epi = (0.5 + 0.02 * cand) * per_sm_ctas / resident;               // exposed epilogue + prologue
-        const double t_agg = ctas * it * stage_bytes / 5e6;
-        const double t = std::max(t_main, t_agg) + t_epi + 2.0 + (sp > 1 ? 0.3 : 0.0);
-        if (t < best) { best = t; bn = cand; best_splits = sp; best_stages = st; }
+  int bn = 0, best_splits = 1, best_stages = 2, best_persist = 0;
+  const double best = 0.0;
+  {
+    const bool small_m = m_tiles <= 2;
+    if (small_m) bn = (N % 64 == 0) ? 64 : 32;
+    else bn = (N % 128 == 0) ? 128 : ((N % 64 == 0) ? 64 : 32);
+    if (small_m && max_splits > 1) {
+      const long long base_tiles = m_tiles * (N / bn);
+      int sp = 1;
+      while (sp * 2 <= max_splits && base_tiles * sp < 128 && iters % (sp * 2) == 0 && iters / (sp * 2) >= 4) sp *= 2;
+      best_splits = sp;
+    }
+    const long long tiles = m_tiles * (N / bn) * best_splits;
+    best_persist = (!small_m && tiles > 148) ? 1 : 0;
+    const int stg = (bn >= 64) ? n_bf16_out * (bn / 64) : 0;
+    const double stage_bytes = 128.0 * bk * 2 + (double)bn * bk * 2;
+    best_stages = 2;
+    for (int st : {8, 6, 4}) {
+      if (bk == 32) break;
+      if (st == 8 && bn == 128) continue;
+      const double ring = st * stage_bytes;
+      const double smem = (best_persist ? ring + stg * 16384.0 : std::max(ring, stg * 16384.0)) + 2048;
+      if (smem <= 226.0 * 1024 && ring <= 200.0 * 1024 && (best_persist || st <= std::max(2, iters / best_splits))) {
+        best_stages = st;
+        break;
       }
     }
+  }
+  if (g_force[0] > 0) {
+    if (N % g_force[0] || iters % std::max(1, g_force[2])) return false;
+    bn = g_force[0]; best_stages = g_force[1]; best_splits = std::max(1, g_force[2]); best_persist = g_force[3];
   }
   if (!bn) return false;
   {
@@ -427,14 +528,38 @@ bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a
   g->nb = nb; g->T = T; g->taps = taps; g->C = C; g->N = N;
   g->box_t = box_t; g->box_b = box_b; g->bn = bn; g->bk = bk;
   g->stages = best_stages; g->splits = best_splits; g->split_ws = nullptr;
+  g->tm_y16 = g->tm_a; g->tm_yraw16 = g->tm_a; g->tma_store = false;
+  g->stg_tiles = (bn >= 64) ? n_bf16_out * (bn / 64) : 0;
+  g->persist = best_persist;
   g->e = TcEpilogue{};
   g->tag = tag;
   g->valid = true;
   static const bool verbose = [] { const char* v = getenv("PTTS_TC_VERBOSE"); return v && v[0] == '1'; }();
   if (verbose)
-    fprintf(stderr, "[gemm_tc] %-10s nb=%d T=%d taps=%d C=%d N=%d -> box %dx%d bn=%d bk=%d stages=%d splits=%d est=%.1fus\n",
-            tag ? tag : "?", nb, T, taps, C, N, box_b, box_t, bn, bk, best_stages, best_splits, best);
+    fprintf(stderr, "[gemm_tc] %-10s nb=%d T=%d taps=%d C=%d N=%d -> box %dx%d bn=%d bk=%d stages=%d splits=%d persist=%d est=%.1fus\n",
+            tag ? tag : "?", nb, T, taps, C, N, box_b, box_t, bn, bk, best_stages, best_splits, best_persist, best);
   return true;
+}
+
+void gemm_tc_bind_outputs(TcGemm* g) {
+  g->tma_store = false;
+  const TcEpilogue& e = g->e;
+  if (!g->valid || g->bn < 64 || g->splits > 1 || (!e.y16 && !e.yraw16)) return;
+  // y16 tiles come first, yraw16 tiles behind them: 2 x (bn/64) slots when both are written
+  const int need = (e.yraw16 ? 2 : 1) * (g->bn / 64);
+  if (g->stg_tiles < need) return;
+  auto make = [&](CUtensorMap* tm, __nv_bfloat16* y, long long bs, long long rs) -> bool {
+    if ((rs % 8) || (bs % 8) || ((uintptr_t)y & 15)) return false;
+    const bool flat = g->nb == 1;
+    const cuuint64_t dims[3] = {(cuuint64_t)g->N, (cuuint64_t)g->T, (cuuint64_t)g->nb};
+    const cuuint64_t str[2] = {(cuuint64_t)rs * 2, (cuuint64_t)(flat ? (long long)g->T * rs : bs) * 2};
+    const cuuint32_t box[3] = {64u, (cuuint32_t)g->box_t, (cuuint32_t)g->box_b};
+    return encode(tm, y, 3, dims, str, box, 64);
+  };
+  bool ok = true;
+  if (e.y16) ok = ok && make(&g->tm_y16, e.y16, e.y16_bs, e.y16_rs);
+  if (e.yraw16) ok = ok && make(&g->tm_yraw16, e.yraw16, e.yraw16_bs, e.yraw16_rs);
+  g->tma_store = ok;
 }
 
 void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
@@ -442,34 +567,48 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   a.nb = g.nb; a.T = g.T; a.taps = g.taps; a.C = g.C; a.N = g.N;
   a.box_t = g.box_t; a.box_b = g.box_b;
   a.tiles_t = (g.T + g.box_t - 1) / g.box_t;
+  a.m_tiles = a.tiles_t * ((g.nb + g.box_b - 1) / g.box_b);
   a.e = g.e;
+  a.tma_store = (g.tma_store && g.splits == 1) ? 1 : 0;
+  a.stg_tiles = g.stg_tiles;
   a.splits = g.splits; a.split_ws = g.split_ws; a.split_stride = (long long)g.nb * g.T * g.N;
-  const int tiles_b = (g.nb + g.box_b - 1) / g.box_b;
-  dim3 grid(g.N / g.bn, a.tiles_t * tiles_b, g.splits), block(kThreads);
+  const long long tiles = (long long)(g.N / g.bn) * a.m_tiles * g.splits;
+  const size_t ring = (size_t)g.stages * (128 * g.bk * 2 + g.bn * g.bk * 2);
+  const size_t stg_b = (size_t)g.stg_tiles * 16384;
+  const size_t smem = (g.persist ? ring + stg_b : std::max(ring, stg_b)) + 1024 + 16 * g.stages + 64;
+  int per_sm = (int)((227 * 1024) / smem);
+  per_sm = std::max(1, std::min(per_sm, std::min(2, 512 / (2 * g.bn))));
+  dim3 grid((unsigned)(g.persist ? std::min<long long>(tiles, 148LL * per_sm) : tiles)), block(kThreads);
   const double flops = 2.0 * g.nb * g.T * (double)g.N * g.taps * g.C;
   const double bytes = (double)g.N * g.taps * g.C * 2 + (double)g.nb * (g.T + g.taps - 1) * g.C * 2 +
                        (double)g.nb * g.T * g.N * ((g.e.y32 ? 4 : 0) + (g.e.y16 ? 2 : 0) + (g.e.yraw16 ? 2 : 0) +
                                                    (g.e.res32 ? 4 : 0) + (g.e.res16 ? 2 : 0));
   ProfScope ps("gemm_tc", g.tag, flops, bytes, s);
-#define PTTS_TC(BN_, BK_)                                                                                       \
-  do {                                                                                                          \
-    switch (g.stages) {                                                                                         \
-      case 8: launch_k(gemm_tc_kernel<BN_, BK_, 8>, grid, block, smem_bytes<BN_, BK_, 8>(), s, g.tm_a, g.tm_b, a); break; \
-      case 6: launch_k(gemm_tc_kernel<BN_, BK_, 6>, grid, block, smem_bytes<BN_, BK_, 6>(), s, g.tm_a, g.tm_b, a); break; \
-      case 4: launch_k(gemm_tc_kernel<BN_, BK_, 4>, grid, block, smem_bytes<BN_, BK_, 4>(), s, g.tm_a, g.tm_b, a); break; \
-      default: launch_k(gemm_tc_kernel<BN_, BK_, 2>, grid, block, smem_bytes<BN_, BK_, 2>(), s, g.tm_a, g.tm_b, a); break; \
-    }                                                                                                           \
+#define PTTS_TC1(BN_, BK_, ST_)                                                                                  \
+  do {                                                                                                           \
+    if (g.persist) launch_k(gemm_tc_kernel<BN_, BK_, ST_, 2>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, a); \
+    else launch_k(gemm_tc_kernel<BN_, BK_, ST_, 1>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, a);           \
+  } while (0)
+#define PTTS_TC(BN_, BK_)                                                                                        \
+  do {                                                                                                           \
+    switch (g.stages) {                                                                                          \
+      case 8: PTTS_TC1(BN_, BK_, 8); break;                                                                      \
+      case 6: PTTS_TC1(BN_, BK_, 6); break;                                                                      \
+      case 4: PTTS_TC1(BN_, BK_, 4); break;                                                                      \
+      default: PTTS_TC1(BN_, BK_, 2); break;                                                                     \
+    }                                                                                                            \
   } while (0)
   if (g.bk == 64) {
     if (g.bn == 128) PTTS_TC(128, 64);
     else if (g.bn == 64) PTTS_TC(64, 64);
     else PTTS_TC(32, 64);
   } else {
-    if (g.bn == 128) PTTS_TC(128, 32);
-    else if (g.bn == 64) PTTS_TC(64, 32);
-    else PTTS_TC(32, 32);
+    if (g.bn == 128) PTTS_TC1(128, 32, 2);
+    else if (g.bn == 64) PTTS_TC1(64, 32, 2);
+    else PTTS_TC1(32, 32, 2);
   }
 #undef PTTS_TC
+#undef PTTS_TC1
   ++g_launches;
 }
 
@@ -499,4 +638,82 @@ int gemm_tc_debug(const LinearParams& p, bool bf16_storage, cudaStream_t s) {
   return rc;
 }
 
+}  // namespace ptts
+
+namespace ptts {
+namespace {
+__global__ void fill_bf16_kernel(__nv_bfloat16* p, long long n, unsigned seed) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    unsigned h = (unsigned)i * 2654435761u + seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    p[i] = __float2bfloat16_rn(((h & 0xffff) / 32768.0f - 1.0f) * 0.25f);
+  }
+}
+}  // namespace
+
+int gemm_tc_bench(int nb, int T, int taps, int C, int N, int epi, const int force[4], int reps, float* us,
+                  int chosen[4], cudaStream_t s) {
+  if (!g_encode) return -1;
+  const int n_out = epi & 3;
+  const bool res = (epi & 4) != 0;
+  const long long na = (long long)nb * (T + taps - 1) * C, nw = (long long)N * taps * C, ny = (long long)nb * T * N;
+  __nv_bfloat16 *a = nullptr, *w = nullptr, *y16 = nullptr, *yraw = nullptr, *r16 = nullptr;
+  float *y32 = nullptr, *bias = nullptr, *ws = nullptr;
+  void* flush = nullptr;
+  const size_t flush_bytes = 192ull << 20;
+  int rc = 0;
+  auto al = [&](void** p, size_t b) { if (cudaMalloc(p, b) != cudaSuccess) rc = -2; };
+  al((void**)&a, na * 2); al((void**)&w, nw * 2); al((void**)&bias, (size_t)N * 4); al(&flush, flush_bytes);
+  if (n_out >= 1) al((void**)&y16, ny * 2);
+  if (n_out >= 2) al((void**)&yraw, ny * 2);
+  if (n_out == 0) al((void**)&y32, ny * 4);
+  if (res) al((void**)&r16, ny * 2);
+  if (rc == 0) {
+    fill_bf16_kernel<<<1184, 256, 0, s>>>(a, na, 1u);
+    fill_bf16_kernel<<<1184, 256, 0, s>>>(w, nw, 2u);
+    if (r16) fill_bf16_kernel<<<1184, 256, 0, s>>>(r16, ny, 3u);
+    cudaMemsetAsync(bias, 0, (size_t)N * 4, s);
+    for (int i = 0; i < 4; ++i) g_force[i] = force ? force[i] : 0;
+    TcGemm g;
+    const bool ok = gemm_tc_plan(&g, a, (long long)(T + taps - 1) * C, C, nb, T, taps, C, w, N, "bench",
+                                 force && force[2] > 1 ? force[2] : 1, n_out);
+    for (int i = 0; i < 4; ++i) g_force[i] = 0;
+    if (!ok) rc = -1;
+    if (rc == 0) {
+      if (g.splits > 1) { al((void**)&ws, (size_t)g.splits * ny * 4); g.split_ws = ws; }
+      g.e.bias = bias;
+      if (y16) { g.e.y16 = y16; g.e.y16_bs = (long long)T * N; g.e.y16_rs = N; g.e.y16_act = ACT_ELU; }
+      if (yraw) { g.e.yraw16 = yraw; g.e.yraw16_bs = (long long)T * N; g.e.yraw16_rs = N; }
+      if (y32) { g.e.y32 = y32; g.e.y32_bs = (long long)T * N; g.e.y32_rs = N; }
+      if (r16) { g.e.res16 = r16; g.e.res16_bs = (long long)T * N; g.e.res16_rs = N; }
+      gemm_tc_bind_outputs(&g);
+      chosen[0] = g.bn; chosen[1] = g.stages; chosen[2] = g.splits; chosen[3] = g.persist;
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      std::vector<float> t;
+      for (int i = 0; i < reps + 1 && rc == 0; ++i) {
+        cudaMemsetAsync(flush, i, flush_bytes, s);
+        cudaEventRecord(e0, s);
+        gemm_tc_launch(g, s);
+        cudaEventRecord(e1, s);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { rc = -2; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (i > 0) t.push_back(ms * 1000.f);
+      }
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      if (rc == 0 && !t.empty()) {
+        std::sort(t.begin(), t.end());
+        *us = t[t.size() / 2];
+      }
+    }
+  }
+  cudaStreamSynchronize(s);
+  if (cudaGetLastError() != cudaSuccess) rc = -2;
+  for (void* p : {(void*)a, (void*)w, (void*)y16, (void*)yraw, (void*)r16, (void*)y32, (void*)bias, (void*)ws, flush})
+    if (p) cudaFree(p);
+  return rc;
+}
 }  // namespace ptts

@@ -30,10 +30,14 @@ struct TcEpilogue {
 
 struct TcGemm {
   CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_y16, tm_yraw16;   // output maps for the TMA-store epilogue (valid when tma_store)
+  bool tma_store = false;
   int nb, T, taps, C, N;
   int box_t, box_b;           // 128-row M tile = box_b sequences x box_t time steps
   int bn, bk;                 // N tile (32/64/128), K chunk in elements (64 or 32)
-  int stages;                 // smem ring depth (2 or 4)
+  int stages;                 // smem ring depth (2..8)
+  int stg_tiles;              // 16 KB staging tiles for TMA-store outputs
+  int persist;                // 1: persistent CTAs with two TMEM accumulator stages; 0: one tile per CTA
   int splits;                 // split-K factor; > 1: raw fp32 partials go to split_ws[z][nb*T][N], epilogue skipped
   float* split_ws;
   TcEpilogue e;
@@ -46,10 +50,19 @@ bool gemm_tc_available();
 // Describe one GEMM call site.  a: bf16 [nb][T+taps-1][C] with strides (a_bs, a_rs) in elements;
 // w: bf16 [N][taps*C].  Returns false when the shape is unsupported (caller keeps the SIMT path).
 bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a_rs, int nb, int T, int taps, int C,
-                  const __nv_bfloat16* w, int N, const char* tag, int max_splits = 1);
+                  const __nv_bfloat16* w, int N, const char* tag, int max_splits = 1, int n_bf16_out = 0);
+// Call after the epilogue pointers are set: bf16 outputs of N-tiles >= 64 leave through a swizzled
+// shared-memory tile and cp.async.bulk.tensor stores instead of per-thread row stores.
+void gemm_tc_bind_outputs(TcGemm* g);
 void gemm_tc_launch(const TcGemm& g, cudaStream_t s);
 // fp32-in / fp32-out debug entry used by ptts_debug_linear(path=3); returns < 0 when unsupported.
 int gemm_tc_debug(const LinearParams& p, bool bf16_storage, cudaStream_t s);
+
+// Kernel-level benchmark (ptts_debug_gemm_bench): median microseconds of `reps` launches on synthetic bf16
+// operands with L2 flushed between launches.  force = {bn, stages, splits, persist} or all zeros for the planner's
+// own choice; epi: number of bf16 outputs (0 = one fp32 output), +4 adds a bf16 residual read.
+int gemm_tc_bench(int nb, int T, int taps, int C, int N, int epi, const int force[4], int reps, float* us,
+                  int chosen[4], cudaStream_t s);
 
 // helpers used by the bf16 pipeline
 void launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t s);

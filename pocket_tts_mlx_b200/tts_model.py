@@ -238,11 +238,13 @@ class TTSModel:
                              frames_after_eos: Union[int, Sequence[int]] = 3,
                              warmup_frames: int = _MIMI_WARMUP_FRAMES, max_frames: Optional[int] = None,
                              noise: Optional[np.ndarray] = None, seed: int = 0,
-                             return_latents: bool = False):
+                             return_latents: bool = False, pipelined: bool = True):
         """Lock-step generation of many single-chunk utterances (token ids already prepared).
 
         noise: optional [1 + max_frames, n, latent_dim] (row 0 is the unused text-prefill draw, as in the
-        reference).  Returns a list of 1-D float32 waveforms (and per-sequence latents when asked)."""
+        reference); without it the host draws N(0,1) from `seed`.  pipelined=True overlaps the Mimi decode of
+        frame t-1 with the FlowLM step of frame t on the GPU (same results, audio arrives one step later).
+        Returns a list of 1-D float32 waveforms (and per-sequence latents when asked)."""
         n = len(model_states)
         fae = [frames_after_eos] * n if isinstance(frames_after_eos, int) else list(frames_after_eos)
         n_tok = [len(t) for t in token_ids]
@@ -251,18 +253,29 @@ class TTSModel:
             limits = [min(l, max_frames) for l in limits]
         req = [int(s["prompt_len"]) + k + l for s, k, l in zip(model_states, n_tok, limits)]
         batch = _native.Batch(self._ctx, [int(s["voice_id"]) for s in model_states], req)
+        rng = np.random.Generator(np.random.PCG64(seed))
+        ldim = self._ctx.config.latent_dim
         try:
             batch.seed(seed)
+            if pipelined:
+                batch.set_pipelined(True)
             batch.warmup_mimi(warmup_frames)
             batch.prefill_text(token_ids)
             eos_step = [None] * n
             done = [False] * n
+            owed = [False] * n                    # pipelined: frame accepted, its audio arrives with the next call
             audio_out: List[List[np.ndarray]] = [[] for _ in range(n)]
             lat_out: List[List[np.ndarray]] = [[] for _ in range(n)]
+            stepped = False
             for step in range(max(limits)):
-                z = None if noise is None else np.asarray(noise[1 + step], dtype=np.float32)
+                z = rng.standard_normal((n, ldim), dtype=np.float32) if noise is None \
+                    else np.asarray(noise[1 + step], dtype=np.float32)
                 lat, logit, audio = batch.step(z, want_audio=True)
+                stepped = True
                 for b in range(n):
+                    if owed[b]:
+                        audio_out[b].append(audio[b].copy())
+                        owed[b] = False
                     if done[b]:
                         continue
                     if step >= limits[b]:
@@ -273,13 +286,21 @@ class TTSModel:
                     if eos_step[b] is not None and step >= eos_step[b] + fae[b]:
                         done[b] = True
                         continue
-                    audio_out[b].append(audio[b].copy())
                     lat_out[b].append(lat[b].copy())
+                    if pipelined:
+                        owed[b] = True
+                    else:
+                        audio_out[b].append(audio[b].copy())
                 if all(done):
                     break
+            if pipelined and stepped and any(owed):
+                audio = batch.flush()
+                for b in range(n):
+                    if owed[b]:
+                        audio_out[b].append(audio[b].copy())
             waves = [np.concatenate(a) if a else np.zeros(0, dtype=np.float32) for a in audio_out]
             if return_latents:
-                return waves, [np.array(l, dtype=np.float32).reshape(-1, self._ctx.config.latent_dim) for l in lat_out]
+                return waves, [np.array(l, dtype=np.float32).reshape(-1, ldim) for l in lat_out]
             return waves
         finally:
             batch.close()

@@ -317,3 +317,22 @@ def test_bf16_tensor_core_batch_vs_oracle(model_bf16, cfg, weights, voices, n_se
     batch.close()
     for b in check:
         assert snr_db(np.concatenate(audio[b]), refs[b]["audio"]) > 30.0
+
+
+def test_pipelined_mode_is_bit_identical(model_bf16):
+    """Throughput mode (FlowLM step t || Mimi decode t-1 as two graph branches) gives exactly the sequential
+    results, one frame later; incl. per-sequence EOS handling in the facade."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    n, frames = 4, 7
+    ids = [rng.integers(0, 4000, size=int(rng.integers(6, 12))).astype(np.int32) for _ in range(n)]
+    noise = rng.standard_normal((1 + frames, n, 32)).astype(np.float32)
+    states = [model_bf16.get_state_for_audio_prompt(v) for v in ("alba", "jean", "alba", "marius")]
+    out = {}
+    for mode in (False, True):
+        out[mode] = model_bf16.generate_audio_batch(states, ids, max_frames=frames, noise=noise, return_latents=True,
+                                                    pipelined=mode)
+    for b in range(n):
+        assert out[True][1][b].shape == (frames, 32)
+        assert np.array_equal(out[True][1][b], out[False][1][b])
+        assert out[True][0][b].shape == (frames * 1920,)
+        assert np.array_equal(out[True][0][b], out[False][0][b])
