@@ -490,7 +490,10 @@ void rows_norm(Ctx& c, const float* X, int M, int C, const float* w, const float
   launch_layernorm(n, c.stream);
 }
 
-bool want_tc(Ctx& c, int M) { return c.bf16 && gemm_tc_available() && M > 16 && !c.force_simt; }
+bool want_tc(Ctx& c, int M) {
+  static const int min_rows = [] { const char* v = getenv("PTTS_TC_MIN_ROWS"); return v ? atoi(v) : 16; }();
+  return c.bf16 && gemm_tc_available() && M >= min_rows && !c.force_simt;
+}
 
 void free_flow_work(FlowWork& w) {
   void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16, w.ws_out, w.ws_ff2};
