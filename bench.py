@@ -218,11 +218,13 @@ def roofline_from_profile(model, state, ids, at_frame: int, peaks):
     rows = batch.profile_step()
     batch.close()
     total = sum(r["ms"] for r in rows)
-    # group per kernel (all call sites) to find the dominant one
+    # One entry per kernel function; the tcgen05 GEMM is kept per call-site family (flow./head./mimi./sn.)
+    # because its launches range from weight-streaming (HBM-bound) to dense contractions (tensor-bound).
     per = {}
     for r in rows:
-        k = r["kernel"].split(":")[0]
-        a = per.setdefault(k, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+        k, _, tag = r["kernel"].partition(":")
+        key = f"{k}:{tag.split('.')[0]}" if k == "gemm_tc" and tag else k
+        a = per.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
         for f in ("ms", "launches", "flops", "bytes"):
             a[f] += r[f]
     top = max(per.items(), key=lambda kv: kv[1]["ms"])
@@ -237,12 +239,51 @@ def roofline_from_profile(model, state, ids, at_frame: int, peaks):
     else:
         roof = {"bound": "tensor", "achieved": tfs, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": tfs / peaks["tf_sustained"]}
+    traffic = None
+    tp = REPO / "profiles" / "r01_ncu_traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get(name, {}).get("dram_bytes_per_launch")
     roof.update({"kernel": name, "share_of_frame": a["ms"] / total if total else None,
                  "launches_per_frame": a["launches"], "avg_launch_ms": a["ms"] / max(1, a["launches"]),
-                 "traffic": None, "peak_source": peaks["source"], "frame_ms_eager": total})
+                 "algorithmic_bytes_per_launch": a["bytes"] / max(1, a["launches"]),
+                 "algorithmic_flops_per_launch": a["flops"] / max(1, a["launches"]),
+                 "traffic": traffic, "peak_source": peaks["source"], "frame_ms_eager": total,
+                 "note": "eager frame, every launch bracketed by CUDA events on the library stream; shared "
+                         "voice-prefix pages are re-read by all sequences and mostly served from L2"})
     breakdown = sorted(({"kernel": k, "ms": v["ms"], "share": v["ms"] / total} for k, v in per.items()),
-                       key=lambda r: -r["ms"])[:8]
+                       key=lambda r: -r["ms"])[:10]
     return roof, breakdown, rows
+
+
+def tensor_pipe_evidence(model, peaks):
+    """Kernel-level tcgen05 GEMM throughput on the dense contractions of the path (text prefill of the whole
+    batch, M = 256 x 60 rows; Mimi ffn, M = 4096 rows), L2 flushed between launches."""
+    out = []
+    for name, (nb, t, taps, c, n, epi) in {
+        "prefill.qkv": (1, N_SEQ * N_TOK, 1, 1024, 3072, 0), "prefill.ff1": (1, N_SEQ * N_TOK, 1, 1024, 4096, 1),
+        "prefill.ff2": (1, N_SEQ * N_TOK, 1, 4096, 1024, 0), "mimi.ff2": (N_SEQ, 16, 1, 2048, 512, 0),
+        "sn.conv0": (N_SEQ, 16, 7, 512, 512, 1),
+    }.items():
+        us, cfg = model._ctx.gemm_bench(nb, t, taps, c, n, epi, reps=5)
+        tf = 2.0 * nb * t * n * taps * c / us / 1e6
+        out.append({"gemm": name, "us": us, "tflops": tf, "frac_of_sustained_peak": tf / peaks["tf_sustained"],
+                    "config": {"bn": cfg[0], "stages": cfg[1], "splits": cfg[2], "persistent": cfg[3]}})
+    return out
+
+
+def section_times(model, state, ids, at_frame):
+    """In-graph time of the frame's sections (each replayed as its own CUDA graph), microseconds."""
+    from pocket_tts_mlx_b200 import _native
+    n = len(ids)
+    batch = _native.Batch(model._ctx, [state["voice_id"]] * n, [state["prompt_len"] + len(t) + at_frame + 64 for t in ids])
+    batch.warmup_mimi(1)
+    batch.prefill_text(ids)
+    for _ in range(at_frame):
+        batch.step_device()
+    model._ctx.sync()
+    sec = batch.profile_sections()
+    batch.close()
+    return {k: round(v * 1e3, 1) for k, v in sec.items()}
 
 
 def cpu_baseline(frames: int, seed: int = 0):
@@ -278,7 +319,7 @@ def _blas_threads():
 def run_reference(args, world, rank):
     if rank != 0:
         return
-    frames = 25
+    frames = 100
     for _ in range(args.warmup):
         cpu_baseline(4)
     t_all, audio = 0.0, 0.0
@@ -293,7 +334,7 @@ def run_reference(args, world, rank):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "config 4 (256 x 60-token utterances, 125-frame voice prefix, 275 frames)",
-                   "note": "reference is batch-1 only: each step = 1 utterance x 25 frames incl. text prefill"},
+                   "note": "reference is batch-1 only: each step = 1 utterance x 100 frames incl. text prefill"},
         "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} x (1 utterance, 60 tokens, {frames} frames), NumPy/OpenBLAS fp32; "
                                    "MLX itself is not installable here"},
@@ -369,12 +410,14 @@ def main():
     if rank == 0:
         roof, breakdown, rows = roofline_from_profile(model, state, ids, min(frames // 2, 137), peaks)
         lat = None if args.skip_latency else latency_bs1(model, state, rng)
+        sections = section_times(model, state, ids, min(frames // 2, 137))
+        tensor = tensor_pipe_evidence(model, peaks)
         cpu = None
         if not args.skip_cpu_baseline:
-            v, dt = cpu_baseline(20)
+            v, dt = cpu_baseline(275)
             cpu = {"value": v, "unit": "audio-s/s", "cores": _blas_threads(), "kind": "port",
-                   "sample": "1 utterance (batch 1: the reference's only batch size), 60 tokens, text prefill + 20 "
-                             f"frames, NumPy/OpenBLAS fp32 oracle, {dt:.1f} s"}
+                   "sample": "1 utterance (batch 1: the reference's only batch size), 60 tokens, text prefill + 275 "
+                             f"frames (one full utterance of the workload), NumPy/OpenBLAS fp32 oracle, {dt:.1f} s"}
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -387,7 +430,9 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d // e2e_steps,
                     "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps},
-            "roofline": roof, "frame_breakdown": breakdown, "cpu_baseline": cpu, "latency_bs1": lat,
+            "roofline": roof, "frame_breakdown": breakdown, "frame_sections_us": sections,
+            "tensor_pipe": tensor, "cpu_baseline": cpu, "latency_bs1": lat,
+            "pipelined": PIPELINED,
             "ms_per_frame": ms / args.steps / frames,
         }
         if args.profile_out:
