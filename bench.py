@@ -366,7 +366,11 @@ def main():
     from pocket_tts_mlx_b200.synthetic import synthetic_token_ids
     n_seq, frames = args.batch, args.frames
     kv_tokens = n_seq * (VOICE_FRAMES + N_TOK + frames + 64) + 4096
+    if rank != 0:
+        _barrier(dist, local)            # rank 0 writes the synthetic bundle first (same files for all ranks)
     model, _ = load_model(local, kv_tokens)
+    if rank == 0:
+        _barrier(dist, local)
     state = model.get_state_for_audio_prompt("alba")
     ids = list(synthetic_token_ids(2 + rank, n_seq, N_TOK))
     rng = np.random.Generator(np.random.PCG64(100 + rank))

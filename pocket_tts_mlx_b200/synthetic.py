@@ -196,7 +196,9 @@ def write_synthetic_bundle(out_dir, base_variant: Optional[str] = None, seed: in
     cfg = load_config(base)
     ckpt = out_dir / f"tts_synthetic_seed{seed}.safetensors"
     if not ckpt.exists():
-        write_safetensors(ckpt, synthetic_state_dict(cfg, seed), bf16=bf16)
+        tmp = ckpt.with_suffix(f".tmp{os.getpid()}")
+        write_safetensors(tmp, synthetic_state_dict(cfg, seed), bf16=bf16)
+        os.replace(tmp, ckpt)            # atomic: concurrent ranks never see a partial file
     for i, name in enumerate(VOICE_NAMES):
         vp = out_dir / "embeddings" / f"{name}.safetensors"
         if not vp.exists():
