@@ -114,6 +114,11 @@ int32_t ptts_batch_warmup_mimi(ptts_batch* batch, int32_t n_frames);
  *   out_audio  [n_seq, 1920] or NULL (NULL also skips the device->host copy, not the decode). */
 int32_t ptts_batch_step(ptts_batch* batch, const float* noise, float* out_latent,
                         float* out_eos_logit, float* out_audio);
+/* Zero-copy variant of ptts_batch_step: the caller writes the noise into, and reads the results from, the
+ * library's pinned staging buffers (noise [n_seq, latent_dim], latent [n_seq, latent_dim], eos_logit [n_seq],
+ * audio [n_seq, 1920]); the pointers stay valid for the life of the batch, the contents until the next step. */
+int32_t ptts_batch_host_buffers(ptts_batch* batch, float** noise, float** latent, float** eos_logit, float** audio);
+int32_t ptts_batch_step_staged(ptts_batch* batch);
 /* Teacher forcing for parity tests: overwrite the latent that the next step feeds back. */
 int32_t ptts_batch_set_prev_latent(ptts_batch* batch, const float* latent);
 /* Same step without the host round trip: results stay on the device (used by bench `value`). */

@@ -24,6 +24,7 @@ EXPORTED = [
     "ptts_batch_seed", "ptts_batch_lengths", "ptts_batch_mimi_decode", "ptts_sync", "ptts_timer_begin",
     "ptts_timer_end", "ptts_launch_count", "ptts_batch_profile_step", "ptts_flush_l2", "ptts_debug_linear",
     "ptts_debug_gemm_bench", "ptts_batch_profile_sections", "ptts_batch_set_pipelined", "ptts_batch_flush",
+    "ptts_batch_host_buffers", "ptts_batch_step_staged",
 ]
 
 
@@ -92,6 +93,8 @@ def lib() -> C.CDLL:
         "ptts_flush_l2": (i32, [vp]),
         "ptts_debug_linear": (i32, [vp, i32, i32, i32, i32, i32, i32, f32p, f32p, f32p, f32p]),
         "ptts_batch_profile_sections": (i32, [vp, f32p, i32]),
+        "ptts_batch_host_buffers": (i32, [vp, C.POINTER(f32p), C.POINTER(f32p), C.POINTER(f32p), C.POINTER(f32p)]),
+        "ptts_batch_step_staged": (i32, [vp]),
         "ptts_batch_set_pipelined": (i32, [vp, i32]),
         "ptts_batch_flush": (i32, [vp, f32p]),
         "ptts_debug_gemm_bench": (i32, [vp, i32, i32, i32, i32, i32, i32, i32p, i32, f32p, i32p]),
@@ -257,6 +260,7 @@ class Batch:
 
     def close(self):
         if self._h:
+            self._staging = None
             lib().ptts_batch_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -294,6 +298,20 @@ class Batch:
         audio = np.empty((self.n, self.frame_samples), dtype=np.float32) if want_audio else None
         check(lib().ptts_batch_flush(self._h, _fp(audio)))
         return audio
+
+    def staging(self):
+        """NumPy views of the library's pinned staging buffers: (noise, latent, eos_logit, audio)."""
+        if getattr(self, "_staging", None) is None:
+            f32p = C.POINTER(C.c_float)
+            ptrs = [f32p() for _ in range(4)]
+            check(lib().ptts_batch_host_buffers(self._h, *[C.byref(p) for p in ptrs]))
+            shapes = [(self.n, self.latent_dim), (self.n, self.latent_dim), (self.n,), (self.n, self.frame_samples)]
+            self._staging = tuple(np.ctypeslib.as_array(p, shape=sh) for p, sh in zip(ptrs, shapes))
+        return self._staging
+
+    def step_staged(self):
+        """One frame with zero host copies: fill staging()[0] with N(0,1) noise, call, read staging()[1:]."""
+        check(lib().ptts_batch_step_staged(self._h))
 
     def step_device(self):
         check(lib().ptts_batch_step_device(self._h))

@@ -1614,6 +1614,30 @@ int32_t ptts_batch_step(ptts_batch* bt, const float* noise, float* out_latent, f
   return 0;
 }
 
+int32_t ptts_batch_host_buffers(ptts_batch* bt, float** noise, float** latent, float** eos_logit, float** audio) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  if (noise) *noise = bt->h_noise;
+  if (latent) *latent = bt->h_latent;
+  if (eos_logit) *eos_logit = bt->h_logit;
+  if (audio) *audio = bt->h_audio;
+  return 0;
+}
+
+int32_t ptts_batch_step_staged(ptts_batch* bt) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  RET(check_step_ready(*bt));
+  if (bt->pipelined) {
+    RET(run_pipelined_step(*bt, true));
+  } else {
+    RET(run_step(*bt, true, true));
+    bt->frame_idx += 1;
+  }
+  CU(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
 int32_t ptts_batch_step_device(ptts_batch* bt) {
   if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
   CU(cudaSetDevice(bt->ctx->device));

@@ -336,3 +336,31 @@ def test_pipelined_mode_is_bit_identical(model_bf16):
         assert np.array_equal(out[True][1][b], out[False][1][b])
         assert out[True][0][b].shape == (frames * 1920,)
         assert np.array_equal(out[True][0][b], out[False][0][b])
+
+
+def test_staged_step_equals_copying_step(model_bf16):
+    """The zero-copy staged step (pinned staging buffers) returns exactly what ptts_batch_step copies out."""
+    from pocket_tts_mlx_b200 import _native
+    rng = np.random.Generator(np.random.PCG64(9))
+    st = model_bf16.get_state_for_audio_prompt("alba")
+    ids = [rng.integers(0, 4000, size=9).astype(np.int32) for _ in range(2)]
+    noise = rng.standard_normal((4, 2, 32)).astype(np.float32)
+    res = []
+    for staged in (False, True):
+        batch = _native.Batch(model_bf16._ctx, [st["voice_id"]] * 2, [st["prompt_len"] + 9 + 8] * 2)
+        batch.warmup_mimi(1)
+        batch.prefill_text(ids)
+        outs = []
+        for f in range(4):
+            if staged:
+                z, lat, logit, audio = batch.staging()
+                z[...] = noise[f]
+                batch.step_staged()
+                outs.append((lat.copy(), logit.copy(), audio.copy()))
+            else:
+                outs.append(batch.step(noise[f]))
+        batch.close()
+        res.append(outs)
+    for a, b in zip(*res):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
