@@ -103,6 +103,7 @@ struct FlowWork {
   int plan_M = 0;
   std::vector<TcGemm> plans;  // 4 per layer: qkv, out, ff1, ff2
   float *ws_out = nullptr, *ws_ff2 = nullptr;   // split-K partial planes [8][M][D] of out-proj / ffn2
+  float* attn_part = nullptr;                   // split-KV attention partials [M][H][8][66] (decode at small batch)
   int pend_n = 0;             // planes of the last ffn2 still to be added to x (consumed by the next norm)
 };
 
@@ -461,12 +462,30 @@ int finalize(Ctx& c) {
 }
 
 // ---- operator dispatch -----------------------------------------------------------------------------------
+void rows_norm(Ctx& c, const float* X, int M, int C, const float* w, const float* b, float eps, float* Y,
+               const float* scale, const float* shift, long long mod_rs, __nv_bfloat16* Y16, const float* acc, int acc_n);
 void run_linear(Ctx& c, const LinW& w, LinearParams p) {
   p.W = w.w; p.w_bf16 = w.bf16; p.N = w.N;
   if (!p.bias) p.bias = w.bias;
   if (p.out_scale == 0.f) p.out_scale = 1.f;
   if (linear_gemv_supported(p)) launch_linear_gemv(p, c.stream);
   else launch_linear_tile(p, c.stream);
+}
+
+// LayerNorm (+ optional AdaLN modulation) followed by a Linear on `M` rows: one GEMV launch with the norm fused
+// into its row staging when the small-M path applies, otherwise the norm kernel writes `scratch` first.
+void run_norm_linear(Ctx& c, const LinW& w, const float* X, int M, int C, const float* lw, const float* lb, float eps,
+                     const float* scale, const float* shift, long long mod_rs, float* scratch, LinearParams p) {
+  p.A = X; p.a_bs = 0; p.a_rs = C; p.nb = 1; p.T = M; p.taps = 1; p.C = C;
+  p.W = w.w; p.w_bf16 = w.bf16; p.N = w.N;
+  if (linear_gemv_supported(p)) {
+    p.ln_on = 1; p.ln_w = lw; p.ln_b = lb; p.ln_eps = eps; p.ln_scale = scale; p.ln_shift = shift; p.ln_mod_rs = mod_rs;
+    run_linear(c, w, p);
+  } else {
+    rows_norm(c, X, M, C, lw, lb, eps, scratch, scale, shift, mod_rs, nullptr, nullptr, 0);
+    p.A = scratch;
+    run_linear(c, w, p);
+  }
 }
 
 LinearParams rows_linear(const float* A, int M, int C, float* Y, int N, const char* tag = nullptr) {
@@ -479,8 +498,7 @@ LinearParams rows_linear(const float* A, int M, int C, float* Y, int N, const ch
 }
 
 void rows_norm(Ctx& c, const float* X, int M, int C, const float* w, const float* b, float eps, float* Y,
-               const float* scale = nullptr, const float* shift = nullptr, long long mod_rs = 0,
-               __nv_bfloat16* Y16 = nullptr, const float* acc = nullptr, int acc_n = 0) {
+               const float* scale, const float* shift, long long mod_rs, __nv_bfloat16* Y16, const float* acc, int acc_n) {
   NormParams n{};
   n.Y16 = Y16;
   n.acc = acc; n.acc_n = acc_n; n.acc_stride = (long long)M * C;
@@ -496,7 +514,7 @@ bool want_tc(Ctx& c, int M) {
 }
 
 void free_flow_work(FlowWork& w) {
-  void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16, w.ws_out, w.ws_ff2};
+  void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16, w.ws_out, w.ws_ff2, w.attn_part};
   for (void* p : ptrs) if (p) cudaFree(p);
   w = FlowWork{};
 }
@@ -509,6 +527,7 @@ int alloc_flow_work(Ctx& c, FlowWork& w, int M) {
   CU(cudaMalloc((void**)&w.x, M * D * 4));
   CU(cudaMalloc((void**)&w.qkv, M * 3 * D * 4));
   CU(cudaMalloc((void**)&w.qrot, M * D * 4));
+  if (M * c.cfg.n_heads < 148) CU(cudaMalloc((void**)&w.attn_part, (size_t)M * c.cfg.n_heads * 8 * 66 * 4));
   if (tc) {
     CU(cudaMalloc((void**)&w.h16, M * D * 2));
     CU(cudaMalloc((void**)&w.att16, M * D * 2));
@@ -576,6 +595,7 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       a.pool = c.pool; a.kv_bf16 = c.bf16; a.layer_stride = c.layer_stride; a.page_stride = c.page_stride;
       a.layer = i; a.row_seq = row_seq; a.row_pos = row_pos; a.page_table = page_table; a.max_pages = max_pages;
       a.M = M; a.H = c.cfg.n_heads; a.freqs = c.freqs_flow; a.total_keys = total_keys;
+      a.part = w.attn_part; a.splits = w.attn_part ? std::min(8, std::max(1, 296 / (M * c.cfg.n_heads))) : 1;
       launch_flow_rope_append(a, c.stream);
       launch_flow_attention(a, c.stream);
       gemm_tc_launch(g[1], c.stream);
@@ -591,22 +611,22 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
   w.pend_n = 0;
   for (int i = 0; i < c.cfg.n_layers; ++i) {
     auto& l = c.fl[i];
-    rows_norm(c, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, w.h);
-    run_linear(c, l.qkv, rows_linear(w.h, M, D, w.qkv, 3 * D, "flow.qkv"));
+    run_norm_linear(c, l.qkv, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, nullptr, nullptr, 0, w.h,
+                    rows_linear(w.h, M, D, w.qkv, 3 * D, "flow.qkv"));
     FlowAttnParams a{};
     a.qkv = w.qkv; a.q_rot = w.qrot; a.out = w.att;
     a.pool = c.pool; a.kv_bf16 = c.bf16; a.layer_stride = c.layer_stride; a.page_stride = c.page_stride;
     a.layer = i; a.row_seq = row_seq; a.row_pos = row_pos; a.page_table = page_table; a.max_pages = max_pages;
     a.M = M; a.H = c.cfg.n_heads; a.freqs = c.freqs_flow; a.total_keys = total_keys;
+    a.part = w.attn_part; a.splits = w.attn_part ? std::min(8, std::max(1, 296 / (M * c.cfg.n_heads))) : 1;
     launch_flow_rope_append(a, c.stream);
     launch_flow_attention(a, c.stream);
     LinearParams o = rows_linear(w.att, M, D, w.x, D, "flow.out");
     o.res = w.x; o.res_bs = 0; o.res_rs = D;
     run_linear(c, l.out, o);
-    rows_norm(c, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, w.h);
     LinearParams f1 = rows_linear(w.h, M, D, w.ff, FF, "flow.ff1");
     f1.act = ACT_GELU;
-    run_linear(c, l.ff1, f1);
+    run_norm_linear(c, l.ff1, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, nullptr, nullptr, 0, w.h, f1);
     LinearParams f2 = rows_linear(w.ff, M, FF, w.x, D, "flow.ff2");
     f2.res = w.x; f2.res_bs = 0; f2.res_rs = D;
     run_linear(c, l.ff2, f2);
@@ -853,12 +873,12 @@ void flow_head_tc(Batch& bt) {
     run_linear(c, c.in_proj, rows_linear(bt.d_x, B, L, bt.d_x1, fd, "head.in"));
     for (int r = 0; r < g.flow_depth; ++r) {
       const float* ada = bt.d_ada + (long long)r * 3 * fd;
-      rows_norm(c, bt.d_x1, B, fd, c.rb[r].lnw, c.rb[r].lnb, 1e-6f, nullptr, ada + fd, ada, c.n_ada, bt.d_hh16);
+      rows_norm(c, bt.d_x1, B, fd, c.rb[r].lnw, c.rb[r].lnb, 1e-6f, nullptr, ada + fd, ada, c.n_ada, bt.d_hh16, nullptr, 0);
       gemm_tc_launch(bt.g_m1[r], c.stream);
       gemm_tc_launch(bt.g_m2[r], c.stream);
     }
     const float* adaf = bt.d_ada + (long long)g.flow_depth * 3 * fd;
-    rows_norm(c, bt.d_x1, B, fd, nullptr, nullptr, 1e-6f, nullptr, adaf + fd, adaf, c.n_ada, bt.d_hh16);
+    rows_norm(c, bt.d_x1, B, fd, nullptr, nullptr, 1e-6f, nullptr, adaf + fd, adaf, c.n_ada, bt.d_hh16, nullptr, 0);
     gemm_tc_launch(bt.g_fin, c.stream);
   }
 }
@@ -1041,21 +1061,19 @@ void flow_step(Batch& bt, bool host_noise, int part = 0, const float* lat_in = n
     run_linear(c, c.in_proj, rows_linear(bt.d_x, B, L, bt.d_x1, fd, "head.in"));
     for (int r = 0; r < g.flow_depth; ++r) {
       const float* ada = bt.d_ada + (long long)r * 3 * fd;
-      rows_norm(c, bt.d_x1, B, fd, c.rb[r].lnw, c.rb[r].lnb, 1e-6f, bt.d_hh, ada + fd, ada, c.n_ada);
       LinearParams m1 = rows_linear(bt.d_hh, B, fd, bt.d_u, fd, "head.m1");
       m1.act = ACT_SILU;
-      run_linear(c, c.rb[r].m1, m1);
+      run_norm_linear(c, c.rb[r].m1, bt.d_x1, B, fd, c.rb[r].lnw, c.rb[r].lnb, 1e-6f, ada + fd, ada, c.n_ada, bt.d_hh, m1);
       LinearParams m2 = rows_linear(bt.d_u, B, fd, bt.d_x1, fd, "head.m2");
       m2.row_gate = ada + 2 * fd; m2.gate_bs = 0; m2.gate_rs = c.n_ada;
       m2.res = bt.d_x1; m2.res_bs = 0; m2.res_rs = fd;
       run_linear(c, c.rb[r].m2, m2);
     }
     const float* adaf = bt.d_ada + (long long)g.flow_depth * 3 * fd;
-    rows_norm(c, bt.d_x1, B, fd, nullptr, nullptr, 1e-6f, bt.d_hh, adaf + fd, adaf, c.n_ada);
     LinearParams fo = rows_linear(bt.d_hh, B, fd, bt.d_x, L, "head.fin");     // x += v / n
     fo.out_scale = 1.0f / (float)n;
     fo.res = bt.d_x; fo.res_bs = 0; fo.res_rs = L;
-    run_linear(c, c.fin, fo);
+    run_norm_linear(c, c.fin, bt.d_x1, B, fd, nullptr, nullptr, 1e-6f, adaf + fd, adaf, c.n_ada, bt.d_hh, fo);
   }
   cudaMemcpyAsync(lat_out, bt.d_x, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, c.stream);
 }

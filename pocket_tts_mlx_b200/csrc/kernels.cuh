@@ -32,6 +32,10 @@ struct LinearParams {
   const float* res; long long res_bs, res_rs; // null or residual with Y's row indexing
   float* Y; long long y_bs, y_rs;
   const char* tag;                            // call-site label for the profiler (may be null)
+  // GEMV path only: LayerNorm (optionally AdaLN-modulated) fused into the row staging -- every CTA holds the full
+  // input rows in shared memory anyway, so the separate norm launch disappears from the batch-1 chain
+  int ln_on; const float* ln_w; const float* ln_b; float ln_eps;
+  const float* ln_scale; const float* ln_shift; long long ln_mod_rs;   // per-row modulation vectors or null
 };
 
 inline double linear_flops(const LinearParams& p) { return 2.0 * p.nb * p.T * (double)p.N * p.taps * p.C; }
@@ -75,6 +79,7 @@ struct FlowAttnParams {
   int M, H;
   const float* freqs;          // [32] RoPE frequencies (fp32, computed like modules/rope.py:17-18)
   long long total_keys;        // host-side sum over rows of (row_pos+1), for the profiler's byte count
+  int splits; float* part;     // split-KV for small batches: partials [M][H][splits][66] merged by a second kernel
 };
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s);
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s);

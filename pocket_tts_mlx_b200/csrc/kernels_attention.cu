@@ -110,7 +110,14 @@ __global__ void __launch_bounds__(128) flow_attention_kernel(const FlowAttnParam
   const int grp = lane >> 3, sl = lane & 7;     // key group within the warp, 8-wide slice of the head
   const int D = p.H * kHeadDim;
   const int seq = p.row_seq ? p.row_seq[m] : m;
-  const int n_keys = p.row_pos[m] + 1;
+  const int n_all = p.row_pos[m] + 1;
+  // split-KV (small batches): CTA z of `splits` owns a 16-aligned slice of the keys and writes a partial
+  int key_lo = 0, n_keys = n_all;
+  if (p.splits > 1) {
+    const int chunk = (((n_all + p.splits - 1) / p.splits) + 15) & ~15;
+    key_lo = blockIdx.z * chunk;
+    n_keys = min(n_all, key_lo + chunk);
+  }
   float q[8];
   {
     const float* qp = p.q_rot + (long long)m * D + h * kHeadDim + sl * 8;
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(128) flow_attention_kernel(const FlowAttnParam
   // each warp takes 16 consecutive keys per step (4 groups of 4, all inside one 32-token page): the 8 16-byte
   // loads of a step are issued before any of them is consumed, so ~8 KB per warp are in flight
   constexpr int U = 1;   // measured: U=2 no gain, U=4 (108 regs) 40% slower -- occupancy beats per-warp unrolling here
-  for (int k0 = warp * 4 * U; k0 < n_keys; k0 += 16 * U) {
+  for (int k0 = key_lo + warp * 4 * U; k0 < n_keys; k0 += 16 * U) {
     const int page = pt[k0 / kPageTokens];
     const KT* pbase = pool + page * p.page_stride + ((long long)h * kPageTokens + (k0 % kPageTokens)) * kHeadDim + sl * 8;
     float kf[U][8], vf[U][8];
@@ -170,10 +177,39 @@ __global__ void __launch_bounds__(128) flow_attention_kernel(const FlowAttnParam
       l += sh_l[w] * c;
       a += sh_acc[w][threadIdx.x] * c;
     }
-    const long long oi = (long long)m * D + h * kHeadDim + threadIdx.x;
-    if (p.out16) p.out16[oi] = __float2bfloat16_rn(a / l);
-    else p.out[oi] = a / l;
+    if (p.splits > 1) {
+      // partial of this key slice: [m][h][z][64 values | max | sum]; an empty slice contributes l = 0
+      float* part = p.part + (((long long)m * p.H + h) * p.splits + blockIdx.z) * 66;
+      part[threadIdx.x] = a;
+      if (threadIdx.x == 0) { part[64] = mx; part[65] = l; }
+    } else {
+      const long long oi = (long long)m * D + h * kHeadDim + threadIdx.x;
+      if (p.out16) p.out16[oi] = __float2bfloat16_rn(a / l);
+      else p.out[oi] = a / l;
+    }
   }
+}
+
+// merge the split-KV partials of one (row, head): grid (M, H), 64 threads
+__global__ void flow_attention_merge_kernel(const FlowAttnParams p) {
+  pdl_sync();
+  const int m = blockIdx.x, h = blockIdx.y;
+  const float* part = p.part + ((long long)m * p.H + h) * p.splits * 66;
+  float mx = -INFINITY;
+  for (int z = 0; z < p.splits; ++z)
+    if (part[z * 66 + 65] > 0.f) mx = fmaxf(mx, part[z * 66 + 64]);
+  float l = 0.f, a = 0.f;
+  for (int z = 0; z < p.splits; ++z) {
+    const float lz = part[z * 66 + 65];
+    if (lz > 0.f) {
+      const float c = __expf(part[z * 66 + 64] - mx);
+      l += lz * c;
+      a += part[z * 66 + threadIdx.x] * c;
+    }
+  }
+  const long long oi = (long long)m * p.H * kHeadDim + h * kHeadDim + threadIdx.x;
+  if (p.out16) p.out16[oi] = __float2bfloat16_rn(a / l);
+  else p.out[oi] = a / l;
 }
 
 // ---- Mimi ---------------------------------------------------------------------------------------------
@@ -482,12 +518,16 @@ void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s) {
 
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
   if (p.M <= 0) return;
-  dim3 grid(p.M, p.H);
+  dim3 grid(p.M, p.H, p.splits > 1 ? p.splits : 1);
   ProfScope ps("flow_attention", nullptr, 4.0 * p.total_keys * p.H * 64,
                2.0 * p.total_keys * p.H * 64 * (p.kv_bf16 ? 2 : 4) + 2.0 * p.M * p.H * 64 * 4, s);
   if (p.kv_bf16) launch_k(flow_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, s, p);
   else launch_k(flow_attention_kernel<float>, dim3(grid), dim3(128), 0, s, p);
   ++g_launches;
+  if (p.splits > 1) {
+    launch_k(flow_attention_merge_kernel, dim3(p.M, p.H), dim3(64), 0, s, p);
+    ++g_launches;
+  }
 }
 
 void launch_mimi_rope_ring(const MimiAttnParams& p, cudaStream_t s) {

@@ -132,13 +132,66 @@ template <> struct WVec<float> {
   }
 };
 
-template <typename WT, int MT>
-__global__ void __launch_bounds__(128) linear_gemv_kernel(const LinearParams p) {
+// grid = ceil(N / (8*R)); 256 threads = 8 warps x R output rows each.  The (T+taps-1) x C input rows of every
+// sequence are staged in shared memory once (prologue activation applied).  A warp walks its R weight rows in
+// steps of U x 256 elements and issues all R*U 16-byte loads of a step before consuming any of them, so each lane
+// keeps R*U*16 bytes in flight (R*U = 8: 32 KB per CTA) -- the kernel is meant to sit on the HBM roofline.
+template <typename WT> struct WRaw;
+template <> struct WRaw<__nv_bfloat16> {
+  uint4 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void unpack(float (&o)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      o[2 * i] = f.x; o[2 * i + 1] = f.y;
+    }
+  }
+};
+template <> struct WRaw<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void unpack(float (&o)[8]) const {
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+};
+
+// grid = ceil(N / (8*R)); 256 threads = 8 warps x R output rows each.  A warp walks its R weight rows in steps of
+// U x 256 elements and issues all R*U 16-byte loads of a step before consuming any of them (R*U = 8: 32 KB in
+// flight per CTA); the first step's loads are issued BEFORE the input rows are staged (and normalised) in shared
+// memory, so the activation round trip hides behind the weight stream -- the kernel is meant to sit on the HBM
+// roofline, not on two serialised DRAM latencies.
+template <typename WT, int MT, int R>
+__global__ void __launch_bounds__(256) linear_gemv_kernel(const LinearParams p) {
   pdl_sync();
   extern __shared__ __align__(16) float xs[];   // [nb][T+taps-1][C]
+  constexpr int U = 8 / R;
   const int rows_per_seq = p.T + p.taps - 1;
   const int C = p.C, K = p.taps * p.C;
   const int M = p.nb * p.T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_base = (blockIdx.x * 8 + warp) * R;
+  const WT* W = reinterpret_cast<const WT*>(p.W);
+  const WT* wrow[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) wrow[r] = W + (long long)min(n_base + r, p.N - 1) * K;
+
+  WRaw<WT> wq[R][U];
+  auto issue = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + 256 * u;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (k < K) wq[r][u].load(wrow[r] + k);
+    }
+  };
+  issue(lane * 8);                                  // weights do not depend on the activations: fetch first
+
   {
     const int c4 = C >> 2;
     const int total = p.nb * rows_per_seq * c4;
@@ -153,52 +206,73 @@ __global__ void __launch_bounds__(128) linear_gemv_kernel(const LinearParams p) 
     }
   }
   __syncthreads();
+  if (p.ln_on) {
+    // fused LayerNorm (taps == 1): warp w normalises rows w, w+8, ... in place, two-pass like layernorm_kernel
+    for (int m = warp; m < M; m += 8) {
+      float* xr = xs + (long long)m * C;
+      float sum = 0.f;
+      for (int c = lane; c < C; c += 32) sum += xr[c];
+      const float mean = warp_sum(sum) / (float)C;
+      float q = 0.f;
+      for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; q += d * d; }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + p.ln_eps);
+      const float* sc = p.ln_scale ? p.ln_scale + (long long)m * p.ln_mod_rs : nullptr;
+      const float* sh = p.ln_shift ? p.ln_shift + (long long)m * p.ln_mod_rs : nullptr;
+      for (int c = lane; c < C; c += 32) {
+        float o = (xr[c] - mean) * rstd;
+        if (p.ln_w) o = o * p.ln_w[c] + p.ln_b[c];
+        if (sc) o = o * (1.0f + sc[c]) + sh[c];
+        xr[c] = o;
+      }
+    }
+    __syncthreads();
+  }
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_base = blockIdx.x * 8 + warp * 2;
-  const WT* W = reinterpret_cast<const WT*>(p.W);
-  float acc[2][MT];
+  float acc[R][MT];
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < R; ++r)
 #pragma unroll
     for (int m = 0; m < MT; ++m) acc[r][m] = 0.f;
 
-  const bool ok0 = n_base < p.N, ok1 = n_base + 1 < p.N;
-  const WT* w0 = W + (long long)(ok0 ? n_base : 0) * K;
-  const WT* w1 = W + (long long)(ok1 ? n_base + 1 : 0) * K;
-
-  for (int k = lane * 8; k < K; k += 256) {
-    float wa[8], wb[8];
-    WVec<WT>::load(w0 + k, wa);
-    WVec<WT>::load(w1 + k, wb);
-    const int tap = k / C, c = k - tap * C;
+  for (int k0 = lane * 8; k0 < K; k0 += 256 * U) {
+    float w[R][U][8];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      if (m < M) {
-        const int b = m / p.T, t = m - b * p.T;
-        const float* xr = xs + ((long long)(b * rows_per_seq + t + tap)) * C + c;
-        float4 x0 = *reinterpret_cast<const float4*>(xr);
-        float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
-        const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[0][m] = fmaf(wa[i], x[i], acc[0][m]);
-          acc[1][m] = fmaf(wb[i], x[i], acc[1][m]);
+      for (int r = 0; r < R; ++r) wq[r][u].unpack(w[r][u]);
+    if (k0 + 256 * U < K) issue(k0 + 256 * U);      // next step's loads fly while this step is multiplied
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + 256 * u;
+      if (k < K) {
+        const int tap = k / C, c = k - tap * C;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          if (m < M) {
+            const int b = m / p.T, t = m - b * p.T;
+            const float* xr = xs + ((long long)(b * rows_per_seq + t + tap)) * C + c;
+            const float4 x0 = *reinterpret_cast<const float4*>(xr);
+            const float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
+            const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[r][m] = fmaf(w[r][u][i], x[i], acc[r][m]);
+          }
         }
       }
     }
   }
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < R; ++r)
 #pragma unroll
     for (int m = 0; m < MT; ++m) acc[r][m] = warp_sum(acc[r][m]);
 
-  // lanes 0..2*MT-1 each finish one (row, m) output
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
+  for (int r = 0; r < R; ++r) {
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      if (lane == r * MT + m && m < M) {
+      if (lane == ((r * MT + m) & 31) && m < M) {
         const int n = n_base + r;
         if (n < p.N) {
           const int b = m / p.T, t = m - b * p.T;
@@ -209,16 +283,16 @@ __global__ void __launch_bounds__(128) linear_gemv_kernel(const LinearParams p) 
   }
 }
 
-template <typename WT>
-void launch_gemv_t(const LinearParams& p, cudaStream_t s) {
+template <typename WT, int R>
+void launch_gemv_r(const LinearParams& p, cudaStream_t s) {
   const int M = p.nb * p.T;
   const size_t smem = (size_t)p.nb * (p.T + p.taps - 1) * p.C * sizeof(float);
-  dim3 grid((p.N + 7) / 8), block(128);
+  dim3 grid((p.N + 8 * R - 1) / (8 * R)), block(256);
 #define PTTS_GEMV(MT)                                                                                   \
   do {                                                                                                  \
-    auto kfn = linear_gemv_kernel<WT, MT>;                                                              \
+    auto kfn = linear_gemv_kernel<WT, MT, R>;                                                           \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    launch_k(kfn, dim3(grid), dim3(block), smem, s, p);                                                                   \
+    launch_k(kfn, grid, block, smem, s, p);                                                             \
   } while (0)
   if (M <= 1) PTTS_GEMV(1);
   else if (M <= 2) PTTS_GEMV(2);
@@ -226,6 +300,14 @@ void launch_gemv_t(const LinearParams& p, cudaStream_t s) {
   else if (M <= 8) PTTS_GEMV(8);
   else PTTS_GEMV(16);
 #undef PTTS_GEMV
+}
+
+template <typename WT>
+void launch_gemv_t(const LinearParams& p, cudaStream_t s) {
+  // rows per warp: enough CTAs to cover the chip first (N / (8R) >= ~150), then loads in flight per lane
+  const int M = p.nb * p.T;
+  if (M > 4 || p.N <= 1536) launch_gemv_r<WT, 1>(p, s);
+  else launch_gemv_r<WT, 2>(p, s);
 }
 
 }  // namespace
