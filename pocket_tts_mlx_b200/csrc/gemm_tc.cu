@@ -27,6 +27,7 @@ struct KArgs {
   int box_t, box_b, tiles_t, m_tiles;
   int tma_store;                // bf16 outputs leave through smem + TMA bulk stores
   int stg_tiles;                // 16 KB staging tiles behind the operand ring
+  int res_tma;                  // bf16 residual tiles are prefetched by TMA (two buffers) instead of per-thread loads
   int splits;                   // gridDim.z; split z covers k-iterations [z*ips, (z+1)*ips)
   long long split_stride;       // elements between the partial planes of split_ws
   float* split_ws;
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                                               const __grid_constant__ CUtensorMap tm_b,
                                                               const __grid_constant__ CUtensorMap tm_y16,
                                                               const __grid_constant__ CUtensorMap tm_yraw16,
+                                                              const __grid_constant__ CUtensorMap tm_res,
                                                               const KArgs g) {
   constexpr int ROW_BYTES = BK * 2;
   constexpr int A_BYTES = 128 * ROW_BYTES, B_BYTES = BN * ROW_BYTES;
@@ -149,10 +151,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   // staging tiles for TMA stores: behind the ring when persistent (the producer is already refilling the ring
   // for the next tile), on top of the idle ring when the CTA owns a single tile
   const uint32_t stg = (ACC == 2) ? sB + STAGES * B_BYTES : base;
-  const uint32_t bars = sB + STAGES * B_BYTES + ((ACC == 2) ? (uint32_t)g.stg_tiles * 16384u : 0u);
-  // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base address word
+  constexpr uint32_t RES_BYTES = (BN >= 64) ? (BN / 64) * 16384u : 0u;     // one residual tile set
+  const uint32_t resb = sB + STAGES * B_BYTES + ((ACC == 2) ? (uint32_t)g.stg_tiles * 16384u : 0u);
+  const uint32_t bars = resb + (g.res_tma ? 2u * RES_BYTES : 0u);
+  // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], res_full[2], res_empty[2]; then the TMEM base word
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16,
-                 tptr = tempty0 + 16;
+                 rfull0 = tempty0 + 16, rempty0 = rfull0 + 16, tptr = rempty0 + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kc_per_tap = g.C / BK;
@@ -170,6 +174,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
       mbar_init(tempty0 + 8 * i, 8);      // one arrival per epilogue warp
+      mbar_init(rfull0 + 8 * i, 1);
+      mbar_init(rempty0 + 8 * i, 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -187,11 +193,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t git = 0;
+      uint32_t git = 0, rcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % n_nt, mt = (tile / n_nt) % g.m_tiles, z = tile / (n_nt * g.m_tiles);
         const int n0 = nt * BN;
         const int b0 = (mt / g.tiles_t) * g.box_b, t0 = (mt % g.tiles_t) * g.box_t;
+        if (BN >= 64 && g.res_tma) {
+          // residual tile of this output tile: in flight during the whole mainloop, two buffers deep
+          const uint32_t rb = rcount & 1, rph = (rcount >> 1) & 1;
+          mbar_wait(rempty0 + 8 * rb, rph ^ 1);
+          mbar_expect_tx(rfull0 + 8 * rb, RES_BYTES);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_3d(resb + rb * RES_BYTES + (uint32_t)j * 16384u, &tm_res, rfull0 + 8 * rb, n0 + 64 * j, t0, b0);
+          ++rcount;
+        }
         for (int it = 0; it < ips; ++it, ++git) {
           const int s = git % STAGES, ph = (git / STAGES) & 1;
           const int kit = z * ips + it;
@@ -248,6 +264,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       mbar_wait(tfull0 + 8 * as, aph);
       tc_fence_after();
+      const uint32_t rb = tcount & 1, rph = (tcount >> 1) & 1;
+      if (BN >= 64 && g.res_tma) mbar_wait(rfull0 + 8 * rb, rph);
       const uint32_t tmem_acc = tmem_base + as * BN + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
       for (int ch = half; ch < CHUNKS; ch += 2) {
@@ -304,7 +322,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
             }
           }
-          if (e.res16) {
+          if (e.res16 && BN >= 64 && g.res_tma) {
+            // residual tile staged by TMA: [128 rows][128 B] per 64-column group, 128B-swizzled
+            const uint32_t tl = resb + rb * RES_BYTES + (uint32_t)(cb / 64) * 16384u + (uint32_t)r * 128u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t chunk = (uint32_t)(((cb & 63) >> 3) + i) ^ (uint32_t)(r & 7);
+              uint4 q;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                           : "r"(tl + chunk * 16u));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h[j]);
+                v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y;
+              }
+            }
+          } else if (e.res16) {
             const uint4* rp = reinterpret_cast<const uint4*>(e.res16 + b * e.res16_bs + t * e.res16_rs + n);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -365,7 +399,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       // this warp is done reading the accumulator stage: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * as) : "memory");
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * as) : "memory");
+        if (BN >= 64 && g.res_tma)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rempty0 + 8 * rb) : "memory");
+      }
       if (g.tma_store) {
         // make the generic-proxy writes visible to the async proxy, then one thread issues the bulk tensor
         // stores; rows beyond T / nb are clipped by the tensor-map bounds
@@ -528,7 +566,7 @@ bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a
   g->nb = nb; g->T = T; g->taps = taps; g->C = C; g->N = N;
   g->box_t = box_t; g->box_b = box_b; g->bn = bn; g->bk = bk;
   g->stages = best_stages; g->splits = best_splits; g->split_ws = nullptr;
-  g->tm_y16 = g->tm_a; g->tm_yraw16 = g->tm_a; g->tma_store = false;
+  g->tm_y16 = g->tm_a; g->tm_yraw16 = g->tm_a; g->tm_res = g->tm_a; g->tma_store = false; g->res_tma = false;
   g->stg_tiles = (bn >= 64) ? n_bf16_out * (bn / 64) : 0;
   g->persist = best_persist;
   g->e = TcEpilogue{};
@@ -540,6 +578,8 @@ bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a
             tag ? tag : "?", nb, T, taps, C, N, box_b, box_t, bn, bk, best_stages, best_splits, best_persist, best);
   return true;
 }
+
+static size_t ring_of(const TcGemm* g) { return (size_t)g->stages * (128 * g->bk * 2 + g->bn * g->bk * 2); }
 
 void gemm_tc_bind_outputs(TcGemm* g) {
   g->tma_store = false;
@@ -560,6 +600,17 @@ void gemm_tc_bind_outputs(TcGemm* g) {
   if (e.y16) ok = ok && make(&g->tm_y16, e.y16, e.y16_bs, e.y16_rs);
   if (e.yraw16) ok = ok && make(&g->tm_yraw16, e.yraw16, e.yraw16_bs, e.yraw16_rs);
   g->tma_store = ok;
+  // residual prefetch: two more tile sets behind the staging area, if they still fit
+  g->res_tma = false;
+  if (ok && e.res16) {
+    const size_t ring = (size_t)g->stages * (128 * g->bk * 2 + g->bn * g->bk * 2);
+    const size_t stg_b = (size_t)g->stg_tiles * 16384, res_b = (size_t)2 * (g->bn / 64) * 16384;
+    while (g->stages > 2 && (g->persist ? ring_of(g) + stg_b : std::max(ring_of(g), stg_b)) + res_b + 2048 > 226 * 1024)
+      g->stages -= 2;
+    (void)ring;
+    if ((g->persist ? ring_of(g) + stg_b : std::max(ring_of(g), stg_b)) + res_b + 2048 <= 226 * 1024)
+      g->res_tma = make(&g->tm_res, const_cast<__nv_bfloat16*>(e.res16), e.res16_bs, e.res16_rs);
+  }
 }
 
 void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
@@ -571,11 +622,13 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   a.e = g.e;
   a.tma_store = (g.tma_store && g.splits == 1) ? 1 : 0;
   a.stg_tiles = g.stg_tiles;
+  a.res_tma = (g.res_tma && a.tma_store) ? 1 : 0;
   a.splits = g.splits; a.split_ws = g.split_ws; a.split_stride = (long long)g.nb * g.T * g.N;
   const long long tiles = (long long)(g.N / g.bn) * a.m_tiles * g.splits;
   const size_t ring = (size_t)g.stages * (128 * g.bk * 2 + g.bn * g.bk * 2);
   const size_t stg_b = (size_t)g.stg_tiles * 16384;
-  const size_t smem = (g.persist ? ring + stg_b : std::max(ring, stg_b)) + 1024 + 16 * g.stages + 64;
+  const size_t res_b = (g.res_tma && g.tma_store && g.splits == 1) ? (size_t)2 * (g.bn / 64) * 16384 : 0;
+  const size_t smem = (g.persist ? ring + stg_b : std::max(ring, stg_b)) + res_b + 1024 + 16 * g.stages + 128;
   int per_sm = (int)((227 * 1024) / smem);
   per_sm = std::max(1, std::min(per_sm, std::min(2, 512 / (2 * g.bn))));
   dim3 grid((unsigned)(g.persist ? std::min<long long>(tiles, 148LL * per_sm) : tiles)), block(kThreads);
@@ -586,8 +639,8 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   ProfScope ps("gemm_tc", g.tag, flops, bytes, s);
 #define PTTS_TC1(BN_, BK_, ST_)                                                                                  \
   do {                                                                                                           \
-    if (g.persist) launch_k(gemm_tc_kernel<BN_, BK_, ST_, 2>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, a); \
-    else launch_k(gemm_tc_kernel<BN_, BK_, ST_, 1>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, a);           \
+    if (g.persist) launch_k(gemm_tc_kernel<BN_, BK_, ST_, 2>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, g.tm_res, a); \
+    else launch_k(gemm_tc_kernel<BN_, BK_, ST_, 1>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, g.tm_res, a);           \
   } while (0)
 #define PTTS_TC(BN_, BK_)                                                                                        \
   do {                                                                                                           \

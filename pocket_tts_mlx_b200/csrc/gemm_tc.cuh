@@ -31,7 +31,9 @@ struct TcEpilogue {
 struct TcGemm {
   CUtensorMap tm_a, tm_b;
   CUtensorMap tm_y16, tm_yraw16;   // output maps for the TMA-store epilogue (valid when tma_store)
+  CUtensorMap tm_res;              // bf16 residual map (valid when res_tma)
   bool tma_store = false;
+  bool res_tma = false;
   int nb, T, taps, C, N;
   int box_t, box_b;           // 128-row M tile = box_b sequences x box_t time steps
   int bn, bk;                 // N tile (32/64/128), K chunk in elements (64 or 32)
