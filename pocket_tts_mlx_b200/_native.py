@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 from pathlib import Path
 from typing import Optional, Sequence
 
@@ -170,11 +171,14 @@ class Context:
     def __init__(self, config: Config, device: int = 0):
         self._h = C.c_void_p()
         self.config = config
+        self._batches = weakref.WeakSet()       # live batches: closed before the context goes away
         check(lib().ptts_ctx_create(device, C.byref(config), C.byref(self._h)))
         self.device = device
 
     def close(self):
         if self._h:
+            for b in list(self._batches):
+                b.close()
             lib().ptts_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -252,6 +256,7 @@ class Batch:
         v = np.ascontiguousarray(voice_ids, dtype=np.int32)
         m = np.ascontiguousarray(max_len, dtype=np.int32)
         check(lib().ptts_batch_create(ctx._h, self.n, _ip(v), _ip(m), C.byref(self._h)))
+        ctx._batches.add(self)
         self.latent_dim = ctx.config.latent_dim
         hop = 1
         for i in range(ctx.config.n_ratios):

@@ -364,3 +364,75 @@ def test_staged_step_equals_copying_step(model_bf16):
     for a, b in zip(*res):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
+
+
+# ---------------------------------------------------------------------------------------- engine behaviour
+def test_kv_pool_exhaustion_is_reported(bundle):
+    from pocket_tts_mlx_b200 import TTSModel, _native
+    m = TTSModel.load_model(str(bundle), eos_threshold=1e30, kv_pool_tokens=1024)   # 32 pages
+    try:
+        st = m.get_state_for_audio_prompt("alba")                                    # 4 pages
+        with pytest.raises(_native.PttsError, match="KV page pool exhausted"):
+            _native.Batch(m._ctx, [st["voice_id"]] * 8, [st["prompt_len"] + 200] * 8)
+        # the failed create returned every page: a batch that fits still works afterwards
+        b = _native.Batch(m._ctx, [st["voice_id"]] * 2, [st["prompt_len"] + 100] * 2)
+        b.close()
+        with pytest.raises(_native.PttsError, match="before ptts_batch_prefill_text"):
+            b2 = _native.Batch(m._ctx, [st["voice_id"]], [st["prompt_len"] + 20])
+            b2.step(np.zeros((1, 32), np.float32))
+    finally:
+        m.close()
+
+
+def test_recycled_batch_arena_equals_fresh(model_bf16):
+    """ptts_batch_destroy parks the device arena + graphs; the next batch of the same shape must start from
+    a clean streaming state (zeroed Mimi ring / conv state, BOS, fresh page tables), whatever ran before."""
+    rng = np.random.Generator(np.random.PCG64(31))
+    ids = [rng.integers(0, 4000, size=8).astype(np.int32) for _ in range(3)]
+    noise = rng.standard_normal((6, 3, 32)).astype(np.float32)
+    sa = [model_bf16.get_state_for_audio_prompt(v) for v in ("alba", "jean", "alba")]
+    sb = [model_bf16.get_state_for_audio_prompt(v) for v in ("cosette", "cosette", "marius")]
+    first = model_bf16.generate_audio_batch(sa, ids, max_frames=5, noise=noise)
+    model_bf16.generate_audio_batch(sb, [i[::-1].copy() for i in ids], max_frames=5, noise=noise[::-1].copy())
+    again = model_bf16.generate_audio_batch(sa, ids, max_frames=5, noise=noise)
+    for a, b in zip(first, again):
+        assert np.array_equal(a, b)
+
+
+def test_voice_lifecycle(model_bf16):
+    ctx = model_bf16._ctx
+    rng = np.random.Generator(np.random.PCG64(8))
+    cond = rng.standard_normal((40, 1024)).astype(np.float32)
+    v = ctx.voice_create(cond)
+    assert ctx.voice_length(v) == 40
+    ctx.voice_destroy(v)
+    from pocket_tts_mlx_b200 import _native
+    with pytest.raises(_native.PttsError):
+        ctx.voice_length(v)
+    v2 = ctx.voice_create(cond[:33])
+    assert ctx.voice_length(v2) == 33
+    ctx.voice_destroy(v2)
+
+
+def test_long_form_kv_beyond_1k_tokens(model_bf16, cfg, weights, voices):
+    """BASELINE config 5 shape: 174 text tokens (max_gen_len 750, KV up to 1049 tokens = 33 pages); a few frames
+    late in the page table, teacher-forced against the oracle."""
+    from pocket_tts_mlx_b200 import _native
+    rng = np.random.Generator(np.random.PCG64(12))
+    ids = rng.integers(0, 4000, size=174).astype(np.int32)
+    assert _native.max_gen_len(174) == 750
+    frames = 4
+    noise = rng.standard_normal((1 + frames, 32)).astype(np.float32)
+    orc, st = _oracle(weights, cfg, voices, "alba", None, eos_threshold=1e30)
+    ref = orc.generate(st, ids, noise, frames_after_eos=3, max_frames=frames)
+    s = model_bf16.get_state_for_audio_prompt("alba")
+    batch = _native.Batch(model_bf16._ctx, [s["voice_id"]] * 2, [s["prompt_len"] + 174 + 750] * 2)
+    batch.warmup_mimi(1)
+    batch.prefill_text([ids, ids])
+    assert batch.lengths().tolist() == [125 + 174] * 2
+    for f in range(frames):
+        lat, _, _ = batch.step(np.stack([noise[1 + f]] * 2))
+        assert rel_l2(lat[0], ref["latents"][f]) < 1e-2
+        assert np.array_equal(lat[0], lat[1])                      # identical sequences stay identical
+        batch.set_prev_latent(np.stack([ref["latents"][f]] * 2))
+    batch.close()
