@@ -104,6 +104,8 @@ struct FlowWork {
   std::vector<TcGemm> plans;  // 4 per layer: qkv, out, ff1, ff2
   float *ws_out = nullptr, *ws_ff2 = nullptr;   // split-K partial planes [8][M][D] of out-proj / ffn2
   float* attn_part = nullptr;                   // split-KV attention partials [M][H][8][66] (decode at small batch)
+  // cascade attention (decode of a batch whose sequences all share one voice prefix)
+  int prefix_len = 0; int* d_prefix_pages = nullptr; float* prefix_part = nullptr;
   int pend_n = 0;             // planes of the last ffn2 still to be added to x (consumed by the next norm)
 };
 
@@ -514,7 +516,8 @@ bool want_tc(Ctx& c, int M) {
 }
 
 void free_flow_work(FlowWork& w) {
-  void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16, w.ws_out, w.ws_ff2, w.attn_part};
+  void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16, w.ws_out, w.ws_ff2, w.attn_part,
+                  w.d_prefix_pages, w.prefix_part};
   for (void* p : ptrs) if (p) cudaFree(p);
   w = FlowWork{};
 }
@@ -596,7 +599,11 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       a.layer = i; a.row_seq = row_seq; a.row_pos = row_pos; a.page_table = page_table; a.max_pages = max_pages;
       a.M = M; a.H = c.cfg.n_heads; a.freqs = c.freqs_flow; a.total_keys = total_keys;
       a.part = w.attn_part; a.splits = w.attn_part ? std::min(8, std::max(1, 296 / (M * c.cfg.n_heads))) : 1;
+      if (!row_seq && w.prefix_len > 0 && a.splits == 1) {
+        a.prefix_len = w.prefix_len; a.prefix_pages = w.d_prefix_pages; a.prefix_part = w.prefix_part;
+      }
       launch_flow_rope_append(a, c.stream);
+      launch_flow_prefix_attention(a, c.stream);
       launch_flow_attention(a, c.stream);
       gemm_tc_launch(g[1], c.stream);
       rows_norm(c, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16, w.ws_out,
@@ -693,6 +700,7 @@ struct ptts_batch {
   // pipelined mode: frame graph = { FlowLM step t } || { Mimi decode of latent t-1 } on two streams.
   // Latents ping-pong between d_latent (even frames) and d_latent_b (odd frames); index = parity*2 + host_io.
   bool pipelined = false;
+  int cascade_len = 0;              // prefix length the captured graphs were built for
   long long frame_idx = 0;          // frames stepped since the last (re)initialisation
   float* d_latent_b = nullptr;
   cudaGraphExec_t pipe_graph[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1396,6 +1404,27 @@ static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32
     CU(cudaMemcpyAsync(t.d_cp_dst, dst.data(), dst.size() * 4, cudaMemcpyHostToDevice, c->stream));
     launch_copy_pages(c->pool, c->bf16, c->layer_stride, c->page_stride, c->cfg.n_layers, t.d_cp_src, t.d_cp_dst,
                       (int)src.size(), c->stream);
+  }
+  // cascade attention: every sequence shares the same voice and the prefix fits the tensor-core prefix kernel
+  {
+    bool same = c->bf16 && t.fw.tc && B >= 32 && getenv("PTTS_NO_CASCADE") == nullptr;
+    for (int b = 1; b < B && same; ++b) same = voice_ids[b] == voice_ids[0];
+    const Voice& v0 = c->voices[voice_ids[0]];
+    t.fw.prefix_len = 0;
+    if (same && v0.len <= 128 && v0.len >= 16) {
+      if (!t.fw.d_prefix_pages) {
+        CU(cudaMalloc((void**)&t.fw.d_prefix_pages, 8 * sizeof(int)));
+        CU(cudaMalloc((void**)&t.fw.prefix_part, (size_t)B * c->cfg.n_heads * 66 * sizeof(float)));
+      }
+      CU(cudaMemcpyAsync(t.fw.d_prefix_pages, v0.pages.data(), v0.pages.size() * sizeof(int), cudaMemcpyHostToDevice,
+                         c->stream));
+      t.fw.prefix_len = v0.len;
+    }
+    if (t.cascade_len != t.fw.prefix_len) {      // the prefix length is baked into the captured graphs
+      for (auto& g : t.step_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+      for (auto& g : t.pipe_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+      t.cascade_len = t.fw.prefix_len;
+    }
   }
   for (auto& z : t.zero_list) CU(cudaMemsetAsync(z.first, 0, z.second, c->stream));
   CU(cudaMemcpyAsync(t.d_len, t.h_len.data(), B * 4, cudaMemcpyHostToDevice, c->stream));

@@ -80,7 +80,12 @@ struct FlowAttnParams {
   const float* freqs;          // [32] RoPE frequencies (fp32, computed like modules/rope.py:17-18)
   long long total_keys;        // host-side sum over rows of (row_pos+1), for the profiler's byte count
   int splits; float* part;     // split-KV for small batches: partials [M][H][splits][66] merged by a second kernel
+  // cascade: all rows share the first prefix_len keys (the voice prompt).  A tensor-core kernel computes that part
+  // once per (row, head) from the voice's own pages into prefix_part [M][H][66]; the per-sequence kernel then
+  // starts at key prefix_len and merges the partial.
+  int prefix_len; const int* prefix_pages; float* prefix_part;
 };
+void launch_flow_prefix_attention(const FlowAttnParams& p, cudaStream_t s);
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s);
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s);
 

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) flow_attention_kernel(const FlowAttnParam
   const int seq = p.row_seq ? p.row_seq[m] : m;
   const int n_all = p.row_pos[m] + 1;
   // split-KV (small batches): CTA z of `splits` owns a 16-aligned slice of the keys and writes a partial
-  int key_lo = 0, n_keys = n_all;
+  int key_lo = p.prefix_len, n_keys = n_all;     // prefix_len > 0: keys [0, prefix_len) come from the cascade partial
   if (p.splits > 1) {
     const int chunk = (((n_all + p.splits - 1) / p.splits) + 15) & ~15;
     key_lo = blockIdx.z * chunk;
@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(128) flow_attention_kernel(const FlowAttnParam
   // each warp takes 16 consecutive keys per step (4 groups of 4, all inside one 32-token page): the 8 16-byte
   // loads of a step are issued before any of them is consumed, so ~8 KB per warp are in flight
   constexpr int U = 1;   // measured: U=2 no gain, U=4 (108 regs) 40% slower -- occupancy beats per-warp unrolling here
-  for (int k0 = key_lo + warp * 4 * U; k0 < n_keys; k0 += 16 * U) {
+  // steps start on a multiple of 4 keys so that the keys of a step share one page; keys below key_lo (the
+  // cascade prefix, or another split's slice) are masked
+  for (int k0 = (key_lo & ~3) + warp * 4 * U; k0 < n_keys; k0 += 16 * U) {
     const int page = pt[k0 / kPageTokens];
     const KT* pbase = pool + page * p.page_stride + ((long long)h * kPageTokens + (k0 % kPageTokens)) * kHeadDim + sl * 8;
     float kf[U][8], vf[U][8];
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(128) flow_attention_kernel(const FlowAttnParam
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int key = k0 + 4 * u + grp;
-      ok[u] = key < n_keys;
+      ok[u] = key >= key_lo && key < n_keys;
       if (ok[u]) {
         const KT* kp = pbase + (4 * u + grp) * kHeadDim;
         KVec<KT>::load8(kp, kf[u]);
@@ -170,12 +172,19 @@ __global__ void __launch_bounds__(128) flow_attention_kernel(const FlowAttnParam
   __syncthreads();
   if (threadIdx.x < kHeadDim) {
     float mx = fmaxf(fmaxf(sh_m[0], sh_m[1]), fmaxf(sh_m[2], sh_m[3]));
+    const float* pp = (p.prefix_len > 0) ? p.prefix_part + ((long long)m * p.H + h) * 66 : nullptr;
+    if (pp) mx = fmaxf(mx, pp[64]);
     float l = 0.f, a = 0.f;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const float c = (sh_m[w] == -INFINITY) ? 0.f : __expf(sh_m[w] - mx);
       l += sh_l[w] * c;
       a += sh_acc[w][threadIdx.x] * c;
+    }
+    if (pp) {
+      const float c = __expf(pp[64] - mx);
+      l += pp[65] * c;
+      a += pp[threadIdx.x] * c;
     }
     if (p.splits > 1) {
       // partial of this key slice: [m][h][z][64 values | max | sum]; an empty slice contributes l = 0
@@ -506,6 +515,123 @@ __global__ void __launch_bounds__(128) mimi_attention_mma_kernel(const MimiAttnP
   }
 }
 
+// ---- cascade: attention of every row over the SHARED voice prefix, on tensor cores ---------------------------
+// grid (ceil(M/64), H), 128 threads.  The prefix K/V of head h (<= 128 keys, read from the voice's own pages)
+// are staged once per CTA; warp w takes rows 16w..16w+15 of the CTA's 64 as one m16 MMA tile against all 128
+// key slots (S = Q K^T: 16 n-tiles x 4 k-steps, O = P V: 8 dim tiles x 8 k-steps) and writes the un-normalised
+// partial {O[64], max, sum} that flow_attention_kernel merges with the per-sequence keys.
+constexpr int kPrefixKeys = 128;
+__global__ void __launch_bounds__(128) flow_prefix_attention_kernel(const FlowAttnParams p) {
+  pdl_sync();
+  extern __shared__ __align__(16) unsigned char pre_smem[];
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(pre_smem);
+  __nv_bfloat16* Vs = Ks + kPrefixKeys * kMimiLd;
+  const int h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int D = p.H * kHeadDim;
+  const int P = p.prefix_len;
+  const __nv_bfloat16* pool = reinterpret_cast<const __nv_bfloat16*>(p.pool) + p.layer * p.layer_stride;
+  const long long kv_half = (long long)p.H * kPageTokens * kHeadDim;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = threadIdx.x + 128 * i;                  // 128 keys x 8 chunks of 16 bytes
+    const int key = idx >> 3, ch = idx & 7;
+    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+    if (key < P) {
+      const int page = p.prefix_pages[key / kPageTokens];
+      const __nv_bfloat16* src = pool + page * p.page_stride + ((long long)h * kPageTokens + (key % kPageTokens)) * kHeadDim + ch * 8;
+      kv = *reinterpret_cast<const uint4*>(src);
+      vv = *reinterpret_cast<const uint4*>(src + kv_half);
+    }
+    *reinterpret_cast<uint4*>(Ks + key * kMimiLd + ch * 8) = kv;
+    *reinterpret_cast<uint4*>(Vs + key * kMimiLd + ch * 8) = vv;
+  }
+  const int row0 = blockIdx.x * 64 + warp * 16;
+  const int m0 = row0 + g, m1 = row0 + g + 8;
+  const bool r0 = m0 < p.M, r1 = m1 < p.M;
+  uint32_t qa[4][4];
+  {
+    const float* q0 = p.q_rot + (long long)(r0 ? m0 : 0) * D + h * kHeadDim;
+    const float* q1 = p.q_rot + (long long)(r1 ? m1 : 0) * D + h * kHeadDim;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int c = 16 * ks + 2 * t4;
+      const float2 a0 = *reinterpret_cast<const float2*>(q0 + c), a2 = *reinterpret_cast<const float2*>(q0 + c + 8);
+      const float2 a1 = *reinterpret_cast<const float2*>(q1 + c), a3 = *reinterpret_cast<const float2*>(q1 + c + 8);
+      qa[ks][0] = pack2_bf16(a0.x * 0.125f, a0.y * 0.125f);
+      qa[ks][1] = pack2_bf16(a1.x * 0.125f, a1.y * 0.125f);
+      qa[ks][2] = pack2_bf16(a2.x * 0.125f, a2.y * 0.125f);
+      qa[ks][3] = pack2_bf16(a3.x * 0.125f, a3.y * 0.125f);
+    }
+  }
+  __syncthreads();
+  float sc[16][4];
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+    sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t kb[4];
+      ldsm_x4(kb, (uint32_t)__cvta_generic_to_shared(Ks + (nt * 8 + (lane & 7)) * kMimiLd + 32 * kk + 8 * (lane >> 3)));
+      mma_bf16_16816(sc[nt], qa[2 * kk], kb[0], kb[1]);
+      mma_bf16_16816(sc[nt], qa[2 * kk + 1], kb[2], kb[3]);
+    }
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (nt * 8 + 2 * t4 + j >= P) { sc[nt][j] = -INFINITY; sc[nt][2 + j] = -INFINITY; }
+      mx0 = fmaxf(mx0, sc[nt][j]);
+      mx1 = fmaxf(mx1, sc[nt][2 + j]);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t pa[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+    const float p00 = __expf(sc[nt][0] - mx0), p01 = __expf(sc[nt][1] - mx0);
+    const float p10 = __expf(sc[nt][2] - mx1), p11 = __expf(sc[nt][3] - mx1);
+    l0 += p00 + p01;
+    l1 += p10 + p11;
+    pa[nt >> 1][(nt & 1) * 2 + 0] = pack2_bf16(p00, p01);
+    pa[nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p10, p11);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  float oc[8][4];
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t vb[4];
+      const int mid = lane >> 3;
+      ldsm_x4_t(vb, (uint32_t)__cvta_generic_to_shared(Vs + (16 * j + 8 * (mid & 1) + (lane & 7)) * kMimiLd +
+                                                        8 * (2 * dp + (mid >> 1))));
+      mma_bf16_16816(oc[2 * dp], pa[j], vb[0], vb[1]);
+      mma_bf16_16816(oc[2 * dp + 1], pa[j], vb[2], vb[3]);
+    }
+  }
+  if (r0) {
+    float* o = p.prefix_part + ((long long)m0 * p.H + h) * 66;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<float2*>(o + dt * 8 + 2 * t4) = make_float2(oc[dt][0], oc[dt][1]);
+    if (t4 == 0) { o[64] = mx0; o[65] = l0; }
+  }
+  if (r1) {
+    float* o = p.prefix_part + ((long long)m1 * p.H + h) * 66;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<float2*>(o + dt * 8 + 2 * t4) = make_float2(oc[dt][2], oc[dt][3]);
+    if (t4 == 0) { o[64] = mx1; o[65] = l1; }
+  }
+}
+
 }  // namespace
 
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s) {
@@ -516,11 +642,21 @@ void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s) {
   ++g_launches;
 }
 
+void launch_flow_prefix_attention(const FlowAttnParams& p, cudaStream_t s) {
+  if (p.M <= 0 || p.prefix_len <= 0) return;
+  const size_t smem = (size_t)2 * kPrefixKeys * kMimiLd * 2;
+  ProfScope ps("flow_prefix_attention", nullptr, 4.0 * p.M * p.H * p.prefix_len * 64,
+               2.0 * p.H * p.prefix_len * 64 * 2 + (double)p.M * p.H * (64 * 4 + 66 * 4), s);
+  launch_k(flow_prefix_attention_kernel, dim3((p.M + 63) / 64, p.H), dim3(128), smem, s, p);
+  ++g_launches;
+}
+
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
   if (p.M <= 0) return;
   dim3 grid(p.M, p.H, p.splits > 1 ? p.splits : 1);
-  ProfScope ps("flow_attention", nullptr, 4.0 * p.total_keys * p.H * 64,
-               2.0 * p.total_keys * p.H * 64 * (p.kv_bf16 ? 2 : 4) + 2.0 * p.M * p.H * 64 * 4, s);
+  const double keys = (double)p.total_keys - (double)p.M * p.prefix_len;     // keys streamed by this kernel
+  ProfScope ps("flow_attention", nullptr, 4.0 * keys * p.H * 64,
+               2.0 * keys * p.H * 64 * (p.kv_bf16 ? 2 : 4) + 2.0 * p.M * p.H * 64 * 4, s);
   if (p.kv_bf16) launch_k(flow_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, s, p);
   else launch_k(flow_attention_kernel<float>, dim3(grid), dim3(128), 0, s, p);
   ++g_launches;

@@ -436,3 +436,25 @@ def test_long_form_kv_beyond_1k_tokens(model_bf16, cfg, weights, voices):
         assert np.array_equal(lat[0], lat[1])                      # identical sequences stay identical
         batch.set_prev_latent(np.stack([ref["latents"][f]] * 2))
     batch.close()
+
+
+def test_cascade_prefix_attention_matches_plain_path(model_bf16, cfg, weights, voices):
+    """Batches of >= 32 sequences sharing one voice take the cascade path (tensor-core attention over the shared
+    prefix + per-sequence kernel over the private keys): latents stay within the bf16 bound of the oracle and
+    agree with the non-cascade path (mixed voices) to bf16 rounding."""
+    from pocket_tts_mlx_b200 import _native
+    rng = np.random.Generator(np.random.PCG64(44))
+    n, frames = 32, 4
+    ids = [rng.integers(0, 4000, size=int(rng.integers(10, 20))).astype(np.int32) for _ in range(n)]
+    noise = rng.standard_normal((1 + frames, n, 32)).astype(np.float32)
+    s_alba = model_bf16.get_state_for_audio_prompt("alba")
+    s_alba2 = model_bf16.get_state_for_conditioning(voices("alba")[0])      # same content, different voice id
+    casc = model_bf16.generate_audio_batch([s_alba] * n, ids, max_frames=frames, noise=noise, return_latents=True)
+    mixed_states = [s_alba if b % 2 else s_alba2 for b in range(n)]          # not all the same id -> plain path
+    plain = model_bf16.generate_audio_batch(mixed_states, ids, max_frames=frames, noise=noise, return_latents=True)
+    for b in (0, 7, 31):
+        assert rel_l2(casc[1][b], plain[1][b]) < 5e-3, rel_l2(casc[1][b], plain[1][b])
+    orc, st = _oracle(weights, cfg, voices, "alba", None, eos_threshold=1e30)
+    ref = orc.generate(st, ids[5], noise[:, 5, :], frames_after_eos=3, max_frames=frames)
+    assert rel_l2(casc[1][5][0], ref["latents"][0]) < 1e-2
+    assert snr_db(casc[0][5][:1920], ref["audio"][:1920]) > 30.0
