@@ -165,7 +165,8 @@ int32_t ptts_debug_linear(ptts_ctx* ctx, int32_t path, int32_t n_b, int32_t n_t,
 /* Kernel-level benchmark of the tcgen05 multi-tap GEMM on synthetic bf16 operands (L2 flushed between
  * launches): median microseconds over `reps`.  force = {N tile, ring stages, split-K, persistent} or NULL for
  * the planner's choice (returned in chosen[4]); epi = number of bf16 outputs (0: one fp32 output), +4 adds a
- * bf16 residual read. */
+ * bf16 residual read.  reps < 0: |reps| warm back-to-back launches on the stream, average per launch;
+ * reps <= -1000: the same |reps|-1000 launches replayed from a captured CUDA graph (the in-frame cost). */
 int32_t ptts_debug_gemm_bench(ptts_ctx* ctx, int32_t n_b, int32_t n_t, int32_t taps, int32_t c_in, int32_t n_out,
                               int32_t epi, const int32_t* force, int32_t reps, float* us, int32_t* chosen);
 
