@@ -690,6 +690,9 @@ struct ptts_batch {
   TcGemm g_conv0;
   struct StageBuf16 { __nv_bfloat16 *ct_in, *r_in, *xraw, *hid; int T_in, T_out; TcGemm ct, r3, r1; };
   std::vector<StageBuf16> sb16;
+  SnTail sn_tail;                   // fused last resblock + output conv (valid: replaces sb16.back().r3/.r1 + final conv)
+  float* d_bnd = nullptr;
+  bool no_tail_env = false;         // PTTS_NO_SNTAIL at creation (a recycled arena must match the current setting)
   int T0 = 0;           // steps per frame at the SEANet input (upsample stride)
   int frame_samples = 0;
   // pinned staging
@@ -859,13 +862,19 @@ void mimi_frame_tc(Batch& bt, const float* latent, int part) {   // part: 0 all,
   }
   if (part == 1) return;
   gemm_tc_launch(bt.g_conv0, c.stream);
-  for (auto& sb : bt.sb16) {
+  for (size_t r = 0; r < bt.sb16.size(); ++r) {
+    auto& sb = bt.sb16[r];
     gemm_tc_launch(sb.ct, c.stream);
+    if (bt.sn_tail.valid && r + 1 == bt.sb16.size()) {
+      sn_tail_launch(bt.sn_tail, c.stream);
+      break;
+    }
     gemm_tc_launch(sb.r3, c.stream);
     gemm_tc_launch(sb.r1, c.stream);
   }
-  launch_final_conv16(bt.d_fin16, (long long)(bt.frame_samples + c.fin_taps - 1) * c.fin_c, c.fin_w, c.fin_b,
-                      bt.d_audio, bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream);
+  if (!bt.sn_tail.valid)
+    launch_final_conv16(bt.d_fin16, (long long)(bt.frame_samples + c.fin_taps - 1) * c.fin_c, c.fin_w, c.fin_b,
+                        bt.d_audio, bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream);
   launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream);
 }
 
@@ -889,6 +898,11 @@ void flow_head_tc(Batch& bt) {
     rows_norm(c, bt.d_x1, B, fd, nullptr, nullptr, 1e-6f, nullptr, adaf + fd, adaf, c.n_ada, bt.d_hh16, nullptr, 0);
     gemm_tc_launch(bt.g_fin, c.stream);
   }
+}
+
+bool sn_tail_disabled() {
+  const char* nt = getenv("PTTS_NO_SNTAIL");
+  return nt && nt[0] == '1';
 }
 
 int build_batch_tc(Batch& t) {
@@ -1021,6 +1035,21 @@ int build_batch_tc(Batch& t) {
       }
     }
     if (!ok) return fail(PTTS_ERR_CUDA, "tcgen05 plan failed for the Mimi decoder (B=%d)", B);
+    {
+      // 64-channel tail: one fused kernel instead of conv_k3 / conv_k1 / output conv (PTTS_NO_SNTAIL=1 keeps them apart)
+      const bool no_tail = sn_tail_disabled();       // read per batch so a test can compare both paths
+      t.no_tail_env = no_tail;
+      auto& st = c.stages[g.n_ratios - 1];
+      auto& b = t.sb16[g.n_ratios - 1];
+      if (!no_tail && c.fin_c == st.c_out && st.r3.w16 && st.r1.w16 &&
+          sn_tail_plan(&t.sn_tail, b.r_in, b.xraw, B, b.T_out, st.c_out, st.hidden, rk, c.fin_taps, st.r3.w16, st.r1.w16)) {
+        const size_t n_bnd = (size_t)B * (b.T_out / 128 + 1) * 4;
+        RET(t.dalloc((void**)&t.d_bnd, n_bnd * 4));
+        t.zero_list.push_back({t.d_bnd, n_bnd * 4});
+        t.sn_tail.b1 = st.r3.bias; t.sn_tail.b2 = st.r1.bias; t.sn_tail.wf = c.fin_w; t.sn_tail.bf = c.fin_b;
+        t.sn_tail.audio = t.d_audio; t.sn_tail.audio_bs = t.frame_samples; t.sn_tail.bnd = t.d_bnd;
+      }
+    }
     for (auto& gm : t.g_mimi) gemm_tc_bind_outputs(&gm);
     gemm_tc_bind_outputs(&t.g_conv0);
     for (auto& b : t.sb16) {
@@ -1452,7 +1481,7 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
   // recycle the arena (device buffers, tensor maps, captured graphs) of a destroyed batch of the same shape
   for (size_t i = 0; i < c->parked.size(); ++i) {
     ptts_batch* p = c->parked[i];
-    if (p->B == B && p->max_pages >= maxp) {
+    if (p->B == B && p->max_pages >= maxp && p->no_tail_env == sn_tail_disabled()) {
       c->parked.erase(c->parked.begin() + i);
       bt.reset(p);
       return batch_init_state(*bt, voice_ids, max_len);

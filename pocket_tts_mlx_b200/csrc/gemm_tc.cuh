@@ -66,6 +66,27 @@ int gemm_tc_debug(const LinearParams& p, bool bf16_storage, cudaStream_t s);
 int gemm_tc_bench(int nb, int T, int taps, int C, int N, int epi, const int force[4], int reps, float* us,
                   int chosen[4], cudaStream_t s);
 
+// bf16 tiled tensor map; swizzle_elems = 64 (128-byte swizzle) or 32 (64-byte swizzle) = inner box extent
+bool tc_encode_bf16(CUtensorMap* tm, const void* base, int rank, const unsigned long long* dims,
+                    const unsigned long long* strides_bytes, const unsigned* box, int swizzle_elems);
+
+// Fused SEANet tail (seanet_tail.cu): the last residual block and the output convolution in one kernel,
+//   y = x + W2 . ELU(W1 (*) ELU(x) + b1) + b2 ;  audio[t] = sum_j wf[j] . ELU(y[t-2+j]) + bf
+// for C = 64 channels, hidden 32, 3-tap causal convs, T % 128 == 0.  `xe` = ELU(x) behind 2 carried state rows
+// ([nb][T+2][64] bf16), `xraw` = x ([nb][T][64] bf16); `bnd` ([nb][T/128+1][4] fp32, zero at stream start) carries
+// the three partial products that cross tile / frame boundaries.
+struct SnTail {
+  CUtensorMap tm_a, tm_w1, tm_w2, tm_res;
+  int nb = 0, T = 0;
+  const float *b1 = nullptr, *b2 = nullptr, *wf = nullptr, *bf = nullptr;
+  float* audio = nullptr; long long audio_bs = 0;
+  float* bnd = nullptr;
+  bool valid = false;
+};
+bool sn_tail_plan(SnTail* p, const __nv_bfloat16* xe, const __nv_bfloat16* xraw, int nb, int T, int C, int hidden,
+                  int taps, int fin_taps, const __nv_bfloat16* w1, const __nv_bfloat16* w2);
+void sn_tail_launch(const SnTail& p, cudaStream_t s);
+
 // helpers used by the bf16 pipeline
 void launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t s);
 

@@ -458,3 +458,48 @@ def test_cascade_prefix_attention_matches_plain_path(model_bf16, cfg, weights, v
     ref = orc.generate(st, ids[5], noise[:, 5, :], frames_after_eos=3, max_frames=frames)
     assert rel_l2(casc[1][5][0], ref["latents"][0]) < 1e-2
     assert snr_db(casc[0][5][:1920], ref["audio"][:1920]) > 30.0
+
+
+def test_fused_seanet_tail_matches_three_kernel_path(model_bf16, monkeypatch):
+    """The fused last-resblock + output-conv kernel (seanet_tail.cu) against the conv_k3 / conv_k1 / output-conv
+    kernels it replaces, over 12 frames and 3 sequences: the partial products carried across 128-step tiles and
+    across frames must line up sample for sample (the fused path keeps y in fp32, so agreement is to bf16 rounding),
+    and both must meet the waveform bar against the reference's golden waveform."""
+    from pocket_tts_mlx_b200 import _native
+    g = np.load(GOLDEN / "ref_long40.npz")
+    lat = np.stack([g["step_latents"][:12], g["step_latents"][12:24], g["step_latents"][5:17]])
+    st = model_bf16.get_state_for_audio_prompt("marius")
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PTTS_NO_SNTAIL", mode)
+        # different max_len per mode so the arena of the other mode is not recycled
+        batch = _native.Batch(model_bf16._ctx, [st["voice_id"]] * 3, [st["prompt_len"] + (40 if mode == "1" else 72)] * 3)
+        batch.warmup_mimi(1)
+        out[mode] = batch.mimi_decode(lat)
+        batch.close()
+    assert snr_db(out["0"][0], g["audio"][:12 * 1920]) > 30.0
+    for b in range(3):
+        assert snr_db(out["0"][b], out["1"][b]) > 40.0, snr_db(out["0"][b], out["1"][b])
+    # tile boundaries (t % 128 in {0, 1}) and frame boundaries are where a mis-carried partial product would show
+    edge = np.zeros(12 * 1920, bool)
+    edge[0::128] = True
+    edge[1::128] = True
+    assert snr_db(out["0"][1][edge], out["1"][1][edge]) > 40.0
+
+
+def test_fused_seanet_tail_many_tiles_per_cta(model_bf16, monkeypatch):
+    """64 sequences x 2 frames = 960 tiles of 128 steps on 148 persistent CTAs: every CTA walks 6-7 tiles, so the
+    operand ring, the residual buffers, both TMEM accumulator stages and the partial-product exchange all wrap."""
+    from pocket_tts_mlx_b200 import _native
+    rng = np.random.Generator(np.random.PCG64(7))
+    lat = rng.standard_normal((64, 2, 32)).astype(np.float32)
+    st = model_bf16.get_state_for_audio_prompt("alba")
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PTTS_NO_SNTAIL", mode)
+        batch = _native.Batch(model_bf16._ctx, [st["voice_id"]] * 64, [st["prompt_len"] + 16] * 64)
+        batch.warmup_mimi(1)
+        out[mode] = batch.mimi_decode(lat)
+        batch.close()
+    for b in (0, 1, 17, 40, 63):
+        assert snr_db(out["0"][b], out["1"][b]) > 40.0, (b, snr_db(out["0"][b], out["1"][b]))
