@@ -107,6 +107,7 @@ struct FlowWork {
   // cascade attention (decode of a batch whose sequences all share one voice prefix)
   int prefix_len = 0; int* d_prefix_pages = nullptr; float* prefix_part = nullptr;
   int pend_n = 0;             // planes of the last ffn2 still to be added to x (consumed by the next norm)
+  float* rope_cs = nullptr;   // [M][64] cos | sin of each row's position (fused RoPE epilogue of the qkv GEMM)
 };
 
 }  // namespace
@@ -517,7 +518,7 @@ bool want_tc(Ctx& c, int M) {
 
 void free_flow_work(FlowWork& w) {
   void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16, w.ws_out, w.ws_ff2, w.attn_part,
-                  w.d_prefix_pages, w.prefix_part};
+                  w.d_prefix_pages, w.prefix_part, w.rope_cs};
   for (void* p : ptrs) if (p) cudaFree(p);
   w = FlowWork{};
 }
@@ -537,6 +538,7 @@ int alloc_flow_work(Ctx& c, FlowWork& w, int M) {
     CU(cudaMalloc((void**)&w.ff16, M * FF * 2));
     CU(cudaMalloc((void**)&w.ws_out, 8 * M * D * 4));
     CU(cudaMalloc((void**)&w.ws_ff2, 8 * M * D * 4));
+    CU(cudaMalloc((void**)&w.rope_cs, (size_t)M * 64 * 4));
   } else {
     CU(cudaMalloc((void**)&w.h, M * D * 4));
     CU(cudaMalloc((void**)&w.att, M * D * 4));
@@ -588,11 +590,25 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
   const int D = c.cfg.d_model, FF = c.cfg.ffn_dim;
   if (w.tc) {
     int pend = 0;   // split-K planes of the previous ffn2 that the next norm must add to x
+    // RoPE + KV append ride in the qkv GEMM's epilogue (PTTS_NO_ROPE_FUSE=1 keeps the separate kernel)
+    static const bool fuse_rope = [] { const char* v = getenv("PTTS_NO_ROPE_FUSE"); return !(v && v[0] == '1'); }();
+    if (fuse_rope) launch_rope_table(row_pos, c.freqs_flow, w.rope_cs, M, c.stream);
     for (int i = 0; i < c.cfg.n_layers; ++i) {
       auto& l = c.fl[i];
       const TcGemm* g = &w.plans[(size_t)i * 4];
       rows_norm(c, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16, w.ws_ff2, pend);
-      gemm_tc_launch(g[0], c.stream);
+      if (fuse_rope) {
+        TcGemm q = g[0];
+        auto& e = q.e;
+        e.y32 = nullptr;
+        e.rope_cs = w.rope_cs; e.q_rot = w.qrot;
+        e.kv_layer = reinterpret_cast<__nv_bfloat16*>(c.pool) + (long long)i * c.layer_stride;
+        e.kv_row_seq = row_seq; e.kv_row_pos = row_pos; e.kv_page_table = page_table;
+        e.kv_max_pages = max_pages; e.kv_heads = c.cfg.n_heads; e.kv_page_stride = c.page_stride;
+        gemm_tc_launch(q, c.stream);
+      } else {
+        gemm_tc_launch(g[0], c.stream);
+      }
       FlowAttnParams a{};
       a.qkv = w.qkv; a.q_rot = w.qrot; a.out16 = w.att16;
       a.pool = c.pool; a.kv_bf16 = c.bf16; a.layer_stride = c.layer_stride; a.page_stride = c.page_stride;
@@ -602,7 +618,7 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       if (!row_seq && w.prefix_len > 0 && a.splits == 1) {
         a.prefix_len = w.prefix_len; a.prefix_pages = w.d_prefix_pages; a.prefix_part = w.prefix_part;
       }
-      launch_flow_rope_append(a, c.stream);
+      if (!fuse_rope) launch_flow_rope_append(a, c.stream);
       launch_flow_prefix_attention(a, c.stream);
       launch_flow_attention(a, c.stream);
       gemm_tc_launch(g[1], c.stream);

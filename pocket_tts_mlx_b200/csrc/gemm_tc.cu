@@ -189,6 +189,46 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           for (int i = 0; i < 8; ++i)
             yp[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
                                 __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+        } else if (row_ok && e.rope_cs) {
+          // fused RoPE + paged KV append (FlowLM qkv): this thread holds 32 consecutive columns = half a head
+          const int n = n0 + cb;
+          const int Dm = e.kv_heads * 64;
+          const int which = n / Dm, within = n - which * Dm;       // 0 q, 1 k, 2 v
+          const int m = b * g.T + t;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          if (which < 2) {
+            const float4* cp = reinterpret_cast<const float4*>(e.rope_cs + (long long)m * 64 + ((within & 63) >> 1));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 c4 = cp[i], s4 = cp[8 + i];
+              const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float xr = v[8 * i + 2 * j], xi = v[8 * i + 2 * j + 1];
+                v[8 * i + 2 * j] = xr * cc[j] - xi * ss[j];
+                v[8 * i + 2 * j + 1] = xr * ss[j] + xi * cc[j];
+              }
+            }
+          }
+          if (which == 0) {
+            float4* qp = reinterpret_cast<float4*>(e.q_rot + (long long)m * Dm + within);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) qp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            const int pos = e.kv_row_pos[m];
+            const int seq = e.kv_row_seq ? e.kv_row_seq[m] : m;
+            const int page = e.kv_page_table[(long long)seq * e.kv_max_pages + pos / 32];
+            const int hh = within >> 6;
+            __nv_bfloat16* dst = e.kv_layer + page * e.kv_page_stride + ((long long)hh * 32 + (pos & 31)) * 64 + (within & 63);
+            if (which == 2) dst += (long long)e.kv_heads * 32 * 64;
+            uint4* dp = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dp[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                 pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+          }
         } else if (row_ok) {
           const int n = n0 + cb;
           float v[32];

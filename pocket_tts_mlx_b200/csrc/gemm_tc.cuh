@@ -26,6 +26,16 @@ struct TcEpilogue {
   float* y32; long long y32_bs, y32_rs;                  // fp32 output or null
   __nv_bfloat16* y16; long long y16_bs, y16_rs; int y16_act;   // bf16 output of act2(v) or null
   __nv_bfloat16* yraw16; long long yraw16_bs, yraw16_rs;       // bf16 copy of v or null
+  // FlowLM qkv projection (N = 3*H*64, columns q | k | v): RoPE and the KV-cache append happen in the epilogue.
+  // q is rotated and stored fp32 to q_rot [M][H*64]; k is rotated and, like v, written as bf16 into the row's page
+  // slot.  rope_cs [M][64] holds cos[32] | sin[32] of each row's position (rope_table_kernel).  Replaces
+  // flow_rope_append_kernel (pocket_tts_mlx/modules/attention.py:145-148,50-61; rope.py:9-42).
+  const float* rope_cs;
+  float* q_rot;
+  __nv_bfloat16* kv_layer;                 // pool + layer * layer_stride
+  const int *kv_row_seq, *kv_row_pos, *kv_page_table;
+  int kv_max_pages, kv_heads;
+  long long kv_page_stride;
 };
 
 struct TcGemm {

@@ -634,6 +634,27 @@ __global__ void __launch_bounds__(128) flow_prefix_attention_kernel(const FlowAt
 
 }  // namespace
 
+// cos / sin of every row's position, shared by the 6 layers of a step: table[m] = cos[32] | sin[32]
+// (angles in fp32 like modules/rope.py:17-24; consumed by the fused qkv epilogue of the tcgen05 GEMM)
+__global__ void rope_table_kernel(const int* __restrict__ row_pos, const float* __restrict__ freqs,
+                                  float* __restrict__ table, int M) {
+  pdl_sync();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * 32) return;
+  const int m = idx >> 5, i = idx & 31;
+  float sn, cs;
+  sincosf((float)row_pos[m] * freqs[i], &sn, &cs);
+  table[(long long)m * 64 + i] = cs;
+  table[(long long)m * 64 + 32 + i] = sn;
+}
+
+void launch_rope_table(const int* row_pos, const float* freqs, float* table, int M, cudaStream_t s) {
+  if (M <= 0) return;
+  ProfScope ps("rope_table", nullptr, 0, (double)M * 64 * 4, s);
+  launch_k(rope_table_kernel, dim3((M * 32 + 255) / 256), dim3(256), 0, s, row_pos, freqs, table, M);
+  ++g_launches;
+}
+
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s) {
   if (p.M <= 0) return;
   ProfScope ps("flow_rope_append", nullptr, 0, (double)p.M * p.H * 64 * (3 * 4 + 4 + 2 * (p.kv_bf16 ? 2 : 4)), s);
