@@ -82,7 +82,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const NormParams p) {
   }
 }
 
-// w_in_t is the transposed input_linear weight [L][D] so that consecutive threads read consecutive addresses
+// w_in_t is the transposed input_linear weight [L][D] so that consecutive threads read consecutive addresses.
+// One thread = one output feature of 4 rows; all L weight loads are issued before the first FMA (the kernel is
+// pure latency: 256 x 1024 outputs of a 32-deep dot product), grid = (rows / 4, D / 256).
+template <int kL>
 __global__ void __launch_bounds__(256) input_rows_kernel(const float* __restrict__ w_in_t, const float* __restrict__ bos,
                                                          const float* __restrict__ prev, const int* __restrict__ bos_flag,
                                                          float* __restrict__ x, int B, int D, int L) {
@@ -94,19 +97,30 @@ __global__ void __launch_bounds__(256) input_rows_kernel(const float* __restrict
     lat[i] = (b < B) ? (bos_flag[b] ? bos[k] : prev[b * L + k]) : 0.f;
   }
   __syncthreads();
-  for (int n = threadIdx.x; n < D; n += blockDim.x) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const int n = blockIdx.y * blockDim.x + threadIdx.x;
+  if (n >= D) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if constexpr (kL > 0) {
+    float w[kL];
+#pragma unroll
+    for (int k = 0; k < kL; ++k) w[k] = __ldg(w_in_t + (long long)k * D + n);
+#pragma unroll
+    for (int k = 0; k < kL; ++k) {
+      a0 = fmaf(w[k], lat[k], a0); a1 = fmaf(w[k], lat[kL + k], a1);
+      a2 = fmaf(w[k], lat[2 * kL + k], a2); a3 = fmaf(w[k], lat[3 * kL + k], a3);
+    }
+  } else {
 #pragma unroll 8
     for (int k = 0; k < L; ++k) {
       const float w = __ldg(w_in_t + (long long)k * D + n);
       a0 = fmaf(w, lat[k], a0); a1 = fmaf(w, lat[L + k], a1);
       a2 = fmaf(w, lat[2 * L + k], a2); a3 = fmaf(w, lat[3 * L + k], a3);
     }
-    if (b0 < B) x[(long long)b0 * D + n] = a0;
-    if (b0 + 1 < B) x[(long long)(b0 + 1) * D + n] = a1;
-    if (b0 + 2 < B) x[(long long)(b0 + 2) * D + n] = a2;
-    if (b0 + 3 < B) x[(long long)(b0 + 3) * D + n] = a3;
   }
+  if (b0 < B) x[(long long)b0 * D + n] = a0;
+  if (b0 + 1 < B) x[(long long)(b0 + 1) * D + n] = a1;
+  if (b0 + 2 < B) x[(long long)(b0 + 2) * D + n] = a2;
+  if (b0 + 3 < B) x[(long long)(b0 + 3) * D + n] = a3;
 }
 
 template <typename WT>
@@ -203,8 +217,10 @@ __global__ void noise_prep_kernel(const float* __restrict__ z, float* __restrict
   x0[i] = v;
 }
 
-// wq_t [L][C] and wu_t [2S][C] are stored transposed (channel fastest) for coalesced reads
-__global__ void __launch_bounds__(256) quant_upsample_kernel(const float* __restrict__ lat, const float* __restrict__ emb_std,
+// wq_t [L][C] and wu_t [2S][C] are stored transposed (channel fastest) for coalesced reads.  One thread = one
+// channel of one sequence; the L + 2S weight loads are all issued up front (latency-bound kernel), grid = (B, C/128).
+template <int kL, int kS>
+__global__ void __launch_bounds__(128) quant_upsample_kernel(const float* __restrict__ lat, const float* __restrict__ emb_std,
                                                              const float* __restrict__ emb_mean,
                                                              const float* __restrict__ wq_t, const float* __restrict__ wu_t,
                                                              float* __restrict__ zprev, float* __restrict__ out,
@@ -214,7 +230,25 @@ __global__ void __launch_bounds__(256) quant_upsample_kernel(const float* __rest
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < L; i += blockDim.x) u[i] = lat[b * L + i] * emb_std[i] + emb_mean[i];
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if constexpr (kL > 0) {
+    float wq[kL], wa[kS], wb[kS];
+#pragma unroll
+    for (int i = 0; i < kL; ++i) wq[i] = __ldg(wq_t + (long long)i * C + c);
+#pragma unroll
+    for (int t = 0; t < kS; ++t) {
+      wa[t] = __ldg(wu_t + (long long)t * C + c);
+      wb[t] = __ldg(wu_t + (long long)(kS + t) * C + c);
+    }
+    const float zp = zprev[(long long)b * C + c];
+    float z = 0.f;
+#pragma unroll
+    for (int i = 0; i < kL; ++i) z = fmaf(wq[i], u[i], z);
+    zprev[(long long)b * C + c] = z;
+#pragma unroll
+    for (int t = 0; t < kS; ++t) out[b * out_bs + (long long)t * C + c] = fmaf(wa[t], z, wb[t] * zp);
+  } else {
     float z = 0.f;
 #pragma unroll 8
     for (int i = 0; i < L; ++i) z = fmaf(__ldg(wq_t + (long long)i * C + c), u[i], z);
@@ -358,7 +392,9 @@ void launch_layernorm(const NormParams& p, cudaStream_t s) {
 void launch_input_rows(const float* w_in, const float* bos, const float* prev, const int* bos_flag, float* x,
                        int B, int D, int L, cudaStream_t s) {
   ProfScope ps("input_rows", nullptr, 0, (double)B * (D + L) * 4 + (double)D * L * 4, s);
-  launch_k(input_rows_kernel, dim3((B + 3) / 4), dim3(256), 4 * L * sizeof(float), s, w_in, bos, prev, bos_flag, x, B, D, L);
+  const dim3 grid((B + 3) / 4, (D + 255) / 256);
+  if (L == 32) launch_k(input_rows_kernel<32>, grid, dim3(256), 4 * L * sizeof(float), s, w_in, bos, prev, bos_flag, x, B, D, L);
+  else launch_k(input_rows_kernel<0>, grid, dim3(256), 4 * L * sizeof(float), s, w_in, bos, prev, bos_flag, x, B, D, L);
   ++g_launches;
 }
 
@@ -391,8 +427,13 @@ void launch_quant_upsample(const float* lat, const float* emb_std, const float* 
                            const float* wu, float* zprev, float* out, long long out_bs, int B, int L, int C,
                            int S, cudaStream_t s) {
   ProfScope ps("quant_upsample", nullptr, 0, (double)B * S * C * 4, s);
-  launch_k(quant_upsample_kernel, dim3(B), dim3(256), L * sizeof(float), s, lat, emb_std, emb_mean, wq, wu, zprev, out, out_bs,
-                                                          L, C, S);
+  const dim3 grid(B, (C + 127) / 128);
+  if (L == 32 && S == 16)
+    launch_k(quant_upsample_kernel<32, 16>, grid, dim3(128), L * sizeof(float), s, lat, emb_std, emb_mean, wq, wu, zprev, out,
+             out_bs, L, C, S);
+  else
+    launch_k(quant_upsample_kernel<0, 0>, grid, dim3(128), L * sizeof(float), s, lat, emb_std, emb_mean, wq, wu, zprev, out,
+             out_bs, L, C, S);
   ++g_launches;
 }
 
