@@ -592,7 +592,7 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
     int pend = 0;   // split-K planes of the previous ffn2 that the next norm must add to x
     // RoPE + KV append ride in the qkv GEMM's epilogue (PTTS_NO_ROPE_FUSE=1 keeps the separate kernel)
     static const bool fuse_rope = [] { const char* v = getenv("PTTS_NO_ROPE_FUSE"); return !(v && v[0] == '1'); }();
-    if (fuse_rope) launch_rope_table(row_pos, c.freqs_flow, w.rope_cs, M, c.stream);
+    if (fuse_rope) launch_rope_table(row_pos, c.freqs_flow, w.rope_cs, M, 1, c.stream);
     for (int i = 0; i < c.cfg.n_layers; ++i) {
       auto& l = c.fl[i];
       const TcGemm* g = &w.plans[(size_t)i * 4];
@@ -706,6 +706,7 @@ struct ptts_batch {
   TcGemm g_conv0;
   struct StageBuf16 { __nv_bfloat16 *ct_in, *r_in, *xraw, *hid; int T_in, T_out; TcGemm ct, r3, r1; };
   std::vector<StageBuf16> sb16;
+  float* d_mrope_cs = nullptr;      // [B*T0][64] cos | sin of this frame's Mimi positions (fused qkv epilogue)
   SnTail sn_tail;                   // fused last resblock + output conv (valid: replaces sb16.back().r3/.r1 + final conv)
   float* d_bnd = nullptr;
   bool no_tail_env = false;         // PTTS_NO_SNTAIL at creation (a recycled arena must match the current setting)
@@ -853,6 +854,8 @@ void mimi_frame_tc(Batch& bt, const float* latent, int part) {   // part: 0 all,
   if (part != 2) {
   launch_quant_upsample(latent, c.emb_std, c.emb_mean, c.wq, c.wu, bt.d_zprev, bt.d_xm, (long long)T * SD, B,
                         g.latent_dim, SD, g.upsample_stride, c.stream);
+  static const bool fuse_rope = [] { const char* v = getenv("PTTS_NO_ROPE_FUSE"); return !(v && v[0] == '1'); }();
+  if (fuse_rope) launch_rope_table(bt.d_mimi_off, c.freqs_mimi, bt.d_mrope_cs, B * T, T, c.stream);
   for (int i = 0; i < g.mimi_layers; ++i) {
     auto& l = c.ml[i];
     const TcGemm* gm = &bt.g_mimi[(size_t)i * 4];
@@ -861,13 +864,24 @@ void mimi_frame_tc(Batch& bt, const float* latent, int part) {   // part: 0 all,
     n.w = l.ln1w; n.b = l.ln1b; n.eps = 1e-5f;
     n.Y16 = bt.d_mh16; n.y_bs = (long long)T * MD; n.y_rs = MD;
     launch_layernorm(n, c.stream);
-    gemm_tc_launch(gm[0], c.stream);
+    if (fuse_rope) {   // RoPE + ring write in the qkv epilogue
+      TcGemm q = gm[0];
+      auto& e = q.e;
+      e.y32 = nullptr;
+      e.rope_cs = bt.d_mrope_cs; e.q_rot = bt.d_mqrot;
+      e.kv_layer = reinterpret_cast<__nv_bfloat16*>(bt.ring) + (long long)i * bt.ring_layer_stride;
+      e.kv_row_pos = bt.d_mimi_off; e.kv_heads = g.mimi_heads;
+      e.kv_ring = g.mimi_context; e.kv_v_offset = bt.ring_kv_stride;
+      gemm_tc_launch(q, c.stream);
+    } else {
+      gemm_tc_launch(gm[0], c.stream);
+    }
     MimiAttnParams a{};
     a.qkv = bt.d_mqkv; a.q_rot = bt.d_mqrot; a.out16 = bt.d_matt16;
     a.ring = bt.ring; a.kv_bf16 = c.bf16; a.layer_stride = bt.ring_layer_stride; a.kv_stride = bt.ring_kv_stride;
     a.layer = i; a.offset = bt.d_mimi_off; a.B = B; a.T = T; a.H = g.mimi_heads; a.context = g.mimi_context;
     a.freqs = c.freqs_mimi;
-    launch_mimi_rope_ring(a, c.stream);
+    if (!fuse_rope) launch_mimi_rope_ring(a, c.stream);
     launch_mimi_attention(a, c.stream);
     gemm_tc_launch(gm[1], c.stream);
     n.w = l.ln2w; n.b = l.ln2b;
@@ -967,6 +981,7 @@ int build_batch_tc(Batch& t) {
     RET(t.dalloc((void**)&t.d_xm, (size_t)B * T * MD * 4));
     t.zero_list.push_back({t.d_xm, (size_t)B * T * MD * 4});
     RET(bz(&t.d_mh16, (size_t)B * T * MD));
+    RET(t.dalloc((void**)&t.d_mrope_cs, (size_t)B * T * 64 * 4));
     RET(bz(&t.d_matt16, (size_t)B * T * MD));
     RET(bz(&t.d_mff16, (size_t)B * T * FFm));
     RET(bz(&t.d_c0_16, (size_t)B * (T + k0 - 1) * SD));

@@ -217,12 +217,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 8; ++i) qp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           } else {
-            const int pos = e.kv_row_pos[m];
-            const int seq = e.kv_row_seq ? e.kv_row_seq[m] : m;
-            const int page = e.kv_page_table[(long long)seq * e.kv_max_pages + pos / 32];
             const int hh = within >> 6;
-            __nv_bfloat16* dst = e.kv_layer + page * e.kv_page_stride + ((long long)hh * 32 + (pos & 31)) * 64 + (within & 63);
-            if (which == 2) dst += (long long)e.kv_heads * 32 * 64;
+            __nv_bfloat16* dst;
+            if (e.kv_ring > 0) {
+              const int slot = (e.kv_row_pos[b] + t) % e.kv_ring;
+              dst = e.kv_layer + (((long long)b * e.kv_heads + hh) * e.kv_ring + slot) * 64 + (within & 63);
+              if (which == 2) dst += e.kv_v_offset;
+            } else {
+              const int pos = e.kv_row_pos[m];
+              const int seq = e.kv_row_seq ? e.kv_row_seq[m] : m;
+              const int page = e.kv_page_table[(long long)seq * e.kv_max_pages + pos / 32];
+              dst = e.kv_layer + page * e.kv_page_stride + ((long long)hh * 32 + (pos & 31)) * 64 + (within & 63);
+              if (which == 2) dst += (long long)e.kv_heads * 32 * 64;
+            }
             uint4* dp = reinterpret_cast<uint4*>(dst);
 #pragma unroll
             for (int i = 0; i < 4; ++i)

@@ -36,6 +36,10 @@ struct TcEpilogue {
   const int *kv_row_seq, *kv_row_pos, *kv_page_table;
   int kv_max_pages, kv_heads;
   long long kv_page_stride;
+  // kv_ring > 0: Mimi ring cache instead of pages (modules/attention.py:67-105): row (b, t) sits at position
+  // kv_row_pos[b] + t, slot = position % kv_ring of [b][head][slot][64]; V lives kv_v_offset elements after K
+  int kv_ring;
+  long long kv_v_offset;
 };
 
 struct TcGemm {

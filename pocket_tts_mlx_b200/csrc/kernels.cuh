@@ -87,7 +87,7 @@ struct FlowAttnParams {
 };
 void launch_flow_prefix_attention(const FlowAttnParams& p, cudaStream_t s);
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s);
-void launch_rope_table(const int* row_pos, const float* freqs, float* table, int M, cudaStream_t s);
+void launch_rope_table(const int* row_pos, const float* freqs, float* table, int M, int T, cudaStream_t s);
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s);
 
 // ---- Mimi ring-buffer attention --------------------------------------------------------------------

@@ -636,22 +636,24 @@ __global__ void __launch_bounds__(128) flow_prefix_attention_kernel(const FlowAt
 
 // cos / sin of every row's position, shared by the 6 layers of a step: table[m] = cos[32] | sin[32]
 // (angles in fp32 like modules/rope.py:17-24; consumed by the fused qkv epilogue of the tcgen05 GEMM)
+// T > 1: row m = (sequence m / T, step m % T) at position row_pos[m / T] + m % T (Mimi: 16 steps per frame)
 __global__ void rope_table_kernel(const int* __restrict__ row_pos, const float* __restrict__ freqs,
-                                  float* __restrict__ table, int M) {
+                                  float* __restrict__ table, int M, int T) {
   pdl_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * 32) return;
   const int m = idx >> 5, i = idx & 31;
+  const int pos = (T > 1) ? row_pos[m / T] + m % T : row_pos[m];
   float sn, cs;
-  sincosf((float)row_pos[m] * freqs[i], &sn, &cs);
+  sincosf((float)pos * freqs[i], &sn, &cs);
   table[(long long)m * 64 + i] = cs;
   table[(long long)m * 64 + 32 + i] = sn;
 }
 
-void launch_rope_table(const int* row_pos, const float* freqs, float* table, int M, cudaStream_t s) {
+void launch_rope_table(const int* row_pos, const float* freqs, float* table, int M, int T, cudaStream_t s) {
   if (M <= 0) return;
   ProfScope ps("rope_table", nullptr, 0, (double)M * 64 * 4, s);
-  launch_k(rope_table_kernel, dim3((M * 32 + 255) / 256), dim3(256), 0, s, row_pos, freqs, table, M);
+  launch_k(rope_table_kernel, dim3((M * 32 + 255) / 256), dim3(256), 0, s, row_pos, freqs, table, M, T);
   ++g_launches;
 }
 
