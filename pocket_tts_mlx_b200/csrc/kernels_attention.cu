@@ -102,7 +102,7 @@ __device__ __forceinline__ void soft_merge_shfl(SoftState& s, int delta) {
 
 // grid (M, H), block 128 = 4 warps; keys 0..pos of the row's sequence are strided over 16 lane-groups.
 template <typename KT>
-__global__ void __launch_bounds__(128) flow_attention_kernel(const FlowAttnParams p) {
+__global__ void __launch_bounds__(128, 16) flow_attention_kernel(const FlowAttnParams p) {
   pdl_sync();
   __shared__ float sh_m[4], sh_l[4], sh_acc[4][kHeadDim];
   const int m = blockIdx.x, h = blockIdx.y;
