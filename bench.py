@@ -223,15 +223,16 @@ def roofline_from_profile(model, state, ids, at_frame: int, peaks):
     rows = batch.profile_step()
     batch.close()
     total = sum(r["ms"] for r in rows)
-    # One entry per kernel function; the tcgen05 GEMM is kept per call-site family (flow./head./mimi./sn.)
-    # because its launches range from weight-streaming (HBM-bound) to dense contractions (tensor-bound).
+    # One entry per (kernel function, call site): launches of one entry share a problem shape, so "bytes per
+    # launch / average launch duration" means something.  The tcgen05 GEMM template serves 30 call sites that
+    # range from weight streaming (HBM-bound) to dense contractions (tensor-bound); its summed share is reported
+    # separately as gemm_tc_all_share.
     per = {}
     for r in rows:
-        k, _, tag = r["kernel"].partition(":")
-        key = f"{k}:{tag.split('.')[0]}" if k == "gemm_tc" and tag else k
-        a = per.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+        a = per.setdefault(r["kernel"], {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
         for f in ("ms", "launches", "flops", "bytes"):
             a[f] += r[f]
+    gemm_all = sum(v["ms"] for k, v in per.items() if k.startswith("gemm_tc"))
     top = max(per.items(), key=lambda kv: kv[1]["ms"])
     name, a = top
     sec = a["ms"] / 1e3
@@ -253,6 +254,7 @@ def roofline_from_profile(model, state, ids, at_frame: int, peaks):
                  "algorithmic_bytes_per_launch": a["bytes"] / max(1, a["launches"]),
                  "algorithmic_flops_per_launch": a["flops"] / max(1, a["launches"]),
                  "traffic": traffic, "peak_source": peaks["source"], "frame_ms_eager": total,
+                 "gemm_tc_all_share": gemm_all / total if total else None,
                  "note": "eager frame, every launch bracketed by CUDA events on the library stream; shared "
                          "voice-prefix pages are re-read by all sequences and mostly served from L2"})
     breakdown = sorted(({"kernel": k, "ms": v["ms"], "share": v["ms"] / total} for k, v in per.items()),
