@@ -43,8 +43,10 @@ struct KArgs {
 //   warp 1   : tcgen05.mma issuer; two TMEM accumulator stages (tmem_full / tmem_empty mbarriers), so the MMAs
 //              of tile i+1 overlap the epilogue of tile i;
 //   warps 2-9: epilogue (TMEM lane quadrant = warp % 4, two warps per quadrant split the columns).
-template <int BN, int BK, int STAGES, int ACC>   // ACC = TMEM accumulator stages: 2 persistent, 1 one tile per CTA
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
+// EPW = epilogue warps (8 or 16).  Sixteen pay off for persistent BN = 128 kernels whose tiles are short in K
+// (SEANet / Mimi): the epilogue is then the critical stage and 2 warps per scheduler run it at ~0.3 IPC (ncu).
+template <int BN, int BK, int STAGES, int ACC, int EPW = 8>   // ACC = TMEM accumulator stages: 2 persistent, 1 one tile per CTA
+__global__ void __launch_bounds__(64 + 32 * EPW, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                               const __grid_constant__ CUtensorMap tm_b,
                                                               const __grid_constant__ CUtensorMap tm_y16,
                                                               const __grid_constant__ CUtensorMap tm_yraw16,
@@ -82,9 +84,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, 8);      // one arrival per epilogue warp
+      mbar_init(tempty0 + 8 * i, EPW);    // one arrival per epilogue warp
       mbar_init(rfull0 + 8 * i, 1);
-      mbar_init(rempty0 + 8 * i, 8);
+      mbar_init(rempty0 + 8 * i, EPW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else {
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;                     // column group of this warp within its lane quadrant
     constexpr int CHUNKS = BN / 32;
     const TcEpilogue& e = g.e;
     const float oscale = e.out_scale == 0.f ? 1.f : e.out_scale;
@@ -166,18 +168,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const int b = b0 + r / g.box_t, t = t0 + r % g.box_t;
       const bool row_ok = (b < g.nb) && (t < g.T);
       const uint32_t as = (ACC == 2) ? (tcount & 1) : 0, aph = (ACC == 2) ? ((tcount >> 1) & 1) : (tcount & 1);
-      if (g.tma_store) {
-        // the previous tile's bulk stores must have finished reading the staging tiles before they are refilled
-        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-      }
+      bool stg_free = !g.tma_store;     // staging tiles may be refilled (checked right before the first staging store)
       mbar_wait(tfull0 + 8 * as, aph);
       tc_fence_after();
       const uint32_t rb = tcount & 1, rph = (tcount >> 1) & 1;
       if (BN >= 64 && g.res_tma) mbar_wait(rfull0 + 8 * rb, rph);
       const uint32_t tmem_acc = tmem_base + as * BN + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-      for (int ch = half; ch < CHUNKS; ch += 2) {
+      for (int ch = half; ch < CHUNKS; ch += EPW / 4) {
         const int cb = ch * 32;
         uint32_t raw[32];
         __syncwarp();
@@ -236,7 +234,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               dp[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
                                  pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
           }
-        } else if (row_ok) {
+        } else if (row_ok || g.tma_store) {
+          // rows beyond nb / T of a ragged tile still walk this branch when the outputs leave through staging
+          // tiles (their math is discarded: global accesses are guarded, the bulk store clips them)
           const int n = n0 + cb;
           float v[32];
 #pragma unroll
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               v[4 * i] *= q.x; v[4 * i + 1] *= q.y; v[4 * i + 2] *= q.z; v[4 * i + 3] *= q.w;
             }
           }
-          if (e.row_gate) {
+          if (e.row_gate && row_ok) {
             const float4* gp = reinterpret_cast<const float4*>(e.row_gate + b * e.gate_bs + t * e.gate_rs + n);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               v[4 * i] *= q.x; v[4 * i + 1] *= q.y; v[4 * i + 2] *= q.z; v[4 * i + 3] *= q.w;
             }
           }
-          if (e.res32) {
+          if (e.res32 && row_ok) {
             const float4* rp = reinterpret_cast<const float4*>(e.res32 + b * e.res32_bs + t * e.res32_rs + n);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y;
               }
             }
-          } else if (e.res16) {
+          } else if (e.res16 && row_ok) {
             const uint4* rp = reinterpret_cast<const uint4*>(e.res16 + b * e.res16_bs + t * e.res16_rs + n);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -307,10 +307,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               }
             }
           }
-          if (e.y32) {
+          if (e.y32 && row_ok) {
             float4* yp = reinterpret_cast<float4*>(e.y32 + b * e.y32_bs + t * e.y32_rs + n);
 #pragma unroll
             for (int i = 0; i < 8; ++i) yp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (!stg_free) {
+            // the previous tile's bulk stores must have finished reading the staging tiles before they are refilled;
+            // waiting here (not at the top of the tile) lets the TMEM load and the epilogue math overlap the drain
+            if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * EPW) : "memory");
+            stg_free = true;
           }
           if (e.yraw16) {
             if (g.tma_store) {
@@ -364,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         // make the generic-proxy writes visible to the async proxy, then one thread issues the bulk tensor
         // stores; rows beyond T / nb are clipped by the tensor-map bounds
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPW) : "memory");
         if (warp == 2 && lane == 0) {
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) {
@@ -405,6 +412,8 @@ void set_attr1() {
   if (ring_bytes<BN, BK, ST>() <= 200 * 1024) {
     cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, ST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, ST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (BN == 128 && BK == 64)
+      cudaFuncSetAttribute(gemm_tc_kernel<128, 64, ST, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
 }
 template <int BN, int BK>
@@ -594,7 +603,9 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   const size_t smem = (g.persist ? ring + stg_b : std::max(ring, stg_b)) + res_b + 1024 + 16 * g.stages + 128;
   int per_sm = (int)((227 * 1024) / smem);
   per_sm = std::max(1, std::min(per_sm, std::min(2, 512 / (2 * g.bn))));
-  dim3 grid((unsigned)(g.persist ? std::min<long long>(tiles, 148LL * per_sm) : tiles)), block(kThreads);
+  static const bool epw16_ok = [] { const char* v = getenv("PTTS_TC_EPW16"); return !(v && v[0] == '0'); }();
+  const bool epw16 = epw16_ok && g.persist && g.bn == 128 && g.bk == 64;
+  dim3 grid((unsigned)(g.persist ? std::min<long long>(tiles, 148LL * per_sm) : tiles)), block(epw16 ? 576 : kThreads);
   const double flops = 2.0 * g.nb * g.T * (double)g.N * g.taps * g.C;
   const double bytes = (double)g.N * g.taps * g.C * 2 + (double)g.nb * (g.T + g.taps - 1) * g.C * 2 +
                        (double)g.nb * g.T * g.N * ((g.e.y32 ? 4 : 0) + (g.e.y16 ? 2 : 0) + (g.e.yraw16 ? 2 : 0) +
@@ -602,7 +613,9 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   ProfScope ps("gemm_tc", g.tag, flops, bytes, s);
 #define PTTS_TC1(BN_, BK_, ST_)                                                                                  \
   do {                                                                                                           \
-    if (g.persist) launch_k(gemm_tc_kernel<BN_, BK_, ST_, 2>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, g.tm_res, a); \
+    if (g.persist && epw16 && BN_ == 128 && BK_ == 64)                                                            \
+      launch_k(gemm_tc_kernel<128, 64, ST_, 2, 16>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, g.tm_res, a);        \
+    else if (g.persist) launch_k(gemm_tc_kernel<BN_, BK_, ST_, 2>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, g.tm_res, a); \
     else launch_k(gemm_tc_kernel<BN_, BK_, ST_, 1>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, g.tm_res, a);           \
   } while (0)
 #define PTTS_TC(BN_, BK_)                                                                                        \
