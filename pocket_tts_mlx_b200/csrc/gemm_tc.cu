@@ -604,7 +604,7 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   int per_sm = (int)((227 * 1024) / smem);
   per_sm = std::max(1, std::min(per_sm, std::min(2, 512 / (2 * g.bn))));
   static const bool epw16_ok = [] { const char* v = getenv("PTTS_TC_EPW16"); return !(v && v[0] == '0'); }();
-  const bool epw16 = epw16_ok && g.persist && g.bn == 128 && g.bk == 64;
+  const bool epw16 = epw16_ok && g.persist && g.bn == 128 && g.bk == 64 && a.tma_store;
   dim3 grid((unsigned)(g.persist ? std::min<long long>(tiles, 148LL * per_sm) : tiles)), block(epw16 ? 576 : kThreads);
   const double flops = 2.0 * g.nb * g.T * (double)g.N * g.taps * g.C;
   const double bytes = (double)g.N * g.taps * g.C * 2 + (double)g.nb * (g.T + g.taps - 1) * g.C * 2 +

@@ -373,19 +373,21 @@ __global__ void __launch_bounds__(128) mimi_attention_mma_kernel(const MimiAttnP
   const __nv_bfloat16* vbase = kbase + p.kv_stride;
   const int slot0 = warp * 64;
   // ---- stage this warp's 64 slots of K and V (16-byte chunks, fully coalesced) ----
+  // cp.async (16 B, L1-bypassing) straight into shared memory: all 32 copies of a lane are in flight at once and
+  // no registers are spent on staging; slots beyond the ring are zero-filled (src-size 0)
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int idx = lane + 32 * i;
     const int row = idx >> 3, ch = idx & 7;
     const int slot = slot0 + row;
-    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
-    if (slot < cap) {
-      kv = *reinterpret_cast<const uint4*>(kbase + (long long)slot * kHeadDim + ch * 8);
-      vv = *reinterpret_cast<const uint4*>(vbase + (long long)slot * kHeadDim + ch * 8);
-    }
-    *reinterpret_cast<uint4*>(Ks + row * kMimiLd + ch * 8) = kv;
-    *reinterpret_cast<uint4*>(Vs + row * kMimiLd + ch * 8) = vv;
+    const int sz = slot < cap ? 16 : 0;
+    const long long off = (long long)(slot < cap ? slot : 0) * kHeadDim + ch * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(Ks + row * kMimiLd + ch * 8)),
+                 "l"(kbase + off), "r"(sz) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(Vs + row * kMimiLd + ch * 8)),
+                 "l"(vbase + off), "r"(sz) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   // ---- Q fragments (rows g and g+8 of the chunk), pre-scaled by 1/sqrt(64) ----
   uint32_t qa[4][4];
   {
@@ -403,6 +405,7 @@ __global__ void __launch_bounds__(128) mimi_attention_mma_kernel(const MimiAttnP
       qa[ks][3] = r1 ? pack2_bf16(a3.x * 0.125f, a3.y * 0.125f) : 0u;
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
   // ---- S = Q K^T : 8 key tiles x 4 k-steps ----
   float sc[8][4];
