@@ -375,9 +375,95 @@ __global__ void inc_kernel(int* v, int inc) {
 
 }  // namespace
 
+// Few rows (decode at batch <= 512): four warps per row, C = 512 * VEC.  Every load of the row and of its split-K
+// planes is issued before the first use, the two reductions go through shared memory; same arithmetic order per
+// element as layernorm_kernel (planes added in index order), so the two kernels agree to rounding of the sums.
+template <int VEC>
+__global__ void __launch_bounds__(128) layernorm_wide_kernel(const NormParams p) {
+  pdl_sync();
+  __shared__ float red[2][4];
+  const int m = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = m / p.T, t = m % p.T;
+  float* xrow = const_cast<float*>(p.X) + b * p.x_bs + t * p.x_rs;
+  const float4* x = reinterpret_cast<const float4*>(xrow);
+  float4 v[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = x[tid + 128 * i];
+  if (p.acc_n > 0) {
+    float4 q[8][VEC];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < p.acc_n) {
+        const float4* a = reinterpret_cast<const float4*>(p.acc + k * p.acc_stride + (long long)m * p.C);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) q[k][i] = a[tid + 128 * i];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < p.acc_n) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { v[i].x += q[k][i].x; v[i].y += q[k][i].y; v[i].z += q[k][i].z; v[i].w += q[k][i].w; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) reinterpret_cast<float4*>(xrow)[tid + 128 * i] = v[i];
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  s = warp_sum(s);
+  if (lane == 0) red[0][warp] = s;
+  __syncthreads();
+  const float mean = ((red[0][0] + red[0][1]) + (red[0][2] + red[0][3])) / (float)p.C;
+  float q2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q2 += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  q2 = warp_sum(q2);
+  if (lane == 0) red[1][warp] = q2;
+  __syncthreads();
+  const float rstd = 1.0f / sqrtf(((red[1][0] + red[1][1]) + (red[1][2] + red[1][3])) / (float)p.C + p.eps);
+  const float4* sc = p.scale ? reinterpret_cast<const float4*>(p.scale + (long long)m * p.mod_rs) : nullptr;
+  const float4* sh = p.shift ? reinterpret_cast<const float4*>(p.shift + (long long)m * p.mod_rs) : nullptr;
+  const float4* w4 = reinterpret_cast<const float4*>(p.w);
+  const float4* b4 = reinterpret_cast<const float4*>(p.b);
+  const long long yo = b * p.y_bs + t * p.y_rs;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c4 = tid + 128 * i;
+    float4 o = make_float4(v[i].x * rstd, v[i].y * rstd, v[i].z * rstd, v[i].w * rstd);
+    if (p.w) {
+      const float4 w = w4[c4], bb = b4[c4];
+      o.x = o.x * w.x + bb.x; o.y = o.y * w.y + bb.y; o.z = o.z * w.z + bb.z; o.w = o.w * w.w + bb.w;
+    }
+    if (sc) {
+      const float4 a = sc[c4], d = sh[c4];
+      o.x = o.x * (1.0f + a.x) + d.x; o.y = o.y * (1.0f + a.y) + d.y;
+      o.z = o.z * (1.0f + a.z) + d.z; o.w = o.w * (1.0f + a.w) + d.w;
+    }
+    if (p.Y16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      *reinterpret_cast<uint2*>(p.Y16 + yo + 4 * c4) = pk;
+    } else {
+      *reinterpret_cast<float4*>(p.Y + yo + 4 * c4) = o;
+    }
+  }
+}
+
 void launch_layernorm(const NormParams& p, cudaStream_t s) {
   ProfScope ps("layernorm", nullptr, 0, 2.0 * p.nb * p.T * p.C * 4, s);
   const int rows = p.nb * p.T;
+  if (rows <= 512 && p.acc_n <= 8 && (p.C == 512 || p.C == 1024)) {
+    if (p.C == 1024) launch_k(layernorm_wide_kernel<2>, dim3(rows), dim3(128), 0, s, p);
+    else launch_k(layernorm_wide_kernel<1>, dim3(rows), dim3(128), 0, s, p);
+    ++g_launches;
+    return;
+  }
   const int rpc = rows >= 2048 ? 8 : (rows >= 512 ? 4 : 1);     // rows per CTA: keep >= ~256 CTAs in flight
   const int grid = (rows + rpc - 1) / rpc, block = 32 * rpc;
   switch (p.C / 128) {
