@@ -917,7 +917,8 @@ void flow_head_tc(Batch& bt) {
   for (int i = 0; i < n; ++i) {
     gemm_tc_launch(bt.g_cond[i], c.stream);
     gemm_tc_launch(bt.g_ada, c.stream);
-    run_linear(c, c.in_proj, rows_linear(bt.d_x, B, L, bt.d_x1, fd, "head.in"));
+    if (!(c.in_proj.w16 && launch_small_k_linear(c.in_proj.w16, c.in_proj.bias, bt.d_x, bt.d_x1, B, L, fd, "head.in", c.stream)))
+      run_linear(c, c.in_proj, rows_linear(bt.d_x, B, L, bt.d_x1, fd, "head.in"));
     for (int r = 0; r < g.flow_depth; ++r) {
       const float* ada = bt.d_ada + (long long)r * 3 * fd;
       rows_norm(c, bt.d_x1, B, fd, c.rb[r].lnw, c.rb[r].lnb, 1e-6f, nullptr, ada + fd, ada, c.n_ada, bt.d_hh16, nullptr, 0);

@@ -47,7 +47,10 @@ inline double linear_bytes(const LinearParams& p) {
 }
 
 void launch_linear_tile(const LinearParams& p, cudaStream_t s);   // any M; SIMT 64x64 tiles
-void launch_linear_gemv(const LinearParams& p, cudaStream_t s);   // M = nb*T <= 16; weight-streaming
+void launch_linear_gemv(const LinearParams& p, cudaStream_t s);
+// y[M][N] = x[M][K] W[N][K]^T + b for K = 32 (bf16 weights); false when the shape is not covered
+bool launch_small_k_linear(const __nv_bfloat16* W, const float* bias, const float* X, float* Y, int M, int K, int N,
+                           const char* tag, cudaStream_t s);   // M = nb*T <= 16; weight-streaming
 bool linear_gemv_supported(const LinearParams& p);
 
 // y = LN(x; w, b, eps) [* (1 + scale) + shift]; rows of width C; scale/shift are per-row vectors

@@ -318,6 +318,51 @@ bool linear_gemv_supported(const LinearParams& p) {
   return M <= 16 && (p.C % 8) == 0 && smem <= 160 * 1024;
 }
 
+// Tiny-K Linear over many rows (flow-head input_proj: K = 32): one thread = one output feature of four rows, its
+// whole bf16 weight row (K * 2 bytes) fetched with 16-byte loads before the first FMA.  y = x W^T + b, fp32 in/out.
+template <int K>
+__global__ void __launch_bounds__(256) small_k_linear_kernel(const __nv_bfloat16* __restrict__ W, const float* __restrict__ bias,
+                                                             const float* __restrict__ X, float* __restrict__ Y, int M, int N) {
+  pdl_sync();
+  __shared__ float xs[4][K];
+  const int m0 = blockIdx.x * 4;
+  for (int i = threadIdx.x; i < 4 * K; i += 256) {
+    const int r = i / K, k = i - r * K;
+    xs[r][k] = (m0 + r < M) ? X[(long long)(m0 + r) * K + k] : 0.f;
+  }
+  __syncthreads();
+  const int n = blockIdx.y * 256 + threadIdx.x;
+  if (n >= N) return;
+  uint4 wq[K / 8];
+#pragma unroll
+  for (int i = 0; i < K / 8; ++i) wq[i] = __ldg(reinterpret_cast<const uint4*>(W + (long long)n * K) + i);
+  const float bb = bias ? bias[n] : 0.f;
+  float a[4] = {bb, bb, bb, bb};
+#pragma unroll
+  for (int i = 0; i < K / 8; ++i) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&wq[i]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 w = __bfloat1622float2(h[j]);
+      const int k = 8 * i + 2 * j;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = fmaf(w.y, xs[r][k + 1], fmaf(w.x, xs[r][k], a[r]));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (m0 + r < M) Y[(long long)(m0 + r) * N + n] = a[r];
+}
+
+bool launch_small_k_linear(const __nv_bfloat16* W, const float* bias, const float* X, float* Y, int M, int K, int N,
+                           const char* tag, cudaStream_t s) {
+  if (K != 32) return false;
+  ProfScope ps("small_k_linear", tag, 2.0 * M * N * K, (double)N * K * 2 + (double)M * (K + N) * 4, s);
+  launch_k(small_k_linear_kernel<32>, dim3((M + 3) / 4, (N + 255) / 256), dim3(256), 0, s, W, bias, X, Y, M, N);
+  ++g_launches;
+  return true;
+}
+
 void launch_linear_tile(const LinearParams& p, cudaStream_t s) {
   const int M = p.nb * p.T;
   dim3 grid((p.N + BN - 1) / BN, (M + BM - 1) / BM), block(256);

@@ -148,6 +148,53 @@ __global__ void __launch_bounds__(128) final_norm_eos_kernel(const float* __rest
   const int b = blockIdx.x;
   const long long row = row_of ? row_of[b] : b;
   const float* xr = x + row * D;
+  if (D == 1024 && acc_n <= 8) {
+    // vectorised path: two float4 per thread, every plane load issued before the first add (latency-bound kernel)
+    const int tid = threadIdx.x;
+    float4 u[2], q4[8][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) u[i] = reinterpret_cast<const float4*>(xr)[tid + 128 * i];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < acc_n) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) q4[k][i] = reinterpret_cast<const float4*>(acc + k * acc_stride + row * D)[tid + 128 * i];
+      }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < acc_n) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { u[i].x += q4[k][i].x; u[i].y += q4[k][i].y; u[i].z += q4[k][i].z; u[i].w += q4[k][i].w; }
+      }
+    float s = (u[0].x + u[0].y) + (u[0].z + u[0].w) + (u[1].x + u[1].y) + (u[1].z + u[1].w);
+    const float mean = block_sum(s, red) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      u[i].x -= mean; u[i].y -= mean; u[i].z -= mean; u[i].w -= mean;
+      q += (u[i].x * u[i].x + u[i].y * u[i].y) + (u[i].z * u[i].z + u[i].w * u[i].w);
+    }
+    const float rstd = 1.0f / sqrtf(block_sum(q, red) / (float)D + 1e-5f);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c4 = tid + 128 * i;
+      const float4 w = reinterpret_cast<const float4*>(ln_w)[c4], bb = reinterpret_cast<const float4*>(ln_b)[c4];
+      const float4 we = reinterpret_cast<const float4*>(w_eos)[c4];
+      const float4 o = make_float4(u[i].x * rstd * w.x + bb.x, u[i].y * rstd * w.y + bb.y, u[i].z * rstd * w.z + bb.z,
+                                   u[i].w * rstd * w.w + bb.w);
+      reinterpret_cast<float4*>(cout + (long long)b * D)[c4] = o;
+      if (cout16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        reinterpret_cast<uint2*>(cout16 + (long long)b * D)[c4] =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+      dot = fmaf(o.x, we.x, dot); dot = fmaf(o.y, we.y, dot); dot = fmaf(o.z, we.z, dot); dot = fmaf(o.w, we.w, dot);
+    }
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) logit[b] = dot + b_eos[0];
+    return;
+  }
   float v[8];
   float s = 0.f;
 #pragma unroll
