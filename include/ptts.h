@@ -123,6 +123,17 @@ int32_t ptts_batch_step_staged(ptts_batch* batch);
 int32_t ptts_batch_set_prev_latent(ptts_batch* batch, const float* latent);
 /* Same step without the host round trip: results stay on the device (used by bench `value`). */
 int32_t ptts_batch_step_device(ptts_batch* batch);
+/* Continuous batching (the reference decodes one utterance at a time, models/tts_model.py:346-361):
+ * a slot whose utterance has ended is re-initialised for the next one while the other sequences keep decoding.
+ * ptts_batch_reset_seq returns the slot's private KV pages, attaches `voice_id`'s prefix (max_len must fit the page
+ * budget the batch was created with), rewinds length / BOS flag and restores the slot's Mimi streaming state to the
+ * one right after ptts_batch_warmup_mimi (= init_states + _warmup_mimi_decoder, models/tts_model.py:378-383,464-476).
+ * Follow it with ptts_batch_prefill_text where every other sequence has an empty token range.
+ * ptts_batch_set_active(slot, 0) parks a slot: it is still computed with the batch but stops growing its KV cache.
+ * Not available in pipelined mode; in a batch that uses cascade attention the voice cannot change. */
+int32_t ptts_batch_reset_seq(ptts_batch* batch, int32_t slot, int32_t voice_id, int32_t max_len);
+int32_t ptts_batch_set_active(ptts_batch* batch, int32_t slot, int32_t active);
+
 /* Throughput mode.  FlowLM step t only needs latent t-1, and so does the Mimi decode of frame t-1, so the two
  * run as concurrent branches of one CUDA graph.  After ptts_batch_set_pipelined(batch, 1) (before the first
  * frame) every step returns latent t and EOS logit t but the AUDIO OF FRAME t-1 (zeros at t = 0);

@@ -25,6 +25,7 @@ EXPORTED = [
     "ptts_batch_seed", "ptts_batch_lengths", "ptts_batch_mimi_decode", "ptts_sync", "ptts_timer_begin",
     "ptts_timer_end", "ptts_launch_count", "ptts_batch_profile_step", "ptts_flush_l2", "ptts_debug_linear",
     "ptts_debug_gemm_bench", "ptts_batch_profile_sections", "ptts_batch_set_pipelined", "ptts_batch_flush",
+    "ptts_batch_reset_seq", "ptts_batch_set_active",
     "ptts_batch_host_buffers", "ptts_batch_step_staged",
 ]
 
@@ -97,6 +98,8 @@ def lib() -> C.CDLL:
         "ptts_batch_host_buffers": (i32, [vp, C.POINTER(f32p), C.POINTER(f32p), C.POINTER(f32p), C.POINTER(f32p)]),
         "ptts_batch_step_staged": (i32, [vp]),
         "ptts_batch_set_pipelined": (i32, [vp, i32]),
+        "ptts_batch_reset_seq": (i32, [vp, i32, i32, i32]),
+        "ptts_batch_set_active": (i32, [vp, i32, i32]),
         "ptts_batch_flush": (i32, [vp, f32p]),
         "ptts_debug_gemm_bench": (i32, [vp, i32, i32, i32, i32, i32, i32, i32p, i32, f32p, i32p]),
     }
@@ -298,6 +301,15 @@ class Batch:
     def set_pipelined(self, on: bool = True):
         """Throughput mode: step() then returns the audio of the PREVIOUS frame; flush() decodes the last one."""
         check(lib().ptts_batch_set_pipelined(self._h, 1 if on else 0))
+
+    def reset_seq(self, slot: int, voice_id: int, max_len: int):
+        """Continuous batching: re-initialise one slot for a new utterance (KV pages, length, BOS, warm Mimi state);
+        follow with prefill_text where the other sequences get empty token lists."""
+        check(lib().ptts_batch_reset_seq(self._h, int(slot), int(voice_id), int(max_len)))
+
+    def set_active(self, slot: int, active: bool):
+        """Park (False) or resume a slot: a parked slot is still computed but stops growing its KV cache."""
+        check(lib().ptts_batch_set_active(self._h, int(slot), 1 if active else 0))
 
     def flush(self, want_audio: bool = True):
         audio = np.empty((self.n, self.frame_samples), dtype=np.float32) if want_audio else None

@@ -673,7 +673,14 @@ int take_pages(Ctx& c, int n, std::vector<int>* out) {
 struct ptts_batch {
   Ctx* ctx = nullptr;
   int B = 0, max_pages = 0;
-  std::vector<int> h_len, voice_ids, max_len, owned_pages;
+  std::vector<int> h_len, voice_ids, max_len;
+  std::vector<std::vector<int>> slot_pages;     // private KV pages of every sequence slot
+  // continuous batching: parked slots (h_active = 0) stop growing; a slot can be re-initialised for a new utterance
+  std::vector<int> h_active, h_page_table;
+  int* d_active = nullptr;
+  std::vector<ShiftEntry> h_shift;              // host copy of the streaming-conv state map
+  void* mimi_tpl = nullptr;                     // Mimi state of one sequence right after the warm-up frames
+  bool has_tpl = false;
   std::vector<void*> allocs;
   std::vector<std::pair<void*, size_t>> zero_list;   // streaming state + scratch that a fresh batch starts zeroed
   int *d_cp_src = nullptr, *d_cp_dst = nullptr;
@@ -1090,6 +1097,7 @@ int build_batch_tc(Batch& t) {
       gemm_tc_bind_outputs(&b.r1);
     }
     t.n_shift = (int)sh.size();
+    t.h_shift = sh;
     RET(t.dalloc((void**)&t.d_shift, sh.size() * sizeof(ShiftEntry)));
     CU(cudaMemcpyAsync(t.d_shift, sh.data(), sh.size() * sizeof(ShiftEntry), cudaMemcpyHostToDevice, c.stream));
   }
@@ -1154,7 +1162,7 @@ void full_step(Batch& bt, bool host_noise, bool copy_out) {
     cudaMemcpyAsync(bt.d_noise, bt.h_noise, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
   flow_step(bt, host_noise);
   mimi_frame(bt, bt.d_latent);
-  launch_advance(bt.d_len, bt.d_bos, bt.d_mimi_off, bt.d_counter, B, 1, bt.T0, c.stream);
+  launch_advance(bt.d_len, bt.d_bos, bt.d_mimi_off, bt.d_counter, B, 1, bt.T0, c.stream, bt.d_active);
   if (copy_out) {
     cudaMemcpyAsync(bt.h_latent, bt.d_latent, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
     cudaMemcpyAsync(bt.h_logit, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
@@ -1184,7 +1192,7 @@ void pipelined_frame(Batch& bt, int parity, bool host_io) {
   if (host_io)
     cudaMemcpyAsync(bt.d_noise, bt.h_noise, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
   flow_step(bt, host_io, 0, lat_prev, lat_cur);
-  launch_advance(bt.d_len, bt.d_bos, nullptr, bt.d_counter, B, 1, 0, c.stream);
+  launch_advance(bt.d_len, bt.d_bos, nullptr, bt.d_counter, B, 1, 0, c.stream, bt.d_active);
   if (host_io) {
     cudaMemcpyAsync(bt.h_latent, lat_cur, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
     cudaMemcpyAsync(bt.h_logit, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
@@ -1200,7 +1208,7 @@ int run_pipelined_step(Batch& bt, bool host_io) {
     if (host_io)
       CU(cudaMemcpyAsync(bt.d_noise, bt.h_noise, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream));
     flow_step(bt, host_io, 0, bt.d_latent, bt.d_latent);
-    launch_advance(bt.d_len, bt.d_bos, nullptr, bt.d_counter, B, 1, 0, c.stream);
+    launch_advance(bt.d_len, bt.d_bos, nullptr, bt.d_counter, B, 1, 0, c.stream, bt.d_active);
     if (host_io) {
       CU(cudaMemcpyAsync(bt.h_latent, bt.d_latent, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
       CU(cudaMemcpyAsync(bt.h_logit, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
@@ -1225,7 +1233,7 @@ int run_pipelined_step(Batch& bt, bool host_io) {
     g_launches += bt.pipe_graph_launches[idx];
   }
   bt.frame_idx += 1;
-  for (auto& l : bt.h_len) l += 1;
+  for (int b = 0; b < bt.B; ++b) bt.h_len[b] += bt.h_active[b];
   return 0;
 }
 
@@ -1250,14 +1258,34 @@ int run_step(Batch& bt, bool host_noise, bool copy_out) {
   const int idx = (host_noise ? 2 : 0) + (copy_out ? 1 : 0);
   CU(cudaGraphLaunch(bt.step_graph[idx], bt.ctx->stream));
   g_launches += bt.step_graph_launches[idx];
-  for (auto& l : bt.h_len) l += 1;
+  for (int b = 0; b < bt.B; ++b) bt.h_len[b] += bt.h_active[b];
   return 0;
+}
+
+// Per-sequence Mimi streaming state as (base, per-slot stride, bytes) pieces: the KV ring slices, the upsample conv's
+// previous column, the ring offset, the carried rows of every streaming conv and the output-conv boundary partials.
+struct StatePiece { char* base; size_t stride, bytes; };
+std::vector<StatePiece> mimi_state_pieces(Batch& t) {
+  Ctx& c = *t.ctx;
+  const ptts_config& g = c.cfg;
+  std::vector<StatePiece> v;
+  const size_t esz = c.bf16 ? 2 : 4;
+  const size_t slice = (size_t)g.mimi_heads * g.mimi_context * kHeadDim * esz;
+  for (int l = 0; l < g.mimi_layers; ++l)
+    for (int kv = 0; kv < 2; ++kv)
+      v.push_back({(char*)t.ring + ((size_t)l * t.ring_layer_stride + (size_t)kv * t.ring_kv_stride) * esz, slice, slice});
+  v.push_back({(char*)t.d_zprev, (size_t)g.seanet_dim * 4, (size_t)g.seanet_dim * 4});
+  v.push_back({(char*)t.d_mimi_off, 4, 4});
+  for (const ShiftEntry& e : t.h_shift)
+    v.push_back({(char*)e.buf, (size_t)e.bs * e.esz, (size_t)e.rows * e.C * e.esz});
+  if (t.d_bnd) v.push_back({(char*)t.d_bnd, (size_t)(t.frame_samples / 128 + 1) * 16, 16});
+  return v;
 }
 
 int check_step_ready(Batch& bt) {
   if (!bt.prefilled) return fail(PTTS_ERR_STATE, "ptts_batch_step called before ptts_batch_prefill_text");
   for (int b = 0; b < bt.B; ++b)
-    if (bt.h_len[b] + 1 > bt.max_len[b])
+    if (bt.h_active[b] && bt.h_len[b] + 1 > bt.max_len[b])
       return fail(PTTS_ERR_STATE, "sequence %d would exceed its max_len %d", b, bt.max_len[b]);
   return 0;
 }
@@ -1444,6 +1472,9 @@ static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32
   t.frame_idx = 0;
   t.pipelined = false;
   std::vector<int> pt((size_t)B * maxp, 0), src, dst;
+  t.slot_pages.assign(B, {});
+  t.h_active.assign(B, 1);
+  t.has_tpl = false;
   for (int b = 0; b < B; ++b) {
     const Voice& v = c->voices[voice_ids[b]];
     t.h_len[b] = v.len;
@@ -1453,13 +1484,15 @@ static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32
     std::vector<int> mine;
     RET(take_pages(*c, need_pages - full, &mine));
     for (int i = full; i < need_pages; ++i) pt[(size_t)b * maxp + i] = mine[i - full];
-    t.owned_pages.insert(t.owned_pages.end(), mine.begin(), mine.end());
+    t.slot_pages[b] = mine;
     if (v.len % kPageTokens) {
       src.push_back(v.pages[full]);
       dst.push_back(mine[0]);
     }
   }
+  t.h_page_table = pt;
   CU(cudaMemcpyAsync(t.d_page_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  launch_fill_u32((unsigned*)t.d_active, 1u, B, c->stream);
   if (!src.empty()) {
     CU(cudaMemcpyAsync(t.d_cp_src, src.data(), src.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(t.d_cp_dst, dst.data(), dst.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -1529,6 +1562,7 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
   RET(t.dalloc((void**)&t.d_cp_dst, B * 4));
   RET(t.dalloc((void**)&t.d_len, B * 4));
   RET(t.dalloc((void**)&t.d_bos, B * 4));
+  RET(t.dalloc((void**)&t.d_active, B * 4));
   RET(t.dalloc((void**)&t.d_mimi_off, B * 4));
   RET(t.dalloc((void**)&t.d_frame_idx, 4));
   RET(t.dalloc((void**)&t.d_counter, 16));
@@ -1593,6 +1627,7 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
   RET(fz(&t.d_fin, (size_t)B * (Tin + c->fin_taps - 1) * c->fin_c));
   if (c->fin_taps > 1) sh.push_back({t.d_fin, (long long)(Tin + c->fin_taps - 1) * c->fin_c, Tin, c->fin_taps - 1, c->fin_c, 4});
   t.n_shift = (int)sh.size();
+  t.h_shift = sh;
   RET(t.dalloc((void**)&t.d_shift, sh.size() * sizeof(ShiftEntry)));
   CU(cudaMemcpyAsync(t.d_shift, sh.data(), sh.size() * sizeof(ShiftEntry), cudaMemcpyHostToDevice, c->stream));
   }
@@ -1621,7 +1656,8 @@ static void batch_free(ptts_batch* bt) {
   if (bt->d_lat_all) cudaFree(bt->d_lat_all);
   if (bt->d_audio_all) cudaFree(bt->d_audio_all);
   cudaFreeHost(bt->h_noise); cudaFreeHost(bt->h_latent); cudaFreeHost(bt->h_logit); cudaFreeHost(bt->h_audio);
-  for (int p : bt->owned_pages) c->free_pages.push_back(p);
+  for (auto& v : bt->slot_pages) for (int p : v) c->free_pages.push_back(p);
+  if (bt->mimi_tpl) cudaFree(bt->mimi_tpl);
   delete bt;
 }
 
@@ -1630,8 +1666,8 @@ void ptts_batch_destroy(ptts_batch* bt) {
   Ctx* c = bt->ctx;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (int p : bt->owned_pages) c->free_pages.push_back(p);
-  bt->owned_pages.clear();
+  for (auto& v : bt->slot_pages) for (int p : v) c->free_pages.push_back(p);
+  bt->slot_pages.clear();
   bt->prefilled = false;
   if (!bt->h_audio || !bt->d_counter) {   // partially constructed: cannot be recycled
     batch_free(bt);
@@ -1694,8 +1730,100 @@ int32_t ptts_batch_warmup_mimi(ptts_batch* bt, int32_t n_frames) {
     mimi_frame(*bt, bt->d_zero_lat);
     launch_advance(nullptr, nullptr, bt->d_mimi_off, nullptr, bt->B, 0, bt->T0, c.stream);
   }
+  // every slot is in the same state now: keep slot 0's as the template that ptts_batch_reset_seq copies into a
+  // slot re-used for a new utterance (the warm-up input is the constant emb_mean, so it is sequence-independent)
+  if (bt->frame_idx == 0) {
+    auto pieces = mimi_state_pieces(*bt);
+    size_t total = 0;
+    for (auto& p : pieces) total += (p.bytes + 15) & ~(size_t)15;
+    if (!bt->mimi_tpl) CU(cudaMalloc(&bt->mimi_tpl, total));
+    size_t off = 0;
+    for (auto& p : pieces) {
+      CU(cudaMemcpyAsync((char*)bt->mimi_tpl + off, p.base, p.bytes, cudaMemcpyDeviceToDevice, c.stream));
+      off += (p.bytes + 15) & ~(size_t)15;
+    }
+    bt->has_tpl = true;
+  }
   CU(cudaStreamSynchronize(c.stream));
   CU(cudaGetLastError());
+  return 0;
+}
+
+int32_t ptts_batch_reset_seq(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_t max_len) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  Batch& t = *bt;
+  if (slot < 0 || slot >= t.B) return fail(PTTS_ERR_INVALID, "slot %d out of range", slot);
+  if (t.pipelined) return fail(PTTS_ERR_STATE, "slots of a pipelined batch cannot be re-used (flush and leave pipelined mode first)");
+  if (voice_id < 0 || voice_id >= (int)c.voices.size() || !c.voices[voice_id].alive)
+    return fail(PTTS_ERR_INVALID, "unknown voice id %d", voice_id);
+  const Voice& v = c.voices[voice_id];
+  if (max_len < v.len) return fail(PTTS_ERR_INVALID, "max_len shorter than the voice prefix");
+  const int need_pages = (max_len + kPageTokens - 1) / kPageTokens;
+  if (need_pages > t.max_pages)
+    return fail(PTTS_ERR_INVALID, "max_len %d needs %d KV pages, the batch was created for %d", max_len, need_pages, t.max_pages);
+  if (t.fw.prefix_len > 0 && voice_id != t.voice_ids[0])
+    return fail(PTTS_ERR_STATE, "this batch attends its shared voice prefix once for all sequences; a slot cannot switch voice");
+  CU(cudaStreamSynchronize(c.stream));
+  // KV: give the old private pages back, share the voice's full pages, copy its partial tail page
+  for (int p : t.slot_pages[slot]) c.free_pages.push_back(p);
+  t.slot_pages[slot].clear();
+  const int full = v.len / kPageTokens;
+  std::vector<int> mine;
+  RET(take_pages(c, need_pages - full, &mine));
+  t.slot_pages[slot] = mine;
+  int* row = t.h_page_table.data() + (size_t)slot * t.max_pages;
+  std::fill(row, row + t.max_pages, 0);
+  for (int i = 0; i < full; ++i) row[i] = v.pages[i];
+  for (int i = full; i < need_pages; ++i) row[i] = mine[i - full];
+  CU(cudaMemcpyAsync(t.d_page_table + (size_t)slot * t.max_pages, row, (size_t)t.max_pages * 4, cudaMemcpyHostToDevice, c.stream));
+  if (v.len % kPageTokens) {
+    const int sp = v.pages[full], dp = mine[0];
+    CU(cudaMemcpyAsync(t.d_cp_src, &sp, 4, cudaMemcpyHostToDevice, c.stream));
+    CU(cudaMemcpyAsync(t.d_cp_dst, &dp, 4, cudaMemcpyHostToDevice, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    launch_copy_pages(c.pool, c.bf16, c.layer_stride, c.page_stride, c.cfg.n_layers, t.d_cp_src, t.d_cp_dst, 1, c.stream);
+  }
+  t.voice_ids[slot] = voice_id;
+  t.max_len[slot] = max_len;
+  t.h_len[slot] = v.len;
+  t.h_active[slot] = 1;
+  const int one = 1;
+  CU(cudaMemcpyAsync(t.d_len + slot, &t.h_len[slot], 4, cudaMemcpyHostToDevice, c.stream));
+  CU(cudaMemcpyAsync(t.d_bos + slot, &one, 4, cudaMemcpyHostToDevice, c.stream));
+  CU(cudaMemcpyAsync(t.d_active + slot, &one, 4, cudaMemcpyHostToDevice, c.stream));
+  // Mimi: back to the post-warm-up state (or to the zero state when the batch was never warmed up)
+  {
+    auto pieces = mimi_state_pieces(t);
+    size_t off = 0;
+    for (auto& p : pieces) {
+      char* dst = p.base + (size_t)slot * p.stride;
+      if (t.has_tpl) CU(cudaMemcpyAsync(dst, (char*)t.mimi_tpl + off, p.bytes, cudaMemcpyDeviceToDevice, c.stream));
+      else CU(cudaMemsetAsync(dst, 0, p.bytes, c.stream));
+      off += (p.bytes + 15) & ~(size_t)15;
+    }
+  }
+  CU(cudaStreamSynchronize(c.stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int32_t ptts_batch_set_active(ptts_batch* bt, int32_t slot, int32_t active) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  if (slot < 0 || slot >= bt->B) return fail(PTTS_ERR_INVALID, "slot %d out of range", slot);
+  const int on = active ? 1 : 0;
+  CU(cudaStreamSynchronize(c.stream));
+  bt->h_active[slot] = on;
+  if (!on && bt->h_len[slot] >= bt->max_len[slot]) {
+    // a parked slot keeps being stepped with the rest of the batch: it must keep writing inside its own pages
+    bt->h_len[slot] = bt->max_len[slot] - 1;
+    CU(cudaMemcpyAsync(bt->d_len + slot, &bt->h_len[slot], 4, cudaMemcpyHostToDevice, c.stream));
+  }
+  CU(cudaMemcpyAsync(bt->d_active + slot, &on, 4, cudaMemcpyHostToDevice, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
   return 0;
 }
 

@@ -138,7 +138,7 @@ struct ShiftEntry { void* buf; long long bs; int T, rows, C, esz; };   // bs in 
 void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s);
 // seq_len += inc_len; bos_flag = 0; mimi_offset += inc_mimi; philox counter += 1
 void launch_advance(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter, int B,
-                    int inc_len, int inc_mimi, cudaStream_t s);
+                    int inc_len, int inc_mimi, cudaStream_t s, const int* active = nullptr);
 // y = a * x + y   (Euler update x += v / n)
 void launch_axpy(const float* x, float* y, float a, int n, cudaStream_t s);
 void launch_copy_pages(void* pool, int kv_bf16, long long layer_stride, long long page_stride, int n_layers,

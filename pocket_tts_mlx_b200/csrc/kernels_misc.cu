@@ -368,12 +368,13 @@ __global__ void state_shift_kernel(const ShiftEntry* __restrict__ entries) {
 }
 
 __global__ void advance_kernel(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter,
-                               int B, int inc_len, int inc_mimi) {
+                               int B, int inc_len, int inc_mimi, const int* active) {
   pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
-    if (seq_len) seq_len[i] += inc_len;
-    if (bos_flag && inc_len) bos_flag[i] = 0;
+    const bool on = !active || active[i];         // parked slots of a continuous batch do not grow their KV
+    if (seq_len && on) seq_len[i] += inc_len;
+    if (bos_flag && inc_len && on) bos_flag[i] = 0;
     if (mimi_offset) mimi_offset[i] += inc_mimi;
   }
   if (i == 0 && counter) *counter += 1ull;
@@ -596,9 +597,10 @@ void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cud
 }
 
 void launch_advance(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter, int B,
-                    int inc_len, int inc_mimi, cudaStream_t s) {
+                    int inc_len, int inc_mimi, cudaStream_t s, const int* active) {
   ProfScope ps("advance", nullptr, 0, 0, s);
-  launch_k(advance_kernel, dim3((B + 255) / 256), dim3(256), 0, s, seq_len, bos_flag, mimi_offset, counter, B, inc_len, inc_mimi);
+  launch_k(advance_kernel, dim3((B + 255) / 256), dim3(256), 0, s, seq_len, bos_flag, mimi_offset, counter, B, inc_len, inc_mimi,
+           active);
   ++g_launches;
 }
 

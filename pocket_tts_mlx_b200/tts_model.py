@@ -305,6 +305,90 @@ class TTSModel:
         finally:
             batch.close()
 
+    def generate_audio_continuous(self, model_states: Sequence[Dict], token_ids: Sequence[Sequence[int]],
+                                  slots: int = 256, frames_after_eos: Union[int, Sequence[int]] = 3,
+                                  warmup_frames: int = _MIMI_WARMUP_FRAMES, max_frames: Optional[int] = None,
+                                  noise: Optional[Sequence[np.ndarray]] = None, seed: int = 0,
+                                  return_latents: bool = False):
+        """Continuous batching over `slots` lock-step sequences: as soon as an utterance ends (EOS rule or frame
+        limit of the reference, tts_model.py:404-426) its slot is re-initialised for the next queued utterance
+        while the others keep decoding, so the batch stays full.  Results per utterance are the
+        same as decoding it in a batch of its own.
+
+        noise: optional per-utterance arrays [1 + frames, latent_dim] (row 0 = the unused prefill draw, like the
+        reference); without it every utterance draws its own N(0,1) stream from (seed, utterance index).
+        Returns the waveforms in input order (and the per-utterance latents when asked)."""
+        n_jobs = len(model_states)
+        if n_jobs == 0:
+            return ([], []) if return_latents else []
+        fae = [frames_after_eos] * n_jobs if isinstance(frames_after_eos, int) else list(frames_after_eos)
+        n_tok = [len(t) for t in token_ids]
+        limits = [self._estimate_max_gen_len(k) for k in n_tok]
+        if max_frames is not None:
+            limits = [min(l, max_frames) for l in limits]
+        need = [int(s["prompt_len"]) + k + l for s, k, l in zip(model_states, n_tok, limits)]
+        n_slots = min(int(slots), n_jobs)
+        cap = max(need)                                   # any utterance fits any slot
+        ldim = self._ctx.config.latent_dim
+        batch = _native.Batch(self._ctx, [int(model_states[j]["voice_id"]) for j in range(n_slots)], [cap] * n_slots)
+        rngs = {}
+
+        def draw(job, frame):
+            if noise is not None:
+                return np.asarray(noise[job][1 + frame], dtype=np.float32)
+            if job not in rngs:
+                rngs[job] = np.random.Generator(np.random.PCG64([seed, job]))
+            return rngs[job].standard_normal(ldim, dtype=np.float32)
+
+        try:
+            batch.seed(seed)
+            batch.warmup_mimi(warmup_frames)
+            batch.prefill_text([token_ids[j] for j in range(n_slots)])
+            job_of = list(range(n_slots))                 # utterance in each slot (None = parked)
+            frame_of = [0] * n_slots
+            eos_at = [None] * n_slots
+            next_job = n_slots
+            audio_out = [[] for _ in range(n_jobs)]
+            lat_out = [[] for _ in range(n_jobs)]
+            z = np.zeros((n_slots, ldim), dtype=np.float32)
+            while any(j is not None for j in job_of):
+                for s_, j in enumerate(job_of):
+                    z[s_] = draw(j, frame_of[s_]) if j is not None else 0.0
+                lat, logit, audio = batch.step(z, want_audio=True)
+                admitted = []
+                for s_, j in enumerate(job_of):
+                    if j is None:
+                        continue
+                    step = frame_of[s_]
+                    ended = False
+                    if logit[s_] > self.eos_threshold and eos_at[s_] is None:
+                        eos_at[s_] = step
+                    if eos_at[s_] is not None and step >= eos_at[s_] + fae[j]:
+                        ended = True                      # the reference breaks before emitting this frame
+                    else:
+                        lat_out[j].append(lat[s_].copy())
+                        audio_out[j].append(audio[s_].copy())
+                        frame_of[s_] = step + 1
+                        ended = frame_of[s_] >= limits[j]
+                    if ended:
+                        if next_job < n_jobs:
+                            nj = next_job
+                            next_job += 1
+                            batch.reset_seq(s_, int(model_states[nj]["voice_id"]), cap)
+                            job_of[s_], frame_of[s_], eos_at[s_] = nj, 0, None
+                            admitted.append(s_)
+                        else:
+                            batch.set_active(s_, False)
+                            job_of[s_] = None
+                if admitted:
+                    batch.prefill_text([token_ids[job_of[s_]] if s_ in admitted else [] for s_ in range(n_slots)])
+            waves = [np.concatenate(a) if a else np.zeros(0, dtype=np.float32) for a in audio_out]
+            if return_latents:
+                return waves, [np.array(l, dtype=np.float32).reshape(-1, ldim) for l in lat_out]
+            return waves
+        finally:
+            batch.close()
+
     def close(self):
         self._ctx.close()
 

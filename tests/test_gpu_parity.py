@@ -503,3 +503,54 @@ def test_fused_seanet_tail_many_tiles_per_cta(model_bf16, monkeypatch):
         batch.close()
     for b in (0, 1, 17, 40, 63):
         assert snr_db(out["0"][b], out["1"][b]) > 40.0, (b, snr_db(out["0"][b], out["1"][b]))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_continuous_batching_matches_standalone(model_fp32, model_bf16, prec):
+    """Five utterances of different lengths and voices through TWO slots: a slot is re-initialised for the next
+    utterance while the other keeps decoding (per-slot KV pages, BOS flag, warm Mimi state).  Every utterance must
+    come out as if it had been decoded in a batch of its own with the same noise."""
+    model = model_fp32 if prec == "fp32" else model_bf16
+    rng = np.random.Generator(np.random.PCG64(21))
+    n_tok = [3, 6, 9, 4, 7]
+    voices = ["alba", "marius", "alba", "javert", "marius"]
+    states = [model.get_state_for_audio_prompt(v) for v in voices]
+    ids = [rng.integers(0, 4000, size=k).astype(np.int32) for k in n_tok]
+    noise = [rng.standard_normal((1 + 70, 32)).astype(np.float32) for _ in n_tok]
+    waves, lats = model.generate_audio_continuous(states, ids, slots=2, noise=noise, return_latents=True)
+    assert [len(l) for l in lats] == [38, 50, 63, 42, 55]            # ceil((n/3 + 2) * 12.5) frames each
+    for j in range(5):
+        w1, l1 = model.generate_audio_batch([states[j]], [ids[j]], noise=noise[j][:, None, :], return_latents=True,
+                                            pipelined=False)
+        assert lats[j].shape == l1[0].shape
+        assert rel_l2(lats[j], l1[0]) < (1e-5 if prec == "fp32" else 2e-3), (j, rel_l2(lats[j], l1[0]))
+        assert snr_db(waves[j], w1[0]) > (80.0 if prec == "fp32" else 40.0), (j, snr_db(waves[j], w1[0]))
+
+
+def test_continuous_batching_with_cascade_attention(model_bf16):
+    """40 same-voice utterances through 32 slots (the batch size where the shared-prefix cascade kernel is on):
+    admitted utterances agree with the ones decoded in a plain 32-batch to the bf16 bound (an utterance admitted on
+    its own is prefilled by the fp32-activation GEMV path, the lock-step batch by the bf16-operand tcgen05 path, so
+    their KV entries differ by bf16 rounding), and a slot cannot change voice."""
+    from pocket_tts_mlx_b200 import _native
+    rng = np.random.Generator(np.random.PCG64(22))
+    st = model_bf16.get_state_for_audio_prompt("alba")
+    n_jobs, frames = 40, 5
+    ids = [rng.integers(0, 4000, size=int(rng.integers(4, 9))).astype(np.int32) for _ in range(n_jobs)]
+    noise = [rng.standard_normal((1 + frames, 32)).astype(np.float32) for _ in range(n_jobs)]
+    waves, lats = model_bf16.generate_audio_continuous([st] * n_jobs, ids, slots=32, noise=noise, max_frames=frames,
+                                                       return_latents=True)
+    assert all(len(l) == frames for l in lats)
+    # second wave: utterances 32..39 in slots 0..7 of a fresh lock-step batch of 32
+    sel = list(range(32, 40)) + list(range(8, 32))
+    nz = np.stack([noise[j] for j in sel], axis=1)
+    w2, l2 = model_bf16.generate_audio_batch([st] * 32, [ids[j] for j in sel], noise=nz, max_frames=frames,
+                                             return_latents=True, pipelined=False)
+    for k, j in enumerate(sel[:8]):
+        assert rel_l2(lats[j], l2[k]) < 1e-2, (j, rel_l2(lats[j], l2[k]))
+        assert snr_db(waves[j], w2[k]) > 30.0
+    other = model_bf16.get_state_for_audio_prompt("marius")
+    batch = _native.Batch(model_bf16._ctx, [st["voice_id"]] * 32, [st["prompt_len"] + 40] * 32)
+    with pytest.raises(_native.PttsError):
+        batch.reset_seq(3, other["voice_id"], other["prompt_len"] + 30)
+    batch.close()
