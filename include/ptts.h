@@ -132,6 +132,9 @@ int32_t ptts_batch_step_device(ptts_batch* batch);
  * ptts_batch_set_active(slot, 0) parks a slot: it is still computed with the batch but stops growing its KV cache.
  * Not available in pipelined mode; in a batch that uses cascade attention the voice cannot change. */
 int32_t ptts_batch_reset_seq(ptts_batch* batch, int32_t slot, int32_t voice_id, int32_t max_len);
+/* the same for n slots with one stream synchronisation */
+int32_t ptts_batch_reset_seqs(ptts_batch* batch, int32_t n, const int32_t* slots, const int32_t* voice_ids,
+                              const int32_t* max_lens);
 int32_t ptts_batch_set_active(ptts_batch* batch, int32_t slot, int32_t active);
 
 /* Throughput mode.  FlowLM step t only needs latent t-1, and so does the Mimi decode of frame t-1, so the two

@@ -25,7 +25,7 @@ EXPORTED = [
     "ptts_batch_seed", "ptts_batch_lengths", "ptts_batch_mimi_decode", "ptts_sync", "ptts_timer_begin",
     "ptts_timer_end", "ptts_launch_count", "ptts_batch_profile_step", "ptts_flush_l2", "ptts_debug_linear",
     "ptts_debug_gemm_bench", "ptts_batch_profile_sections", "ptts_batch_set_pipelined", "ptts_batch_flush",
-    "ptts_batch_reset_seq", "ptts_batch_set_active",
+    "ptts_batch_reset_seq", "ptts_batch_reset_seqs", "ptts_batch_set_active",
     "ptts_batch_host_buffers", "ptts_batch_step_staged",
 ]
 
@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
         "ptts_batch_step_staged": (i32, [vp]),
         "ptts_batch_set_pipelined": (i32, [vp, i32]),
         "ptts_batch_reset_seq": (i32, [vp, i32, i32, i32]),
+        "ptts_batch_reset_seqs": (i32, [vp, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "ptts_batch_set_active": (i32, [vp, i32, i32]),
         "ptts_batch_flush": (i32, [vp, f32p]),
         "ptts_debug_gemm_bench": (i32, [vp, i32, i32, i32, i32, i32, i32, i32p, i32, f32p, i32p]),
@@ -306,6 +307,11 @@ class Batch:
         """Continuous batching: re-initialise one slot for a new utterance (KV pages, length, BOS, warm Mimi state);
         follow with prefill_text where the other sequences get empty token lists."""
         check(lib().ptts_batch_reset_seq(self._h, int(slot), int(voice_id), int(max_len)))
+
+    def reset_seqs(self, slots: Sequence[int], voice_ids: Sequence[int], max_lens: Sequence[int]):
+        """reset_seq for several slots with one synchronisation."""
+        a, v, m = (np.ascontiguousarray(x, dtype=np.int32) for x in (slots, voice_ids, max_lens))
+        check(lib().ptts_batch_reset_seqs(self._h, len(a), _ip(a), _ip(v), _ip(m)))
 
     def set_active(self, slot: int, active: bool):
         """Park (False) or resume a slot: a parked slot is still computed but stops growing its KV cache."""

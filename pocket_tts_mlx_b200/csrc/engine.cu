@@ -1749,10 +1749,8 @@ int32_t ptts_batch_warmup_mimi(ptts_batch* bt, int32_t n_frames) {
   return 0;
 }
 
-int32_t ptts_batch_reset_seq(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_t max_len) {
-  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+static int reset_seq_impl(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_t max_len) {
   Ctx& c = *bt->ctx;
-  CU(cudaSetDevice(c.device));
   Batch& t = *bt;
   if (slot < 0 || slot >= t.B) return fail(PTTS_ERR_INVALID, "slot %d out of range", slot);
   if (t.pipelined) return fail(PTTS_ERR_STATE, "slots of a pipelined batch cannot be re-used (flush and leave pipelined mode first)");
@@ -1765,7 +1763,6 @@ int32_t ptts_batch_reset_seq(ptts_batch* bt, int32_t slot, int32_t voice_id, int
     return fail(PTTS_ERR_INVALID, "max_len %d needs %d KV pages, the batch was created for %d", max_len, need_pages, t.max_pages);
   if (t.fw.prefix_len > 0 && voice_id != t.voice_ids[0])
     return fail(PTTS_ERR_STATE, "this batch attends its shared voice prefix once for all sequences; a slot cannot switch voice");
-  CU(cudaStreamSynchronize(c.stream));
   // KV: give the old private pages back, share the voice's full pages, copy its partial tail page
   for (int p : t.slot_pages[slot]) c.free_pages.push_back(p);
   t.slot_pages[slot].clear();
@@ -1779,11 +1776,12 @@ int32_t ptts_batch_reset_seq(ptts_batch* bt, int32_t slot, int32_t voice_id, int
   for (int i = full; i < need_pages; ++i) row[i] = mine[i - full];
   CU(cudaMemcpyAsync(t.d_page_table + (size_t)slot * t.max_pages, row, (size_t)t.max_pages * 4, cudaMemcpyHostToDevice, c.stream));
   if (v.len % kPageTokens) {
+    // pageable host -> device copies of 4 bytes complete before cudaMemcpyAsync returns, so the locals may die
     const int sp = v.pages[full], dp = mine[0];
-    CU(cudaMemcpyAsync(t.d_cp_src, &sp, 4, cudaMemcpyHostToDevice, c.stream));
-    CU(cudaMemcpyAsync(t.d_cp_dst, &dp, 4, cudaMemcpyHostToDevice, c.stream));
-    CU(cudaStreamSynchronize(c.stream));
-    launch_copy_pages(c.pool, c.bf16, c.layer_stride, c.page_stride, c.cfg.n_layers, t.d_cp_src, t.d_cp_dst, 1, c.stream);
+    CU(cudaMemcpyAsync(t.d_cp_src + slot, &sp, 4, cudaMemcpyHostToDevice, c.stream));
+    CU(cudaMemcpyAsync(t.d_cp_dst + slot, &dp, 4, cudaMemcpyHostToDevice, c.stream));
+    launch_copy_pages(c.pool, c.bf16, c.layer_stride, c.page_stride, c.cfg.n_layers, t.d_cp_src + slot, t.d_cp_dst + slot, 1,
+                      c.stream);
   }
   t.voice_ids[slot] = voice_id;
   t.max_len[slot] = max_len;
@@ -1804,9 +1802,23 @@ int32_t ptts_batch_reset_seq(ptts_batch* bt, int32_t slot, int32_t voice_id, int
       off += (p.bytes + 15) & ~(size_t)15;
     }
   }
+  return 0;
+}
+
+int32_t ptts_batch_reset_seqs(ptts_batch* bt, int32_t n, const int32_t* slots, const int32_t* voice_ids,
+                              const int32_t* max_lens) {
+  if (!bt || (n > 0 && (!slots || !voice_ids || !max_lens))) return fail(PTTS_ERR_INVALID, "null argument");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  CU(cudaStreamSynchronize(c.stream));
+  for (int i = 0; i < n; ++i) RET(reset_seq_impl(bt, slots[i], voice_ids[i], max_lens[i]));
   CU(cudaStreamSynchronize(c.stream));
   CU(cudaGetLastError());
   return 0;
+}
+
+int32_t ptts_batch_reset_seq(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_t max_len) {
+  return ptts_batch_reset_seqs(bt, 1, &slot, &voice_id, &max_len);
 }
 
 int32_t ptts_batch_set_active(ptts_batch* bt, int32_t slot, int32_t active) {

@@ -280,17 +280,22 @@ class TTSModel:
                         continue
                     if step >= limits[b]:
                         done[b] = True
+                        batch.set_active(b, False)        # parked: computed with the batch, KV no longer grows
                         continue
                     if logit[b] > self.eos_threshold and eos_step[b] is None:
                         eos_step[b] = step
                     if eos_step[b] is not None and step >= eos_step[b] + fae[b]:
                         done[b] = True
+                        batch.set_active(b, False)
                         continue
                     lat_out[b].append(lat[b].copy())
                     if pipelined:
                         owed[b] = True
                     else:
                         audio_out[b].append(audio[b].copy())
+                    if step + 1 >= limits[b] and not all(step + 1 >= l for l in limits):
+                        done[b] = True                    # frame budget used up while others continue: park now,
+                        batch.set_active(b, False)        # the next step must not grow this sequence's KV
                 if all(done):
                     break
             if pipelined and stepped and any(owed):
@@ -309,14 +314,16 @@ class TTSModel:
                                   slots: int = 256, frames_after_eos: Union[int, Sequence[int]] = 3,
                                   warmup_frames: int = _MIMI_WARMUP_FRAMES, max_frames: Optional[int] = None,
                                   noise: Optional[Sequence[np.ndarray]] = None, seed: int = 0,
-                                  return_latents: bool = False):
-        """Continuous batching over `slots` lock-step sequences: as soon as an utterance ends (EOS rule or frame
-        limit of the reference, tts_model.py:404-426) its slot is re-initialised for the next queued utterance
-        while the others keep decoding, so the batch stays full.  Results per utterance are the
-        same as decoding it in a batch of its own.
+                                  return_latents: bool = False, min_admit: Optional[int] = None):
+        """Continuous batching over `slots` lock-step sequences: when an utterance ends (EOS rule or frame limit of
+        the reference, tts_model.py:404-426) its slot is parked and later re-initialised for the next queued
+        utterance while the others keep decoding, so the batch stays full.  Admissions are
+        grouped: freed slots wait until `min_admit` of them (default slots/16) can be prefilled together, which turns
+        the text prefill into one dense GEMM pass instead of one GEMV pass per utterance.  Results per utterance are
+        the same as decoding it in a batch of its own.
 
         noise: optional per-utterance arrays [1 + frames, latent_dim] (row 0 = the unused prefill draw, like the
-        reference); without it every utterance draws its own N(0,1) stream from (seed, utterance index).
+        reference); without it the host draws one N(0,1) block per step from `seed`.
         Returns the waveforms in input order (and the per-utterance latents when asked)."""
         n_jobs = len(model_states)
         if n_jobs == 0:
@@ -329,16 +336,10 @@ class TTSModel:
         need = [int(s["prompt_len"]) + k + l for s, k, l in zip(model_states, n_tok, limits)]
         n_slots = min(int(slots), n_jobs)
         cap = max(need)                                   # any utterance fits any slot
+        group = max(1, n_slots // 16) if min_admit is None else max(1, int(min_admit))
         ldim = self._ctx.config.latent_dim
         batch = _native.Batch(self._ctx, [int(model_states[j]["voice_id"]) for j in range(n_slots)], [cap] * n_slots)
-        rngs = {}
-
-        def draw(job, frame):
-            if noise is not None:
-                return np.asarray(noise[job][1 + frame], dtype=np.float32)
-            if job not in rngs:
-                rngs[job] = np.random.Generator(np.random.PCG64([seed, job]))
-            return rngs[job].standard_normal(ldim, dtype=np.float32)
+        rng = np.random.Generator(np.random.PCG64(seed))
 
         try:
             batch.seed(seed)
@@ -347,41 +348,64 @@ class TTSModel:
             job_of = list(range(n_slots))                 # utterance in each slot (None = parked)
             frame_of = [0] * n_slots
             eos_at = [None] * n_slots
+            free: List[int] = []                          # parked slots waiting for the next admission round
             next_job = n_slots
-            audio_out = [[] for _ in range(n_jobs)]
-            lat_out = [[] for _ in range(n_jobs)]
+            audio_out: List[List[np.ndarray]] = [[] for _ in range(n_jobs)]
+            lat_out: List[List[np.ndarray]] = [[] for _ in range(n_jobs)]
             z = np.zeros((n_slots, ldim), dtype=np.float32)
-            while any(j is not None for j in job_of):
-                for s_, j in enumerate(job_of):
-                    z[s_] = draw(j, frame_of[s_]) if j is not None else 0.0
-                lat, logit, audio = batch.step(z, want_audio=True)
-                admitted = []
+            thr = self.eos_threshold
+            live = n_slots
+            import time as _t, os as _os
+            prof = {"steps": 0, "rounds": 0, "t_step": 0.0, "t_loop": 0.0, "t_admit": 0.0, "t_noise": 0.0}
+            while live > 0:
+                _t0 = _t.perf_counter()
+                if noise is None:
+                    z = rng.standard_normal((n_slots, ldim), dtype=np.float32)      # one draw per step for all slots
+                else:
+                    for s_, j in enumerate(job_of):
+                        if j is not None:
+                            z[s_] = noise[j][1 + frame_of[s_]]
+                _t1 = _t.perf_counter()
+                lat, logit, audio = batch.step(z, want_audio=True)      # fresh arrays every step: rows are kept as views
+                _t2 = _t.perf_counter()
+                prof["steps"] += 1; prof["t_noise"] += _t1 - _t0; prof["t_step"] += _t2 - _t1
                 for s_, j in enumerate(job_of):
                     if j is None:
                         continue
                     step = frame_of[s_]
-                    ended = False
-                    if logit[s_] > self.eos_threshold and eos_at[s_] is None:
+                    if eos_at[s_] is None and logit[s_] > thr:
                         eos_at[s_] = step
                     if eos_at[s_] is not None and step >= eos_at[s_] + fae[j]:
                         ended = True                      # the reference breaks before emitting this frame
                     else:
-                        lat_out[j].append(lat[s_].copy())
-                        audio_out[j].append(audio[s_].copy())
+                        lat_out[j].append(lat[s_])
+                        audio_out[j].append(audio[s_])
                         frame_of[s_] = step + 1
-                        ended = frame_of[s_] >= limits[j]
+                        ended = step + 1 >= limits[j]
                     if ended:
-                        if next_job < n_jobs:
-                            nj = next_job
-                            next_job += 1
-                            batch.reset_seq(s_, int(model_states[nj]["voice_id"]), cap)
-                            job_of[s_], frame_of[s_], eos_at[s_] = nj, 0, None
-                            admitted.append(s_)
-                        else:
-                            batch.set_active(s_, False)
-                            job_of[s_] = None
-                if admitted:
-                    batch.prefill_text([token_ids[job_of[s_]] if s_ in admitted else [] for s_ in range(n_slots)])
+                        batch.set_active(s_, False)
+                        job_of[s_] = None
+                        free.append(s_)
+                        live -= 1
+                _t3 = _t.perf_counter()
+                prof["t_loop"] += _t3 - _t2
+                pending = n_jobs - next_job
+                if pending > 0 and free and (len(free) >= min(group, pending) or live == 0):
+                    prof["rounds"] += 1
+                    take = free[:pending]
+                    free = free[len(take):]
+                    jobs = list(range(next_job, next_job + len(take)))
+                    next_job += len(take)
+                    batch.reset_seqs(take, [int(model_states[j]["voice_id"]) for j in jobs], [cap] * len(take))
+                    toks: List[Sequence[int]] = [[] for _ in range(n_slots)]
+                    for s_, j in zip(take, jobs):
+                        job_of[s_], frame_of[s_], eos_at[s_] = j, 0, None
+                        toks[s_] = token_ids[j]
+                    batch.prefill_text(toks)
+                    live += len(take)
+                    prof["t_admit"] += _t.perf_counter() - _t3
+            if _os.environ.get("PTTS_SCHED_PROFILE"):
+                print("scheduler profile:", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in prof.items()})
             waves = [np.concatenate(a) if a else np.zeros(0, dtype=np.float32) for a in audio_out]
             if return_latents:
                 return waves, [np.array(l, dtype=np.float32).reshape(-1, ldim) for l in lat_out]
