@@ -632,17 +632,31 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
     return;
   }
   w.pend_n = 0;
+  static const bool fuse_rope_gemv = [] { const char* v = getenv("PTTS_NO_ROPE_FUSE"); return !(v && v[0] == '1'); }();
   for (int i = 0; i < c.cfg.n_layers; ++i) {
     auto& l = c.fl[i];
-    run_norm_linear(c, l.qkv, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, nullptr, nullptr, 0, w.h,
-                    rows_linear(w.h, M, D, w.qkv, 3 * D, "flow.qkv"));
+    LinearParams q = rows_linear(w.h, M, D, w.qkv, 3 * D, "flow.qkv");
+    bool roped = false;
+    {
+      // batch <= 4 (the latency path): RoPE + KV append ride in the GEMV epilogue, one launch less per layer
+      LinearParams probe = q;
+      probe.A = w.x; probe.a_bs = 0; probe.a_rs = D; probe.nb = 1; probe.T = M; probe.taps = 1; probe.C = D; probe.N = l.qkv.N;
+      if (fuse_rope_gemv && linear_gemv_rope_supported(probe)) {
+        roped = true;
+        q.rope_on = 1; q.q_rot = w.qrot; q.kv_bf16 = c.bf16;
+        q.kv_layer = (char*)c.pool + (size_t)i * c.layer_stride * (c.bf16 ? 2 : 4);
+        q.kv_row_seq = row_seq; q.kv_row_pos = row_pos; q.kv_page_table = page_table; q.kv_max_pages = max_pages;
+        q.kv_heads = c.cfg.n_heads; q.kv_page_stride = c.page_stride; q.rope_freqs = c.freqs_flow;
+      }
+    }
+    run_norm_linear(c, l.qkv, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, nullptr, nullptr, 0, w.h, q);
     FlowAttnParams a{};
     a.qkv = w.qkv; a.q_rot = w.qrot; a.out = w.att;
     a.pool = c.pool; a.kv_bf16 = c.bf16; a.layer_stride = c.layer_stride; a.page_stride = c.page_stride;
     a.layer = i; a.row_seq = row_seq; a.row_pos = row_pos; a.page_table = page_table; a.max_pages = max_pages;
     a.M = M; a.H = c.cfg.n_heads; a.freqs = c.freqs_flow; a.total_keys = total_keys;
     a.part = w.attn_part; a.splits = w.attn_part ? std::min(8, std::max(1, 296 / (M * c.cfg.n_heads))) : 1;
-    launch_flow_rope_append(a, c.stream);
+    if (!roped) launch_flow_rope_append(a, c.stream);
     launch_flow_attention(a, c.stream);
     LinearParams o = rows_linear(w.att, M, D, w.x, D, "flow.out");
     o.res = w.x; o.res_bs = 0; o.res_rs = D;
@@ -1764,9 +1778,12 @@ static int reset_seq_impl(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_
   if (t.fw.prefix_len > 0 && voice_id != t.voice_ids[0])
     return fail(PTTS_ERR_STATE, "this batch attends its shared voice prefix once for all sequences; a slot cannot switch voice");
   // KV: give the old private pages back, share the voice's full pages, copy its partial tail page
+  const int full = v.len / kPageTokens;
+  if ((int)(c.free_pages.size() + t.slot_pages[slot].size()) < need_pages - full)   // checked first: the slot keeps its pages on failure
+    return fail(PTTS_ERR_NOMEM, "KV page pool exhausted: slot %d needs %d pages, %zu free", slot, need_pages - full,
+                c.free_pages.size() + t.slot_pages[slot].size());
   for (int p : t.slot_pages[slot]) c.free_pages.push_back(p);
   t.slot_pages[slot].clear();
-  const int full = v.len / kPageTokens;
   std::vector<int> mine;
   RET(take_pages(c, need_pages - full, &mine));
   t.slot_pages[slot] = mine;

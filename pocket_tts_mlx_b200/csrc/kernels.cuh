@@ -36,7 +36,13 @@ struct LinearParams {
   // input rows in shared memory anyway, so the separate norm launch disappears from the batch-1 chain
   int ln_on; const float* ln_w; const float* ln_b; float ln_eps;
   const float* ln_scale; const float* ln_shift; long long ln_mod_rs;   // per-row modulation vectors or null
+  // GEMV path, FlowLM qkv at <= 4 rows (two output features per warp = one RoPE pair): rotate q / k and append k, v to
+  // the paged cache in the epilogue instead of a separate flow_rope_append launch.  Y is not written.
+  int rope_on; float* q_rot; void* kv_layer; int kv_bf16;
+  const int *kv_row_seq, *kv_row_pos, *kv_page_table; int kv_max_pages, kv_heads; long long kv_page_stride;
+  const float* rope_freqs;
 };
+bool linear_gemv_rope_supported(const LinearParams& p);   // GEMV path with a (2i, 2i+1) pair per warp
 
 inline double linear_flops(const LinearParams& p) { return 2.0 * p.nb * p.T * (double)p.N * p.taps * p.C; }
 inline double linear_bytes(const LinearParams& p) {
@@ -83,6 +89,7 @@ struct FlowAttnParams {
   const float* freqs;          // [32] RoPE frequencies (fp32, computed like modules/rope.py:17-18)
   long long total_keys;        // host-side sum over rows of (row_pos+1), for the profiler's byte count
   int splits; float* part;     // split-KV for small batches: partials [M][H][splits][66] merged by a second kernel
+                               // (a last-slice-merges variant with an arrival counter was measured: +10 us per frame)
   // cascade: all rows share the first prefix_len keys (the voice prompt).  A tensor-core kernel computes that part
   // once per (row, head) from the voice's own pages into prefix_part [M][H][66]; the per-sequence kernel then
   // starts at key prefix_len and merges the partial.

@@ -268,6 +268,38 @@ __global__ void __launch_bounds__(256) linear_gemv_kernel(const LinearParams p) 
 #pragma unroll
     for (int m = 0; m < MT; ++m) acc[r][m] = warp_sum(acc[r][m]);
 
+  if constexpr (R == 2) {
+    if (p.rope_on) {
+      // fused RoPE + KV append: this warp owns the interleaved pair (n_base, n_base + 1) of every row
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (lane == (m & 31) && m < M && n_base + 1 < p.N) {
+          const int Dm = p.kv_heads * kHeadDim;
+          const int which = n_base / Dm, within = n_base - which * Dm;      // 0 q, 1 k, 2 v
+          const int pos = p.kv_row_pos[m];
+          float x = acc[0][m], y = acc[1][m];
+          if (which < 2) {
+            float sn, cs;
+            sincosf((float)pos * p.rope_freqs[(within & 63) >> 1], &sn, &cs);
+            const float xr = x * cs - y * sn, yr = x * sn + y * cs;
+            x = xr; y = yr;
+          }
+          if (which == 0) {
+            p.q_rot[(long long)m * Dm + within] = x;
+            p.q_rot[(long long)m * Dm + within + 1] = y;
+          } else {
+            const int seq = p.kv_row_seq ? p.kv_row_seq[m] : m;
+            const int page = p.kv_page_table[(long long)seq * p.kv_max_pages + pos / kPageTokens];
+            const long long off = page * p.kv_page_stride + ((long long)(within >> 6) * kPageTokens + pos % kPageTokens) * kHeadDim +
+                                  (within & 63) + (which == 2 ? (long long)p.kv_heads * kPageTokens * kHeadDim : 0);
+            if (p.kv_bf16) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.kv_layer) + off) = __floats2bfloat162_rn(x, y);
+            else *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.kv_layer) + off) = make_float2(x, y);
+          }
+        }
+      }
+      return;
+    }
+  }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
 #pragma unroll
@@ -311,6 +343,11 @@ void launch_gemv_t(const LinearParams& p, cudaStream_t s) {
 }
 
 }  // namespace
+
+bool linear_gemv_rope_supported(const LinearParams& p) {
+  const int M = p.nb * p.T;
+  return linear_gemv_supported(p) && M <= 4 && p.N > 1536 && (p.N % 2) == 0;     // the R = 2 instantiation
+}
 
 bool linear_gemv_supported(const LinearParams& p) {
   const int M = p.nb * p.T;
