@@ -761,11 +761,12 @@ namespace {
 
 using Batch = ptts_batch;
 
-void mimi_frame_tc(Batch& bt, const float* latent, int part = 0);
+void mimi_frame_tc(Batch& bt, const float* latent, int part = 0, bool advance = false);
 
 // one Mimi frame for every sequence: latent [B][L] -> audio [B][frame_samples]
-void mimi_frame(Batch& bt, const float* latent) {
-  if (bt.tc_mimi) return mimi_frame_tc(bt, latent);
+// advance: also move every sequence's ring offset on by one frame (folded into the end-of-frame launch)
+void mimi_frame(Batch& bt, const float* latent, bool advance = false) {
+  if (bt.tc_mimi) return mimi_frame_tc(bt, latent, 0, advance);
   Ctx& c = *bt.ctx;
   const ptts_config& g = c.cfg;
   const int B = bt.B, T = bt.T0, MD = g.mimi_d, SD = g.seanet_dim;
@@ -863,12 +864,12 @@ void mimi_frame(Batch& bt, const float* latent) {
   }
   launch_final_conv(bt.d_fin, (long long)(bt.frame_samples + c.fin_taps - 1) * c.fin_c, c.fin_w, c.fin_b, bt.d_audio,
                     bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream);
-  launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream);
+  launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream, nullptr, 0, nullptr, 0, advance ? bt.d_mimi_off : nullptr, bt.T0);
 }
 
 // Mimi frame on the tensor-core path: bf16 operands everywhere, every conv / transposed conv / linear is a
 // tcgen05 GEMM whose epilogue already writes the next GEMM's (ELU'd) bf16 input, incl. the carried state rows.
-void mimi_frame_tc(Batch& bt, const float* latent, int part) {   // part: 0 all, 1 transformer, 2 SEANet
+void mimi_frame_tc(Batch& bt, const float* latent, int part, bool advance) {   // part: 0 all, 1 transformer, 2 SEANet
   Ctx& c = *bt.ctx;
   const ptts_config& g = c.cfg;
   const int B = bt.B, T = bt.T0, MD = g.mimi_d, SD = g.seanet_dim;
@@ -917,7 +918,7 @@ void mimi_frame_tc(Batch& bt, const float* latent, int part) {   // part: 0 all,
     auto& sb = bt.sb16[r];
     gemm_tc_launch(sb.ct, c.stream);
     if (bt.sn_tail.valid && r + 1 == bt.sb16.size()) {
-      sn_tail_launch(bt.sn_tail, c.stream);
+      sn_tail_launch(bt.sn_tail, c.stream, false);     // its boundary fix-up rides in the state-shift launch below
       break;
     }
     gemm_tc_launch(sb.r3, c.stream);
@@ -926,11 +927,12 @@ void mimi_frame_tc(Batch& bt, const float* latent, int part) {   // part: 0 all,
   if (!bt.sn_tail.valid)
     launch_final_conv16(bt.d_fin16, (long long)(bt.frame_samples + c.fin_taps - 1) * c.fin_c, c.fin_w, c.fin_b,
                         bt.d_audio, bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream);
-  launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream);
+  launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream, bt.d_audio, bt.frame_samples, bt.sn_tail.valid ? bt.d_bnd : nullptr,
+                     bt.frame_samples / 128, advance ? bt.d_mimi_off : nullptr, bt.T0);
 }
 
 // flow head on the tensor-core path (M = B rows)
-void flow_head_tc(Batch& bt) {
+void flow_head_tc(Batch& bt, float* lat_out) {
   Ctx& c = *bt.ctx;
   const ptts_config& g = c.cfg;
   const int B = bt.B, L = g.latent_dim, fd = g.flow_dim;
@@ -948,7 +950,13 @@ void flow_head_tc(Batch& bt) {
     }
     const float* adaf = bt.d_ada + (long long)g.flow_depth * 3 * fd;
     rows_norm(c, bt.d_x1, B, fd, nullptr, nullptr, 1e-6f, nullptr, adaf + fd, adaf, c.n_ada, bt.d_hh16, nullptr, 0);
-    gemm_tc_launch(bt.g_fin, c.stream);
+    if (i == n - 1) {
+      TcGemm f = bt.g_fin;          // x + v / n of the last step is the frame's latent
+      f.e.y32 = lat_out;
+      gemm_tc_launch(f, c.stream);
+    } else {
+      gemm_tc_launch(bt.g_fin, c.stream);
+    }
   }
 }
 
@@ -1133,14 +1141,20 @@ void flow_step(Batch& bt, bool host_noise, int part = 0, const float* lat_in = n
     flow_layers(c, bt.fw, B, nullptr, bt.d_len, bt.d_page_table, bt.max_pages, total_keys);
   }
   if (part == 1) return;
-  launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.tc_head ? bt.d_c16 : nullptr,
-                        bt.d_logit, B, D, bt.fw.ws_ff2, bt.fw.pend_n, (long long)B * D, c.stream);
-  launch_noise_prep(bt.d_noise, bt.d_x, B * L, sqrtf(g.temp), (g.noise_clamp >= 0.f) ? g.noise_clamp : -1.f,
-                    host_noise ? 0 : 1, bt.d_counter, c.stream);
+  // out_norm + EOS logit, and in the same launch the start noise x0 of the flow head (Philox or the host's draw)
+  const float nclamp = (g.noise_clamp >= 0.f) ? g.noise_clamp : -1.f;
+  if (L <= 128) {
+    launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.tc_head ? bt.d_c16 : nullptr,
+                          bt.d_logit, B, D, bt.fw.ws_ff2, bt.fw.pend_n, (long long)B * D, c.stream,
+                          bt.d_noise, bt.d_x, L, sqrtf(g.temp), nclamp, host_noise ? 0 : 1, bt.d_counter);
+  } else {
+    launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.tc_head ? bt.d_c16 : nullptr,
+                          bt.d_logit, B, D, bt.fw.ws_ff2, bt.fw.pend_n, (long long)B * D, c.stream);
+    launch_noise_prep(bt.d_noise, bt.d_x, B * L, sqrtf(g.temp), nclamp, host_noise ? 0 : 1, bt.d_counter, c.stream);
+  }
   const int n = g.lsd_decode_steps;
   if (bt.tc_head) {
-    flow_head_tc(bt);
-    cudaMemcpyAsync(lat_out, bt.d_x, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, c.stream);
+    flow_head_tc(bt, lat_out);      // the last Euler step writes the new latent straight to lat_out
     return;
   }
   for (int i = 0; i < n; ++i) {
@@ -1161,12 +1175,11 @@ void flow_step(Batch& bt, bool host_noise, int part = 0, const float* lat_in = n
       run_linear(c, c.rb[r].m2, m2);
     }
     const float* adaf = bt.d_ada + (long long)g.flow_depth * 3 * fd;
-    LinearParams fo = rows_linear(bt.d_hh, B, fd, bt.d_x, L, "head.fin");     // x += v / n
+    LinearParams fo = rows_linear(bt.d_hh, B, fd, (i == n - 1) ? lat_out : bt.d_x, L, "head.fin");     // x += v / n
     fo.out_scale = 1.0f / (float)n;
     fo.res = bt.d_x; fo.res_bs = 0; fo.res_rs = L;
     run_norm_linear(c, c.fin, bt.d_x1, B, fd, nullptr, nullptr, 1e-6f, adaf + fd, adaf, c.n_ada, bt.d_hh, fo);
   }
-  cudaMemcpyAsync(lat_out, bt.d_x, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, c.stream);
 }
 
 void full_step(Batch& bt, bool host_noise, bool copy_out) {
@@ -1175,8 +1188,8 @@ void full_step(Batch& bt, bool host_noise, bool copy_out) {
   if (host_noise)
     cudaMemcpyAsync(bt.d_noise, bt.h_noise, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
   flow_step(bt, host_noise);
-  mimi_frame(bt, bt.d_latent);
-  launch_advance(bt.d_len, bt.d_bos, bt.d_mimi_off, bt.d_counter, B, 1, bt.T0, c.stream, bt.d_active);
+  mimi_frame(bt, bt.d_latent, true);
+  launch_advance(bt.d_len, bt.d_bos, nullptr, bt.d_counter, B, 1, 0, c.stream, bt.d_active);
   if (copy_out) {
     cudaMemcpyAsync(bt.h_latent, bt.d_latent, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
     cudaMemcpyAsync(bt.h_logit, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
@@ -1197,8 +1210,7 @@ void pipelined_frame(Batch& bt, int parity, bool host_io) {
   cudaEventRecord(c.ev_fork, main);
   cudaStreamWaitEvent(c.stream2, c.ev_fork, 0);
   c.stream = c.stream2;                                   // every launcher below targets the Mimi branch
-  mimi_frame(bt, lat_prev);
-  launch_advance(nullptr, nullptr, bt.d_mimi_off, nullptr, B, 0, bt.T0, c.stream);
+  mimi_frame(bt, lat_prev, true);
   if (host_io)
     cudaMemcpyAsync(bt.h_audio, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
   cudaEventRecord(c.ev_join, c.stream2);
@@ -1741,8 +1753,7 @@ int32_t ptts_batch_warmup_mimi(ptts_batch* bt, int32_t n_frames) {
   Ctx& c = *bt->ctx;
   CU(cudaSetDevice(c.device));
   for (int i = 0; i < n_frames; ++i) {
-    mimi_frame(*bt, bt->d_zero_lat);
-    launch_advance(nullptr, nullptr, bt->d_mimi_off, nullptr, bt->B, 0, bt->T0, c.stream);
+    mimi_frame(*bt, bt->d_zero_lat, true);
   }
   // every slot is in the same state now: keep slot 0's as the template that ptts_batch_reset_seq copies into a
   // slot re-used for a new utterance (the warm-up input is the constant emb_mean, so it is sequence-independent)
@@ -1926,8 +1937,7 @@ int32_t ptts_batch_flush(ptts_batch* bt, float* out_audio) {
   if (!bt->pipelined || bt->frame_idx == 0) return fail(PTTS_ERR_STATE, "nothing to flush");
   // decode the latent of the last stepped frame (it sits in the buffer of parity (frame_idx-1)&1)
   const float* lat = ((bt->frame_idx - 1) & 1) ? bt->d_latent_b : bt->d_latent;
-  mimi_frame(*bt, lat);
-  launch_advance(nullptr, nullptr, bt->d_mimi_off, nullptr, bt->B, 0, bt->T0, c.stream);
+  mimi_frame(*bt, lat, true);
   if (out_audio)
     CU(cudaMemcpyAsync(bt->h_audio, bt->d_audio, (size_t)bt->B * bt->frame_samples * 4, cudaMemcpyDeviceToHost, c.stream));
   CU(cudaStreamSynchronize(c.stream));
@@ -1989,9 +1999,8 @@ int32_t ptts_batch_mimi_decode(ptts_batch* bt, const float* latents, int32_t F, 
     cudaGraph_t graph;
     CU(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed));
     launch_gather_frame(bt->d_lat_all, bt->d_x, B, F, L, bt->d_frame_idx, c.stream);
-    mimi_frame(*bt, bt->d_x);
+    mimi_frame(*bt, bt->d_x, true);
     launch_scatter_audio(bt->d_audio, bt->d_audio_all, B, F, n, bt->d_frame_idx, c.stream);
-    launch_advance(nullptr, nullptr, bt->d_mimi_off, nullptr, B, 0, bt->T0, c.stream);
     launch_inc(bt->d_frame_idx, 1, c.stream);
     CU(cudaStreamEndCapture(c.stream, &graph));
     const long long cnt = g_launches - before;

@@ -99,7 +99,9 @@ struct SnTail {
 };
 bool sn_tail_plan(SnTail* p, const __nv_bfloat16* xe, const __nv_bfloat16* xraw, int nb, int T, int C, int hidden,
                   int taps, int fin_taps, const __nv_bfloat16* w1, const __nv_bfloat16* w2);
-void sn_tail_launch(const SnTail& p, cudaStream_t s);
+// with_fix = false: the caller finishes the first two samples of every tile itself (state_shift_kernel does it in the
+// Mimi decoder's end-of-frame launch)
+void sn_tail_launch(const SnTail& p, cudaStream_t s, bool with_fix = true);
 
 // helpers used by the bf16 pipeline
 void launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t s);

@@ -126,7 +126,10 @@ void launch_embed_rows(const void* table, int table_bf16, const int* ids, float*
 // c = LN(x[row_of[b]]); logit = w_eos . c + b_eos      (models/flow_lm.py:120,100)
 void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w, const float* ln_b,
                            const float* w_eos, const float* b_eos, float* c, __nv_bfloat16* c16, float* logit,
-                           int B, int D, const float* acc, int acc_n, long long acc_stride, cudaStream_t s);
+                           int B, int D, const float* acc, int acc_n, long long acc_stride, cudaStream_t s,
+                           // optional: the flow head's start noise of each row is prepared by the same launch
+                           const float* nz = nullptr, float* x0 = nullptr, int nL = 0, float nstd = 1.f,
+                           float nclamp = -1.f, int use_philox = 0, const unsigned long long* counter = nullptr);
 // x0 = clip(sqrt(temp) * z); z from the host buffer or a Philox4x32-10 + Box-Muller stream
 void launch_noise_prep(const float* z, float* x0, int n, float std, float clamp, int use_philox,
                        const unsigned long long* counter, cudaStream_t s);
@@ -142,7 +145,9 @@ void launch_final_conv16(const __nv_bfloat16* x, long long x_bs, const float* w,
                          long long audio_bs, int B, int T, int C, int taps, cudaStream_t s);
 // carried conv state: move the last `rows` time rows of each sequence's buffer to its front
 struct ShiftEntry { void* buf; long long bs; int T, rows, C, esz; };   // bs in elements, esz = bytes/element
-void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s);
+void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s, float* audio = nullptr,
+                        long long audio_bs = 0, float* bnd = nullptr, int tiles_t = 0, int* mimi_offset = nullptr,
+                        int inc_mimi = 0);
 // seq_len += inc_len; bos_flag = 0; mimi_offset += inc_mimi; philox counter += 1
 void launch_advance(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter, int B,
                     int inc_len, int inc_mimi, cudaStream_t s, const int* active = nullptr);

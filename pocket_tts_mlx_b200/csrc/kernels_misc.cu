@@ -132,6 +132,39 @@ __global__ void embed_rows_kernel(const WT* __restrict__ table, const int* __res
   for (int c = threadIdx.x; c < D; c += blockDim.x) rows[(long long)m * D + c] = (float)src[c];
 }
 
+// Philox4x32-10 (Salmon et al. 2011), one 128-bit block per pair of outputs is plenty here.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  constexpr unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+
+// x0[i] = clamp(g_i * std): g from the host buffer z or from Philox(seed, frame counter, i)
+__device__ __forceinline__ void noise_prep_one(const float* __restrict__ z, float* __restrict__ x0, int i, float std,
+                                               float clamp, int use_philox,
+                                               const unsigned long long* __restrict__ counter) {
+  float g;
+  if (use_philox) {
+    const unsigned long long step = counter[0], seed = counter[1];   // {frame counter, seed} live on the device
+    uint4 r = philox4x32(make_uint4((unsigned)i, (unsigned)step, (unsigned)(step >> 32), 0u),
+                         make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const float u1 = ((r.x >> 8) + 1u) * (1.0f / 16777216.0f);   // (0,1]
+    const float u2 = (r.y >> 8) * (1.0f / 16777216.0f);
+    g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+  } else {
+    g = z[i];
+  }
+  float v = g * std;
+  if (clamp >= 0.f) v = fminf(fmaxf(v, -clamp), clamp);
+  x0[i] = v;
+}
+
 __global__ void __launch_bounds__(128) final_norm_eos_kernel(const float* __restrict__ x,
                                                              const int* __restrict__ row_of,
                                                              const float* __restrict__ ln_w,
@@ -142,10 +175,15 @@ __global__ void __launch_bounds__(128) final_norm_eos_kernel(const float* __rest
                                                              __nv_bfloat16* __restrict__ cout16,
                                                              float* __restrict__ logit, int D,
                                                              const float* __restrict__ acc, int acc_n,
-                                                             long long acc_stride) {
+                                                             long long acc_stride,
+                                                             // flow-head start noise of the same row (x0 null: skip)
+                                                             const float* __restrict__ nz, float* __restrict__ x0, int nL,
+                                                             float nstd, float nclamp, int use_philox,
+                                                             const unsigned long long* __restrict__ counter) {
   pdl_sync();
   __shared__ float red[32];
   const int b = blockIdx.x;
+  if (x0 && (int)threadIdx.x < nL) noise_prep_one(nz, x0, b * nL + threadIdx.x, nstd, nclamp, use_philox, counter);
   const long long row = row_of ? row_of[b] : b;
   const float* xr = x + row * D;
   if (D == 1024 && acc_n <= 8) {
@@ -229,39 +267,13 @@ __global__ void __launch_bounds__(128) final_norm_eos_kernel(const float* __rest
   if (threadIdx.x == 0) logit[b] = dot + b_eos[0];
 }
 
-// Philox4x32-10 (Salmon et al. 2011), one 128-bit block per pair of outputs is plenty here.
-__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
-  constexpr unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0; key.y += W1;
-  }
-  return ctr;
-}
-
 __global__ void noise_prep_kernel(const float* __restrict__ z, float* __restrict__ x0, int n, float std,
                                   float clamp, int use_philox,
                                   const unsigned long long* __restrict__ counter) {
   pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float g;
-  if (use_philox) {
-    const unsigned long long step = counter[0], seed = counter[1];   // {frame counter, seed} live on the device
-    uint4 r = philox4x32(make_uint4((unsigned)i, (unsigned)step, (unsigned)(step >> 32), 0u),
-                         make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
-    const float u1 = ((r.x >> 8) + 1u) * (1.0f / 16777216.0f);   // (0,1]
-    const float u2 = (r.y >> 8) * (1.0f / 16777216.0f);
-    g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-  } else {
-    g = z[i];
-  }
-  float v = g * std;
-  if (clamp >= 0.f) v = fminf(fmaxf(v, -clamp), clamp);
-  x0[i] = v;
+  noise_prep_one(z, x0, i, std, clamp, use_philox, counter);
 }
 
 // wq_t [L][C] and wu_t [2S][C] are stored transposed (channel fastest) for coalesced reads.  One thread = one
@@ -356,10 +368,33 @@ __global__ void __launch_bounds__(128) final_conv_kernel(const XT* __restrict__ 
   audio[b * audio_bs + t] = a;
 }
 
-__global__ void state_shift_kernel(const ShiftEntry* __restrict__ entries) {
+// End-of-frame bookkeeping of the Mimi decoder in one launch: blockIdx.y < n_entries moves the last taps-1 rows of a
+// streaming conv input to the front (its carried state); blockIdx.y == n_entries finishes the fused SEANet tail for
+// sequence blockIdx.x (first two samples of every 128-step tile + carry of the boundary partials, see seanet_tail.cu)
+// and advances the sequence's ring offset.
+__global__ void state_shift_kernel(const ShiftEntry* __restrict__ entries, int n_entries, float* __restrict__ audio,
+                                   long long audio_bs, float* __restrict__ bnd, int tiles_t,
+                                   int* __restrict__ mimi_offset, int inc_mimi) {
   pdl_sync();
-  const ShiftEntry e = entries[blockIdx.y];
   const int b = blockIdx.x;
+  if ((int)blockIdx.y == n_entries) {
+    if (bnd) {
+      for (int k = threadIdx.x; k < tiles_t; k += blockDim.x) {
+        const float* slot = bnd + ((long long)b * (tiles_t + 1) + k) * 4;
+        float* a = audio + b * audio_bs + (long long)k * 128;
+        a[0] += slot[0] + slot[2];
+        a[1] += slot[1];
+      }
+      __syncthreads();
+      if (threadIdx.x < 3) {
+        float* first = bnd + (long long)b * (tiles_t + 1) * 4;
+        first[threadIdx.x] = first[(long long)tiles_t * 4 + threadIdx.x];
+      }
+    }
+    if (mimi_offset && threadIdx.x == 0) mimi_offset[b] += inc_mimi;
+    return;
+  }
+  const ShiftEntry e = entries[blockIdx.y];
   // rows*C*esz is a multiple of 4 bytes for every buffer of the decoder (C >= 64)
   unsigned* base = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(e.buf) + b * e.bs * e.esz);
   const int n = e.rows * e.C * e.esz / 4;
@@ -544,9 +579,13 @@ void launch_embed_rows(const void* table, int table_bf16, const int* ids, float*
 
 void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w, const float* ln_b,
                            const float* w_eos, const float* b_eos, float* c, __nv_bfloat16* c16, float* logit,
-                           int B, int D, const float* acc, int acc_n, long long acc_stride, cudaStream_t s) {
+                           int B, int D, const float* acc, int acc_n, long long acc_stride, cudaStream_t s,
+                           const float* nz, float* x0, int nL, float nstd, float nclamp, int use_philox,
+                           const unsigned long long* counter) {
   ProfScope ps("final_norm_eos", nullptr, 0, 2.0 * B * D * 4, s);
-  launch_k(final_norm_eos_kernel, dim3(B), dim3(128), 0, s, x, row_of, ln_w, ln_b, w_eos, b_eos, c, c16, logit, D, acc, acc_n, acc_stride);
+  if (nL > 128) { x0 = nullptr; }
+  launch_k(final_norm_eos_kernel, dim3(B), dim3(128), 0, s, x, row_of, ln_w, ln_b, w_eos, b_eos, c, c16, logit, D, acc, acc_n, acc_stride,
+           nz, x0, nL, nstd, nclamp, use_philox, counter);
   ++g_launches;
 }
 
@@ -589,10 +628,13 @@ void launch_final_conv16(const __nv_bfloat16* x, long long x_bs, const float* w,
   ++g_launches;
 }
 
-void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s) {
+void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s, float* audio,
+                        long long audio_bs, float* bnd, int tiles_t, int* mimi_offset, int inc_mimi) {
   ProfScope ps("state_shift", nullptr, 0, 0, s);
-  dim3 grid(B, n_entries);
-  launch_k(state_shift_kernel, dim3(grid), dim3(256), 0, s, entries_dev);
+  const bool extra = bnd || mimi_offset;
+  dim3 grid(B, n_entries + (extra ? 1 : 0));
+  launch_k(state_shift_kernel, dim3(grid), dim3(256), 0, s, entries_dev, n_entries, audio, audio_bs, bnd, tiles_t, mimi_offset,
+           inc_mimi);
   ++g_launches;
 }
 

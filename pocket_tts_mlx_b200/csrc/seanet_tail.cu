@@ -370,7 +370,7 @@ bool sn_tail_plan(SnTail* p, const __nv_bfloat16* xe, const __nv_bfloat16* xraw,
   return ok;
 }
 
-void sn_tail_launch(const SnTail& p, cudaStream_t s) {
+void sn_tail_launch(const SnTail& p, cudaStream_t s, bool with_fix) {
   TailArgs a;
   a.nb = p.nb; a.T = p.T; a.tiles_t = p.T / 128; a.total_tiles = p.nb * a.tiles_t;
   a.b1 = p.b1; a.b2 = p.b2; a.wf = p.wf; a.bf = p.bf;
@@ -382,7 +382,7 @@ void sn_tail_launch(const SnTail& p, cudaStream_t s) {
              p.tm_a, p.tm_w1, p.tm_w2, p.tm_res, a);
     ++g_launches;
   }
-  {
+  if (with_fix) {
     ProfScope ps("sn_tail_fix", nullptr, 0, 0, s);
     launch_k(sn_tail_fix_kernel, dim3((unsigned)((a.total_tiles + 127) / 128)), dim3(128), 0, s, p.audio, p.audio_bs, p.bnd,
              p.nb, a.tiles_t);
