@@ -83,7 +83,43 @@ def run_reference(yaml_path, text, voice, seed, max_frames=None, frames_after_eo
                 n_frames=np.int32(len(chunks)))
 
 
+def gen_voice_clone():
+    """Golden vector for the voice-cloning branch: the reference's own `_encode_audio` (Mimi encoder, encoder
+    transformer, downsample, speaker projection; tts_model.py:271-276) on a synthetic 3-second waveform, and the
+    FlowLM state it prompts (frame count).  3 s = 600 encoder steps > the 250-step attention window."""
+    _install_stubs()
+    import mlx.core as mx
+    from pocket_tts_mlx import TTSModel
+    from pocket_tts_mlx_b200.synthetic import write_synthetic_bundle
+
+    yml = write_synthetic_bundle(BUNDLE, seed=0)
+    out = REPO / "tests" / "golden"
+    model = TTSModel.load_model(str(yml))
+    assert model.has_voice_cloning
+    rng = np.random.Generator(np.random.PCG64(99))
+    t = np.arange(71000) / 24000.0                                  # not a multiple of the 1920-sample frame
+    audio = (0.3 * np.sin(2 * np.pi * 220.0 * t) * (1 + 0.5 * np.sin(2 * np.pi * 3.0 * t))
+             + 0.05 * rng.standard_normal(t.shape[0])).astype(np.float32)
+    # `TTSModel._encode_audio` (tts_model.py:271-276) calls mx.transpose(encoded, (-1, -2)) on a 3-D array, which
+    # MLX (and the shim) reject: the upstream voice-cloning branch cannot run as written.  The part that does run
+    # unmodified is MimiModel.encode_to_latent; the two remaining lines (swap the last two axes, multiply by
+    # speaker_proj_weight^T) are applied here as they were evidently meant.
+    try:
+        model._encode_audio(mx.array(audio[None, :])[None, ...])
+        upstream_ok = True
+    except ValueError:
+        upstream_ok = False
+    encoded = np.asarray(model.mimi.encode_to_latent(mx.array(audio[None, :])[None, ...]))     # [1, 512, T_v]
+    latents = np.swapaxes(encoded, -1, -2).astype(np.float32)[0]                               # [T_v, 512]
+    cond = latents @ np.asarray(model.flow_lm.speaker_proj_weight).T
+    np.savez(out / "ref_voice_clone.npz", audio=audio, encoded=latents, conditioning=cond.astype(np.float32),
+             upstream_encode_audio_runs=np.bool_(upstream_ok))
+    print("voice clone:", audio.shape[0], "samples ->", cond.shape, "| upstream _encode_audio runs:", upstream_ok)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "voice_clone":
+        return gen_voice_clone()
     _install_stubs()
     from oracle.ptts_oracle import Oracle
     from pocket_tts_mlx_b200.config import load_config

@@ -417,6 +417,80 @@ class Oracle:
             self.mimi_decode_frame(st, np.zeros(self.ldim, dtype=self.dt))
 
     # ------------------------------------------------------------------ generation loop
+    # ------------------------------------------------------------------ voice cloning (Mimi encode side)
+    def _conv_ns(self, name, x, stride=1, replicate=False, bias=True):
+        """Non-streaming call of StreamingConv1d (model_state=None => fresh state, modules/conv.py:121-150):
+        left context = kernel - stride columns, zeros or (pad_mode="replicate") copies of the first column;
+        y[t] = b + sum_j W[:,:,j] x~[t*stride + j].  x [T, C_in] -> [T/stride, C_out]."""
+        wt = self.w[name + ".weight"]          # [out, in, k]
+        k = wt.shape[2]
+        t = x.shape[0]
+        assert t % stride == 0
+        tp = k - stride
+        if tp > 0:
+            head = np.repeat(x[:1], tp, axis=0) if replicate else np.zeros((tp, x.shape[1]), dtype=self.dt)
+            xx = np.concatenate([head, x], axis=0)
+        else:
+            xx = x
+        t_out = t // stride
+        y = np.zeros((t_out, wt.shape[0]), dtype=self.dt)
+        if bias:
+            y += self.w[name + ".bias"]
+        for j in range(k):
+            y += xx[j: j + (t_out - 1) * stride + 1: stride] @ wt[:, :, j].T
+        return y
+
+    def _enc_attention(self, i, x):
+        """Non-streaming windowed causal attention of the encoder transformer (modules/attention.py:210-264 with
+        model_state=None): positions 0..T-1, key visible iff 0 <= q - k < context."""
+        w = self.w
+        p = f"mimi.encoder_transformer.transformer.layers.{i}.self_attn"
+        t = x.shape[0]
+        dh = self.md // self.mh
+        qkv = (x @ w[p + ".in_proj.weight"].T).reshape(t, 3, self.mh, dh)
+        pos = np.arange(t)
+        q = rope_rotate(qkv[:, 0], pos, self.m_max_period)
+        k = rope_rotate(qkv[:, 1], pos, self.m_max_period)
+        dq = pos[:, None] - pos[None, :]
+        visible = (dq >= 0) & (dq < self.context)
+        sc = np.einsum("thd,lhd->htl", q, k) * self.dt.type(1.0 / math.sqrt(dh))
+        sc = sc + np.where(visible, 0.0, -1e9).astype(self.dt)[None]
+        pr = softmax_rows(sc)
+        a = np.einsum("htl,lhd->thd", pr, qkv[:, 2]).reshape(t, self.md)
+        return a @ w[p + ".out_proj.weight"].T
+
+    def encode_audio(self, audio):
+        """Waveform [T] (24 kHz mono) -> FlowLM conditioning [T_v, d_model]: zero-pad the end to whole frames
+        (conv.py:12-26), SEANet encoder (seanet.py:45-108), encoder transformer, stride-16 replicate-padded
+        downsample (resample.py:8-24), speaker projection (tts_model.py:271-276)."""
+        w = self.w
+        sn = self.cfg.mimi.seanet
+        x = np.asarray(audio, dtype=self.dt).reshape(-1)
+        frame = int(self.cfg.mimi.sample_rate / self.frame_rate)
+        n_frames = math.ceil((x.shape[0] - frame) / frame + 1)
+        ideal = (n_frames - 1) * frame + frame
+        if ideal > x.shape[0]:
+            x = np.concatenate([x, np.zeros(ideal - x.shape[0], dtype=self.dt)])
+        h = self._conv_ns("mimi.encoder.model.0.conv", x[:, None])
+        idx = 1
+        for r in reversed(sn.ratios):
+            pre = f"mimi.encoder.model.{idx}.block"
+            y = self._conv_ns(pre + ".1.conv", elu(h))
+            h = h + self._conv_ns(pre + ".3.conv", elu(y))
+            idx += 2
+            h = self._conv_ns(f"mimi.encoder.model.{idx}.conv", elu(h), stride=r)
+            idx += 1
+        idx += 1
+        h = self._conv_ns(f"mimi.encoder.model.{idx}.conv", elu(h))
+        for i in range(self.m_layers):
+            p = f"mimi.encoder_transformer.transformer.layers.{i}"
+            a = self._enc_attention(i, layer_norm(h, w[p + ".norm1.weight"], w[p + ".norm1.bias"], 1e-5))
+            h = h + a * w[p + ".layer_scale_1.scale"]
+            f = gelu_erf(layer_norm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], 1e-5) @ w[p + ".linear1.weight"].T)
+            h = h + (f @ w[p + ".linear2.weight"].T) * w[p + ".layer_scale_2.scale"]
+        lat = self._conv_ns("mimi.downsample.conv.conv", h, stride=self.up, replicate=True, bias=False)
+        return (lat @ w["flow_lm.speaker_proj_weight"].T).astype(self.dt)
+
     def max_gen_len(self, n_tok: int) -> int:
         """ceil((n_tok/3 + 2) * frame_rate) (tts_model.py:440-444)."""
         return math.ceil((n_tok / 3.0 + 2.0) * self.frame_rate)

@@ -131,6 +131,35 @@ def synthetic_state_dict(cfg: Config, seed: int = 0) -> Dict[str, np.ndarray]:
         mult //= 2
     idx += 1  # ELU
     conv(f"mimi.decoder.model.{idx}.conv", sn.channels, sn.n_filters, sn.last_kernel_size)
+
+    # ---- Mimi encode side (voice cloning; drawn after everything else so that the decode-path weights of a seed
+    #      are the same with and without it).  Module tree of modules/seanet.py:45-108, models/mimi.py:28-52.
+    mult = 1
+    idx = 0
+    conv(f"mimi.encoder.model.{idx}.conv", mult * sn.n_filters, sn.channels, sn.kernel_size)
+    idx += 1
+    for r in reversed(sn.ratios):
+        c = mult * sn.n_filters
+        hidden = c // sn.compress
+        conv(f"mimi.encoder.model.{idx}.block.1.conv", hidden, c, sn.residual_kernel_size)
+        conv(f"mimi.encoder.model.{idx}.block.3.conv", c, hidden, 1)
+        idx += 2  # resblock, ELU
+        conv(f"mimi.encoder.model.{idx}.conv", 2 * c, c, 2 * r)
+        idx += 1
+        mult *= 2
+    idx += 1  # ELU
+    conv(f"mimi.encoder.model.{idx}.conv", sn.dimension, mult * sn.n_filters, sn.last_kernel_size)
+    for i in range(mm.transformer.num_layers):
+        p = f"mimi.encoder_transformer.transformer.layers.{i}"
+        lin(p + ".self_attn.in_proj", 3 * dm, dm, bias=False)
+        lin(p + ".self_attn.out_proj", dm, dm, bias=False)
+        ln(p + ".norm1", dm)
+        ln(p + ".norm2", dm)
+        lin(p + ".linear1", mm.transformer.dim_feedforward, dm, bias=False)
+        lin(p + ".linear2", dm, mm.transformer.dim_feedforward, bias=False)
+        sd[p + ".layer_scale_1.scale"] = rng.uniform(0.05, 0.5, size=dm).astype(np.float32)
+        sd[p + ".layer_scale_2.scale"] = rng.uniform(0.05, 0.5, size=dm).astype(np.float32)
+    sd["mimi.downsample.conv.conv.weight"] = _uniform(rng, (sn.dimension, sn.dimension, 2 * up), 2 * up * sn.dimension)
     return sd
 
 
@@ -194,7 +223,7 @@ def write_synthetic_bundle(out_dir, base_variant: Optional[str] = None, seed: in
     (out_dir / "embeddings").mkdir(parents=True, exist_ok=True)
     base = Path(base_variant) if base_variant else _PKG_DIR / "config" / "b6369a24.yaml"
     cfg = load_config(base)
-    ckpt = out_dir / f"tts_synthetic_seed{seed}.safetensors"
+    ckpt = out_dir / f"tts_synthetic_enc_seed{seed}.safetensors"
     if not ckpt.exists():
         tmp = ckpt.with_suffix(f".tmp{os.getpid()}")
         write_safetensors(tmp, synthetic_state_dict(cfg, seed), bf16=bf16)

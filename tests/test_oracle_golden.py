@@ -96,3 +96,17 @@ def test_text_split_matches_reference(bundle):
         assert [tok.encode(ch).tolist() for ch in chunks] == c["ids"]
     with pytest.raises(ValueError, match="Text prompt cannot be empty"):
         prepare_text_prompt("   ")
+
+
+def test_voice_clone_encoder_matches_reference(cfg, weights):
+    """Voice-cloning branch: the oracle's Mimi encoder (SEANet encoder, encoder transformer with its 250-step causal
+    window, replicate-padded stride-16 downsample, speaker projection) against the reference's own
+    MimiModel.encode_to_latent run over the NumPy MLX shim on a 71 000-sample waveform (600 encoder steps, 37
+    frames).  The golden file also records that upstream `TTSModel._encode_audio` itself raises (it transposes a
+    3-D array with two axes), so the last two lines are pinned by intent, not by execution."""
+    g = np.load(GOLDEN / "ref_voice_clone.npz")
+    assert not bool(g["upstream_encode_audio_runs"])
+    orc = Oracle(weights, cfg, dtype=np.float32)
+    cond = orc.encode_audio(g["audio"])
+    assert cond.shape == g["conditioning"].shape == (37, 1024)
+    assert rel_l2(cond, g["conditioning"]) < 1e-5
