@@ -87,6 +87,16 @@ int32_t ptts_load_weight(ptts_ctx* ctx, const char* name, int32_t dtype, int32_t
  * embeddings of the LSD schedule, modules/mlp.py:53-74), convert to the storage precision, upload. */
 int32_t ptts_finalize_weights(ptts_ctx* ctx);
 
+/* Voice cloning.  ptts_has_voice_cloning: 1 when the loaded checkpoint carried the Mimi encoder
+ * (mimi.encoder.*, mimi.encoder_transformer.*, mimi.downsample.*, flow_lm.speaker_proj_weight), like the reference's
+ * `has_voice_cloning` (models/tts_model.py:77,145-151).  ptts_encode_audio turns a mono waveform at the model sample
+ * rate into the conditioning that ptts_voice_create prefills: MimiModel.encode_to_latent (models/mimi.py:77-85: zero
+ * padding to whole frames, SEANet encoder, encoder transformer, stride-16 downsample) followed by the speaker
+ * projection (models/tts_model.py:271-276).  out_cond holds max_frames x d_model floats; *n_frames = ceil(n / 1920). */
+int32_t ptts_has_voice_cloning(ptts_ctx* ctx);
+int32_t ptts_encode_audio(ptts_ctx* ctx, const float* audio, int64_t n_samples, float* out_cond, int32_t max_frames,
+                          int32_t* n_frames);
+
 /* ---- voice prompt -------------------------------------------------------------------------
  * Replaces get_state_for_audio_prompt's prefill (models/tts_model.py:510-518): runs cond
  * [n_frames, d_model] through the backbone and keeps the KV pages as an immutable prefix that any

@@ -26,6 +26,7 @@ EXPORTED = [
     "ptts_timer_end", "ptts_launch_count", "ptts_batch_profile_step", "ptts_flush_l2", "ptts_debug_linear",
     "ptts_debug_gemm_bench", "ptts_batch_profile_sections", "ptts_batch_set_pipelined", "ptts_batch_flush",
     "ptts_batch_reset_seq", "ptts_batch_reset_seqs", "ptts_batch_set_active",
+    "ptts_has_voice_cloning", "ptts_encode_audio",
     "ptts_batch_host_buffers", "ptts_batch_step_staged",
 ]
 
@@ -98,6 +99,8 @@ def lib() -> C.CDLL:
         "ptts_batch_host_buffers": (i32, [vp, C.POINTER(f32p), C.POINTER(f32p), C.POINTER(f32p), C.POINTER(f32p)]),
         "ptts_batch_step_staged": (i32, [vp]),
         "ptts_batch_set_pipelined": (i32, [vp, i32]),
+        "ptts_has_voice_cloning": (i32, [vp]),
+        "ptts_encode_audio": (i32, [vp, f32p, C.c_int64, f32p, i32, i32p]),
         "ptts_batch_reset_seq": (i32, [vp, i32, i32, i32]),
         "ptts_batch_reset_seqs": (i32, [vp, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "ptts_batch_set_active": (i32, [vp, i32, i32]),
@@ -204,6 +207,20 @@ class Context:
     def voice_create(self, cond: np.ndarray) -> int:
         a = _f32(cond).reshape(-1, self.config.d_model)
         return check(lib().ptts_voice_create(self._h, _fp(a), a.shape[0]))
+
+    @property
+    def has_voice_cloning(self) -> bool:
+        return bool(lib().ptts_has_voice_cloning(self._h))
+
+    def encode_audio(self, audio: np.ndarray, frame_samples: int = 1920) -> np.ndarray:
+        """Mono waveform at the model sample rate -> conditioning [ceil(T / frame), d_model] (Mimi encoder +
+        speaker projection)."""
+        a = _f32(audio).reshape(-1)
+        max_frames = (a.shape[0] + frame_samples - 1) // frame_samples + 1
+        out = np.empty((max_frames, self.config.d_model), dtype=np.float32)
+        n = C.c_int32(0)
+        check(lib().ptts_encode_audio(self._h, _fp(a), a.shape[0], _fp(out), max_frames, C.byref(n)))
+        return out[: n.value].copy()
 
     def voice_destroy(self, vid: int):
         check(lib().ptts_voice_destroy(self._h, vid))

@@ -143,6 +143,13 @@ struct ptts_ctx {
   float *fin_w = nullptr, *fin_b = nullptr;
   int fin_taps = 0, fin_c = 0;
   float *freqs_flow = nullptr, *freqs_mimi = nullptr;
+  // voice cloning (Mimi encode side; loaded when the checkpoint carries mimi.encoder.*), fp32 weights
+  bool has_encoder = false;
+  float *enc0_w = nullptr, *enc0_b = nullptr;              // first conv: [n_filters][k], 1 input channel
+  struct EncStage { int stride, c_in; LinW r3, r1, down; };
+  std::vector<EncStage> enc_stages;
+  LinW enc_last, enc_down, speaker_proj;
+  std::vector<MimiLayer> el;
 
   void* pool = nullptr;
   long long n_pages = 0, page_stride = 0, layer_stride = 0;
@@ -199,9 +206,11 @@ int upload_vec(Ctx& c, const std::string& name, int64_t n, float** dst) {
 }
 
 // matrix [N][K] in storage precision (+ bf16 copy when storage is fp32 is NOT made: fp32 mode is SIMT-only)
+bool g_upload_fp32 = false;   // set while the voice-cloning encoder is loaded: it always runs in fp32
 int upload_mat(Ctx& c, const std::vector<float>& w, int N, int K, LinW* out) {
-  out->N = N; out->K = K; out->bf16 = c.bf16 ? 1 : 0;
-  if (c.bf16) {
+  const bool bf = c.bf16 && !g_upload_fp32;
+  out->N = N; out->K = K; out->bf16 = bf ? 1 : 0;
+  if (bf) {
     std::vector<uint16_t> h((size_t)N * K);
     for (size_t i = 0; i < h.size(); ++i) h[i] = f2bf(w[i]);
     RET(c.dalloc(&out->w, h.size() * 2));
@@ -459,6 +468,70 @@ int finalize(Ctx& c) {
   RET(c.dalloc(&c.pool, (size_t)g.n_layers * c.layer_stride * esz));
   c.free_pages.resize(c.n_pages);
   for (long long i = 0; i < c.n_pages; ++i) c.free_pages[i] = (int)(c.n_pages - 1 - i);
+  // ---- voice cloning: SEANet encoder, encoder transformer, downsample, speaker projection (fp32) ----
+  if (find(c, "mimi.encoder.model.0.conv.weight") && find(c, "mimi.downsample.conv.conv.weight") &&
+      find(c, "flow_lm.speaker_proj_weight")) {
+    g_upload_fp32 = true;
+    auto done = [&](int rc) { g_upload_fp32 = false; return rc; };
+    const HostTensor *t0, *b0;
+    if (int rc = need(c, "mimi.encoder.model.0.conv.weight", {g.n_filters, 1, g.kernel_size}, &t0)) return done(rc);
+    if (int rc = need(c, "mimi.encoder.model.0.conv.bias", {g.n_filters}, &b0)) return done(rc);
+    if (int rc = upload_f32(c, t0->data.data(), t0->data.size(), &c.enc0_w)) return done(rc);
+    if (int rc = upload_f32(c, b0->data.data(), b0->data.size(), &c.enc0_b)) return done(rc);
+    int emult = 1, eidx = 1;
+    c.enc_stages.resize(g.n_ratios);
+    for (int r = 0; r < g.n_ratios; ++r) {
+      auto& st = c.enc_stages[r];
+      st.stride = g.ratios[g.n_ratios - 1 - r];          // the encoder walks the ratios in reverse
+      st.c_in = emult * g.n_filters;
+      const std::string rp = "mimi.encoder.model." + std::to_string(eidx) + ".block.";
+      if (int rc = load_conv(c, rp + "1.conv", st.c_in / g.compress, st.c_in, g.res_kernel_size, &st.r3)) return done(rc);
+      if (int rc = load_conv(c, rp + "3.conv", st.c_in, st.c_in / g.compress, 1, &st.r1)) return done(rc);
+      eidx += 2;
+      if (int rc = load_conv(c, "mimi.encoder.model." + std::to_string(eidx) + ".conv", 2 * st.c_in, st.c_in, 2 * st.stride,
+                             &st.down)) return done(rc);
+      eidx += 1;
+      emult *= 2;
+    }
+    eidx += 1;
+    if (int rc = load_conv(c, "mimi.encoder.model." + std::to_string(eidx) + ".conv", SD, emult * g.n_filters,
+                           g.last_kernel_size, &c.enc_last)) return done(rc);
+    c.el.resize(g.mimi_layers);
+    for (int i = 0; i < g.mimi_layers; ++i) {
+      const std::string p = "mimi.encoder_transformer.transformer.layers." + std::to_string(i);
+      auto& l = c.el[i];
+      int rc = 0;
+      rc = rc ? rc : upload_vec(c, p + ".norm1.weight", MD, &l.ln1w);
+      rc = rc ? rc : upload_vec(c, p + ".norm1.bias", MD, &l.ln1b);
+      rc = rc ? rc : upload_vec(c, p + ".norm2.weight", MD, &l.ln2w);
+      rc = rc ? rc : upload_vec(c, p + ".norm2.bias", MD, &l.ln2b);
+      rc = rc ? rc : upload_vec(c, p + ".layer_scale_1.scale", MD, &l.ls1);
+      rc = rc ? rc : upload_vec(c, p + ".layer_scale_2.scale", MD, &l.ls2);
+      rc = rc ? rc : load_linear(c, p + ".self_attn.in_proj", 3 * MD, MD, false, &l.qkv);
+      rc = rc ? rc : load_linear(c, p + ".self_attn.out_proj", MD, MD, false, &l.out);
+      rc = rc ? rc : load_linear(c, p + ".linear1", g.mimi_ffn, MD, false, &l.ff1);
+      rc = rc ? rc : load_linear(c, p + ".linear2", MD, g.mimi_ffn, false, &l.ff2);
+      if (rc) return done(rc);
+    }
+    {
+      // downsample: Conv1d (out,in,2s) without bias -> [out][j*in + c]
+      const HostTensor* t;
+      const int s2 = 2 * g.upsample_stride;
+      if (int rc = need(c, "mimi.downsample.conv.conv.weight", {SD, SD, s2}, &t)) return done(rc);
+      std::vector<float> w((size_t)SD * s2 * SD);
+      for (int o = 0; o < SD; ++o)
+        for (int ci = 0; ci < SD; ++ci)
+          for (int j = 0; j < s2; ++j) w[((size_t)o * s2 + j) * SD + ci] = t->data[((size_t)o * SD + ci) * s2 + j];
+      if (int rc = upload_mat(c, w, SD, s2 * SD, &c.enc_down)) return done(rc);
+    }
+    {
+      const HostTensor* t;
+      if (int rc = need(c, "flow_lm.speaker_proj_weight", {D, SD}, &t)) return done(rc);
+      if (int rc = upload_mat(c, t->data, D, SD, &c.speaker_proj)) return done(rc);
+    }
+    g_upload_fp32 = false;
+    c.has_encoder = true;
+  }
   c.host.clear();
   c.finalized = true;
   return 0;
@@ -1398,7 +1471,6 @@ int32_t ptts_load_weight(ptts_ctx* c, const char* name, int32_t dtype, int32_t n
   if (c->finalized) return fail(PTTS_ERR_STATE, "weights already finalized");
   const std::string nm(name);
   if (nm.rfind("flow_lm.", 0) != 0 && nm.rfind("mimi.", 0) != 0) return 1;
-  if (nm.rfind("mimi.encoder", 0) == 0 || nm.rfind("mimi.downsample", 0) == 0) return 1;   // voice cloning: out of scope
   HostTensor t;
   t.shape.assign(shape, shape + ndim);
   const int64_t n = t.numel();
@@ -1416,6 +1488,133 @@ int32_t ptts_finalize_weights(ptts_ctx* c) {
   if (c->finalized) return fail(PTTS_ERR_STATE, "weights already finalized");
   CU(cudaSetDevice(c->device));
   return finalize(*c);
+}
+
+int32_t ptts_has_voice_cloning(ptts_ctx* c) { return (c && c->finalized && c->has_encoder) ? 1 : 0; }
+
+// Voice cloning: waveform -> FlowLM conditioning (MimiModel.encode_to_latent + the speaker projection,
+// models/mimi.py:77-85, models/tts_model.py:271-276).  One-off per voice, fp32 throughout, CUDA-core kernels:
+// every conv is the multi-tap linear operator (a stride-s conv with kernel 2s is a 2-tap GEMM over rows of s*C
+// channels: the "space to depth" view of the contiguous [T][C] buffer), the encoder transformer is the
+// non-streaming windowed form of the Mimi transformer.
+int32_t ptts_encode_audio(ptts_ctx* cp, const float* audio, int64_t n_samples, float* out_cond, int32_t max_frames,
+                          int32_t* n_frames_out) {
+  if (!cp || !audio || !out_cond || !n_frames_out) return fail(PTTS_ERR_INVALID, "null argument");
+  Ctx& c = *cp;
+  if (!c.finalized) return fail(PTTS_ERR_STATE, "weights are not finalized");
+  if (!c.has_encoder) return fail(PTTS_ERR_STATE, "the checkpoint was loaded without the Mimi encoder (no voice cloning)");
+  if (n_samples <= 0) return fail(PTTS_ERR_INVALID, "empty audio");
+  CU(cudaSetDevice(c.device));
+  const ptts_config& g = c.cfg;
+  const int S = g.upsample_stride, SD = g.seanet_dim, MD = g.mimi_d, D = g.d_model;
+  long long hop = 1;
+  for (int r = 0; r < g.n_ratios; ++r) hop *= g.ratios[r];
+  const long long frame = hop * S;
+  const long long n_frames = (n_samples + frame - 1) / frame;        // zero-padded at the end to whole frames
+  if (n_frames > max_frames) return fail(PTTS_ERR_INVALID, "audio gives %lld frames, the output buffer holds %d", n_frames, max_frames);
+  const long long T = n_frames * frame;
+  const int k0 = g.kernel_size, rk = g.res_kernel_size, lk = g.last_kernel_size;
+  std::vector<void*> tmp;
+  auto alloc = [&](float** p, size_t n, bool zero) -> int {
+    CU(cudaMalloc((void**)p, n * sizeof(float)));
+    tmp.push_back(*p);
+    if (zero) CU(cudaMemsetAsync(*p, 0, n * sizeof(float), c.stream));
+    return 0;
+  };
+  auto cleanup = [&](int rc) {
+    cudaStreamSynchronize(c.stream);
+    for (void* p : tmp) cudaFree(p);
+    return rc;
+  };
+#define ENC(x) do { int rc_ = (x); if (rc_ != 0) return cleanup(rc_); } while (0)
+  float* xpad;
+  ENC(alloc(&xpad, (size_t)(T + k0 - 1), true));
+  if (cudaMemcpyAsync(xpad + (k0 - 1), audio, (size_t)n_samples * sizeof(float), cudaMemcpyHostToDevice, c.stream) != cudaSuccess)
+    return cleanup(fail(PTTS_ERR_CUDA, "audio upload failed"));
+  // level 0: conv0 output behind the rk-1 zero rows of the first resblock conv
+  long long Tr = T;
+  int C = g.n_filters;
+  float* h;
+  ENC(alloc(&h, (size_t)(Tr + rk - 1) * C, true));
+  launch_enc_conv0(xpad, c.enc0_w, c.enc0_b, h + (size_t)(rk - 1) * C, Tr, C, k0, c.stream);
+  for (int r = 0; r < g.n_ratios; ++r) {
+    auto& st = c.enc_stages[r];
+    const int s = st.stride, Ch = C / g.compress;
+    float *u, *h2, *hn;
+    ENC(alloc(&u, (size_t)Tr * Ch, false));
+    ENC(alloc(&h2, (size_t)(Tr + s) * C, true));
+    {   // u = conv_k3(ELU(h))
+      LinearParams p{};
+      p.tag = "enc.r3"; p.A = h; p.a_bs = 0; p.a_rs = C; p.nb = 1; p.T = (int)Tr; p.taps = rk; p.C = C;
+      p.a_pro = ACT_ELU; p.Y = u; p.y_rs = Ch; p.out_scale = 1.f;
+      run_linear(c, st.r3, p);
+    }
+    {   // h2 = h + conv_k1(ELU(u)), written behind the s zero rows of the strided conv
+      LinearParams p = rows_linear(u, (int)Tr, Ch, h2 + (size_t)s * C, C, "enc.r1");
+      p.a_pro = ACT_ELU;
+      p.res = h + (size_t)(rk - 1) * C; p.res_rs = C;
+      run_linear(c, st.r1, p);
+    }
+    const long long Tn = Tr / s;
+    const int Cn = 2 * C;
+    const int pad_next = ((r + 1 < g.n_ratios) ? rk : lk) - 1;
+    ENC(alloc(&hn, (size_t)(Tn + pad_next) * Cn, true));
+    {   // stride-s conv with kernel 2s = 2-tap GEMM over rows of s*C channels
+      LinearParams p{};
+      p.tag = "enc.down"; p.A = h2; p.a_bs = 0; p.a_rs = (long long)s * C; p.nb = 1; p.T = (int)Tn; p.taps = 2; p.C = s * C;
+      p.a_pro = ACT_ELU; p.Y = hn + (size_t)pad_next * Cn; p.y_rs = Cn; p.out_scale = 1.f;
+      run_linear(c, st.down, p);
+    }
+    h = hn; Tr = Tn; C = Cn;
+  }
+  const int T3 = (int)Tr;                     // encoder steps (S per frame)
+  float *xd, *hb, *qkv, *att, *ff, *lat, *cond;
+  ENC(alloc(&xd, (size_t)(T3 + S) * SD, false));
+  float* x = xd + (size_t)S * SD;
+  {   // last conv: ELU, kernel lk
+    LinearParams p{};
+    p.tag = "enc.last"; p.A = h; p.a_bs = 0; p.a_rs = C; p.nb = 1; p.T = T3; p.taps = lk; p.C = C;
+    p.a_pro = ACT_ELU; p.Y = x; p.y_rs = SD; p.out_scale = 1.f;
+    run_linear(c, c.enc_last, p);
+  }
+  ENC(alloc(&hb, (size_t)T3 * MD, false));
+  ENC(alloc(&qkv, (size_t)T3 * 3 * MD, false));
+  ENC(alloc(&att, (size_t)T3 * MD, false));
+  ENC(alloc(&ff, (size_t)T3 * g.mimi_ffn, false));
+  for (int i = 0; i < g.mimi_layers; ++i) {
+    auto& l = c.el[i];
+    rows_norm(c, x, T3, MD, l.ln1w, l.ln1b, 1e-5f, hb, nullptr, nullptr, 0, nullptr, nullptr, 0);
+    run_linear(c, l.qkv, rows_linear(hb, T3, MD, qkv, 3 * MD, "enc.qkv"));
+    launch_enc_attention(qkv, att, c.freqs_mimi, T3, g.mimi_heads, g.mimi_context, c.stream);
+    LinearParams o = rows_linear(att, T3, MD, x, MD, "enc.out");
+    o.col_scale = l.ls1; o.res = x; o.res_rs = MD;
+    run_linear(c, l.out, o);
+    rows_norm(c, x, T3, MD, l.ln2w, l.ln2b, 1e-5f, hb, nullptr, nullptr, 0, nullptr, nullptr, 0);
+    LinearParams f1 = rows_linear(hb, T3, MD, ff, g.mimi_ffn, "enc.ff1");
+    f1.act = ACT_GELU;
+    run_linear(c, l.ff1, f1);
+    LinearParams f2 = rows_linear(ff, T3, g.mimi_ffn, x, MD, "enc.ff2");
+    f2.col_scale = l.ls2; f2.res = x; f2.res_rs = MD;
+    run_linear(c, l.ff2, f2);
+  }
+  // downsample: stride S, kernel 2S, replicate padding (S copies of the first step), no bias
+  launch_replicate_row(xd, x, S, SD, c.stream);
+  ENC(alloc(&lat, (size_t)n_frames * SD, false));
+  {
+    LinearParams p{};
+    p.tag = "enc.downsample"; p.A = xd; p.a_bs = 0; p.a_rs = (long long)S * SD; p.nb = 1; p.T = (int)n_frames; p.taps = 2;
+    p.C = S * SD; p.Y = lat; p.y_rs = SD; p.out_scale = 1.f;
+    run_linear(c, c.enc_down, p);
+  }
+  ENC(alloc(&cond, (size_t)n_frames * D, false));
+  run_linear(c, c.speaker_proj, rows_linear(lat, (int)n_frames, SD, cond, D, "enc.speaker_proj"));
+  if (cudaMemcpyAsync(out_cond, cond, (size_t)n_frames * D * sizeof(float), cudaMemcpyDeviceToHost, c.stream) != cudaSuccess)
+    return cleanup(fail(PTTS_ERR_CUDA, "conditioning download failed"));
+  if (cudaStreamSynchronize(c.stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+    return cleanup(fail(PTTS_ERR_CUDA, "encoder kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
+#undef ENC
+  *n_frames_out = (int32_t)n_frames;
+  return cleanup(0);
 }
 
 int32_t ptts_voice_create(ptts_ctx* c, const float* cond, int32_t n_frames) {

@@ -96,6 +96,10 @@ struct FlowAttnParams {
   int prefix_len; const int* prefix_pages; float* prefix_part;
 };
 void launch_flow_prefix_attention(const FlowAttnParams& p, cudaStream_t s);
+// Mimi encoder (voice cloning): RoPE in place on q,k of qkv [T][3*H*64], then windowed causal attention -> out [T][H*64]
+void launch_enc_attention(float* qkv, float* out, const float* freqs, int T, int H, int context, cudaStream_t s);
+void launch_enc_conv0(const float* xpad, const float* w, const float* b, float* y, long long T, int N, int k, cudaStream_t s);
+void launch_replicate_row(float* dst, const float* src, int n, int C, cudaStream_t s);
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s);
 void launch_rope_table(const int* row_pos, const float* freqs, float* table, int M, int T, cudaStream_t s);
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s);

@@ -692,6 +692,74 @@ void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
   }
 }
 
+// ---- Mimi ENCODER transformer (voice cloning; one-off per voice, fp32, not a hot path) -----------------------
+// Non-streaming call of MimiStreamingMultiheadAttention (modules/attention.py:210-264 with model_state=None):
+// positions 0..T-1, interleaved-pair RoPE, key j visible to query t iff 0 <= t - j < context.
+__global__ void enc_rope_kernel(float* __restrict__ qkv, const float* __restrict__ freqs, int T, int H) {
+  const int t = blockIdx.x;
+  const int h = threadIdx.x >> 5, i = threadIdx.x & 31;
+  const int D = H * kHeadDim;
+  float sn, cs;
+  sincosf((float)t * freqs[i], &sn, &cs);
+  float* row = qkv + (long long)t * 3 * D + h * kHeadDim + 2 * i;
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const float xr = row[which * D], xi = row[which * D + 1];
+    row[which * D] = xr * cs - xi * sn;
+    row[which * D + 1] = xr * sn + xi * cs;
+  }
+}
+
+// grid (T, H), 128 threads: scores of the <= 256-key window in shared memory, two-pass softmax, P.V
+__global__ void __launch_bounds__(128) enc_window_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                                   int T, int H, int context) {
+  __shared__ float sq[kHeadDim], sc[256], red[4], so[2][kHeadDim];
+  const int t = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int D = H * kHeadDim;
+  const int lo = max(0, t - context + 1), n = t - lo + 1;
+  if (tid < kHeadDim) sq[tid] = qkv[(long long)t * 3 * D + h * kHeadDim + tid] * 0.125f;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = tid; j < n; j += 128) {
+    const float* k = qkv + (long long)(lo + j) * 3 * D + D + h * kHeadDim;
+    float a = 0.f;
+#pragma unroll 16
+    for (int d = 0; d < kHeadDim; ++d) a = fmaf(sq[d], k[d], a);
+    sc[j] = a;
+    mx = fmaxf(mx, a);
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float l = 0.f;
+  for (int j = tid; j < n; j += 128) {
+    const float p = __expf(sc[j] - mx);
+    sc[j] = p;
+    l += p;
+  }
+  l = warp_sum(l);
+  if ((tid & 31) == 0) red[tid >> 5] = l;
+  __syncthreads();
+  l = (red[0] + red[1]) + (red[2] + red[3]);
+  const int d = tid & 63, half = tid >> 6;
+  float a = 0.f;
+  for (int j = half; j < n; j += 2) a = fmaf(sc[j], qkv[(long long)(lo + j) * 3 * D + 2 * D + h * kHeadDim + d], a);
+  so[half][d] = a;
+  __syncthreads();
+  if (tid < kHeadDim) out[(long long)t * D + h * kHeadDim + tid] = (so[0][tid] + so[1][tid]) / l;
+}
+
+void launch_enc_attention(float* qkv, float* out, const float* freqs, int T, int H, int context, cudaStream_t s) {
+  if (T <= 0) return;
+  launch_k(enc_rope_kernel, dim3(T), dim3(H * 32), 0, s, qkv, freqs, T, H);
+  launch_k(enc_window_attention_kernel, dim3(T, H), dim3(128), 0, s, (const float*)qkv, out, T, H, context);
+  g_launches += 2;
+}
+
 void launch_mimi_rope_ring(const MimiAttnParams& p, cudaStream_t s) {
   ProfScope ps("mimi_rope_ring", nullptr, 0, (double)p.B * p.T * p.H * 64 * (3 * 4 + 4 + 2 * (p.kv_bf16 ? 2 : 4)), s);
   if (p.kv_bf16) launch_k(mimi_rope_ring_kernel<__nv_bfloat16>, dim3(p.B * p.T), dim3(p.H * 32), 0, s, p);

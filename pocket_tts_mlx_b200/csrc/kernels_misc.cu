@@ -538,6 +538,41 @@ __global__ void __launch_bounds__(128) layernorm_wide_kernel(const NormParams p)
   }
 }
 
+// ---- Mimi encoder helpers (voice cloning, one-off per voice) --------------------------------------------------
+// First SEANet-encoder conv: 1 input channel, k taps, causal (k-1 zeros in front of x): y[t][n] = b[n] + sum_j w[n][j] x~[t+j]
+__global__ void enc_conv0_kernel(const float* __restrict__ xpad, const float* __restrict__ w, const float* __restrict__ b,
+                                 float* __restrict__ y, long long T, int N, int k) {
+  extern __shared__ float sw[];          // [N][k] | [N]
+  for (int i = threadIdx.x; i < N * k; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sw[N * k + i] = b[i];
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T * N) return;
+  const long long t = idx / N;
+  const int n = (int)(idx - t * N);
+  float a = sw[N * k + n];
+  for (int j = 0; j < k; ++j) a = fmaf(sw[n * k + j], xpad[t + j], a);
+  y[idx] = a;
+}
+
+void launch_enc_conv0(const float* xpad, const float* w, const float* b, float* y, long long T, int N, int k, cudaStream_t s) {
+  const long long total = T * N;
+  launch_k(enc_conv0_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(N * k + N) * sizeof(float), s, xpad, w, b,
+           y, T, N, k);
+  ++g_launches;
+}
+
+// dst rows 0..n-1 <- src row (replicate padding of the downsample conv)
+__global__ void replicate_row_kernel(float* __restrict__ dst, const float* __restrict__ src, int n, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * C) dst[i] = src[i % C];
+}
+
+void launch_replicate_row(float* dst, const float* src, int n, int C, cudaStream_t s) {
+  launch_k(replicate_row_kernel, dim3((n * C + 255) / 256), dim3(256), 0, s, dst, src, n, C);
+  ++g_launches;
+}
+
 void launch_layernorm(const NormParams& p, cudaStream_t s) {
   ProfScope ps("layernorm", nullptr, 0, 2.0 * p.nb * p.T * p.C * 4, s);
   const int rows = p.nb * p.T;

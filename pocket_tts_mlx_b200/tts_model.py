@@ -63,7 +63,7 @@ class TTSModel:
         self.lsd_decode_steps = lsd_decode_steps
         self.noise_clamp = noise_clamp
         self.eos_threshold = eos_threshold
-        self.has_voice_cloning = False
+        self.has_voice_cloning = bool(ctx.has_voice_cloning)     # the checkpoint carried the Mimi encoder
         self.precision = precision
         self._ctx = ctx
         self._tokenizer = tokenizer
@@ -163,8 +163,34 @@ class TTSModel:
                     and "/" not in audio_conditioning and "." not in audio_conditioning:
                 raise ValueError(
                     f"Predefined voice '{audio_conditioning}' not found, available voices are {list(PREDEFINED_VOICES)}.")
+            if not self.has_voice_cloning:
+                raise ValueError(VOICE_CLONING_UNSUPPORTED)
+            # voice cloning from a file (reference tts_model.py:493-508): read, optional 30 s truncation, mono 24 kHz
+            from .audio import audio_read, convert_audio
+            audio, rate = audio_read(Path(audio_conditioning))
+            if truncate:
+                max_samples = int(30 * rate)
+                if audio.shape[-1] > max_samples:
+                    audio = audio[..., :max_samples]
+                    logger.info("Audio truncated to 30 seconds")
+            audio_conditioning = convert_audio(audio, rate, self.config.mimi.sample_rate, 1)
+        # an array is a waveform [1, T] / [T] at the model sample rate, like the reference's mx.array branch
+        if not self.has_voice_cloning:
             raise ValueError(VOICE_CLONING_UNSUPPORTED)
-        raise ValueError(VOICE_CLONING_UNSUPPORTED)
+        wave_ = np.asarray(audio_conditioning, dtype=np.float32)
+        if wave_.ndim == 2:
+            if wave_.shape[0] != 1:
+                raise ValueError("voice cloning takes mono audio [1, T]")
+            wave_ = wave_[0]
+        if wave_.ndim != 1 or wave_.shape[0] == 0:
+            raise ValueError("voice cloning takes a non-empty waveform [T] or [1, T]")
+        return self.get_state_for_conditioning(self.encode_audio(wave_))
+
+    def encode_audio(self, audio: np.ndarray) -> np.ndarray:
+        """Waveform (mono, model sample rate) -> FlowLM conditioning [T_v, d_model]: the reference's
+        `_encode_audio` (tts_model.py:271-276) = Mimi encoder + speaker projection, on the GPU."""
+        frame = int(self.config.mimi.sample_rate / self.config.mimi.frame_rate)
+        return self._ctx.encode_audio(audio, frame)
 
     # ------------------------------------------------------------------ generation
     def _estimate_max_gen_len(self, token_count: int) -> int:

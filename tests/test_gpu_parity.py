@@ -554,3 +554,51 @@ def test_continuous_batching_with_cascade_attention(model_bf16):
     with pytest.raises(_native.PttsError):
         batch.reset_seq(3, other["voice_id"], other["prompt_len"] + 30)
     batch.close()
+
+
+# ---------------------------------------------------------------------------------------- voice cloning
+def test_voice_clone_encoder_matches_reference_golden(model_fp32, model_bf16):
+    """Mimi encode path on the GPU (SEANet encoder as multi-tap / space-to-depth GEMMs, non-streaming windowed
+    encoder transformer, replicate-padded downsample, speaker projection) against the conditioning the REFERENCE's
+    own encode_to_latent produced for the same 71 000-sample waveform (tests/golden/ref_voice_clone.npz).  The
+    encoder always runs in fp32, also in a bf16 model."""
+    g = np.load(GOLDEN / "ref_voice_clone.npz")
+    for m in (model_fp32, model_bf16):
+        assert m.has_voice_cloning
+        cond = m.encode_audio(g["audio"])
+        assert cond.shape == g["conditioning"].shape
+        assert rel_l2(cond, g["conditioning"]) < 1e-4, rel_l2(cond, g["conditioning"])
+
+
+def test_voice_clone_end_to_end(model_fp32, cfg, weights, tmp_path):
+    """WAV file -> cloned voice state -> speech: the file branch of get_state_for_audio_prompt (16-bit PCM read,
+    48 kHz stereo -> 24 kHz mono polyphase resampling, Mimi encoder, prompt prefill) and generation with it agree
+    with the oracle fed the oracle's own encoding of the same samples."""
+    from oracle.ptts_oracle import Oracle
+    from pocket_tts_mlx_b200.audio import audio_read, convert_audio, write_wav
+    import wave
+    rng = np.random.Generator(np.random.PCG64(31))
+    t = np.arange(48000) / 48000.0
+    left = 0.4 * np.sin(2 * np.pi * 180.0 * t) + 0.02 * rng.standard_normal(t.shape[0])
+    right = 0.3 * np.sin(2 * np.pi * 260.0 * t)
+    pcm = (np.stack([left, right], axis=1).clip(-1, 1) * 32767).astype(np.int16)
+    path = tmp_path / "voice.wav"
+    with wave.open(str(path), "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(48000); f.writeframes(pcm.tobytes())
+    state = model_fp32.get_state_for_audio_prompt(path)
+    a, rate = audio_read(path)
+    mono = convert_audio(a, rate, 24000, 1)[0]
+    assert state["prompt_len"] == int(np.ceil(mono.shape[0] / 1920))
+    orc = Oracle(weights, cfg, dtype=np.float32, eos_threshold=1e30)
+    cond = orc.encode_audio(mono)
+    st = orc.new_flow_state()
+    orc.prefill_audio(st, cond, z=None)
+    ids = rng.integers(0, 4000, size=7).astype(np.int32)
+    noise = rng.standard_normal((1 + 6, 32)).astype(np.float32)
+    ref = orc.generate(st, ids, noise, frames_after_eos=3, max_frames=6)
+    waves, lats = model_fp32.generate_audio_batch([state], [ids], noise=noise[:, None, :], max_frames=6,
+                                                  return_latents=True, pipelined=False)
+    assert rel_l2(lats[0], ref["latents"][:6]) < 1e-4
+    assert snr_db(waves[0], ref["audio"][: 6 * 1920]) > 60.0
+    write_wav(tmp_path / "out.wav", waves[0], 24000)
+    assert audio_read(tmp_path / "out.wav")[1] == 24000
