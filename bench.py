@@ -159,16 +159,37 @@ def one_job(model, state, ids, frames, host_io: bool, rng, cap_frames=None):
         if host_io:
             # host buffers = the library's pinned staging arrays (zero-copy C-ABI variant): the host writes this
             # frame's noise, the graph copies it in, runs, and copies latents / EOS logits / 1920-sample frames out
-            z, lat, logit, audio = batch.staging()
             sink = 0.0
-            for f in range(frames):
-                rng.standard_normal(z.shape, dtype=np.float32, out=z)
-                batch.step_staged()
-                sink += float(logit[0]) + float(audio[0, 0]) + float(lat[0, 0])      # the host reads the results
-                h2d += z.nbytes
-                d2h += lat.nbytes + logit.nbytes + audio.nbytes
             if PIPELINED:
+                # two sets of staging buffers: the host draws the noise of frame t+1 and enqueues it while frame t
+                # is still running, then waits for frame t and reads its results (every frame still does its own
+                # H2D of noise and D2H of latents / EOS logits / audio inside the timed region)
+                batch.set_async_staging(True)
+                sets = batch.staging_sets()
+                pending = None
+                for f in range(frames):
+                    z, lat, logit, audio = sets[f & 1]
+                    rng.standard_normal(z.shape, dtype=np.float32, out=z)
+                    k = batch.step_staged_async()
+                    if pending is not None:
+                        batch.staged_wait(pending)
+                        _, plat, plogit, paudio = sets[pending]
+                        sink += float(plogit[0]) + float(paudio[0, 0]) + float(plat[0, 0])     # the host reads the results
+                    pending = k
+                    h2d += z.nbytes
+                    d2h += lat.nbytes + logit.nbytes + audio.nbytes
+                batch.staged_wait(pending)
+                _, plat, plogit, paudio = sets[pending]
+                sink += float(plogit[0]) + float(paudio[0, 0]) + float(plat[0, 0])
                 batch.flush()               # audio of the last frame (the first step returned an empty frame)
+            else:
+                z, lat, logit, audio = batch.staging()
+                for f in range(frames):
+                    rng.standard_normal(z.shape, dtype=np.float32, out=z)
+                    batch.step_staged()
+                    sink += float(logit[0]) + float(audio[0, 0]) + float(lat[0, 0])      # the host reads the results
+                    h2d += z.nbytes
+                    d2h += lat.nbytes + logit.nbytes + audio.nbytes
         else:
             for f in range(frames):
                 batch.step_device()

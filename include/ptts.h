@@ -131,6 +131,17 @@ int32_t ptts_batch_host_buffers(ptts_batch* batch, float** noise, float** latent
 int32_t ptts_batch_step_staged(ptts_batch* batch);
 /* Teacher forcing for parity tests: overwrite the latent that the next step feeds back. */
 int32_t ptts_batch_set_prev_latent(ptts_batch* batch, const float* latent);
+/* Asynchronous staged steps (pipelined mode): frames alternate between two sets of pinned staging buffers, so the
+ * host can write the noise of frame t+1 and enqueue it (ptts_batch_step_staged_async returns the set it used,
+ * = frame index & 1) while frame t is still running, then ptts_batch_staged_wait(set) before reading that frame's
+ * latents / EOS logits / previous-frame audio from the set.  Enable with ptts_batch_set_async_staging(batch, 1)
+ * after ptts_batch_set_pipelined and before the first frame. */
+int32_t ptts_batch_set_async_staging(ptts_batch* batch, int32_t on);
+int32_t ptts_batch_host_buffers_set(ptts_batch* batch, int32_t set, float** noise, float** latent, float** eos_logit,
+                                    float** audio);
+int32_t ptts_batch_step_staged_async(ptts_batch* batch, int32_t* set_out);
+int32_t ptts_batch_staged_wait(ptts_batch* batch, int32_t set);
+
 /* Same step without the host round trip: results stay on the device (used by bench `value`). */
 int32_t ptts_batch_step_device(ptts_batch* batch);
 /* Continuous batching (the reference decodes one utterance at a time, models/tts_model.py:346-361):

@@ -27,6 +27,7 @@ EXPORTED = [
     "ptts_debug_gemm_bench", "ptts_batch_profile_sections", "ptts_batch_set_pipelined", "ptts_batch_flush",
     "ptts_batch_reset_seq", "ptts_batch_reset_seqs", "ptts_batch_set_active",
     "ptts_has_voice_cloning", "ptts_encode_audio",
+    "ptts_batch_set_async_staging", "ptts_batch_host_buffers_set", "ptts_batch_step_staged_async", "ptts_batch_staged_wait",
     "ptts_batch_host_buffers", "ptts_batch_step_staged",
 ]
 
@@ -99,6 +100,10 @@ def lib() -> C.CDLL:
         "ptts_batch_host_buffers": (i32, [vp, C.POINTER(f32p), C.POINTER(f32p), C.POINTER(f32p), C.POINTER(f32p)]),
         "ptts_batch_step_staged": (i32, [vp]),
         "ptts_batch_set_pipelined": (i32, [vp, i32]),
+        "ptts_batch_set_async_staging": (i32, [vp, i32]),
+        "ptts_batch_host_buffers_set": (i32, [vp, i32, C.POINTER(f32p), C.POINTER(f32p), C.POINTER(f32p), C.POINTER(f32p)]),
+        "ptts_batch_step_staged_async": (i32, [vp, i32p]),
+        "ptts_batch_staged_wait": (i32, [vp, i32]),
         "ptts_has_voice_cloning": (i32, [vp]),
         "ptts_encode_audio": (i32, [vp, f32p, C.c_int64, f32p, i32, i32p]),
         "ptts_batch_reset_seq": (i32, [vp, i32, i32, i32]),
@@ -348,6 +353,34 @@ class Batch:
             shapes = [(self.n, self.latent_dim), (self.n, self.latent_dim), (self.n,), (self.n, self.frame_samples)]
             self._staging = tuple(np.ctypeslib.as_array(p, shape=sh) for p, sh in zip(ptrs, shapes))
         return self._staging
+
+    def set_async_staging(self, on: bool = True):
+        """Pipelined mode only, before the first frame: frames alternate between two pinned buffer sets so that
+        step_staged_async() can be called for frame t+1 while frame t is still running."""
+        check(lib().ptts_batch_set_async_staging(self._h, 1 if on else 0))
+        self._staging_sets = None
+
+    def staging_sets(self):
+        """[(noise, latent, eos_logit, audio)] * 2: frame t reads / writes set t & 1."""
+        if getattr(self, "_staging_sets", None) is None:
+            f32p = C.POINTER(C.c_float)
+            shapes = [(self.n, self.latent_dim), (self.n, self.latent_dim), (self.n,), (self.n, self.frame_samples)]
+            sets = []
+            for k in range(2):
+                ptrs = [f32p() for _ in range(4)]
+                check(lib().ptts_batch_host_buffers_set(self._h, k, *[C.byref(p) for p in ptrs]))
+                sets.append(tuple(np.ctypeslib.as_array(p, shape=sh) for p, sh in zip(ptrs, shapes)))
+            self._staging_sets = sets
+        return self._staging_sets
+
+    def step_staged_async(self) -> int:
+        """Enqueue one frame (noise taken from the current set); returns the set index to staged_wait() on."""
+        k = C.c_int32(0)
+        check(lib().ptts_batch_step_staged_async(self._h, C.byref(k)))
+        return k.value
+
+    def staged_wait(self, k: int):
+        check(lib().ptts_batch_staged_wait(self._h, int(k)))
 
     def step_staged(self):
         """One frame with zero host copies: fill staging()[0] with N(0,1) noise, call, read staging()[1:]."""

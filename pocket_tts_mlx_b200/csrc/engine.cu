@@ -808,6 +808,11 @@ struct ptts_batch {
   int frame_samples = 0;
   // pinned staging
   float *h_noise = nullptr, *h_latent = nullptr, *h_logit = nullptr, *h_audio = nullptr;
+  // asynchronous staged steps (pipelined mode): odd frames use a second set of pinned buffers, so the host can fill
+  // the noise of frame t+1 and enqueue it while frame t is still running; one completion event per set
+  float *h2_noise = nullptr, *h2_latent = nullptr, *h2_logit = nullptr, *h2_audio = nullptr;
+  bool async_staging = false, graphs_async = false;
+  cudaEvent_t ev_set[2] = {nullptr, nullptr};
   // graphs: index = host_noise*2 + copy_out
   cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr};
   long long step_graph_launches[4] = {0, 0, 0, 0};
@@ -1283,18 +1288,21 @@ void pipelined_frame(Batch& bt, int parity, bool host_io) {
   cudaEventRecord(c.ev_fork, main);
   cudaStreamWaitEvent(c.stream2, c.ev_fork, 0);
   c.stream = c.stream2;                                   // every launcher below targets the Mimi branch
+  const bool alt = bt.async_staging && parity == 1;        // odd frames of an async-staged batch: second buffer set
+  float *hn = alt ? bt.h2_noise : bt.h_noise, *hl = alt ? bt.h2_latent : bt.h_latent, *hg = alt ? bt.h2_logit : bt.h_logit,
+        *ha = alt ? bt.h2_audio : bt.h_audio;
   mimi_frame(bt, lat_prev, true);
   if (host_io)
-    cudaMemcpyAsync(bt.h_audio, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpyAsync(ha, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
   cudaEventRecord(c.ev_join, c.stream2);
   c.stream = main;
   if (host_io)
-    cudaMemcpyAsync(bt.d_noise, bt.h_noise, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
+    cudaMemcpyAsync(bt.d_noise, hn, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
   flow_step(bt, host_io, 0, lat_prev, lat_cur);
   launch_advance(bt.d_len, bt.d_bos, nullptr, bt.d_counter, B, 1, 0, c.stream, bt.d_active);
   if (host_io) {
-    cudaMemcpyAsync(bt.h_latent, lat_cur, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
-    cudaMemcpyAsync(bt.h_logit, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpyAsync(hl, lat_cur, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpyAsync(hg, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
   }
   cudaStreamWaitEvent(main, c.ev_join, 0);
 }
@@ -1696,6 +1704,7 @@ static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32
   t.prefilled = false;
   t.frame_idx = 0;
   t.pipelined = false;
+  t.async_staging = false;
   std::vector<int> pt((size_t)B * maxp, 0), src, dst;
   t.slot_pages.assign(B, {});
   t.h_active.assign(B, 1);
@@ -1881,6 +1890,8 @@ static void batch_free(ptts_batch* bt) {
   if (bt->d_lat_all) cudaFree(bt->d_lat_all);
   if (bt->d_audio_all) cudaFree(bt->d_audio_all);
   cudaFreeHost(bt->h_noise); cudaFreeHost(bt->h_latent); cudaFreeHost(bt->h_logit); cudaFreeHost(bt->h_audio);
+  if (bt->h2_noise) { cudaFreeHost(bt->h2_noise); cudaFreeHost(bt->h2_latent); cudaFreeHost(bt->h2_logit); cudaFreeHost(bt->h2_audio); }
+  for (auto& e : bt->ev_set) if (e) cudaEventDestroy(e);
   for (auto& v : bt->slot_pages) for (int p : v) c->free_pages.push_back(p);
   if (bt->mimi_tpl) cudaFree(bt->mimi_tpl);
   delete bt;
@@ -2110,6 +2121,60 @@ int32_t ptts_batch_step_staged(ptts_batch* bt) {
     bt->frame_idx += 1;
   }
   CU(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int32_t ptts_batch_set_async_staging(ptts_batch* bt, int32_t on) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  if (bt->frame_idx != 0) return fail(PTTS_ERR_STATE, "async staging can only be switched before the first frame");
+  if (on && !bt->pipelined) return fail(PTTS_ERR_STATE, "async staging needs pipelined mode");
+  if (on && !bt->h2_noise) {
+    const int B = bt->B, L = c.cfg.latent_dim;
+    CU(cudaMallocHost((void**)&bt->h2_noise, (size_t)B * L * 4));
+    CU(cudaMallocHost((void**)&bt->h2_latent, (size_t)B * L * 4));
+    CU(cudaMallocHost((void**)&bt->h2_logit, (size_t)B * 4));
+    CU(cudaMallocHost((void**)&bt->h2_audio, (size_t)B * bt->frame_samples * 4));
+    for (auto& e : bt->ev_set) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  bt->async_staging = on != 0;
+  if (bt->graphs_async != bt->async_staging) {        // the host pointers are baked into the captured copy nodes
+    for (auto& g : bt->pipe_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    bt->graphs_async = bt->async_staging;
+  }
+  return 0;
+}
+
+int32_t ptts_batch_host_buffers_set(ptts_batch* bt, int32_t set, float** noise, float** latent, float** eos_logit,
+                                    float** audio) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  if (set == 0) return ptts_batch_host_buffers(bt, noise, latent, eos_logit, audio);
+  if (set != 1 || !bt->h2_noise) return fail(PTTS_ERR_STATE, "buffer set %d is not allocated (ptts_batch_set_async_staging)", set);
+  if (noise) *noise = bt->h2_noise;
+  if (latent) *latent = bt->h2_latent;
+  if (eos_logit) *eos_logit = bt->h2_logit;
+  if (audio) *audio = bt->h2_audio;
+  return 0;
+}
+
+int32_t ptts_batch_step_staged_async(ptts_batch* bt, int32_t* set_out) {
+  if (!bt || !set_out) return fail(PTTS_ERR_INVALID, "null argument");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  if (!bt->pipelined || !bt->async_staging) return fail(PTTS_ERR_STATE, "enable pipelined mode and async staging first");
+  RET(check_step_ready(*bt));
+  const int set = (int)(bt->frame_idx & 1);
+  RET(run_pipelined_step(*bt, true));
+  CU(cudaEventRecord(bt->ev_set[set], c.stream));
+  *set_out = set;
+  return 0;
+}
+
+int32_t ptts_batch_staged_wait(ptts_batch* bt, int32_t set) {
+  if (!bt || set < 0 || set > 1 || !bt->ev_set[set]) return fail(PTTS_ERR_INVALID, "bad buffer set");
+  CU(cudaSetDevice(bt->ctx->device));
+  CU(cudaEventSynchronize(bt->ev_set[set]));
   return 0;
 }
 

@@ -602,3 +602,45 @@ def test_voice_clone_end_to_end(model_fp32, cfg, weights, tmp_path):
     assert snr_db(waves[0], ref["audio"][: 6 * 1920]) > 60.0
     write_wav(tmp_path / "out.wav", waves[0], 24000)
     assert audio_read(tmp_path / "out.wav")[1] == 24000
+
+
+def test_async_staged_steps_equal_synchronous(model_bf16):
+    """Double-buffered asynchronous staged steps (frame t+1 enqueued before frame t is read) return exactly what the
+    synchronous pipelined staged steps return."""
+    from pocket_tts_mlx_b200 import _native
+    rng = np.random.Generator(np.random.PCG64(41))
+    st = model_bf16.get_state_for_audio_prompt("alba")
+    ids = [rng.integers(0, 4000, size=5).astype(np.int32) for _ in range(3)]
+    noise = rng.standard_normal((7, 3, 32)).astype(np.float32)
+    out = {}
+    for mode in ("sync", "async"):
+        batch = _native.Batch(model_bf16._ctx, [st["voice_id"]] * 3, [st["prompt_len"] + 5 + 12] * 3)
+        batch.set_pipelined(True)
+        batch.warmup_mimi(1)
+        batch.prefill_text(ids)
+        rec = []
+        if mode == "sync":
+            z, lat, logit, audio = batch.staging()
+            for f in range(7):
+                z[...] = noise[f]
+                batch.step_staged()
+                rec.append((lat.copy(), logit.copy(), audio.copy()))
+        else:
+            batch.set_async_staging(True)
+            sets = batch.staging_sets()
+            pending = None
+            for f in range(7):
+                sets[f & 1][0][...] = noise[f]
+                k = batch.step_staged_async()
+                assert k == (f & 1)
+                if pending is not None:
+                    batch.staged_wait(pending)
+                    rec.append(tuple(a.copy() for a in sets[pending][1:]))
+                pending = k
+            batch.staged_wait(pending)
+            rec.append(tuple(a.copy() for a in sets[pending][1:]))
+        out[mode] = rec
+        batch.close()
+    for f in range(7):
+        for a, b in zip(out["sync"][f], out["async"][f]):
+            assert np.array_equal(a, b), f
