@@ -228,23 +228,31 @@ def write_synthetic_bundle(out_dir, base_variant: Optional[str] = None, seed: in
         tmp = ckpt.with_suffix(f".tmp{os.getpid()}")
         write_safetensors(tmp, synthetic_state_dict(cfg, seed), bf16=bf16)
         os.replace(tmp, ckpt)            # atomic: concurrent ranks never see a partial file
+    def atomic(path: Path, write) -> None:
+        """Write through a per-process temporary file + rename: concurrent ranks (torchrun) never read a partial file."""
+        tmp = path.with_name(f".{path.name}.tmp{os.getpid()}")
+        write(tmp)
+        os.replace(tmp, path)
+
     for i, name in enumerate(VOICE_NAMES):
         vp = out_dir / "embeddings" / f"{name}.safetensors"
         if not vp.exists():
-            write_safetensors(vp, {"audio_prompt": synthetic_voice(1000 + i, voice_frames,
-                                                                   cfg.flow_lm.transformer.d_model)})
+            voice = synthetic_voice(1000 + i, voice_frames, cfg.flow_lm.transformer.d_model)
+            atomic(vp, lambda t, voice=voice: write_safetensors(t, {"audio_prompt": voice}))
     tok = out_dir / "tokenizer.model"
     if not tok.exists():
         if DEFAULT_TOKENIZER.exists():
-            tok.write_bytes(DEFAULT_TOKENIZER.read_bytes())
+            atomic(tok, lambda t: t.write_bytes(DEFAULT_TOKENIZER.read_bytes()))
         else:
-            train_synthetic_tokenizer(tok, cfg.flow_lm.lookup_table.n_bins)
+            atomic(tok, lambda t: train_synthetic_tokenizer(t, cfg.flow_lm.lookup_table.n_bins))
     doc = yaml.safe_load(base.read_text())
     doc["weights_path"] = str(ckpt)
     doc["weights_path_without_voice_cloning"] = str(ckpt)
     doc["flow_lm"]["lookup_table"]["tokenizer_path"] = str(tok)
     yml = out_dir / "synthetic.yaml"
-    yml.write_text(yaml.safe_dump(doc, sort_keys=False))
+    text = yaml.safe_dump(doc, sort_keys=False)
+    if not (yml.exists() and yml.read_text() == text):
+        atomic(yml, lambda t: t.write_text(text))
     return yml
 
 
