@@ -446,10 +446,13 @@ def main():
         tensor = tensor_pipe_evidence(model, peaks)
         cpu = None
         if not args.skip_cpu_baseline:
-            v, dt = cpu_baseline(275)
+            n_utt, dt = 2, 0.0
+            for k in range(n_utt):                      # about 12 s of CPU work: two whole utterances of the workload
+                dt += cpu_baseline(275, seed=k)[1]
+            v = n_utt * 275 * FRAME_SEC / dt
             cpu = {"value": v, "unit": "audio-s/s", "cores": _blas_threads(), "kind": "port",
-                   "sample": "1 utterance (batch 1: the reference's only batch size), 60 tokens, text prefill + 275 "
-                             f"frames (one full utterance of the workload), NumPy/OpenBLAS fp32 oracle, {dt:.1f} s"}
+                   "sample": f"{n_utt} utterances one after the other (batch 1: the reference's only batch size), 60 tokens "
+                             f"each, text prefill + 275 frames, NumPy/OpenBLAS fp32 oracle, {dt:.1f} s"}
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -287,51 +287,51 @@ class TTSModel:
                 batch.set_pipelined(True)
             batch.warmup_mimi(warmup_frames)
             batch.prefill_text(token_ids)
-            eos_step = [None] * n
-            done = [False] * n
-            owed = [False] * n                    # pipelined: frame accepted, its audio arrives with the next call
-            audio_out: List[List[np.ndarray]] = [[] for _ in range(n)]
-            lat_out: List[List[np.ndarray]] = [[] for _ in range(n)]
-            stepped = False
-            for step in range(max(limits)):
+            # Lock-step bookkeeping on whole arrays: every sequence accepts frames 0 .. n_acc-1, so the per-step
+            # [n, .] blocks returned by step() are kept as they are and sliced per sequence at the end.
+            lim = np.asarray(limits, dtype=np.int64)
+            fae_a = np.asarray(fae, dtype=np.int64)
+            eos_step = np.full(n, -1, dtype=np.int64)
+            done = np.zeros(n, dtype=bool)
+            n_acc = np.zeros(n, dtype=np.int64)
+            lat_steps: List[np.ndarray] = []
+            audio_steps: List[np.ndarray] = []            # audio_steps[s] = waveform block of frame s
+            thr = self.eos_threshold
+            for step in range(int(lim.max()) if n else 0):
                 z = rng.standard_normal((n, ldim), dtype=np.float32) if noise is None \
                     else np.asarray(noise[1 + step], dtype=np.float32)
-                lat, logit, audio = batch.step(z, want_audio=True)
-                stepped = True
-                for b in range(n):
-                    if owed[b]:
-                        audio_out[b].append(audio[b].copy())
-                        owed[b] = False
-                    if done[b]:
-                        continue
-                    if step >= limits[b]:
-                        done[b] = True
-                        batch.set_active(b, False)        # parked: computed with the batch, KV no longer grows
-                        continue
-                    if logit[b] > self.eos_threshold and eos_step[b] is None:
-                        eos_step[b] = step
-                    if eos_step[b] is not None and step >= eos_step[b] + fae[b]:
-                        done[b] = True
-                        batch.set_active(b, False)
-                        continue
-                    lat_out[b].append(lat[b].copy())
-                    if pipelined:
-                        owed[b] = True
-                    else:
-                        audio_out[b].append(audio[b].copy())
-                    if step + 1 >= limits[b] and not all(step + 1 >= l for l in limits):
-                        done[b] = True                    # frame budget used up while others continue: park now,
-                        batch.set_active(b, False)        # the next step must not grow this sequence's KV
-                if all(done):
+                lat, logit, audio = batch.step(z, want_audio=True)          # fresh arrays every call
+                if pipelined:
+                    if step > 0:
+                        audio_steps.append(audio)                            # audio of frame step-1
+                else:
+                    audio_steps.append(audio)
+                lat_steps.append(lat)
+                live = ~done
+                first = live & (eos_step < 0) & (logit > thr)
+                eos_step[first] = step
+                stop = live & (eos_step >= 0) & (step >= eos_step + fae_a)  # the reference breaks before this frame
+                accept = live & ~stop
+                n_acc[accept] = step + 1
+                full = accept & (step + 1 >= lim)                            # frame budget used up
+                newly = stop | full
+                done |= newly
+                if done.all():
                     break
-            if pipelined and stepped and any(owed):
-                audio = batch.flush()
-                for b in range(n):
-                    if owed[b]:
-                        audio_out[b].append(audio[b].copy())
-            waves = [np.concatenate(a) if a else np.zeros(0, dtype=np.float32) for a in audio_out]
+                for b in np.nonzero(newly)[0]:
+                    batch.set_active(int(b), False)     # parked: computed with the batch, KV no longer grows
+            if pipelined and len(audio_steps) < len(lat_steps):
+                audio_steps.append(batch.flush())        # audio of the last frame stepped
+            waves, lats = [], []
+            if lat_steps:
+                lat_all = np.stack(lat_steps)                                # [steps, n, L]
+                aud_all = np.stack(audio_steps)                              # [steps, n, frame]
+            for b in range(n):
+                k = int(n_acc[b])
+                waves.append(np.ascontiguousarray(aud_all[:k, b]).reshape(-1) if k else np.zeros(0, dtype=np.float32))
+                lats.append(np.ascontiguousarray(lat_all[:k, b]) if k else np.zeros((0, ldim), dtype=np.float32))
             if return_latents:
-                return waves, [np.array(l, dtype=np.float32).reshape(-1, ldim) for l in lat_out]
+                return waves, lats
             return waves
         finally:
             batch.close()
