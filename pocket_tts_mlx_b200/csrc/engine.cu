@@ -108,6 +108,9 @@ struct FlowWork {
   int prefix_len = 0; int* d_prefix_pages = nullptr; float* prefix_part = nullptr;
   int pend_n = 0;             // planes of the last ffn2 still to be added to x (consumed by the next norm)
   float* rope_cs = nullptr;   // [M][64] cos | sin of each row's position (fused RoPE epilogue of the qkv GEMM)
+  // set by the prefill callers around flow_layers: row ranges / start positions per sequence (device arrays), which
+  // let whole chunks go through the tensor-core prefill attention instead of the per-row decode kernel
+  const int* seq_row0 = nullptr; const int* seq_pos0 = nullptr; int n_seq = 0, max_rows_per_seq = 0;
 };
 
 }  // namespace
@@ -692,8 +695,14 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
         a.prefix_len = w.prefix_len; a.prefix_pages = w.d_prefix_pages; a.prefix_part = w.prefix_part;
       }
       if (!fuse_rope) launch_flow_rope_append(a, c.stream);
-      launch_flow_prefix_attention(a, c.stream);
-      launch_flow_attention(a, c.stream);
+      a.seq_row0 = w.seq_row0; a.seq_pos0 = w.seq_pos0; a.n_seq = w.n_seq; a.max_rows_per_seq = w.max_rows_per_seq;
+      static const bool no_tc_prefill = [] { const char* v = getenv("PTTS_NO_TC_PREFILL_ATTN"); return v && v[0] == '1'; }();
+      if (row_seq && !no_tc_prefill && launch_flow_prefill_attention(a, c.stream)) {
+        // whole prefill chunks: FlashAttention-2 style mma.sync kernel (64 query rows per CTA)
+      } else {
+        launch_flow_prefix_attention(a, c.stream);
+        launch_flow_attention(a, c.stream);
+      }
       gemm_tc_launch(g[1], c.stream);
       rows_norm(c, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16, w.ws_out,
                 g[1].splits > 1 ? g[1].splits : 0);
@@ -1646,10 +1655,17 @@ int32_t ptts_voice_create(ptts_ctx* c, const float* cond, int32_t n_frames) {
   CU(cudaMemcpyAsync(d_pos, pos.data(), n_frames * 4, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(d_pt, v.pages.data(), np * 4, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->prefill_work.x, cond, (size_t)n_frames * D * 4, cudaMemcpyHostToDevice, c->stream));
+  int* d_rows;                                         // {row0 = 0, row1 = n_frames, pos0 = 0}
+  const int rows3[3] = {0, n_frames, 0};
+  CU(cudaMalloc(&d_rows, 3 * 4));
+  CU(cudaMemcpyAsync(d_rows, rows3, 3 * 4, cudaMemcpyHostToDevice, c->stream));
+  c->prefill_work.seq_row0 = d_rows; c->prefill_work.seq_pos0 = d_rows + 2;
+  c->prefill_work.n_seq = 1; c->prefill_work.max_rows_per_seq = n_frames;
   flow_layers(*c, c->prefill_work, n_frames, d_seq, d_pos, d_pt, np, (long long)n_frames * (n_frames + 1) / 2);
+  c->prefill_work.seq_row0 = c->prefill_work.seq_pos0 = nullptr; c->prefill_work.n_seq = 0;
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
-  cudaFree(d_seq); cudaFree(d_pos); cudaFree(d_pt);
+  cudaFree(d_seq); cudaFree(d_pos); cudaFree(d_pt); cudaFree(d_rows);
   v.alive = true;
   for (size_t i = 0; i < c->voices.size(); ++i)
     if (!c->voices[i].alive && c->voices[i].pages.empty()) {
@@ -1947,12 +1963,26 @@ int32_t ptts_batch_prefill_text(ptts_batch* bt, const int32_t* ids, const int32_
     launch_embed_rows(c.embed, c.bf16, d_ids, c.prefill_work.x, M, c.cfg.d_model, c.stream);
     long long total_keys = 0;
     for (int i = 0; i < M; ++i) total_keys += pos[i] + 1;
+    // per-sequence row ranges and start positions for the tensor-core prefill attention
+    std::vector<int> rows(2 * B + 1);
+    int max_rows = 0;
+    for (int b = 0; b <= B; ++b) rows[b] = offsets[b] - offsets[0];
+    for (int b = 0; b < B; ++b) {
+      rows[B + 1 + b] = bt->h_len[b];
+      max_rows = std::max(max_rows, offsets[b + 1] - offsets[b]);
+    }
+    int* d_rows;
+    CU(cudaMalloc(&d_rows, rows.size() * 4));
+    CU(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, c.stream));
+    c.prefill_work.seq_row0 = d_rows; c.prefill_work.seq_pos0 = d_rows + B + 1;
+    c.prefill_work.n_seq = B; c.prefill_work.max_rows_per_seq = max_rows;
     flow_layers(c, c.prefill_work, M, d_seq, d_pos, bt->d_page_table, bt->max_pages, total_keys);
+    c.prefill_work.seq_row0 = c.prefill_work.seq_pos0 = nullptr; c.prefill_work.n_seq = 0;
     for (int b = 0; b < B; ++b) bt->h_len[b] += offsets[b + 1] - offsets[b];
     CU(cudaMemcpyAsync(bt->d_len, bt->h_len.data(), B * 4, cudaMemcpyHostToDevice, c.stream));
     CU(cudaStreamSynchronize(c.stream));
     CU(cudaGetLastError());
-    cudaFree(d_seq); cudaFree(d_pos); cudaFree(d_ids);
+    cudaFree(d_seq); cudaFree(d_pos); cudaFree(d_ids); cudaFree(d_rows);
   }
   bt->prefilled = true;
   return 0;

@@ -94,8 +94,13 @@ struct FlowAttnParams {
   // once per (row, head) from the voice's own pages into prefix_part [M][H][66]; the per-sequence kernel then
   // starts at key prefix_len and merges the partial.
   int prefix_len; const int* prefix_pages; float* prefix_part;
+  // prefill (many rows per sequence): rows of sequence s are seq_row0[s] .. seq_row0[s+1]-1 at positions
+  // seq_pos0[s] + t; set by the text / voice prefill so that the tensor-core prefill kernel can be used
+  const int* seq_row0; const int* seq_pos0; int n_seq, max_rows_per_seq;
 };
 void launch_flow_prefix_attention(const FlowAttnParams& p, cudaStream_t s);
+// causal attention of whole prefill chunks on tensor cores (bf16 KV, bf16 output); false when not applicable
+bool launch_flow_prefill_attention(const FlowAttnParams& p, cudaStream_t s);
 // Mimi encoder (voice cloning): RoPE in place on q,k of qkv [T][3*H*64], then windowed causal attention -> out [T][H*64]
 void launch_enc_attention(float* qkv, float* out, const float* freqs, int T, int H, int context, cudaStream_t s);
 void launch_enc_conv0(const float* xpad, const float* w, const float* b, float* y, long long T, int N, int k, cudaStream_t s);

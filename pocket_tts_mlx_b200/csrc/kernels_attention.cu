@@ -692,6 +692,153 @@ void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
   }
 }
 
+// ---- FlowLM prefill attention on tensor cores ---------------------------------------------------------------
+// Text / voice prefill: a sequence contributes T rows at positions pos0 .. pos0+T-1 that attend causally to the paged
+// keys 0 .. pos (modules/attention.py:164-182 with T > 1).  The per-row decode kernel reads every key once per ROW;
+// here a CTA owns 64 query rows of one (sequence, head): the keys are staged 64 at a time in shared memory (cp.async
+// from the pages, 4 KB per page and head) and S = Q K^T, online softmax and O += P V run on mma.sync m16n8k16 in
+// the FlashAttention-2 arrangement (4 warps x 16 rows, running max / sum per row, O rescaled per key block).
+__global__ void __launch_bounds__(128) flow_prefill_attention_kernel(const FlowAttnParams p) {
+  pdl_sync();
+  __shared__ __align__(16) __nv_bfloat16 Ks[64 * kMimiLd];
+  __shared__ __align__(16) __nv_bfloat16 Vs[64 * kMimiLd];
+  const int sq = blockIdx.x, h = blockIdx.y, qt = blockIdx.z;
+  const int row_lo = p.seq_row0[sq], T = p.seq_row0[sq + 1] - row_lo;
+  if (qt * 64 >= T) return;
+  const int pos0 = p.seq_pos0[sq];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int D = p.H * kHeadDim;
+  const __nv_bfloat16* pool = reinterpret_cast<const __nv_bfloat16*>(p.pool) + p.layer * p.layer_stride;
+  const long long kv_half = (long long)p.H * kPageTokens * kHeadDim;
+  const int* pt = p.page_table + (long long)sq * p.max_pages;
+  const int tl0 = qt * 64 + warp * 16 + g, tl1 = tl0 + 8;         // local row indices of this lane's two rows
+  const bool r0 = tl0 < T, r1 = tl1 < T;
+  const int qpos0 = pos0 + tl0, qpos1 = pos0 + tl1;
+  uint32_t qa[4][4];
+  {
+    const float* q0 = p.q_rot + (long long)(row_lo + (r0 ? tl0 : 0)) * D + h * kHeadDim;
+    const float* q1 = p.q_rot + (long long)(row_lo + (r1 ? tl1 : 0)) * D + h * kHeadDim;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int c = 16 * ks + 2 * t4;
+      const float2 a0 = *reinterpret_cast<const float2*>(q0 + c), a2 = *reinterpret_cast<const float2*>(q0 + c + 8);
+      const float2 a1 = *reinterpret_cast<const float2*>(q1 + c), a3 = *reinterpret_cast<const float2*>(q1 + c + 8);
+      qa[ks][0] = pack2_bf16(a0.x * 0.125f, a0.y * 0.125f);
+      qa[ks][1] = pack2_bf16(a1.x * 0.125f, a1.y * 0.125f);
+      qa[ks][2] = pack2_bf16(a2.x * 0.125f, a2.y * 0.125f);
+      qa[ks][3] = pack2_bf16(a3.x * 0.125f, a3.y * 0.125f);
+    }
+  }
+  float oc[8][4];
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int n_keys = pos0 + min(T, qt * 64 + 64);                  // keys any row of this tile may see
+  for (int k0 = 0; k0 < n_keys; k0 += 64) {
+    __syncthreads();                                               // previous block fully consumed
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = threadIdx.x + 128 * i;                       // 64 keys x 8 chunks of 16 bytes
+      const int kr = idx >> 3, ch = idx & 7;
+      const int key = k0 + kr;
+      const int sz = key < n_keys ? 16 : 0;
+      const int kk = key < n_keys ? key : 0;
+      const __nv_bfloat16* src = pool + pt[kk / kPageTokens] * p.page_stride +
+                                 ((long long)h * kPageTokens + (kk % kPageTokens)) * kHeadDim + ch * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(Ks + kr * kMimiLd + ch * 8)),
+                   "l"(src), "r"(sz) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(Vs + kr * kMimiLd + ch * 8)),
+                   "l"(src + kv_half), "r"(sz) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float sc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        uint32_t kb[4];
+        ldsm_x4(kb, (uint32_t)__cvta_generic_to_shared(Ks + (nt * 8 + (lane & 7)) * kMimiLd + 32 * kk + 8 * (lane >> 3)));
+        mma_bf16_16816(sc[nt], qa[2 * kk], kb[0], kb[1]);
+        mma_bf16_16816(sc[nt], qa[2 * kk + 1], kb[2], kb[3]);
+      }
+    }
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int key = k0 + nt * 8 + 2 * t4 + j;
+        if (key > qpos0 || !r0) sc[nt][j] = -INFINITY;             // causal: key position <= query position
+        if (key > qpos1 || !r1) sc[nt][2 + j] = -INFINITY;
+        bm0 = fmaxf(bm0, sc[nt][j]);
+        bm1 = fmaxf(bm1, sc[nt][2 + j]);
+      }
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
+    const float e0 = (nm0 == -INFINITY) ? 0.f : nm0, e1 = (nm1 == -INFINITY) ? 0.f : nm1;
+    const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - e0), c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - e1);
+    m0 = nm0; m1 = nm1;
+    float s0 = 0.f, s1 = 0.f;
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p00 = __expf(sc[nt][0] - e0), p01 = __expf(sc[nt][1] - e0);
+      const float p10 = __expf(sc[nt][2] - e1), p11 = __expf(sc[nt][3] - e1);
+      s0 += p00 + p01;
+      s1 += p10 + p11;
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack2_bf16(p00, p01);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p10, p11);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    l0 = l0 * c0 + s0;
+    l1 = l1 * c1 + s1;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) { oc[dt][0] *= c0; oc[dt][1] *= c0; oc[dt][2] *= c1; oc[dt][3] *= c1; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t vb[4];
+        const int mid = lane >> 3;
+        ldsm_x4_t(vb, (uint32_t)__cvta_generic_to_shared(Vs + (16 * j + 8 * (mid & 1) + (lane & 7)) * kMimiLd +
+                                                          8 * (2 * dp + (mid >> 1))));
+        mma_bf16_16816(oc[2 * dp], pa[j], vb[0], vb[1]);
+        mma_bf16_16816(oc[2 * dp + 1], pa[j], vb[2], vb[3]);
+      }
+    }
+  }
+  const float i0 = r0 ? 1.0f / l0 : 0.f, i1 = r1 ? 1.0f / l1 : 0.f;
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) {
+    const int d = dt * 8 + 2 * t4;
+    if (r0) {
+      const long long oi = (long long)(row_lo + tl0) * D + h * kHeadDim + d;
+      if (p.out16) *reinterpret_cast<__nv_bfloat162*>(p.out16 + oi) = __floats2bfloat162_rn(oc[dt][0] * i0, oc[dt][1] * i0);
+      else { p.out[oi] = oc[dt][0] * i0; p.out[oi + 1] = oc[dt][1] * i0; }
+    }
+    if (r1) {
+      const long long oi = (long long)(row_lo + tl1) * D + h * kHeadDim + d;
+      if (p.out16) *reinterpret_cast<__nv_bfloat162*>(p.out16 + oi) = __floats2bfloat162_rn(oc[dt][2] * i1, oc[dt][3] * i1);
+      else { p.out[oi] = oc[dt][2] * i1; p.out[oi + 1] = oc[dt][3] * i1; }
+    }
+  }
+}
+
+bool launch_flow_prefill_attention(const FlowAttnParams& p, cudaStream_t s) {
+  if (!p.kv_bf16 || !p.seq_row0 || !p.seq_pos0 || p.n_seq <= 0 || p.max_rows_per_seq <= 0) return false;
+  ProfScope ps("flow_prefill_attention", nullptr, 4.0 * p.total_keys * p.H * 64, 2.0 * p.total_keys * p.H * 64 * 2 / 32, s);
+  launch_k(flow_prefill_attention_kernel, dim3(p.n_seq, p.H, (p.max_rows_per_seq + 63) / 64), dim3(128), 0, s, p);
+  ++g_launches;
+  return true;
+}
+
 // ---- Mimi ENCODER transformer (voice cloning; one-off per voice, fp32, not a hot path) -----------------------
 // Non-streaming call of MimiStreamingMultiheadAttention (modules/attention.py:210-264 with model_state=None):
 // positions 0..T-1, interleaved-pair RoPE, key j visible to query t iff 0 <= t - j < context.
