@@ -2094,8 +2094,9 @@ int32_t ptts_batch_set_active(ptts_batch* bt, int32_t slot, int32_t active) {
   Ctx& c = *bt->ctx;
   CU(cudaSetDevice(c.device));
   if (slot < 0 || slot >= bt->B) return fail(PTTS_ERR_INVALID, "slot %d out of range", slot);
+  // stream-ordered and synchronisation-free (4-byte copies from pageable memory are staged before the call returns):
+  // frames already enqueued still see the old value, the next one the new value
   const int on = active ? 1 : 0;
-  CU(cudaStreamSynchronize(c.stream));
   bt->h_active[slot] = on;
   if (!on && bt->h_len[slot] >= bt->max_len[slot]) {
     // a parked slot keeps being stepped with the rest of the batch: it must keep writing inside its own pages
@@ -2103,7 +2104,6 @@ int32_t ptts_batch_set_active(ptts_batch* bt, int32_t slot, int32_t active) {
     CU(cudaMemcpyAsync(bt->d_len + slot, &bt->h_len[slot], 4, cudaMemcpyHostToDevice, c.stream));
   }
   CU(cudaMemcpyAsync(bt->d_active + slot, &on, 4, cudaMemcpyHostToDevice, c.stream));
-  CU(cudaStreamSynchronize(c.stream));
   return 0;
 }
 

@@ -277,7 +277,9 @@ class TTSModel:
         limits = [self._estimate_max_gen_len(k) for k in n_tok]
         if max_frames is not None:
             limits = [min(l, max_frames) for l in limits]
-        req = [int(s["prompt_len"]) + k + l for s, k, l in zip(model_states, n_tok, limits)]
+        # pipelined mode runs one frame ahead of the host's bookkeeping (asynchronous staged steps): a sequence is
+        # parked one frame after its last accepted one, hence the slack in its KV reservation
+        req = [int(s["prompt_len"]) + k + l + (2 if pipelined else 0) for s, k, l in zip(model_states, n_tok, limits)]
         batch = _native.Batch(self._ctx, [int(s["voice_id"]) for s in model_states], req)
         rng = np.random.Generator(np.random.PCG64(seed))
         ldim = self._ctx.config.latent_dim
@@ -285,6 +287,7 @@ class TTSModel:
             batch.seed(seed)
             if pipelined:
                 batch.set_pipelined(True)
+                batch.set_async_staging(True)
             batch.warmup_mimi(warmup_frames)
             batch.prefill_text(token_ids)
             # Lock-step bookkeeping on whole arrays: every sequence accepts frames 0 .. n_acc-1, so the per-step
@@ -294,42 +297,74 @@ class TTSModel:
             eos_step = np.full(n, -1, dtype=np.int64)
             done = np.zeros(n, dtype=bool)
             n_acc = np.zeros(n, dtype=np.int64)
-            lat_steps: List[np.ndarray] = []
-            audio_steps: List[np.ndarray] = []            # audio_steps[s] = waveform block of frame s
+            n_steps = int(lim.max()) if n else 0
+            # sequence-major output arrays: step blocks are written straight into them, and a sequence's waveform /
+            # latents are a contiguous slice (returned as a view, no concatenation at the end)
+            aud_all = np.empty((n, n_steps, self.frame_samples), dtype=np.float32)
+            lat_all = np.empty((n, n_steps, ldim), dtype=np.float32)
+            counts = {"lat": 0, "audio": 0}
             thr = self.eos_threshold
-            for step in range(int(lim.max()) if n else 0):
-                z = rng.standard_normal((n, ldim), dtype=np.float32) if noise is None \
-                    else np.asarray(noise[1 + step], dtype=np.float32)
-                lat, logit, audio = batch.step(z, want_audio=True)          # fresh arrays every call
-                if pipelined:
-                    if step > 0:
-                        audio_steps.append(audio)                            # audio of frame step-1
-                else:
-                    audio_steps.append(audio)
-                lat_steps.append(lat)
+
+            def put_audio(block):
+                aud_all[:, counts["audio"], :] = block
+                counts["audio"] += 1
+
+            def account(step, lat, logit):
+                """EOS / frame-budget bookkeeping of frame `step` (reference tts_model.py:404-426), all sequences."""
+                lat_all[:, counts["lat"], :] = lat
+                counts["lat"] += 1
                 live = ~done
                 first = live & (eos_step < 0) & (logit > thr)
                 eos_step[first] = step
-                stop = live & (eos_step >= 0) & (step >= eos_step + fae_a)  # the reference breaks before this frame
+                stop = live & (eos_step >= 0) & (step >= eos_step + fae_a)   # the reference breaks before this frame
                 accept = live & ~stop
                 n_acc[accept] = step + 1
-                full = accept & (step + 1 >= lim)                            # frame budget used up
-                newly = stop | full
-                done |= newly
-                if done.all():
-                    break
-                for b in np.nonzero(newly)[0]:
-                    batch.set_active(int(b), False)     # parked: computed with the batch, KV no longer grows
-            if pipelined and len(audio_steps) < len(lat_steps):
-                audio_steps.append(batch.flush())        # audio of the last frame stepped
-            waves, lats = [], []
-            if lat_steps:
-                lat_all = np.stack(lat_steps)                                # [steps, n, L]
-                aud_all = np.stack(audio_steps)                              # [steps, n, frame]
-            for b in range(n):
-                k = int(n_acc[b])
-                waves.append(np.ascontiguousarray(aud_all[:k, b]).reshape(-1) if k else np.zeros(0, dtype=np.float32))
-                lats.append(np.ascontiguousarray(lat_all[:k, b]) if k else np.zeros((0, ldim), dtype=np.float32))
+                newly = stop | (accept & (step + 1 >= lim))                  # ... or its frame budget is used up
+                done[newly] = True
+                if not done.all():
+                    for b in np.nonzero(newly)[0]:
+                        batch.set_active(int(b), False)     # parked: computed with the batch, KV no longer grows
+
+            if pipelined:
+                # frame s is enqueued before frame s-1 is read back: the GPU never waits for the host
+                sets = batch.staging_sets()
+                enq = 0
+                for step in range(n_steps):
+                    zbuf = sets[step & 1][0]
+                    if noise is None:
+                        rng.standard_normal(zbuf.shape, dtype=np.float32, out=zbuf)
+                    else:
+                        zbuf[...] = np.asarray(noise[1 + step], dtype=np.float32)
+                    batch.step_staged_async()
+                    enq = step + 1
+                    if step >= 1:
+                        k = (step - 1) & 1
+                        batch.staged_wait(k)
+                        if step >= 2:
+                            put_audio(sets[k][3])                            # audio of frame step-2
+                        account(step - 1, sets[k][1], sets[k][2].copy())
+                        if done.all():
+                            break
+                if enq:
+                    k = (enq - 1) & 1
+                    batch.staged_wait(k)
+                    if enq >= 2:
+                        put_audio(sets[k][3])                                # audio of frame enq-2
+                    if not done.all():
+                        account(enq - 1, sets[k][1], sets[k][2].copy())
+                    if counts["audio"] < counts["lat"]:
+                        put_audio(batch.flush())                             # audio of the last accounted frame
+            else:
+                for step in range(n_steps):
+                    z = rng.standard_normal((n, ldim), dtype=np.float32) if noise is None \
+                        else np.asarray(noise[1 + step], dtype=np.float32)
+                    lat, logit, audio = batch.step(z, want_audio=True)
+                    put_audio(audio)
+                    account(step, lat, logit)
+                    if done.all():
+                        break
+            waves = [aud_all[b, :int(n_acc[b])].reshape(-1) for b in range(n)]
+            lats = [lat_all[b, :int(n_acc[b])] for b in range(n)]
             if return_latents:
                 return waves, lats
             return waves

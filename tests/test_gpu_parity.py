@@ -644,3 +644,29 @@ def test_async_staged_steps_equal_synchronous(model_bf16):
     for f in range(7):
         for a, b in zip(out["sync"][f], out["async"][f]):
             assert np.array_equal(a, b), f
+
+
+def test_public_batch_api_async_pipeline_equals_synchronous(model_bf16, monkeypatch):
+    """generate_audio_batch in pipelined mode runs one frame ahead of its own bookkeeping (asynchronous staged
+    steps, sequences parked one frame late); with ragged frame budgets and a live EOS threshold it must return
+    exactly the frames and samples of the synchronous, non-pipelined loop."""
+    rng = np.random.Generator(np.random.PCG64(51))
+    st = model_bf16.get_state_for_audio_prompt("alba")
+    ids = [rng.integers(0, 4000, size=k).astype(np.int32) for k in (3, 6, 9, 4)]
+    noise = rng.standard_normal((1 + 64, 4, 32)).astype(np.float32)
+    ref_w, ref_l = model_bf16.generate_audio_batch([st] * 4, ids, noise=noise, return_latents=True, pipelined=False)
+    assert [len(l) for l in ref_l] == [38, 50, 63, 42]
+    w, l = model_bf16.generate_audio_batch([st] * 4, ids, noise=noise, return_latents=True, pipelined=True)
+    for b in range(4):
+        assert np.array_equal(l[b], ref_l[b]) and np.array_equal(w[b], ref_w[b])
+    # live EOS: a threshold inside the range of the logits seen by sequence 2 stops it early in both modes
+    orc_free = model_bf16.generate_audio_batch([st], [ids[2]], noise=noise[:, 2:3], return_latents=True, pipelined=False)
+    monkeypatch.setattr(model_bf16, "eos_threshold", -1e30)          # every frame "ends": stop after frames_after_eos
+    a = model_bf16.generate_audio_batch([st] * 4, ids, noise=noise, frames_after_eos=[2, 5, 9, 1], return_latents=True,
+                                        pipelined=False)
+    b_ = model_bf16.generate_audio_batch([st] * 4, ids, noise=noise, frames_after_eos=[2, 5, 9, 1], return_latents=True,
+                                         pipelined=True)
+    assert [len(x) for x in a[1]] == [2, 5, 9, 1]
+    for k in range(4):
+        assert np.array_equal(a[1][k], b_[1][k]) and np.array_equal(a[0][k], b_[0][k])
+    assert len(orc_free[1][0]) == 63
