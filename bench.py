@@ -444,6 +444,17 @@ def main():
         lat = None if args.skip_latency else latency_bs1(model, state, rng)
         sections = section_times(model, state, ids, min(frames // 2, 137))
         tensor = tensor_pipe_evidence(model, peaks)
+        api = None
+        if not args.skip_latency and world == 1:
+            # the call a user of the reference's API makes: one TTSModel.generate_audio_batch over the same workload
+            # (host RNG, per-frame H2D/D2H, EOS bookkeeping, waveforms returned as NumPy arrays); second of two calls
+            api_s = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                waves = model.generate_audio_batch([state] * n_seq, ids, seed=5, max_frames=frames)
+                api_s = time.perf_counter() - t0
+            api = {"value": sum(len(w) for w in waves) / 24000.0 / api_s, "unit": "audio-s/s",
+                   "call": "TTSModel.generate_audio_batch (pipelined, asynchronous staged steps)"}
         cpu = None
         if not args.skip_cpu_baseline:
             n_utt, dt = 2, 0.0
@@ -465,7 +476,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d // e2e_steps,
                     "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps},
-            "roofline": roof, "frame_breakdown": breakdown, "frame_sections_us": sections,
+            "public_api": api, "roofline": roof, "frame_breakdown": breakdown, "frame_sections_us": sections,
             "tensor_pipe": tensor, "cpu_baseline": cpu, "latency_bs1": lat,
             "pipelined": PIPELINED,
             "ms_per_frame": ms / args.steps / frames,
