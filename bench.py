@@ -316,6 +316,7 @@ def section_times(model, state, ids, at_frame):
 
 def cpu_baseline(frames: int, seed: int = 0):
     """The oracle (NumPy restatement of the reference's path), batch 1, on this box's host cores."""
+    _use_all_host_threads()
     from oracle.ptts_oracle import Oracle
     from pocket_tts_mlx_b200.config import load_config
     from pocket_tts_mlx_b200.safetensors_io import read_safetensors
@@ -336,6 +337,15 @@ def cpu_baseline(frames: int, seed: int = 0):
     return frames * FRAME_SEC / dt, dt
 
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms (rank 0 only) are meant to use the whole host."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+    except Exception:
+        pass
+
+
 def _blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -345,6 +355,7 @@ def _blas_threads():
 
 
 def run_reference(args, world, rank):
+    _use_all_host_threads()
     if rank != 0:
         return
     frames = 100
