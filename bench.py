@@ -467,7 +467,7 @@ def main():
             api = {"value": sum(len(w) for w in waves) / 24000.0 / api_s, "unit": "audio-s/s",
                    "call": "TTSModel.generate_audio_batch (pipelined, asynchronous staged steps)"}
         cpu = None
-        if not args.skip_cpu_baseline:
+        if not args.skip_cpu_baseline and world == 1:        # reported at N = 1 only (it is the same host either way)
             n_utt, dt = 2, 0.0
             for k in range(n_utt):                      # about 12 s of CPU work: two whole utterances of the workload
                 dt += cpu_baseline(275, seed=k)[1]
