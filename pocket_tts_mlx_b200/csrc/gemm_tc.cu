@@ -46,7 +46,10 @@ struct KArgs {
 // EPW = epilogue warps (8 or 16).  Sixteen pay off for persistent BN = 128 kernels whose tiles are short in K
 // (SEANet / Mimi): the epilogue is then the critical stage and 2 warps per scheduler run it at ~0.3 IPC (ncu).
 template <int BN, int BK, int STAGES, int ACC, int EPW = 8>   // ACC = TMEM accumulator stages: 2 persistent, 1 one tile per CTA
-__global__ void __launch_bounds__(64 + 32 * EPW, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
+// The persistent 8-warp variant is compiled for 2 CTAs per SM (96 registers): it never runs two of its own CTAs on an
+// SM (shared memory), but the smaller register footprint lets CTAs of the other branch of the pipelined frame graph
+// (FlowLM attention next to Mimi GEMMs) co-reside: sequential frame +3 us, pipelined job -1.2 ms.
+__global__ void __launch_bounds__(64 + 32 * EPW, (EPW == 8 && ACC == 2) ? 2 : 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                               const __grid_constant__ CUtensorMap tm_b,
                                                               const __grid_constant__ CUtensorMap tm_y16,
                                                               const __grid_constant__ CUtensorMap tm_yraw16,
