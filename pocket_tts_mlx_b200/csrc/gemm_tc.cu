@@ -521,7 +521,9 @@ bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a
       if (st == 8 && bn == 128) continue;
       const double ring = st * stage_bytes;
       const double smem = (best_persist ? ring + stg * 16384.0 : std::max(ring, stg * 16384.0)) + 2048;
-      if (smem <= 226.0 * 1024 && ring <= 200.0 * 1024 && (best_persist || st <= std::max(2, iters / best_splits))) {
+      // PTTS_TC_SMEM_CAP_KB: experiment knob, per-CTA shared-memory budget (co-residency of the two graph branches)
+      static const double cap_kb = [] { const char* v = getenv("PTTS_TC_SMEM_CAP_KB"); return v ? atof(v) : 226.0; }();
+      if (smem <= cap_kb * 1024 && ring <= 200.0 * 1024 && (best_persist || st <= std::max(2, iters / best_splits))) {
         best_stages = st;
         break;
       }
