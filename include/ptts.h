@@ -131,11 +131,11 @@ int32_t ptts_batch_host_buffers(ptts_batch* batch, float** noise, float** latent
 int32_t ptts_batch_step_staged(ptts_batch* batch);
 /* Teacher forcing for parity tests: overwrite the latent that the next step feeds back. */
 int32_t ptts_batch_set_prev_latent(ptts_batch* batch, const float* latent);
-/* Asynchronous staged steps (pipelined mode): frames alternate between two sets of pinned staging buffers, so the
+/* Asynchronous staged steps (either mode): frames alternate between two sets of pinned staging buffers, so the
  * host can write the noise of frame t+1 and enqueue it (ptts_batch_step_staged_async returns the set it used,
  * = frame index & 1) while frame t is still running, then ptts_batch_staged_wait(set) before reading that frame's
- * latents / EOS logits / previous-frame audio from the set.  Enable with ptts_batch_set_async_staging(batch, 1)
- * after ptts_batch_set_pipelined and before the first frame. */
+ * latents / EOS logits / audio (the previous frame's in pipelined mode) from the set.  Enable with
+ * ptts_batch_set_async_staging(batch, 1) before the first frame (after ptts_batch_set_pipelined, if that is used). */
 int32_t ptts_batch_set_async_staging(ptts_batch* batch, int32_t on);
 int32_t ptts_batch_host_buffers_set(ptts_batch* batch, int32_t set, float** noise, float** latent, float** eos_logit,
                                     float** audio);

@@ -824,6 +824,8 @@ struct ptts_batch {
   cudaEvent_t ev_set[2] = {nullptr, nullptr};
   // graphs: index = host_noise*2 + copy_out
   cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaGraphExec_t step_graph_alt = nullptr;      // host-I/O frame through the second staging set (async staged steps)
+  long long step_graph_alt_launches = 0;
   long long step_graph_launches[4] = {0, 0, 0, 0};
   // pipelined mode: frame graph = { FlowLM step t } || { Mimi decode of latent t-1 } on two streams.
   // Latents ping-pong between d_latent (even frames) and d_latent_b (odd frames); index = parity*2 + host_io.
@@ -1269,19 +1271,21 @@ void flow_step(Batch& bt, bool host_noise, int part = 0, const float* lat_in = n
   }
 }
 
-void full_step(Batch& bt, bool host_noise, bool copy_out) {
+void full_step(Batch& bt, bool host_noise, bool copy_out, bool alt = false) {
   Ctx& c = *bt.ctx;
   const int B = bt.B, L = c.cfg.latent_dim;
+  // alt: second set of pinned staging buffers (odd frames of an async-staged batch)
+  float *hn = alt ? bt.h2_noise : bt.h_noise, *hl = alt ? bt.h2_latent : bt.h_latent, *hg = alt ? bt.h2_logit : bt.h_logit,
+        *ha = alt ? bt.h2_audio : bt.h_audio;
   if (host_noise)
-    cudaMemcpyAsync(bt.d_noise, bt.h_noise, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
+    cudaMemcpyAsync(bt.d_noise, hn, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
   flow_step(bt, host_noise);
   mimi_frame(bt, bt.d_latent, true);
   launch_advance(bt.d_len, bt.d_bos, nullptr, bt.d_counter, B, 1, 0, c.stream, bt.d_active);
   if (copy_out) {
-    cudaMemcpyAsync(bt.h_latent, bt.d_latent, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
-    cudaMemcpyAsync(bt.h_logit, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
-    cudaMemcpyAsync(bt.h_audio, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost,
-                    c.stream);
+    cudaMemcpyAsync(hl, bt.d_latent, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpyAsync(hg, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpyAsync(ha, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
   }
 }
 
@@ -1374,6 +1378,26 @@ int run_step(Batch& bt, bool host_noise, bool copy_out) {
   const int idx = (host_noise ? 2 : 0) + (copy_out ? 1 : 0);
   CU(cudaGraphLaunch(bt.step_graph[idx], bt.ctx->stream));
   g_launches += bt.step_graph_launches[idx];
+  for (int b = 0; b < bt.B; ++b) bt.h_len[b] += bt.h_active[b];
+  return 0;
+}
+
+// sequential (non-pipelined) frame with host I/O through the second staging set
+int run_step_alt(Batch& bt) {
+  Ctx& c = *bt.ctx;
+  if (!bt.step_graph_alt) {
+    const long long before = g_launches;
+    cudaGraph_t graph;
+    CU(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed));
+    full_step(bt, true, true, true);
+    CU(cudaStreamEndCapture(c.stream, &graph));
+    bt.step_graph_alt_launches = g_launches - before;
+    g_launches = before;
+    CU(cudaGraphInstantiate(&bt.step_graph_alt, graph, 0));
+    CU(cudaGraphDestroy(graph));
+  }
+  CU(cudaGraphLaunch(bt.step_graph_alt, c.stream));
+  g_launches += bt.step_graph_alt_launches;
   for (int b = 0; b < bt.B; ++b) bt.h_len[b] += bt.h_active[b];
   return 0;
 }
@@ -1766,6 +1790,7 @@ static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32
     }
     if (t.cascade_len != t.fw.prefix_len) {      // the prefix length is baked into the captured graphs
       for (auto& g : t.step_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+      if (t.step_graph_alt) { cudaGraphExecDestroy(t.step_graph_alt); t.step_graph_alt = nullptr; }
       for (auto& g : t.pipe_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
       t.cascade_len = t.fw.prefix_len;
     }
@@ -1899,6 +1924,7 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
 static void batch_free(ptts_batch* bt) {
   Ctx* c = bt->ctx;
   for (auto& g : bt->step_graph) if (g) cudaGraphExecDestroy(g);
+  if (bt->step_graph_alt) cudaGraphExecDestroy(bt->step_graph_alt);
   for (auto& g : bt->pipe_graph) if (g) cudaGraphExecDestroy(g);
   for (auto& kv : bt->mimi_graphs) cudaGraphExecDestroy(kv.second.first);
   free_flow_work(bt->fw);
@@ -2159,7 +2185,6 @@ int32_t ptts_batch_set_async_staging(ptts_batch* bt, int32_t on) {
   Ctx& c = *bt->ctx;
   CU(cudaSetDevice(c.device));
   if (bt->frame_idx != 0) return fail(PTTS_ERR_STATE, "async staging can only be switched before the first frame");
-  if (on && !bt->pipelined) return fail(PTTS_ERR_STATE, "async staging needs pipelined mode");
   if (on && !bt->h2_noise) {
     const int B = bt->B, L = c.cfg.latent_dim;
     CU(cudaMallocHost((void**)&bt->h2_noise, (size_t)B * L * 4));
@@ -2192,10 +2217,16 @@ int32_t ptts_batch_step_staged_async(ptts_batch* bt, int32_t* set_out) {
   if (!bt || !set_out) return fail(PTTS_ERR_INVALID, "null argument");
   Ctx& c = *bt->ctx;
   CU(cudaSetDevice(c.device));
-  if (!bt->pipelined || !bt->async_staging) return fail(PTTS_ERR_STATE, "enable pipelined mode and async staging first");
+  if (!bt->async_staging) return fail(PTTS_ERR_STATE, "enable async staging first (ptts_batch_set_async_staging)");
   RET(check_step_ready(*bt));
   const int set = (int)(bt->frame_idx & 1);
-  RET(run_pipelined_step(*bt, true));
+  if (bt->pipelined) {
+    RET(run_pipelined_step(*bt, true));
+  } else {
+    if (set) RET(run_step_alt(*bt));
+    else RET(run_step(*bt, true, true));
+    bt->frame_idx += 1;
+  }
   CU(cudaEventRecord(bt->ev_set[set], c.stream));
   *set_out = set;
   return 0;

@@ -396,80 +396,125 @@ class TTSModel:
             limits = [min(l, max_frames) for l in limits]
         need = [int(s["prompt_len"]) + k + l for s, k, l in zip(model_states, n_tok, limits)]
         n_slots = min(int(slots), n_jobs)
-        cap = max(need)                                   # any utterance fits any slot
+        cap = max(need) + 2                               # any utterance fits any slot; +2: a slot is parked one frame late
         group = max(1, n_slots // 16) if min_admit is None else max(1, int(min_admit))
         ldim = self._ctx.config.latent_dim
         batch = _native.Batch(self._ctx, [int(model_states[j]["voice_id"]) for j in range(n_slots)], [cap] * n_slots)
         rng = np.random.Generator(np.random.PCG64(seed))
-
         try:
             batch.seed(seed)
+            batch.set_async_staging(True)                 # frame t+1 is enqueued before frame t is read back
+            sets = batch.staging_sets()
             batch.warmup_mimi(warmup_frames)
             batch.prefill_text([token_ids[j] for j in range(n_slots)])
-            job_of = list(range(n_slots))                 # utterance in each slot (None = parked)
-            frame_of = [0] * n_slots
-            eos_at = [None] * n_slots
+            # Whole-array bookkeeping.  Per slot: the utterance it holds (-1 = parked), the frame index its next
+            # enqueued step produces, the frame of the first EOS crossing (-1 = none yet), its frame budget / EOS tail.
+            job = np.arange(n_slots, dtype=np.int64)
+            frame = np.zeros(n_slots, dtype=np.int64)
+            eos_at = np.full(n_slots, -1, dtype=np.int64)
+            lim_all = np.asarray(limits, dtype=np.int64)
+            fae_all = np.asarray(fae, dtype=np.int64)
+            # Per utterance: slot, index of the processed block holding its frame 0, accepted frames.  Every enqueued
+            # step is read back exactly once and in order, so an utterance's frames sit in consecutive blocks.
+            slot_of = np.full(n_jobs, -1, dtype=np.int64)
+            t0_of = np.zeros(n_jobs, dtype=np.int64)
+            n_of = np.zeros(n_jobs, dtype=np.int64)
+            slot_of[:n_slots] = np.arange(n_slots)
             free: List[int] = []                          # parked slots waiting for the next admission round
             next_job = n_slots
-            audio_out: List[List[np.ndarray]] = [[] for _ in range(n_jobs)]
-            lat_out: List[List[np.ndarray]] = [[] for _ in range(n_jobs)]
-            z = np.zeros((n_slots, ldim), dtype=np.float32)
+            est_steps = int(np.ceil(lim_all.sum() / n_slots * 1.25)) + int(lim_all.max()) + 8
+            # slot-major, so that an utterance's waveform is one contiguous slice (returned as a view, no final gather)
+            aud = np.empty((n_slots, est_steps, self.frame_samples), dtype=np.float32)   # pages are touched on write
+            lat_b = np.empty((n_slots, est_steps, ldim), dtype=np.float32)
             thr = self.eos_threshold
-            live = n_slots
-            import time as _t, os as _os
-            prof = {"steps": 0, "rounds": 0, "t_step": 0.0, "t_loop": 0.0, "t_admit": 0.0, "t_noise": 0.0}
-            while live > 0:
-                _t0 = _t.perf_counter()
+            state = {"live": n_slots, "enq": 0, "done_blocks": 0}
+
+            def enqueue():
+                """Fill the noise of the next frame, enqueue it, remember which (utterance, frame) each slot computes."""
+                z = sets[state["enq"] & 1][0]
                 if noise is None:
-                    z = rng.standard_normal((n_slots, ldim), dtype=np.float32)      # one draw per step for all slots
+                    rng.standard_normal(z.shape, dtype=np.float32, out=z)
                 else:
-                    for s_, j in enumerate(job_of):
-                        if j is not None:
-                            z[s_] = noise[j][1 + frame_of[s_]]
+                    for s_ in np.nonzero(job >= 0)[0]:      # (the frame enqueued past an utterance's last one is discarded)
+                        nz = noise[int(job[s_])]
+                        z[s_] = nz[min(1 + int(frame[s_]), len(nz) - 1)]
+                k = batch.step_staged_async()
+                snap = (k, job.copy(), frame.copy())
+                frame[job >= 0] += 1
+                state["enq"] += 1
+                return snap
+
+            def process(snap):
+                """Read one finished frame back and apply the reference's EOS / frame-budget rule to every slot."""
+                nonlocal aud, lat_b
+                k, jobs, frames = snap
+                batch.staged_wait(k)
+                t = state["done_blocks"]
+                if t >= aud.shape[1]:                    # estimate exceeded: grow
+                    aud = np.concatenate([aud, np.empty_like(aud)], axis=1)
+                    lat_b = np.concatenate([lat_b, np.empty_like(lat_b)], axis=1)
+                aud[:, t] = sets[k][3]
+                lat_b[:, t] = sets[k][1]
+                logit = sets[k][2]
+                state["done_blocks"] = t + 1
+                valid = (jobs >= 0) & (job == jobs)      # not parked, and not ended while this frame was in flight
+                jj = np.where(valid, jobs, 0)
+                first = valid & (eos_at < 0) & (logit > thr)
+                eos_at[first] = frames[first]
+                stop = valid & (eos_at >= 0) & (frames >= eos_at + fae_all[jj])    # the reference breaks before this frame
+                accept = valid & ~stop
+                n_of[jobs[accept]] += 1
+                ended = stop | (accept & (frames + 1 >= lim_all[jj]))
+                for s_ in np.nonzero(ended)[0]:
+                    batch.set_active(int(s_), False)
+                    job[s_] = -1
+                    free.append(int(s_))
+                    state["live"] -= 1
+
+            import os as _os, time as _t
+            prof = {"enqueue": 0.0, "process": 0.0, "admit": 0.0, "rounds": 0}
+            inflight = None
+            while state["live"] > 0 or inflight is not None:
+                _t0 = _t.perf_counter()
+                nxt = enqueue() if state["live"] > 0 else None
                 _t1 = _t.perf_counter()
-                lat, logit, audio = batch.step(z, want_audio=True)      # fresh arrays every step: rows are kept as views
+                if inflight is not None:
+                    process(inflight)
                 _t2 = _t.perf_counter()
-                prof["steps"] += 1; prof["t_noise"] += _t1 - _t0; prof["t_step"] += _t2 - _t1
-                for s_, j in enumerate(job_of):
-                    if j is None:
-                        continue
-                    step = frame_of[s_]
-                    if eos_at[s_] is None and logit[s_] > thr:
-                        eos_at[s_] = step
-                    if eos_at[s_] is not None and step >= eos_at[s_] + fae[j]:
-                        ended = True                      # the reference breaks before emitting this frame
-                    else:
-                        lat_out[j].append(lat[s_])
-                        audio_out[j].append(audio[s_])
-                        frame_of[s_] = step + 1
-                        ended = step + 1 >= limits[j]
-                    if ended:
-                        batch.set_active(s_, False)
-                        job_of[s_] = None
-                        free.append(s_)
-                        live -= 1
-                _t3 = _t.perf_counter()
-                prof["t_loop"] += _t3 - _t2
+                prof["enqueue"] += _t1 - _t0
+                prof["process"] += _t2 - _t1
+                inflight = nxt
                 pending = n_jobs - next_job
-                if pending > 0 and free and (len(free) >= min(group, pending) or live == 0):
+                if pending > 0 and free and (len(free) >= min(group, pending) or state["live"] == 0):
                     prof["rounds"] += 1
+                    if inflight is not None:              # drain before slots are re-initialised
+                        process(inflight)
+                        inflight = None
                     take = free[:pending]
-                    free = free[len(take):]
-                    jobs = list(range(next_job, next_job + len(take)))
+                    del free[:len(take)]
+                    jobs_new = list(range(next_job, next_job + len(take)))
                     next_job += len(take)
-                    batch.reset_seqs(take, [int(model_states[j]["voice_id"]) for j in jobs], [cap] * len(take))
+                    batch.reset_seqs(take, [int(model_states[j]["voice_id"]) for j in jobs_new], [cap] * len(take))
                     toks: List[Sequence[int]] = [[] for _ in range(n_slots)]
-                    for s_, j in zip(take, jobs):
-                        job_of[s_], frame_of[s_], eos_at[s_] = j, 0, None
+                    for s_, j in zip(take, jobs_new):
+                        job[s_], frame[s_], eos_at[s_] = j, 0, -1
+                        slot_of[j], t0_of[j] = s_, state["enq"]      # its frame 0 is the next enqueued step
                         toks[s_] = token_ids[j]
                     batch.prefill_text(toks)
-                    live += len(take)
-                    prof["t_admit"] += _t.perf_counter() - _t3
+                    state["live"] += len(take)
+                    prof["admit"] += _t.perf_counter() - _t2
+            _t3 = _t.perf_counter()
+            waves, lats = [], []
+            for j in range(n_jobs):
+                s_, t0, k = int(slot_of[j]), int(t0_of[j]), int(n_of[j])
+                waves.append(aud[s_, t0:t0 + k].reshape(-1))
+                lats.append(lat_b[s_, t0:t0 + k])
             if _os.environ.get("PTTS_SCHED_PROFILE"):
+                prof["gather"] = _t.perf_counter() - _t3
+                prof["steps"] = state["enq"]
                 print("scheduler profile:", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in prof.items()})
-            waves = [np.concatenate(a) if a else np.zeros(0, dtype=np.float32) for a in audio_out]
             if return_latents:
-                return waves, [np.array(l, dtype=np.float32).reshape(-1, ldim) for l in lat_out]
+                return waves, lats
             return waves
         finally:
             batch.close()

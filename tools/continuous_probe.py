@@ -23,13 +23,13 @@ for rep in range(2):
     assert [len(w) // 1920 for w in waves] == frames
     print(f"continuous, {slots} slots: {dt:.2f} s -> {audio_s / dt:.0f} audio-s/s")
 
-for rep in range(2):
+for pipelined in (True, True, False):
     t0 = time.perf_counter()
     done = 0
     for w0 in range(0, n_jobs, slots):
         sel = list(range(w0, min(n_jobs, w0 + slots)))
-        out = model.generate_audio_batch([state] * len(sel), [ids[j] for j in sel], seed=1, pipelined=False)
+        out = model.generate_audio_batch([state] * len(sel), [ids[j] for j in sel], seed=1, pipelined=pipelined)
         done += sum(len(w) // 1920 for w in out)
     dt = time.perf_counter() - t0
     assert done == sum(frames)
-    print(f"lock-step waves of {slots} (arrival order): {dt:.2f} s -> {audio_s / dt:.0f} audio-s/s")
+    print(f"lock-step waves of {slots} (arrival order, pipelined={pipelined}): {dt:.2f} s -> {audio_s / dt:.0f} audio-s/s")
