@@ -604,9 +604,10 @@ def test_voice_clone_end_to_end(model_fp32, cfg, weights, tmp_path):
     assert audio_read(tmp_path / "out.wav")[1] == 24000
 
 
-def test_async_staged_steps_equal_synchronous(model_bf16):
+@pytest.mark.parametrize("pipelined", [True, False])
+def test_async_staged_steps_equal_synchronous(model_bf16, pipelined):
     """Double-buffered asynchronous staged steps (frame t+1 enqueued before frame t is read) return exactly what the
-    synchronous pipelined staged steps return."""
+    synchronous staged steps return, for the two-branch (pipelined) and the sequential frame graph."""
     from pocket_tts_mlx_b200 import _native
     rng = np.random.Generator(np.random.PCG64(41))
     st = model_bf16.get_state_for_audio_prompt("alba")
@@ -615,7 +616,7 @@ def test_async_staged_steps_equal_synchronous(model_bf16):
     out = {}
     for mode in ("sync", "async"):
         batch = _native.Batch(model_bf16._ctx, [st["voice_id"]] * 3, [st["prompt_len"] + 5 + 12] * 3)
-        batch.set_pipelined(True)
+        batch.set_pipelined(pipelined)
         batch.warmup_mimi(1)
         batch.prefill_text(ids)
         rec = []
