@@ -15,6 +15,7 @@ Extensions (keyword-only, all optional): `precision`, `device_id`, `kv_pool_toke
 from __future__ import annotations
 
 import logging
+import os
 import time
 from pathlib import Path
 from typing import Dict, Generator, List, Optional, Sequence, Union
@@ -395,6 +396,23 @@ class TTSModel:
         if max_frames is not None:
             limits = [min(l, max_frames) for l in limits]
         need = [int(s["prompt_len"]) + k + l for s, k, l in zip(model_states, n_tok, limits)]
+        # host memory: the frames of all utterances of one run are kept in one slot-major array (waveforms are views
+        # into it); very long job lists are cut into runs of at most ~max_host_gb of output each
+        max_host_gb = float(os.environ.get("PTTS_CONT_MAX_GB", "6"))
+        bytes_per_frame = 4.0 * (self.frame_samples + self._ctx.config.latent_dim)
+        if n_jobs > int(slots) and sum(limits) * bytes_per_frame * 1.3 > max_host_gb * 2 ** 30:
+            per_run = max(int(slots), int(n_jobs * max_host_gb * 2 ** 30 / (sum(limits) * bytes_per_frame * 1.3)))
+            waves_all, lats_all = [], []
+            for lo in range(0, n_jobs, per_run):
+                hi = min(n_jobs, lo + per_run)
+                r = self.generate_audio_continuous(
+                    model_states[lo:hi], token_ids[lo:hi], slots=slots, frames_after_eos=fae[lo:hi],
+                    warmup_frames=warmup_frames, max_frames=max_frames,
+                    noise=None if noise is None else noise[lo:hi], seed=seed + lo, return_latents=True,
+                    min_admit=min_admit)
+                waves_all += r[0]
+                lats_all += r[1]
+            return (waves_all, lats_all) if return_latents else waves_all
         n_slots = min(int(slots), n_jobs)
         cap = max(need) + 2                               # any utterance fits any slot; +2: a slot is parked one frame late
         group = max(1, n_slots // 16) if min_admit is None else max(1, int(min_admit))

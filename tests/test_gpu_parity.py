@@ -671,3 +671,20 @@ def test_public_batch_api_async_pipeline_equals_synchronous(model_bf16, monkeypa
     for k in range(4):
         assert np.array_equal(a[1][k], b_[1][k]) and np.array_equal(a[0][k], b_[0][k])
     assert len(orc_free[1][0]) == 63
+
+
+def test_continuous_batching_split_runs(model_bf16, monkeypatch):
+    """A job list whose output would exceed the host-memory budget is cut into consecutive runs; the utterances
+    still come back in input order and agree with the unsplit schedule (to rounding: an utterance prefilled together
+    with another one goes through a different GEMV instantiation than one prefilled alone)."""
+    rng = np.random.Generator(np.random.PCG64(61))
+    st = model_bf16.get_state_for_audio_prompt("alba")
+    ids = [rng.integers(0, 4000, size=k).astype(np.int32) for k in (3, 4, 5, 3, 4)]
+    noise = [rng.standard_normal((1 + 50, 32)).astype(np.float32) for _ in ids]
+    ref_w, ref_l = model_bf16.generate_audio_continuous([st] * 5, ids, slots=2, noise=noise, return_latents=True)
+    monkeypatch.setenv("PTTS_CONT_MAX_GB", "1e-9")
+    w, l = model_bf16.generate_audio_continuous([st] * 5, ids, slots=2, noise=noise, return_latents=True)
+    assert len(w) == 5
+    for j in range(5):
+        assert l[j].shape == ref_l[j].shape
+        assert rel_l2(l[j], ref_l[j]) < 2e-3 and snr_db(w[j], ref_w[j]) > 40.0
