@@ -100,7 +100,10 @@ int32_t ptts_encode_audio(ptts_ctx* ctx, const float* audio, int64_t n_samples, 
 /* ---- voice prompt -------------------------------------------------------------------------
  * Replaces get_state_for_audio_prompt's prefill (models/tts_model.py:510-518): runs cond
  * [n_frames, d_model] through the backbone and keeps the KV pages as an immutable prefix that any
- * number of sequences share.  Returns the voice id (>= 0). */
+ * number of sequences share.  Returns the voice id (>= 0).
+ * ptts_voice_destroy releases the prefix pages (the reference's state dict is garbage-collected).  Batch slots hold
+ * a reference on their voice: destroying a voice that live slots still attend only retires the id, its pages return
+ * to the pool when the last such slot is re-initialised or its batch destroyed. */
 int32_t ptts_voice_create(ptts_ctx* ctx, const float* cond, int32_t n_frames);
 int32_t ptts_voice_destroy(ptts_ctx* ctx, int32_t voice_id);
 int32_t ptts_voice_length(ptts_ctx* ctx, int32_t voice_id);
@@ -135,7 +138,8 @@ int32_t ptts_batch_set_prev_latent(ptts_batch* batch, const float* latent);
  * host can write the noise of frame t+1 and enqueue it (ptts_batch_step_staged_async returns the set it used,
  * = frame index & 1) while frame t is still running, then ptts_batch_staged_wait(set) before reading that frame's
  * latents / EOS logits / audio (the previous frame's in pipelined mode) from the set.  Enable with
- * ptts_batch_set_async_staging(batch, 1) before the first frame (after ptts_batch_set_pipelined, if that is used). */
+ * ptts_batch_set_async_staging(batch, 1) before the first frame (after ptts_batch_set_pipelined, if that is used).
+ * While it is on, ptts_batch_step / ptts_batch_step_staged (which only know set 0) return PTTS_ERR_STATE. */
 int32_t ptts_batch_set_async_staging(ptts_batch* batch, int32_t on);
 int32_t ptts_batch_host_buffers_set(ptts_batch* batch, int32_t set, float** noise, float** latent, float** eos_logit,
                                     float** audio);
@@ -150,8 +154,10 @@ int32_t ptts_batch_step_device(ptts_batch* batch);
  * budget the batch was created with), rewinds length / BOS flag and restores the slot's Mimi streaming state to the
  * one right after ptts_batch_warmup_mimi (= init_states + _warmup_mimi_decoder, models/tts_model.py:378-383,464-476).
  * Follow it with ptts_batch_prefill_text where every other sequence has an empty token range.
- * ptts_batch_set_active(slot, 0) parks a slot: it is still computed with the batch but stops growing its KV cache.
- * Not available in pipelined mode; in a batch that uses cascade attention the voice cannot change. */
+ * ptts_batch_set_active(slot, 0) parks a slot: it is still computed with the batch but stops growing its KV cache
+ * (stream-ordered, allowed in every mode).  ptts_batch_reset_seq(s) is refused in pipelined mode (flush and leave it
+ * first).  A batch whose sequences all share one voice attends the shared prefix once (cascade attention); the first
+ * slot that switches to another voice turns that off for the batch (the frame graphs are re-captured). */
 int32_t ptts_batch_reset_seq(ptts_batch* batch, int32_t slot, int32_t voice_id, int32_t max_len);
 /* the same for n slots with one stream synchronisation */
 int32_t ptts_batch_reset_seqs(ptts_batch* batch, int32_t n, const int32_t* slots, const int32_t* voice_ids,
@@ -164,6 +170,14 @@ int32_t ptts_batch_set_active(ptts_batch* batch, int32_t slot, int32_t active);
  * ptts_batch_flush decodes the last frame.  Results are identical to the sequential mode, one frame later. */
 int32_t ptts_batch_set_pipelined(ptts_batch* batch, int32_t on);
 int32_t ptts_batch_flush(ptts_batch* batch, float* out_audio);
+/* 16-bit PCM output (replaces StreamingWAVWriter.write_pcm_data's host conversion, data/audio.py:64-70): after
+ * ptts_batch_set_pcm16(batch, 1) (before the first frame) the kernels that produce a frame's final samples also store
+ * them as int16 = trunc(clip(v, -1, 1) * 32767), and every host step copies THOSE out instead of the fp32 samples
+ * (half the device->host bytes).  The frame's PCM lands in the pinned buffer ptts_batch_host_pcm returns for the
+ * staging set the step used (set 0 for ptts_batch_step / _step_staged / _flush), [n_seq, 1920] int16; pass
+ * out_audio = NULL to ptts_batch_step / ptts_batch_flush while it is on. */
+int32_t ptts_batch_set_pcm16(ptts_batch* batch, int32_t on);
+int32_t ptts_batch_host_pcm(ptts_batch* batch, int32_t set, int16_t** pcm);
 int32_t ptts_batch_seed(ptts_batch* batch, uint64_t seed);
 int32_t ptts_batch_lengths(ptts_batch* batch, int32_t* out_len);
 

@@ -29,6 +29,7 @@ EXPORTED = [
     "ptts_has_voice_cloning", "ptts_encode_audio",
     "ptts_batch_set_async_staging", "ptts_batch_host_buffers_set", "ptts_batch_step_staged_async", "ptts_batch_staged_wait",
     "ptts_batch_host_buffers", "ptts_batch_step_staged",
+    "ptts_batch_set_pcm16", "ptts_batch_host_pcm",
 ]
 
 
@@ -110,6 +111,8 @@ def lib() -> C.CDLL:
         "ptts_batch_reset_seqs": (i32, [vp, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "ptts_batch_set_active": (i32, [vp, i32, i32]),
         "ptts_batch_flush": (i32, [vp, f32p]),
+        "ptts_batch_set_pcm16": (i32, [vp, i32]),
+        "ptts_batch_host_pcm": (i32, [vp, i32, C.POINTER(C.POINTER(C.c_int16))]),
         "ptts_debug_gemm_bench": (i32, [vp, i32, i32, i32, i32, i32, i32, i32p, i32, f32p, i32p]),
     }
     for name, (res, args) in sig.items():
@@ -292,6 +295,8 @@ class Batch:
     def close(self):
         if self._h:
             self._staging = None
+            self._staging_sets = None
+            self._pcm_views = {}
             lib().ptts_batch_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -317,9 +322,30 @@ class Batch:
         z = _f32(noise).reshape(self.n, self.latent_dim) if noise is not None else None
         lat = np.empty((self.n, self.latent_dim), dtype=np.float32)
         logit = np.empty((self.n,), dtype=np.float32)
+        if getattr(self, "_pcm16", False):       # int16 samples come back through the pinned PCM buffer
+            check(lib().ptts_batch_step(self._h, _fp(z), _fp(lat), _fp(logit), None))
+            return lat, logit, (self.pcm(0).copy() if want_audio else None)
         audio = np.empty((self.n, self.frame_samples), dtype=np.float32) if want_audio else None
         check(lib().ptts_batch_step(self._h, _fp(z), _fp(lat), _fp(logit), _fp(audio)))
         return lat, logit, audio
+
+    def set_pcm16(self, on: bool = True):
+        """16-bit PCM output: the final-sample kernels also store int16 = trunc(clip(v, -1, 1) * 32767) and host steps
+        copy those out instead of the fp32 samples; read them with pcm(set).  Before the first frame only."""
+        check(lib().ptts_batch_set_pcm16(self._h, 1 if on else 0))
+        self._pcm16 = bool(on)
+        self._pcm_views = {}
+
+    def pcm(self, k: int = 0) -> np.ndarray:
+        """int16 [n, frame_samples] view of the pinned PCM buffer of staging set k."""
+        views = getattr(self, "_pcm_views", None)
+        if views is None:
+            views = self._pcm_views = {}
+        if k not in views:
+            ptr = C.POINTER(C.c_int16)()
+            check(lib().ptts_batch_host_pcm(self._h, int(k), C.byref(ptr)))
+            views[k] = np.ctypeslib.as_array(ptr, shape=(self.n, self.frame_samples))
+        return views[k]
 
     def set_pipelined(self, on: bool = True):
         """Throughput mode: step() then returns the audio of the PREVIOUS frame; flush() decodes the last one."""
@@ -340,6 +366,9 @@ class Batch:
         check(lib().ptts_batch_set_active(self._h, int(slot), 1 if active else 0))
 
     def flush(self, want_audio: bool = True):
+        if getattr(self, "_pcm16", False):
+            check(lib().ptts_batch_flush(self._h, None))
+            return self.pcm(0).copy() if want_audio else None
         audio = np.empty((self.n, self.frame_samples), dtype=np.float32) if want_audio else None
         check(lib().ptts_batch_flush(self._h, _fp(audio)))
         return audio

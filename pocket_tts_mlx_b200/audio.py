@@ -7,11 +7,17 @@ by averaging, polyphase resampling with `scipy.signal.resample_poly`)."""
 from __future__ import annotations
 
 import math
+import os
+import sys
 import wave
+from contextlib import nullcontext
 from pathlib import Path
-from typing import Tuple, Union
+from typing import Any, Iterable, Optional, Tuple, Union
 
 import numpy as np
+
+# seconds of audio held back before the first bytes are written (same environment knob as the reference)
+FIRST_CHUNK_LENGTH_SECONDS = float(os.environ.get("FIRST_CHUNK_LENGTH_SECONDS", "0"))
 
 
 def audio_read(filepath: Union[str, Path]) -> Tuple[np.ndarray, int]:
@@ -62,3 +68,89 @@ def write_wav(path: Union[str, Path], audio: np.ndarray, sample_rate: int) -> No
         f.setsampwidth(2)
         f.setframerate(int(sample_rate))
         f.writeframes((pcm * 32767.0).astype(np.int16).tobytes())
+
+
+# ---- streaming output (reference data/audio.py:48-130) ---------------------------------------------------
+def to_pcm16(chunk: Any) -> np.ndarray:
+    """Float samples -> int16 the way the reference does it (`clip(x, -1, 1) * 32767` truncated, data/audio.py:70).
+    int16 input passes through untouched: with `pcm16=True` the GPU already produced exactly these values in the
+    kernels that make the final samples, so no host conversion is left."""
+    a = np.asarray(chunk)
+    if a.dtype == np.int16:
+        return a.reshape(-1)
+    return (np.clip(a.reshape(-1), -1, 1) * 32767).astype(np.int16)
+
+
+class StreamingWAVWriter:
+    """WAV stream whose length is not known when the header goes out (data/audio.py:48-100): the header announces
+    10^9 frames, PCM is appended with `writeframesraw`, the first bytes can be held back until
+    FIRST_CHUNK_LENGTH_SECONDS of audio exist, `finalize` appends 0.2 s of silence and closes without patching the
+    header (the sink may be a pipe)."""
+
+    PLACEHOLDER_FRAMES = 1_000_000_000
+    TRAILING_SILENCE_SECONDS = 0.2
+
+    def __init__(self, output_stream, sample_rate: int):
+        self.output_stream = output_stream
+        self.sample_rate = int(sample_rate)
+        self.wave_writer: Optional[wave.Wave_write] = None
+        self.first_chunk_buffer: Optional[list] = []
+
+    def write_header(self, sample_rate: Optional[int] = None):
+        if sample_rate is not None:
+            self.sample_rate = int(sample_rate)
+        w = wave.open(self.output_stream, "wb")
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(self.sample_rate)
+        w.setnframes(self.PLACEHOLDER_FRAMES)
+        self.wave_writer = w
+
+    def write_pcm_data(self, audio_chunk: Any):
+        data = to_pcm16(audio_chunk).astype("<i2", copy=False).tobytes()
+        if self.first_chunk_buffer is not None:
+            self.first_chunk_buffer.append(data)
+            held = sum(len(c) for c in self.first_chunk_buffer)
+            if held < int(self.sample_rate * FIRST_CHUNK_LENGTH_SECONDS) * 2:
+                return
+            self._flush()
+            return
+        self.wave_writer.writeframesraw(data)
+
+    def _flush(self):
+        if self.first_chunk_buffer is not None:
+            self.wave_writer.writeframesraw(b"".join(self.first_chunk_buffer))
+            self.first_chunk_buffer = None
+
+    def finalize(self):
+        self._flush()
+        self.wave_writer.writeframesraw(bytes(int(self.sample_rate * self.TRAILING_SILENCE_SECONDS) * 2))
+        self.wave_writer._patchheader = lambda: None      # keep the placeholder length: the sink may not be seekable
+        self.wave_writer.close()
+
+
+def is_file_like(obj) -> bool:
+    return all(hasattr(obj, a) for a in ("write", "close"))
+
+
+def stream_audio_chunks(path, audio_chunks: Iterable[Any], sample_rate: int) -> None:
+    """Drain a chunk generator into a WAV stream: a path, an open binary handle, "-" for stdout, or None to only run
+    the generator (data/audio.py:108-130)."""
+    if path == "-":
+        f = sys.stdout.buffer
+    elif path is None:
+        f = nullcontext()
+    elif is_file_like(path):
+        f = path
+    else:
+        f = open(path, "wb")
+    with f:
+        writer = None
+        if path is not None:
+            writer = StreamingWAVWriter(f, sample_rate)
+            writer.write_header(sample_rate)
+        for chunk in audio_chunks:
+            if writer is not None:
+                writer.write_pcm_data(chunk)
+        if writer is not None:
+            writer.finalize()

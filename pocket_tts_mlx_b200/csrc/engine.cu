@@ -93,6 +93,10 @@ struct Voice {
   int len = 0;
   std::vector<int> pages;
   bool alive = false;
+  // Live batch slots attached to this voice share its full prefix pages: ptts_voice_destroy on a voice that is still
+  // in use only marks it (doomed); the pages go back to the pool when the last slot lets go.
+  int refs = 0;
+  bool doomed = false;
 };
 
 struct FlowWork {
@@ -763,6 +767,16 @@ int take_pages(Ctx& c, int n, std::vector<int>* out) {
   return 0;
 }
 
+void voice_unref(Ctx& c, int id) {
+  if (id < 0 || id >= (int)c.voices.size()) return;
+  Voice& v = c.voices[id];
+  if (v.refs > 0) --v.refs;
+  if (v.refs == 0 && v.doomed) {
+    for (int p : v.pages) c.free_pages.push_back(p);
+    v = Voice{};
+  }
+}
+
 }  // namespace
 
 // ---- batch -----------------------------------------------------------------------------------------------
@@ -771,6 +785,7 @@ struct ptts_batch {
   int B = 0, max_pages = 0;
   std::vector<int> h_len, voice_ids, max_len;
   std::vector<std::vector<int>> slot_pages;     // private KV pages of every sequence slot
+  std::vector<int> slot_voice;                  // voice each slot holds a reference on (-1: none)
   // continuous batching: parked slots (h_active = 0) stop growing; a slot can be re-initialised for a new utterance
   std::vector<int> h_active, h_page_table;
   int* d_active = nullptr;
@@ -815,6 +830,11 @@ struct ptts_batch {
   bool no_tail_env = false;         // PTTS_NO_SNTAIL at creation (a recycled arena must match the current setting)
   int T0 = 0;           // steps per frame at the SEANet input (upsample stride)
   int frame_samples = 0;
+  // 16-bit PCM output: the kernels that produce the final samples also write them as int16, and the
+  // frame's copy-out moves those (half the D2H bytes) instead of the fp32 samples
+  bool pcm16 = false, graphs_pcm = false;
+  short* d_pcm = nullptr;
+  short *h_pcm = nullptr, *h2_pcm = nullptr;
   // pinned staging
   float *h_noise = nullptr, *h_latent = nullptr, *h_logit = nullptr, *h_audio = nullptr;
   // asynchronous staged steps (pipelined mode): odd frames use a second set of pinned buffers, so the host can fill
@@ -952,7 +972,7 @@ void mimi_frame(Batch& bt, const float* latent, bool advance = false) {
     }
   }
   launch_final_conv(bt.d_fin, (long long)(bt.frame_samples + c.fin_taps - 1) * c.fin_c, c.fin_w, c.fin_b, bt.d_audio,
-                    bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream);
+                    bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream, bt.pcm16 ? bt.d_pcm : nullptr);
   launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream, nullptr, 0, nullptr, 0, advance ? bt.d_mimi_off : nullptr, bt.T0);
 }
 
@@ -1007,7 +1027,9 @@ void mimi_frame_tc(Batch& bt, const float* latent, int part, bool advance) {   /
     auto& sb = bt.sb16[r];
     gemm_tc_launch(sb.ct, c.stream);
     if (bt.sn_tail.valid && r + 1 == bt.sb16.size()) {
-      sn_tail_launch(bt.sn_tail, c.stream, false);     // its boundary fix-up rides in the state-shift launch below
+      SnTail tl = bt.sn_tail;
+      tl.pcm = bt.pcm16 ? bt.d_pcm : nullptr;
+      sn_tail_launch(tl, c.stream, false);             // its boundary fix-up rides in the state-shift launch below
       break;
     }
     gemm_tc_launch(sb.r3, c.stream);
@@ -1015,9 +1037,10 @@ void mimi_frame_tc(Batch& bt, const float* latent, int part, bool advance) {   /
   }
   if (!bt.sn_tail.valid)
     launch_final_conv16(bt.d_fin16, (long long)(bt.frame_samples + c.fin_taps - 1) * c.fin_c, c.fin_w, c.fin_b,
-                        bt.d_audio, bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream);
+                        bt.d_audio, bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream,
+                        bt.pcm16 ? bt.d_pcm : nullptr);
   launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream, bt.d_audio, bt.frame_samples, bt.sn_tail.valid ? bt.d_bnd : nullptr,
-                     bt.frame_samples / 128, advance ? bt.d_mimi_off : nullptr, bt.T0);
+                     bt.frame_samples / 128, advance ? bt.d_mimi_off : nullptr, bt.T0, bt.pcm16 ? bt.d_pcm : nullptr);
 }
 
 // flow head on the tensor-core path (M = B rows)
@@ -1277,6 +1300,7 @@ void full_step(Batch& bt, bool host_noise, bool copy_out, bool alt = false) {
   // alt: second set of pinned staging buffers (odd frames of an async-staged batch)
   float *hn = alt ? bt.h2_noise : bt.h_noise, *hl = alt ? bt.h2_latent : bt.h_latent, *hg = alt ? bt.h2_logit : bt.h_logit,
         *ha = alt ? bt.h2_audio : bt.h_audio;
+  short* hp = alt ? bt.h2_pcm : bt.h_pcm;
   if (host_noise)
     cudaMemcpyAsync(bt.d_noise, hn, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
   flow_step(bt, host_noise);
@@ -1285,7 +1309,8 @@ void full_step(Batch& bt, bool host_noise, bool copy_out, bool alt = false) {
   if (copy_out) {
     cudaMemcpyAsync(hl, bt.d_latent, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
     cudaMemcpyAsync(hg, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
-    cudaMemcpyAsync(ha, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+    if (bt.pcm16) cudaMemcpyAsync(hp, bt.d_pcm, (size_t)B * bt.frame_samples * sizeof(short), cudaMemcpyDeviceToHost, c.stream);
+    else cudaMemcpyAsync(ha, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
   }
 }
 
@@ -1304,9 +1329,12 @@ void pipelined_frame(Batch& bt, int parity, bool host_io) {
   const bool alt = bt.async_staging && parity == 1;        // odd frames of an async-staged batch: second buffer set
   float *hn = alt ? bt.h2_noise : bt.h_noise, *hl = alt ? bt.h2_latent : bt.h_latent, *hg = alt ? bt.h2_logit : bt.h_logit,
         *ha = alt ? bt.h2_audio : bt.h_audio;
+  short* hp = alt ? bt.h2_pcm : bt.h_pcm;
   mimi_frame(bt, lat_prev, true);
-  if (host_io)
-    cudaMemcpyAsync(ha, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+  if (host_io) {
+    if (bt.pcm16) cudaMemcpyAsync(hp, bt.d_pcm, (size_t)B * bt.frame_samples * sizeof(short), cudaMemcpyDeviceToHost, c.stream);
+    else cudaMemcpyAsync(ha, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+  }
   cudaEventRecord(c.ev_join, c.stream2);
   c.stream = main;
   if (host_io)
@@ -1332,8 +1360,12 @@ int run_pipelined_step(Batch& bt, bool host_io) {
     if (host_io) {
       CU(cudaMemcpyAsync(bt.h_latent, bt.d_latent, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
       CU(cudaMemcpyAsync(bt.h_logit, bt.d_logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
-      CU(cudaMemsetAsync(bt.d_audio, 0, (size_t)B * bt.frame_samples * sizeof(float), c.stream));
-      CU(cudaMemcpyAsync(bt.h_audio, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+      if (bt.pcm16) {
+        memset(bt.h_pcm, 0, (size_t)B * bt.frame_samples * sizeof(short));
+      } else {
+        CU(cudaMemsetAsync(bt.d_audio, 0, (size_t)B * bt.frame_samples * sizeof(float), c.stream));
+        CU(cudaMemcpyAsync(bt.h_audio, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+      }
     }
   } else {
     const int parity = (int)(bt.frame_idx & 1);
@@ -1420,6 +1452,15 @@ std::vector<StatePiece> mimi_state_pieces(Batch& t) {
     v.push_back({(char*)e.buf, (size_t)e.bs * e.esz, (size_t)e.rows * e.C * e.esz});
   if (t.d_bnd) v.push_back({(char*)t.d_bnd, (size_t)(t.frame_samples / 128 + 1) * 16, 16});
   return v;
+}
+
+// captured frame graphs bake pointers and modes in (staging sets, cascade prefix length, PCM output): drop them all
+void drop_graphs(Batch& t) {
+  for (auto& g : t.step_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  if (t.step_graph_alt) { cudaGraphExecDestroy(t.step_graph_alt); t.step_graph_alt = nullptr; }
+  for (auto& g : t.pipe_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  for (auto& kv : t.mimi_graphs) cudaGraphExecDestroy(kv.second.first);
+  t.mimi_graphs.clear();
 }
 
 int check_step_ready(Batch& bt) {
@@ -1703,8 +1744,14 @@ int32_t ptts_voice_create(ptts_ctx* c, const float* cond, int32_t n_frames) {
 int32_t ptts_voice_destroy(ptts_ctx* c, int32_t id) {
   if (!c || id < 0 || id >= (int)c->voices.size() || !c->voices[id].alive)
     return fail(PTTS_ERR_INVALID, "unknown voice id %d", id);
-  for (int p : c->voices[id].pages) c->free_pages.push_back(p);
-  c->voices[id] = Voice{};
+  Voice& v = c->voices[id];
+  if (v.refs > 0) {        // live slots still read its prefix pages: freed by the last voice_unref
+    v.alive = false;
+    v.doomed = true;
+    return 0;
+  }
+  for (int p : v.pages) c->free_pages.push_back(p);
+  v = Voice{};
   return 0;
 }
 
@@ -1745,8 +1792,14 @@ static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32
   t.frame_idx = 0;
   t.pipelined = false;
   t.async_staging = false;
+  t.pcm16 = false;
+  if (t.graphs_pcm) {          // a recycled arena whose graphs were captured with the PCM output on
+    drop_graphs(t);
+    t.graphs_pcm = false;
+  }
   std::vector<int> pt((size_t)B * maxp, 0), src, dst;
   t.slot_pages.assign(B, {});
+  t.slot_voice.assign(B, -1);
   t.h_active.assign(B, 1);
   t.has_tpl = false;
   for (int b = 0; b < B; ++b) {
@@ -1759,6 +1812,8 @@ static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32
     RET(take_pages(*c, need_pages - full, &mine));
     for (int i = full; i < need_pages; ++i) pt[(size_t)b * maxp + i] = mine[i - full];
     t.slot_pages[b] = mine;
+    t.slot_voice[b] = voice_ids[b];
+    c->voices[voice_ids[b]].refs += 1;
     if (v.len % kPageTokens) {
       src.push_back(v.pages[full]);
       dst.push_back(mine[0]);
@@ -1921,6 +1976,15 @@ static int batch_create_impl(ptts_ctx* c, int32_t B, const int32_t* voice_ids, c
   return batch_init_state(t, voice_ids, max_len);
 }
 
+// give the private KV pages of every slot back to the pool and drop the slots' references on their voices
+static void release_slots(ptts_batch* bt) {
+  Ctx* c = bt->ctx;
+  for (auto& v : bt->slot_pages) for (int p : v) c->free_pages.push_back(p);
+  bt->slot_pages.clear();
+  for (int v : bt->slot_voice) voice_unref(*c, v);
+  bt->slot_voice.clear();
+}
+
 static void batch_free(ptts_batch* bt) {
   Ctx* c = bt->ctx;
   for (auto& g : bt->step_graph) if (g) cudaGraphExecDestroy(g);
@@ -1933,8 +1997,10 @@ static void batch_free(ptts_batch* bt) {
   if (bt->d_audio_all) cudaFree(bt->d_audio_all);
   cudaFreeHost(bt->h_noise); cudaFreeHost(bt->h_latent); cudaFreeHost(bt->h_logit); cudaFreeHost(bt->h_audio);
   if (bt->h2_noise) { cudaFreeHost(bt->h2_noise); cudaFreeHost(bt->h2_latent); cudaFreeHost(bt->h2_logit); cudaFreeHost(bt->h2_audio); }
+  if (bt->h_pcm) cudaFreeHost(bt->h_pcm);
+  if (bt->h2_pcm) cudaFreeHost(bt->h2_pcm);
   for (auto& e : bt->ev_set) if (e) cudaEventDestroy(e);
-  for (auto& v : bt->slot_pages) for (int p : v) c->free_pages.push_back(p);
+  release_slots(bt);
   if (bt->mimi_tpl) cudaFree(bt->mimi_tpl);
   delete bt;
 }
@@ -1944,8 +2010,7 @@ void ptts_batch_destroy(ptts_batch* bt) {
   Ctx* c = bt->ctx;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (auto& v : bt->slot_pages) for (int p : v) c->free_pages.push_back(p);
-  bt->slot_pages.clear();
+  release_slots(bt);
   bt->prefilled = false;
   if (!bt->h_audio || !bt->d_counter) {   // partially constructed: cannot be recycled
     batch_free(bt);
@@ -2052,8 +2117,16 @@ static int reset_seq_impl(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_
   const int need_pages = (max_len + kPageTokens - 1) / kPageTokens;
   if (need_pages > t.max_pages)
     return fail(PTTS_ERR_INVALID, "max_len %d needs %d KV pages, the batch was created for %d", max_len, need_pages, t.max_pages);
-  if (t.fw.prefix_len > 0 && voice_id != t.voice_ids[0])
-    return fail(PTTS_ERR_STATE, "this batch attends its shared voice prefix once for all sequences; a slot cannot switch voice");
+  if (t.fw.prefix_len > 0 && voice_id != t.voice_ids[0]) {
+    // The batch attends its shared voice prefix once for all sequences (cascade); a slot that switches voice ends
+    // that: fall back to the plain per-sequence attention.  The page tables already cover every sequence's whole
+    // prefix, so only the prefix length baked into the captured graphs has to go.
+    t.fw.prefix_len = 0;
+    t.cascade_len = 0;
+    for (auto& g : t.step_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    if (t.step_graph_alt) { cudaGraphExecDestroy(t.step_graph_alt); t.step_graph_alt = nullptr; }
+    for (auto& g : t.pipe_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  }
   // KV: give the old private pages back, share the voice's full pages, copy its partial tail page
   const int full = v.len / kPageTokens;
   if ((int)(c.free_pages.size() + t.slot_pages[slot].size()) < need_pages - full)   // checked first: the slot keeps its pages on failure
@@ -2076,6 +2149,11 @@ static int reset_seq_impl(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_
     CU(cudaMemcpyAsync(t.d_cp_dst + slot, &dp, 4, cudaMemcpyHostToDevice, c.stream));
     launch_copy_pages(c.pool, c.bf16, c.layer_stride, c.page_stride, c.cfg.n_layers, t.d_cp_src + slot, t.d_cp_dst + slot, 1,
                       c.stream);
+  }
+  if (t.slot_voice[slot] != voice_id) {
+    c.voices[voice_id].refs += 1;          // take the new reference first: v must stay valid below
+    voice_unref(c, t.slot_voice[slot]);
+    t.slot_voice[slot] = voice_id;
   }
   t.voice_ids[slot] = voice_id;
   t.max_len[slot] = max_len;
@@ -2139,8 +2217,12 @@ int32_t ptts_batch_step(ptts_batch* bt, const float* noise, float* out_latent, f
   Ctx& c = *bt->ctx;
   CU(cudaSetDevice(c.device));
   RET(check_step_ready(*bt));
+  if (bt->async_staging)
+    return fail(PTTS_ERR_STATE, "async staging is on: frames alternate between two staging sets, use ptts_batch_step_staged_async");
+  if (bt->pcm16 && out_audio)
+    return fail(PTTS_ERR_INVALID, "16-bit PCM output is on: pass out_audio = NULL and read ptts_batch_host_pcm");
   const int B = bt->B, L = c.cfg.latent_dim;
-  const bool copy_out = out_latent || out_eos_logit || out_audio;
+  const bool copy_out = out_latent || out_eos_logit || out_audio || bt->pcm16;
   if (noise) memcpy(bt->h_noise, noise, (size_t)B * L * 4);
   if (bt->pipelined) {
     if (!noise) return fail(PTTS_ERR_INVALID, "pipelined host steps take host noise (use ptts_batch_step_device otherwise)");
@@ -2170,6 +2252,8 @@ int32_t ptts_batch_step_staged(ptts_batch* bt) {
   Ctx& c = *bt->ctx;
   CU(cudaSetDevice(c.device));
   RET(check_step_ready(*bt));
+  if (bt->async_staging)
+    return fail(PTTS_ERR_STATE, "async staging is on: frames alternate between two staging sets, use ptts_batch_step_staged_async");
   if (bt->pipelined) {
     RET(run_pipelined_step(*bt, true));
   } else {
@@ -2193,6 +2277,7 @@ int32_t ptts_batch_set_async_staging(ptts_batch* bt, int32_t on) {
     CU(cudaMallocHost((void**)&bt->h2_audio, (size_t)B * bt->frame_samples * 4));
     for (auto& e : bt->ev_set) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
+  if (on && bt->pcm16 && !bt->h2_pcm) CU(cudaMallocHost((void**)&bt->h2_pcm, (size_t)bt->B * bt->frame_samples * sizeof(short)));
   bt->async_staging = on != 0;
   if (bt->graphs_async != bt->async_staging) {        // the host pointers are baked into the captured copy nodes
     for (auto& g : bt->pipe_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
@@ -2255,6 +2340,33 @@ int32_t ptts_batch_set_pipelined(ptts_batch* bt, int32_t on) {
   return 0;
 }
 
+int32_t ptts_batch_set_pcm16(ptts_batch* bt, int32_t on) {
+  if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
+  Ctx& c = *bt->ctx;
+  CU(cudaSetDevice(c.device));
+  if (bt->frame_idx != 0) return fail(PTTS_ERR_STATE, "the PCM output can only be switched before the first frame");
+  const size_t n = (size_t)bt->B * bt->frame_samples;
+  if (on && !bt->d_pcm) {
+    RET(bt->dalloc((void**)&bt->d_pcm, n * sizeof(short)));
+    CU(cudaMallocHost((void**)&bt->h_pcm, n * sizeof(short)));
+  }
+  if (on && bt->h2_noise && !bt->h2_pcm) CU(cudaMallocHost((void**)&bt->h2_pcm, n * sizeof(short)));
+  bt->pcm16 = on != 0;
+  if (bt->graphs_pcm != bt->pcm16) {
+    drop_graphs(*bt);
+    bt->graphs_pcm = bt->pcm16;
+  }
+  return 0;
+}
+
+int32_t ptts_batch_host_pcm(ptts_batch* bt, int32_t set, int16_t** pcm) {
+  if (!bt || !pcm) return fail(PTTS_ERR_INVALID, "null argument");
+  short* p = set == 0 ? bt->h_pcm : (set == 1 ? bt->h2_pcm : nullptr);
+  if (!p) return fail(PTTS_ERR_STATE, "PCM buffer set %d is not allocated (ptts_batch_set_pcm16 / ptts_batch_set_async_staging)", set);
+  *pcm = reinterpret_cast<int16_t*>(p);
+  return 0;
+}
+
 int32_t ptts_batch_flush(ptts_batch* bt, float* out_audio) {
   if (!bt) return fail(PTTS_ERR_INVALID, "null batch");
   Ctx& c = *bt->ctx;
@@ -2262,9 +2374,13 @@ int32_t ptts_batch_flush(ptts_batch* bt, float* out_audio) {
   if (!bt->pipelined || bt->frame_idx == 0) return fail(PTTS_ERR_STATE, "nothing to flush");
   // decode the latent of the last stepped frame (it sits in the buffer of parity (frame_idx-1)&1)
   const float* lat = ((bt->frame_idx - 1) & 1) ? bt->d_latent_b : bt->d_latent;
+  if (bt->pcm16 && out_audio)
+    return fail(PTTS_ERR_INVALID, "16-bit PCM output is on: pass out_audio = NULL and read ptts_batch_host_pcm (set 0)");
   mimi_frame(*bt, lat, true);
   if (out_audio)
     CU(cudaMemcpyAsync(bt->h_audio, bt->d_audio, (size_t)bt->B * bt->frame_samples * 4, cudaMemcpyDeviceToHost, c.stream));
+  if (bt->pcm16)
+    CU(cudaMemcpyAsync(bt->h_pcm, bt->d_pcm, (size_t)bt->B * bt->frame_samples * sizeof(short), cudaMemcpyDeviceToHost, c.stream));
   CU(cudaStreamSynchronize(c.stream));
   CU(cudaGetLastError());
   if (out_audio) memcpy(out_audio, bt->h_audio, (size_t)bt->B * bt->frame_samples * 4);

@@ -95,6 +95,7 @@ struct SnTail {
   const float *b1 = nullptr, *b2 = nullptr, *wf = nullptr, *bf = nullptr;
   float* audio = nullptr; long long audio_bs = 0;
   float* bnd = nullptr;
+  short* pcm = nullptr;       // optional int16 PCM output (same strides as audio)
   bool valid = false;
 };
 bool sn_tail_plan(SnTail* p, const __nv_bfloat16* xe, const __nv_bfloat16* xraw, int nb, int T, int C, int hidden,

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace ptts {
 
 constexpr int kHeadDim = 64;      // both transformers use 64-wide heads (b6369a24.yaml)
@@ -147,16 +149,18 @@ void launch_quant_upsample(const float* lat, const float* emb_std, const float* 
                            const float* wu, float* zprev, float* out, long long out_bs, int B, int L, int C,
                            int S, cudaStream_t s);
 // audio[b,t] = bias + sum_{j<taps} sum_c elu(x~[b,t+j,c]) w[j*C+c]      (SEANet last conv, N = 1)
+// pcm (optional, same indexing as audio): the sample as 16-bit PCM, clip(v, -1, 1) * 32767 truncated toward zero --
+// the conversion of the reference's StreamingWAVWriter.write_pcm_data (data/audio.py:64-70) done where the sample is made
 void launch_final_conv(const float* x, long long x_bs, const float* w, const float* bias, float* audio,
-                       long long audio_bs, int B, int T, int C, int taps, cudaStream_t s);
+                       long long audio_bs, int B, int T, int C, int taps, cudaStream_t s, short* pcm = nullptr);
 // same with a bf16 input that already went through ELU in the producer's epilogue
 void launch_final_conv16(const __nv_bfloat16* x, long long x_bs, const float* w, const float* bias, float* audio,
-                         long long audio_bs, int B, int T, int C, int taps, cudaStream_t s);
+                         long long audio_bs, int B, int T, int C, int taps, cudaStream_t s, short* pcm = nullptr);
 // carried conv state: move the last `rows` time rows of each sequence's buffer to its front
 struct ShiftEntry { void* buf; long long bs; int T, rows, C, esz; };   // bs in elements, esz = bytes/element
 void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s, float* audio = nullptr,
                         long long audio_bs = 0, float* bnd = nullptr, int tiles_t = 0, int* mimi_offset = nullptr,
-                        int inc_mimi = 0);
+                        int inc_mimi = 0, short* pcm = nullptr);
 // seq_len += inc_len; bos_flag = 0; mimi_offset += inc_mimi; philox counter += 1
 void launch_advance(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter, int B,
                     int inc_len, int inc_mimi, cudaStream_t s, const int* active = nullptr);
@@ -174,7 +178,7 @@ void launch_inc(int* v, int inc, cudaStream_t s);
 // launch accounting (ptts_launch_count) and the eager per-kernel profiler (ptts_batch_profile_step):
 // every launcher opens a ProfScope; when profiling is on it brackets the launch with CUDA events on the
 // launching stream and books the ALGORITHMIC flops / bytes of that launch under "kernel:tag".
-extern long long g_launches;
+extern std::atomic<long long> g_launches;   // process-wide: contexts may be driven from different threads
 extern bool g_prof_on;
 struct ProfScope {
   int slot = -1;
@@ -191,7 +195,7 @@ const char* prof_report();
 // its predecessor in the stream / graph is still draining.  Kernels call pdl_trigger() first (lets THEIR
 // successor be scheduled early) and pdl_wait() before the first access to global memory that the predecessor
 // may have written (griddepcontrol.wait returns once the predecessor grid has completed and flushed).
-extern bool g_pdl_on;   // PTTS_NO_PDL=1 turns the launch attribute off (the device calls are then no-ops)
+extern std::atomic<bool> g_pdl_on;   // PTTS_NO_PDL=1 turns the launch attribute off (the device calls are then no-ops)
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
@@ -215,6 +219,11 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     case ACT_ELU: return v > 0.0f ? v : expm1f(v);
     default: return v;
   }
+}
+
+// float sample -> 16-bit PCM exactly as NumPy does it in the reference: (clip(v, -1, 1) * 32767).astype(int16)
+__device__ __forceinline__ short pcm16_of(float v) {
+  return (short)__float2int_rz(fminf(fmaxf(v, -1.0f), 1.0f) * 32767.0f);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

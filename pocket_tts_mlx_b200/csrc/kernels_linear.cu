@@ -8,8 +8,8 @@
 
 namespace ptts {
 
-long long g_launches = 0;
-bool g_pdl_on = false;
+std::atomic<long long> g_launches{0};
+std::atomic<bool> g_pdl_on{false};
 
 namespace {
 

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(128) final_conv_kernel(const XT* __restrict__ 
                                                          const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          float* __restrict__ audio, long long audio_bs,
-                                                         int T, int C, int taps) {
+                                                         int T, int C, int taps, short* __restrict__ pcm) {
   pdl_sync();
   extern __shared__ float sm[];
   float* ws = sm;                       // [taps*C]
@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(128) final_conv_kernel(const XT* __restrict__ 
     for (int c = 0; c < C; ++c) a = fmaf(xr[c], wr[c], a);
   }
   audio[b * audio_bs + t] = a;
+  if (pcm) pcm[b * audio_bs + t] = pcm16_of(a);
 }
 
 // End-of-frame bookkeeping of the Mimi decoder in one launch: blockIdx.y < n_entries moves the last taps-1 rows of a
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(128) final_conv_kernel(const XT* __restrict__ 
 // and advances the sequence's ring offset.
 __global__ void state_shift_kernel(const ShiftEntry* __restrict__ entries, int n_entries, float* __restrict__ audio,
                                    long long audio_bs, float* __restrict__ bnd, int tiles_t,
-                                   int* __restrict__ mimi_offset, int inc_mimi) {
+                                   int* __restrict__ mimi_offset, int inc_mimi, short* __restrict__ pcm) {
   pdl_sync();
   const int b = blockIdx.x;
   if ((int)blockIdx.y == n_entries) {
@@ -382,8 +383,14 @@ __global__ void state_shift_kernel(const ShiftEntry* __restrict__ entries, int n
       for (int k = threadIdx.x; k < tiles_t; k += blockDim.x) {
         const float* slot = bnd + ((long long)b * (tiles_t + 1) + k) * 4;
         float* a = audio + b * audio_bs + (long long)k * 128;
-        a[0] += slot[0] + slot[2];
-        a[1] += slot[1];
+        const float a0 = a[0] + slot[0] + slot[2], a1 = a[1] + slot[1];
+        a[0] = a0;
+        a[1] = a1;
+        if (pcm) {                                  // the tail kernel converted every other sample of the tile
+          short* q = pcm + b * audio_bs + (long long)k * 128;
+          q[0] = pcm16_of(a0);
+          q[1] = pcm16_of(a1);
+        }
       }
       __syncthreads();
       if (threadIdx.x < 3) {
@@ -646,30 +653,30 @@ void launch_quant_upsample(const float* lat, const float* emb_std, const float* 
 }
 
 void launch_final_conv(const float* x, long long x_bs, const float* w, const float* bias, float* audio,
-                       long long audio_bs, int B, int T, int C, int taps, cudaStream_t s) {
+                       long long audio_bs, int B, int T, int C, int taps, cudaStream_t s, short* pcm) {
   ProfScope ps("final_conv", nullptr, 0, (double)B * T * (C + 1) * 4, s);
   const size_t smem = (size_t)(taps * C + (128 + taps - 1) * (C + 1)) * sizeof(float);
   dim3 grid((T + 127) / 128, B);
-  launch_k(final_conv_kernel<float, true>, dim3(grid), dim3(128), smem, s, x, x_bs, w, bias, audio, audio_bs, T, C, taps);
+  launch_k(final_conv_kernel<float, true>, dim3(grid), dim3(128), smem, s, x, x_bs, w, bias, audio, audio_bs, T, C, taps, pcm);
   ++g_launches;
 }
 
 void launch_final_conv16(const __nv_bfloat16* x, long long x_bs, const float* w, const float* bias, float* audio,
-                         long long audio_bs, int B, int T, int C, int taps, cudaStream_t s) {
+                         long long audio_bs, int B, int T, int C, int taps, cudaStream_t s, short* pcm) {
   ProfScope ps("final_conv", nullptr, 0, (double)B * T * (C / 2 + 1) * 4, s);
   const size_t smem = (size_t)(taps * C + (128 + taps - 1) * (C + 1)) * sizeof(float);
   dim3 grid((T + 127) / 128, B);
-  launch_k(final_conv_kernel<__nv_bfloat16, false>, dim3(grid), dim3(128), smem, s, x, x_bs, w, bias, audio, audio_bs, T, C, taps);
+  launch_k(final_conv_kernel<__nv_bfloat16, false>, dim3(grid), dim3(128), smem, s, x, x_bs, w, bias, audio, audio_bs, T, C, taps, pcm);
   ++g_launches;
 }
 
 void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cudaStream_t s, float* audio,
-                        long long audio_bs, float* bnd, int tiles_t, int* mimi_offset, int inc_mimi) {
+                        long long audio_bs, float* bnd, int tiles_t, int* mimi_offset, int inc_mimi, short* pcm) {
   ProfScope ps("state_shift", nullptr, 0, 0, s);
   const bool extra = bnd || mimi_offset;
   dim3 grid(B, n_entries + (extra ? 1 : 0));
   launch_k(state_shift_kernel, dim3(grid), dim3(256), 0, s, entries_dev, n_entries, audio, audio_bs, bnd, tiles_t, mimi_offset,
-           inc_mimi);
+           inc_mimi, pcm);
   ++g_launches;
 }
 

@@ -45,6 +45,7 @@ struct TailArgs {
   float* audio;
   long long audio_bs;
   float* bnd;
+  short* pcm;            // optional 16-bit PCM copy of the samples (samples 0, 1 of a tile are finished by the fix-up)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) sn_tail_kernel(const __grid_c
         if (r >= 2) out += pa[r - 2] + pb[r - 2] + pa[128 + r - 1] + pb[128 + r - 1];
         else if (r == 1) out += pa[128] + pb[128];
         g.audio[b * g.audio_bs + t0 + r] = out;
+        if (g.pcm) g.pcm[b * g.audio_bs + t0 + r] = pcm16_of(out);
         if (r == 127) {
           float* bd = g.bnd + ((long long)b * (g.tiles_t + 1) + tt + 1) * 4;
           bd[0] = pa[126] + pb[126]; bd[1] = pa[127] + pb[127]; bd[2] = pa[255] + pb[255];
@@ -374,7 +376,7 @@ void sn_tail_launch(const SnTail& p, cudaStream_t s, bool with_fix) {
   TailArgs a;
   a.nb = p.nb; a.T = p.T; a.tiles_t = p.T / 128; a.total_tiles = p.nb * a.tiles_t;
   a.b1 = p.b1; a.b2 = p.b2; a.wf = p.wf; a.bf = p.bf;
-  a.audio = p.audio; a.audio_bs = p.audio_bs; a.bnd = p.bnd;
+  a.audio = p.audio; a.audio_bs = p.audio_bs; a.bnd = p.bnd; a.pcm = p.pcm;
   {
     const double rows = (double)p.nb * p.T;
     ProfScope ps("sn_tail", nullptr, 2.0 * rows * (192.0 * 32 + 32.0 * 64 + 192.0), rows * (64 * 2 * 2 + 4), s);

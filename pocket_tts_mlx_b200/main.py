@@ -37,6 +37,9 @@ def main(argv=None) -> int:
     p.add_argument("--verbose", "-V", action="store_true", help="Verbose logging")
     p.add_argument("--config", default=None, help="(extension) model variant name or .yaml path")
     p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="(extension) storage precision")
+    p.add_argument("--stream", action="store_true",
+                   help="(extension) write the WAV while generating (16-bit PCM converted on the GPU, placeholder-length "
+                        "header, 0.2 s trailing silence); implied by --output -  (stdout)")
     args = p.parse_args(argv)
     logging.basicConfig(level=logging.DEBUG if args.verbose else logging.INFO, format="%(message)s")
     try:
@@ -45,6 +48,16 @@ def main(argv=None) -> int:
         logger.info("Loading voice: %s", args.voice)
         state = model.get_state_for_audio_prompt(args.voice)
         logger.info("Generating audio...")
+        if args.stream or args.output == "-":
+            # streaming sink of the reference's data/audio.py:108-130; trim / fade need the whole waveform and are skipped
+            from .audio import stream_audio_chunks
+            if args.output != "-":
+                Path(args.output).parent.mkdir(parents=True, exist_ok=True)
+            chunks = model.generate_audio_stream(model_state=state, text_to_generate=args.text, max_tokens=args.max_tokens,
+                                                 frames_after_eos=args.frames_after_eos, warmup_frames=args.warmup_frames,
+                                                 pcm16=True)
+            stream_audio_chunks(args.output, chunks, model.config.mimi.sample_rate)
+            return 0
         audio = model.generate_audio(model_state=state, text_to_generate=args.text, max_tokens=args.max_tokens,
                                      frames_after_eos=args.frames_after_eos, trim_start_ms=args.trim_start_ms,
                                      fade_in_ms=args.fade_in_ms, warmup_frames=args.warmup_frames)

@@ -17,6 +17,9 @@ from __future__ import annotations
 import logging
 import os
 import time
+import weakref
+from collections import OrderedDict
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 from typing import Dict, Generator, List, Optional, Sequence, Union
 
@@ -51,6 +54,32 @@ VOICE_CLONING_UNSUPPORTED = (
 )
 
 
+class VoiceHandle:
+    """Owner of one voice's KV prefix pages on the GPU.  The reference's model state is a dict that the garbage
+    collector frees; here the state dict carries this handle, and when the last state (or copy of it) that refers
+    to the handle dies, the pages go back to the pool (`ptts_voice_destroy`; slots of live batches that still attend
+    the prefix keep it alive on the C side).  `copy.deepcopy(state)` shares the handle: the prefix is immutable."""
+
+    def __init__(self, ctx: "_native.Context", voice_id: int):
+        self.voice_id = int(voice_id)
+        self._fin = weakref.finalize(self, VoiceHandle._release, weakref.ref(ctx), self.voice_id)
+
+    @staticmethod
+    def _release(ctx_ref, voice_id):
+        ctx = ctx_ref()
+        if ctx is not None and ctx._h:
+            try:
+                ctx.voice_destroy(voice_id)
+            except Exception:      # the context may already be closing
+                pass
+
+    def __deepcopy__(self, memo):
+        return self
+
+    def __copy__(self):
+        return self
+
+
 class TTSModel:
     _TOKENS_PER_SECOND_ESTIMATE = 3.0
     _GEN_SECONDS_PADDING = 2.0
@@ -69,7 +98,7 @@ class TTSModel:
         self._ctx = ctx
         self._tokenizer = tokenizer
         self._weights_file = Path(weights_file)
-        self._voice_cache: Dict[str, Dict] = {}
+        self._state_cache: "OrderedDict" = OrderedDict()     # _cached_get_state_for_audio_prompt (LRU, 2 entries)
 
     # ------------------------------------------------------------------ properties
     @property
@@ -150,7 +179,22 @@ class TTSModel:
         t0 = time.monotonic()
         vid = self._ctx.voice_create(cond)
         logger.info("Prompting audio took %d ms", int((time.monotonic() - t0) * 1000))
-        return {"voice_id": vid, "prompt_len": int(cond.shape[0])}
+        return {"voice_id": vid, "prompt_len": int(cond.shape[0]), "_handle": VoiceHandle(self._ctx, vid)}
+
+    def _cached_get_state_for_audio_prompt(self, audio_conditioning, truncate: bool = False) -> Dict:
+        """The reference's `lru_cache(maxsize=2)` variant (models/tts_model.py:478-482): repeated prompts (a server that
+        speaks with the same few voices) reuse the prefilled state instead of prefilling -- and pinning KV pages -- again.
+        Keys are hashable prompts only (voice names, paths), like the reference's."""
+        key = (str(audio_conditioning) if isinstance(audio_conditioning, Path) else audio_conditioning, bool(truncate))
+        hash(key)
+        if key in self._state_cache:
+            self._state_cache.move_to_end(key)
+            return self._state_cache[key]
+        state = self.get_state_for_audio_prompt(audio_conditioning, truncate)
+        self._state_cache[key] = state
+        while len(self._state_cache) > 2:
+            self._state_cache.popitem(last=False)     # the evicted state's pages are freed once nobody holds it
+        return state
 
     def get_state_for_audio_prompt(self, audio_conditioning, truncate: bool = False) -> Dict:
         if isinstance(audio_conditioning, str) and audio_conditioning in PREDEFINED_VOICES:
@@ -210,7 +254,13 @@ class TTSModel:
     def generate_audio_stream(self, model_state: Dict, text_to_generate: str, max_tokens: int = MAX_TOKEN_PER_CHUNK,
                               frames_after_eos: Optional[int] = None, copy_state: bool = True,
                               warmup_frames: int = _MIMI_WARMUP_FRAMES, *, noise: Optional[np.ndarray] = None,
-                              seed: Optional[int] = None) -> Generator[np.ndarray, None, None]:
+                              seed: Optional[int] = None, pcm16: bool = False) -> Generator[np.ndarray, None, None]:
+        """Yields one 1920-sample frame at a time.  pcm16=True yields int16 frames converted on the GPU in the kernels
+        that produce the samples (the format `StreamingWAVWriter` / `stream_audio_chunks` write, data/audio.py:64-70)."""
+        if not copy_state:
+            # the reference appends the utterance to the passed state (later calls then attend to it); here a voice
+            # prefix is immutable shared KV pages, so every chunk starts from the prefix alone
+            logger.warning("copy_state=False is not supported: the voice state is immutable and is never modified")
         chunks = split_into_best_sentences(self._tokenizer, text_to_generate, max_tokens)
         noise_rows = None if noise is None else np.asarray(noise, dtype=np.float32).reshape(-1, self._ctx.config.latent_dim)
         cursor = 0
@@ -220,11 +270,11 @@ class TTSModel:
             sub_noise = None if noise_rows is None else noise_rows[cursor:]
             used = [0]
             yield from self._generate_chunk(model_state, chunk, effective, warmup_frames, sub_noise,
-                                            None if seed is None else seed + ci, used)
+                                            None if seed is None else seed + ci, used, pcm16)
             cursor += used[0]
 
     def _generate_chunk(self, model_state: Dict, chunk: str, frames_after_eos: int, warmup_frames: int,
-                        noise_rows: Optional[np.ndarray], seed: Optional[int], used: List[int]):
+                        noise_rows: Optional[np.ndarray], seed: Optional[int], used: List[int], pcm16: bool = False):
         tokens = self._tokenizer.encode(chunk)
         n_tok = int(tokens.shape[0])
         max_gen_len = self._estimate_max_gen_len(n_tok)
@@ -234,6 +284,8 @@ class TTSModel:
             if seed is None:
                 seed = int(np.random.SeedSequence().entropy % (1 << 63))
             batch.seed(seed)
+            if pcm16:
+                batch.set_pcm16(True)
             batch.warmup_mimi(warmup_frames)
             t_gen = time.monotonic()
             batch.prefill_text([tokens])
@@ -265,14 +317,19 @@ class TTSModel:
                              frames_after_eos: Union[int, Sequence[int]] = 3,
                              warmup_frames: int = _MIMI_WARMUP_FRAMES, max_frames: Optional[int] = None,
                              noise: Optional[np.ndarray] = None, seed: int = 0,
-                             return_latents: bool = False, pipelined: bool = True):
+                             return_latents: bool = False, pipelined: bool = True, pcm16: bool = False):
         """Lock-step generation of many single-chunk utterances (token ids already prepared).
+
+        pcm16=True returns int16 waveforms (`trunc(clip(x, -1, 1) * 32767)`, the reference's streaming-WAV sample
+        format, data/audio.py:70) converted on the GPU where the samples are produced; half the device->host bytes.
 
         noise: optional [1 + max_frames, n, latent_dim] (row 0 is the unused text-prefill draw, as in the
         reference); without it the host draws N(0,1) from `seed`.  pipelined=True overlaps the Mimi decode of
         frame t-1 with the FlowLM step of frame t on the GPU (same results, audio arrives one step later).
         Returns a list of 1-D float32 waveforms (and per-sequence latents when asked)."""
         n = len(model_states)
+        if n == 0:
+            return ([], []) if return_latents else []
         fae = [frames_after_eos] * n if isinstance(frames_after_eos, int) else list(frames_after_eos)
         n_tok = [len(t) for t in token_ids]
         limits = [self._estimate_max_gen_len(k) for k in n_tok]
@@ -289,6 +346,8 @@ class TTSModel:
             if pipelined:
                 batch.set_pipelined(True)
                 batch.set_async_staging(True)
+            if pcm16:
+                batch.set_pcm16(True)
             batch.warmup_mimi(warmup_frames)
             batch.prefill_text(token_ids)
             # Lock-step bookkeeping on whole arrays: every sequence accepts frames 0 .. n_acc-1, so the per-step
@@ -301,13 +360,21 @@ class TTSModel:
             n_steps = int(lim.max()) if n else 0
             # sequence-major output arrays: step blocks are written straight into them, and a sequence's waveform /
             # latents are a contiguous slice (returned as a view, no concatenation at the end)
-            aud_all = np.empty((n, n_steps, self.frame_samples), dtype=np.float32)
+            aud_all = np.empty((n, n_steps, self.frame_samples), dtype=np.int16 if pcm16 else np.float32)
             lat_all = np.empty((n, n_steps, ldim), dtype=np.float32)
             counts = {"lat": 0, "audio": 0}
             thr = self.eos_threshold
+            # A frame's [n, 1920] block becomes column `k` of the sequence-major array: an n-way strided scatter into
+            # memory that is touched for the first time (page faults).  For large batches that is ~1 ms of host work per
+            # frame, so it is taken off the thread that feeds the GPU: the block is copied (contiguously) out of the
+            # pinned staging buffer into a small ring and worker threads scatter it.
+            scatter = _BlockScatter(aud_all) if n * self.frame_samples * aud_all.itemsize >= (1 << 19) else None
 
             def put_audio(block):
-                aud_all[:, counts["audio"], :] = block
+                if scatter is not None:
+                    scatter.put(counts["audio"], block)
+                else:
+                    aud_all[:, counts["audio"], :] = block
                 counts["audio"] += 1
 
             def account(step, lat, logit):
@@ -329,6 +396,7 @@ class TTSModel:
             if pipelined:
                 # frame s is enqueued before frame s-1 is read back: the GPU never waits for the host
                 sets = batch.staging_sets()
+                aud_of = (lambda k: batch.pcm(k)) if pcm16 else (lambda k: sets[k][3])
                 enq = 0
                 for step in range(n_steps):
                     zbuf = sets[step & 1][0]
@@ -342,7 +410,7 @@ class TTSModel:
                         k = (step - 1) & 1
                         batch.staged_wait(k)
                         if step >= 2:
-                            put_audio(sets[k][3])                            # audio of frame step-2
+                            put_audio(aud_of(k))                             # audio of frame step-2
                         account(step - 1, sets[k][1], sets[k][2].copy())
                         if done.all():
                             break
@@ -350,7 +418,7 @@ class TTSModel:
                     k = (enq - 1) & 1
                     batch.staged_wait(k)
                     if enq >= 2:
-                        put_audio(sets[k][3])                                # audio of frame enq-2
+                        put_audio(aud_of(k))                                 # audio of frame enq-2
                     if not done.all():
                         account(enq - 1, sets[k][1], sets[k][2].copy())
                     if counts["audio"] < counts["lat"]:
@@ -364,12 +432,17 @@ class TTSModel:
                     account(step, lat, logit)
                     if done.all():
                         break
+            if scatter is not None:
+                scatter.close()
+                scatter = None
             waves = [aud_all[b, :int(n_acc[b])].reshape(-1) for b in range(n)]
             lats = [lat_all[b, :int(n_acc[b])] for b in range(n)]
             if return_latents:
                 return waves, lats
             return waves
         finally:
+            if scatter is not None:
+                scatter.close()
             batch.close()
 
     def generate_audio_continuous(self, model_states: Sequence[Dict], token_ids: Sequence[Sequence[int]],
@@ -489,22 +562,14 @@ class TTSModel:
                     free.append(int(s_))
                     state["live"] -= 1
 
-            import os as _os, time as _t
-            prof = {"enqueue": 0.0, "process": 0.0, "admit": 0.0, "rounds": 0}
             inflight = None
             while state["live"] > 0 or inflight is not None:
-                _t0 = _t.perf_counter()
                 nxt = enqueue() if state["live"] > 0 else None
-                _t1 = _t.perf_counter()
                 if inflight is not None:
                     process(inflight)
-                _t2 = _t.perf_counter()
-                prof["enqueue"] += _t1 - _t0
-                prof["process"] += _t2 - _t1
                 inflight = nxt
                 pending = n_jobs - next_job
                 if pending > 0 and free and (len(free) >= min(group, pending) or state["live"] == 0):
-                    prof["rounds"] += 1
                     if inflight is not None:              # drain before slots are re-initialised
                         process(inflight)
                         inflight = None
@@ -520,25 +585,60 @@ class TTSModel:
                         toks[s_] = token_ids[j]
                     batch.prefill_text(toks)
                     state["live"] += len(take)
-                    prof["admit"] += _t.perf_counter() - _t2
-            _t3 = _t.perf_counter()
             waves, lats = [], []
             for j in range(n_jobs):
                 s_, t0, k = int(slot_of[j]), int(t0_of[j]), int(n_of[j])
                 waves.append(aud[s_, t0:t0 + k].reshape(-1))
                 lats.append(lat_b[s_, t0:t0 + k])
-            if _os.environ.get("PTTS_SCHED_PROFILE"):
-                prof["gather"] = _t.perf_counter() - _t3
-                prof["steps"] = state["enq"]
-                print("scheduler profile:", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in prof.items()})
             if return_latents:
                 return waves, lats
             return waves
         finally:
             batch.close()
 
+    def generate_audio_sharded(self, model_states: Sequence[Dict], token_ids: Sequence[Sequence[int]], *,
+                               rank: Optional[int] = None, world_size: Optional[int] = None, slots: int = 256,
+                               gather: bool = False, **kwargs):
+        """Multi-GPU entry point (one process per GPU, e.g. under torchrun): decode this rank's share of the utterance
+        set on this model's GPU; see `sharding.generate_sharded`.  rank / world_size default to the launcher's
+        environment (RANK / WORLD_SIZE)."""
+        from .sharding import dist_env, generate_sharded
+        w, r, _ = dist_env()
+        return generate_sharded(self, model_states, token_ids, rank=r if rank is None else rank,
+                                world_size=w if world_size is None else world_size, slots=slots, gather=gather, **kwargs)
+
     def close(self):
+        self._state_cache.clear()
         self._ctx.close()
+
+
+class _BlockScatter:
+    """Writes per-frame blocks [n, w] into column k of a sequence-major array [n, steps, w] on worker threads."""
+
+    RING = 8
+
+    def __init__(self, dst: np.ndarray, workers: int = 3):
+        self.dst = dst
+        self.ring = np.empty((self.RING,) + (dst.shape[0], dst.shape[2]), dtype=dst.dtype)
+        self.futs = [None] * self.RING
+        self.pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="ptts-scatter")
+
+    def _scatter(self, k: int, slot: int):
+        self.dst[:, k, :] = self.ring[slot]
+
+    def put(self, k: int, block: np.ndarray):
+        slot = k % self.RING
+        if self.futs[slot] is not None:
+            self.futs[slot].result()
+        np.copyto(self.ring[slot], block)
+        self.futs[slot] = self.pool.submit(self._scatter, k, slot)
+
+    def close(self):
+        for i, f in enumerate(self.futs):
+            if f is not None:
+                f.result()
+                self.futs[i] = None
+        self.pool.shutdown(wait=True)
 
 
 def postprocess_audio_start(audio: np.ndarray, sample_rate: int, trim_start_ms: int = 0, fade_in_ms: int = 0):
