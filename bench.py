@@ -314,6 +314,104 @@ def section_times(model, state, ids, at_frame):
     return {k: round(v * 1e3, 1) for k, v in sec.items()}
 
 
+def parity_check(model, state, ids, frames=3, sample=(0, 255)):
+    """Outside the timed region: the job's own batch shape (all sequences, pipelined frame graph) stepped `frames`
+    frames with host noise, teacher-forced, and the sampled sequences compared with the oracle (the checker, never the
+    thing measured).  -> dict for the bench line."""
+    from oracle.ptts_oracle import Oracle
+    from pocket_tts_mlx_b200 import _native
+    from pocket_tts_mlx_b200.config import load_config
+    from pocket_tts_mlx_b200.safetensors_io import read_safetensors
+    from pocket_tts_mlx_b200.synthetic import default_bundle_dir, write_synthetic_bundle
+    yml = write_synthetic_bundle(default_bundle_dir(), seed=0)
+    cfg = load_config(yml)
+    n = len(ids)
+    sample = [b for b in sample if b < n]
+    rng = np.random.Generator(np.random.PCG64(4242))
+    noise = rng.standard_normal((1 + frames, n, 32)).astype(np.float32)
+    orc = Oracle(read_safetensors(cfg.weights_path), cfg, dtype=np.float32, eos_threshold=1e30)
+    voice = read_safetensors(Path(yml).parent / "embeddings" / "alba.safetensors")["audio_prompt"]
+    st = orc.new_flow_state()
+    orc.prefill_audio(st, voice[0])
+    refs = {b: orc.generate(st, ids[b], noise[:, b, :], frames_after_eos=3, max_frames=frames) for b in sample}
+    batch = _native.Batch(model._ctx, [state["voice_id"]] * n, [state["prompt_len"] + len(t) + frames + 4 for t in ids])
+    worst, audio = 0.0, {b: [] for b in sample}
+    try:
+        batch.set_pipelined(PIPELINED)
+        batch.warmup_mimi(1)
+        batch.prefill_text(ids)
+        for f in range(frames):
+            lat, _, au = batch.step(noise[1 + f])
+            forced = lat.copy()
+            for b in sample:
+                r = refs[b]["latents"][f]
+                worst = max(worst, float(np.linalg.norm(lat[b] - r) / np.linalg.norm(r)))
+                forced[b] = r
+                if not PIPELINED or f >= 1:
+                    audio[b].append(au[b].copy())
+            batch.set_prev_latent(forced)
+        if PIPELINED:
+            last = batch.flush()
+            for b in sample:
+                audio[b].append(last[b].copy())
+    finally:
+        batch.close()
+    snr = []
+    for b in sample:
+        a, r = np.concatenate(audio[b]).astype(np.float64), refs[b]["audio"].astype(np.float64)
+        snr.append(float(10 * np.log10((r ** 2).sum() / max(((a - r) ** 2).sum(), 1e-300))))
+    ok = bool(worst < 1e-2 and min(snr) > 30.0)
+    return {"ok": ok, "latent_rel_l2_max": worst, "waveform_snr_db_min": min(snr), "frames": frames, "sequences": sample,
+            "batch": n, "tolerance": "latents 1e-2 rel-L2 (bf16, teacher-forced), waveform 30 dB", "against": "oracle (fp32 NumPy)"}
+
+
+def workload3(model, state, peaks, n_seq=256, frames=250, steps=2):
+    """BASELINE config 3: Mimi decoder only, n_seq synthetic latent sequences x 250 frames (20 s) -> 24 kHz waveform.
+    `value`: latents resident on the device side of the call (the small H2D of the latents is inside, the waveform stays
+    on the device); `e2e`: the same call returning the waveform to host memory."""
+    from pocket_tts_mlx_b200 import _native
+    rng = np.random.Generator(np.random.PCG64(33))
+    lat = rng.standard_normal((n_seq, frames, 32)).astype(np.float32)
+    audio_sec = n_seq * frames * FRAME_SEC
+    batch = _native.Batch(model._ctx, [state["voice_id"]] * n_seq, [state["prompt_len"] + 8] * n_seq)
+    try:
+        batch.warmup_mimi(1)
+        batch.mimi_decode(lat[:, :8], want_audio=False)
+        batch.mimi_decode(lat, want_audio=False)                    # captures the graph for this frame count
+        model._ctx.sync()
+        model._ctx.timer_begin()
+        for _ in range(steps):
+            batch.mimi_decode(lat, want_audio=False)
+        ms = model._ctx.timer_end() / steps
+        t0 = time.perf_counter()
+        out = batch.mimi_decode(lat, want_audio=True)
+        e2e_s = time.perf_counter() - t0
+    finally:
+        batch.close()
+    # algorithmic work of one Mimi frame for one sequence (DESIGN section 4): transformer 201.6 MFLOP, SEANet 323.7 MFLOP
+    flops = (51.6e9 + 82.9e9) / 256 * n_seq * frames
+    tf = flops / (ms / 1e3) / 1e12
+    return {"workload": f"config 3: Mimi decoder only, {n_seq} latent sequences x {frames} frames -> 24 kHz waveform",
+            "value": audio_sec / (ms / 1e3), "unit": "audio-s/s", "ms_per_step": ms, "ms_per_frame": ms / frames,
+            "e2e": {"value": audio_sec / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": int(lat.nbytes),
+                    "d2h_bytes_per_step": int(out.nbytes)},
+            "tensor": {"achieved_tflops": tf, "peak": peaks["tf_sustained"], "frac": tf / peaks["tf_sustained"],
+                       "flops_per_frame": flops / frames}}
+
+
+def workload5(model, state, world, rank, n_total=4096, n_tok=174, slots=256, max_frames=None):
+    """BASELINE config 5: n_total independent long-form utterances (174 tokens -> 750 frames = 60 s, KV up to 1049
+    tokens), sharded over the ranks (strong scaling: the set is fixed, each rank decodes its share through the
+    continuous-batching scheduler of the public API).  Returns (audio seconds this rank produced, wall seconds)."""
+    from pocket_tts_mlx_b200.synthetic import synthetic_token_ids
+    ids = list(synthetic_token_ids(11, n_total, n_tok))
+    t0 = time.perf_counter()
+    mine, waves = model.generate_audio_sharded([state] * n_total, ids, rank=rank, world_size=world, slots=slots,
+                                               seed=17, max_frames=max_frames)
+    dt = time.perf_counter() - t0
+    return sum(len(w) for w in waves) / 24000.0, dt, len(mine)
+
+
 def cpu_baseline(frames: int, seed: int = 0):
     """The oracle (NumPy restatement of the reference's path), batch 1, on this box's host cores."""
     _use_all_host_threads()
@@ -393,6 +491,11 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-latency", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel frame profile (JSON) here")
+    ap.add_argument("--workload", type=int, default=4, choices=[3, 4, 5],
+                    help="BASELINE config: 4 = headline (256 x 60-token utterances), 3 = Mimi decoder only, "
+                         "5 = 4096 long-form utterances sharded over the GPUs (strong scaling)")
+    ap.add_argument("--utterances", type=int, default=4096, help="workload 5: size of the utterance set")
+    ap.add_argument("--skip-parity", action="store_true")
     args = ap.parse_args()
     world, rank, local = _dist()
     if args.impl == "reference":
@@ -404,6 +507,8 @@ def main():
     peaks = _peaks()
     from pocket_tts_mlx_b200.synthetic import synthetic_token_ids
     n_seq, frames = args.batch, args.frames
+    if args.workload in (3, 5):
+        return run_other_workload(args, world, rank, local, dist, peaks)
     kv_tokens = n_seq * (VOICE_FRAMES + N_TOK + frames + 64) + 4096
     if rank != 0:
         _barrier(dist, local)            # rank 0 writes the synthetic bundle first (same files for all ranks)
@@ -439,7 +544,7 @@ def main():
     model._ctx.sync()
     t0 = time.perf_counter()
     h2d = d2h = 0
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, min(args.steps, 5))
     for _ in range(e2e_steps):
         a, b = one_job(model, state, ids, frames, True, rng)
         h2d += a
@@ -455,6 +560,18 @@ def main():
         lat = None if args.skip_latency else latency_bs1(model, state, rng)
         sections = section_times(model, state, ids, min(frames // 2, 137))
         tensor = tensor_pipe_evidence(model, peaks)
+        # the two branches of the pipelined frame graph (in-graph section times) against the pipelined frame itself
+        br_flow = sections.get("flow_backbone", 0.0) + sections.get("eos_flow_head", 0.0)
+        br_mimi = sections.get("mimi_transformer", 0.0) + sections.get("seanet", 0.0)
+        frame_us = ms / args.steps / frames * 1e3
+        branches = {"flow_branch_us": round(br_flow, 1), "mimi_branch_us": round(br_mimi, 1),
+                    "pipelined_frame_us": round(frame_us, 1),
+                    "overlap_fraction": round(max(0.0, br_flow + br_mimi - frame_us) / max(1e-9, min(br_flow, br_mimi)), 3),
+                    "note": "overlap = (flow + mimi - frame) / min(flow, mimi); frame = whole job / frames, incl. prefill"}
+        parity = None if args.skip_parity else parity_check(model, state, ids)
+        extra3 = extra5 = None
+        if world == 1 and not args.skip_latency:
+            extra3 = workload3(model, state, peaks, steps=2)
         api = None
         if not args.skip_latency and world == 1:
             # the call a user of the reference's API makes: one TTSModel.generate_audio_batch over the same workload
@@ -488,14 +605,80 @@ def main():
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d // e2e_steps,
                     "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps},
             "public_api": api, "roofline": roof, "frame_breakdown": breakdown, "frame_sections_us": sections,
+            "branches": branches, "parity_checked": bool(parity and parity["ok"]), "parity": parity,
             "tensor_pipe": tensor, "cpu_baseline": cpu, "latency_bs1": lat,
             "pipelined": PIPELINED,
             "ms_per_frame": ms / args.steps / frames,
+            "config3_mimi_only": extra3,
         }
         if args.profile_out:
             Path(args.profile_out).parent.mkdir(parents=True, exist_ok=True)
             Path(args.profile_out).write_text(json.dumps({"rows": rows, "roofline": roof}, indent=1))
         print(json.dumps(line), flush=True)
+    _barrier(dist, local)
+    model.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_other_workload(args, world, rank, local, dist, peaks):
+    """--workload 3 (Mimi decoder only, one GPU) and --workload 5 (long-form utterances, strong scaling over GPUs)."""
+    n_tok5 = 174
+    if args.workload == 3:
+        kv_tokens = args.batch * 64 + VOICE_FRAMES + 4096
+    else:
+        kv_tokens = 256 * (VOICE_FRAMES + n_tok5 + 750 + 40) + 4096
+    if rank != 0:
+        _barrier(dist, local)
+    model, _ = load_model(local, kv_tokens)
+    if rank == 0:
+        _barrier(dist, local)
+    state = model.get_state_for_audio_prompt("alba")
+    sampler = ClockSampler(local)
+    if args.workload == 3:
+        if rank == 0:
+            workload3(model, state, peaks, n_seq=args.batch, frames=64, steps=1)           # warm-up
+            sampler.start()
+            r = workload3(model, state, peaks, n_seq=args.batch, frames=250, steps=max(1, args.steps))
+            clocks = sampler.stop()
+            line = {"metric": "audio_seconds_per_second", "value": r["value"], "unit": "audio-s/s", "n_gpus": 1,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                    "config": {"workload": r["workload"], "l2": "activations of one frame (> 1 GB at batch 256) exceed L2"},
+                    "clocks": clocks, "e2e": r["e2e"],
+                    "roofline": {"bound": "tensor", "achieved": r["tensor"]["achieved_tflops"], "peak": r["tensor"]["peak"],
+                                 "unit": "TFLOP/s", "frac": r["tensor"]["frac"], "traffic": None,
+                                 "kernel": "whole Mimi frame (all GEMMs + attention)",
+                                 "peak_source": peaks["source"]},
+                    "ms_per_frame": r["ms_per_frame"]}
+            print(json.dumps(line), flush=True)
+    else:
+        # warm-up: graphs, arenas, allocator (a short run of the same shape)
+        workload5(model, state, world, rank, n_total=256 * world, n_tok=n_tok5, max_frames=24)
+        _barrier(dist, local)
+        model._ctx.launch_count(reset=True)
+        if rank == 0:
+            sampler.start()
+        audio, dt, n_mine = workload5(model, state, world, rank, n_total=args.utterances, n_tok=n_tok5)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = model._ctx.launch_count()
+        dt = _barrier_max(dist, local, dt)
+        total_audio = args.utterances * 750 * FRAME_SEC
+        if rank == 0:
+            line = {"metric": "audio_seconds_per_second", "value": total_audio / dt, "unit": "audio-s/s", "n_gpus": world,
+                    "steps": 1, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+                    "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                    "config": {"workload": f"config 5: {args.utterances} independent {n_tok5}-token utterances x 750 frames "
+                                           f"(60 s, KV up to 1049 tokens), sharded over {world} GPU(s) by frame budget, 256 "
+                                           "slots per GPU through TTSModel.generate_audio_sharded (continuous batching)",
+                               "utterances_rank0": n_mine, "l2": "inputs larger than L2"},
+                    "clocks": clocks, "gpu_launches": int(launches),
+                    "e2e": {"value": total_audio / dt, "unit": "audio-s/s",
+                            "h2d_bytes_per_step": int(n_mine * 750 * 32 * 4),
+                            "d2h_bytes_per_step": int(n_mine * 750 * (1920 + 33) * 4)},
+                    "note": "timed on the host around the public API call (host RNG, per-frame H2D/D2H, EOS bookkeeping, "
+                            "waveforms returned), max over ranks; value == e2e for this workload"}
+            print(json.dumps(line), flush=True)
     _barrier(dist, local)
     model.close()
     if dist is not None:

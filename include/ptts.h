@@ -86,6 +86,10 @@ int32_t ptts_load_weight(ptts_ctx* ctx, const char* name, int32_t dtype, int32_t
 /* Re-pack (conv taps -> GEMM K axis, transposed convs -> polyphase), fold constants (time
  * embeddings of the LSD schedule, modules/mlp.py:53-74), convert to the storage precision, upload. */
 int32_t ptts_finalize_weights(ptts_ctx* ctx);
+/* After ptts_finalize_weights: the flow_lm.* / mimi.* keys that were loaded but that nothing on the path consumed, one
+ * per line (empty string when every key was used).  The reference only counts such keys ("skipped",
+ * models/tts_model.py:171-173,190-192); a loader uses this to validate its key map against a real checkpoint. */
+const char* ptts_unused_weights(ptts_ctx* ctx);
 
 /* Voice cloning.  ptts_has_voice_cloning: 1 when the loaded checkpoint carried the Mimi encoder
  * (mimi.encoder.*, mimi.encoder_transformer.*, mimi.downsample.*, flow_lm.speaker_proj_weight), like the reference's

@@ -117,9 +117,57 @@ def gen_voice_clone():
     print("voice clone:", audio.shape[0], "samples ->", cond.shape, "| upstream _encode_audio runs:", upstream_ok)
 
 
+TEXT_MULTI = "First sentence here. Second one follows! Is this the third? Yes it is."
+
+
+def gen_multichunk():
+    """Full multi-chunk run of the public generate_audio: max_tokens=8 cuts the text into several chunks, every
+    frame counts as EOS (threshold -1e30) so each chunk stops after its own `frames_after_eos` guess + 2 frames
+    (tts_model.py:346-361, 402-412), the noise stream runs on across chunks, trim + fade at the end."""
+    _install_stubs()
+    from pocket_tts_mlx_b200.synthetic import write_synthetic_bundle
+    yml = write_synthetic_bundle(BUNDLE, seed=0)
+    out = REPO / "tests" / "golden"
+    g = run_reference(yml, TEXT_MULTI, "cosette", seed=13, eos_threshold=-1e30, max_tokens=8, frames_after_eos=None,
+                      trim_start_ms=10, fade_in_ms=25)
+    from pocket_tts_mlx.models.tts_model import split_into_best_sentences
+    from pocket_tts_mlx import TTSModel
+    tok = TTSModel.load_model(str(yml)).flow_lm.conditioner.tokenizer
+    g["n_chunks"] = np.int32(len(split_into_best_sentences(tok, TEXT_MULTI, 8)))
+    np.savez(out / "ref_multichunk.npz", **g)
+    print("multichunk:", int(g["n_chunks"]), "chunks,", int(g["n_frames"]), "frames,", g["noise"].shape[0], "noise draws")
+
+
+def gen_stream_wav():
+    """Bytes the reference's StreamingWAVWriter / stream_audio_chunks (data/audio.py:48-130) produce for seeded float
+    chunks, incl. samples beyond [-1, 1] (clipped) and the 0.2 s trailing silence."""
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location("ref_audio", str(REF / "pocket_tts_mlx" / "data" / "audio.py"))
+    ra = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ra)
+    rng = np.random.Generator(np.random.PCG64(5))
+    chunks = [(rng.standard_normal(1920) * 0.7).astype(np.float32) for _ in range(4)]
+
+    class Keep(io.BytesIO):
+        def close(self):
+            self.final = self.getvalue()
+            super().close()
+
+    sink = Keep()
+    ra.stream_audio_chunks(sink, iter(chunks), 24000)
+    np.savez(REPO / "tests" / "golden" / "ref_stream_wav.npz", chunks=np.stack(chunks),
+             wav_bytes=np.frombuffer(sink.final, dtype=np.uint8))
+    print("stream wav:", len(sink.final), "bytes")
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "voice_clone":
         return gen_voice_clone()
+    if len(sys.argv) > 1 and sys.argv[1] == "multichunk":
+        return gen_multichunk()
+    if len(sys.argv) > 1 and sys.argv[1] == "stream_wav":
+        return gen_stream_wav()
     _install_stubs()
     from oracle.ptts_oracle import Oracle
     from pocket_tts_mlx_b200.config import load_config

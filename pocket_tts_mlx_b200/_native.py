@@ -29,7 +29,7 @@ EXPORTED = [
     "ptts_has_voice_cloning", "ptts_encode_audio",
     "ptts_batch_set_async_staging", "ptts_batch_host_buffers_set", "ptts_batch_step_staged_async", "ptts_batch_staged_wait",
     "ptts_batch_host_buffers", "ptts_batch_step_staged",
-    "ptts_batch_set_pcm16", "ptts_batch_host_pcm",
+    "ptts_batch_set_pcm16", "ptts_batch_host_pcm", "ptts_unused_weights",
 ]
 
 
@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
         "ptts_ctx_destroy": (None, [vp]),
         "ptts_load_weight": (i32, [vp, C.c_char_p, i32, i32, C.POINTER(C.c_int64), vp]),
         "ptts_finalize_weights": (i32, [vp]),
+        "ptts_unused_weights": (C.c_char_p, [vp]),
         "ptts_voice_create": (i32, [vp, f32p, i32]),
         "ptts_voice_destroy": (i32, [vp, i32]),
         "ptts_voice_length": (i32, [vp, i32]),
@@ -211,6 +212,10 @@ class Context:
 
     def finalize(self):
         check(lib().ptts_finalize_weights(self._h))
+
+    def unused_weights(self):
+        """Checkpoint keys that were offered to load_weight but that nothing consumed."""
+        return [k for k in lib().ptts_unused_weights(self._h).decode().splitlines() if k]
 
     def voice_create(self, cond: np.ndarray) -> int:
         a = _f32(cond).reshape(-1, self.config.d_model)

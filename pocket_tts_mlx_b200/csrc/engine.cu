@@ -6,6 +6,7 @@
 //   models/tts_model.py:484-518  voice prefill                    -> voice_create (immutable KV pages)
 //   models/tts_model.py:363-428  per-chunk state + frame loop     -> Batch (+ step graph)
 //   modules/stateful_module.py   dict-of-dicts streaming state    -> device buffers owned by Batch
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -15,6 +16,7 @@
 #include <memory>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/ptts.h"
@@ -129,6 +131,8 @@ struct ptts_ctx {
   bool bf16 = true;
   bool force_simt = false;     // PTTS_FORCE_SIMT=1: keep the CUDA-core GEMMs (A/B comparisons)
   std::unordered_map<std::string, HostTensor> host;
+  std::unordered_set<std::string> used;      // checkpoint keys finalize() consumed
+  std::string unused_report;                  // loaded flow_lm.* / mimi.* keys nothing consumed, one per line
   std::vector<void*> allocs;
 
   struct FlowLayer { float *ln1w, *ln1b, *ln2w, *ln2b; LinW qkv, out, ff1, ff2; };
@@ -182,7 +186,9 @@ using Ctx = ptts_ctx;
 // ---- weight staging ---------------------------------------------------------------------------------------
 const HostTensor* find(Ctx& c, const std::string& name) {
   auto it = c.host.find(name);
-  return it == c.host.end() ? nullptr : &it->second;
+  if (it == c.host.end()) return nullptr;
+  c.used.insert(name);
+  return &it->second;
 }
 
 int need(Ctx& c, const std::string& name, std::initializer_list<int64_t> shape, const HostTensor** out) {
@@ -539,7 +545,17 @@ int finalize(Ctx& c) {
     g_upload_fp32 = false;
     c.has_encoder = true;
   }
+  {
+    // keys that were offered but that no part of the path reads (the reference counts them as "skipped",
+    // models/tts_model.py:171-173,190-192): kept so that a loader can check its key map against a real checkpoint.
+    // When the encoder is not loaded as a whole, its keys are expected leftovers and still listed.
+    std::vector<std::string> left;
+    for (auto& kv : c.host) if (!c.used.count(kv.first)) left.push_back(kv.first);
+    std::sort(left.begin(), left.end());
+    for (auto& n : left) { c.unused_report += n; c.unused_report += '\n'; }
+  }
   c.host.clear();
+  c.used.clear();
   c.finalized = true;
   return 0;
 }
@@ -1571,6 +1587,8 @@ int32_t ptts_finalize_weights(ptts_ctx* c) {
   CU(cudaSetDevice(c->device));
   return finalize(*c);
 }
+
+const char* ptts_unused_weights(ptts_ctx* c) { return (c && c->finalized) ? c->unused_report.c_str() : ""; }
 
 int32_t ptts_has_voice_cloning(ptts_ctx* c) { return (c && c->finalized && c->has_encoder) ? 1 : 0; }
 

@@ -156,8 +156,13 @@ class TTSModel:
             else:
                 skipped += 1
         ctx.finalize()
-        logger.info("Loaded %d weights, skipped %d", loaded, skipped)
-        return cls(cfg, ctx, tokenizer, temp, lsd_decode_steps, noise_clamp, eos_threshold, precision, weights_file)
+        unused = ctx.unused_weights()
+        logger.info("Loaded %d weights, skipped %d", loaded - len(unused), skipped + len(unused))
+        if unused:
+            logger.debug("checkpoint keys nothing consumed: %s", unused)
+        model = cls(cfg, ctx, tokenizer, temp, lsd_decode_steps, noise_clamp, eos_threshold, precision, weights_file)
+        model.unused_checkpoint_keys = unused
+        return model
 
     # ------------------------------------------------------------------ voices
     def _voice_file(self, name: str) -> Path:
@@ -368,7 +373,7 @@ class TTSModel:
             # memory that is touched for the first time (page faults).  For large batches that is ~1 ms of host work per
             # frame, so it is taken off the thread that feeds the GPU: the block is copied (contiguously) out of the
             # pinned staging buffer into a small ring and worker threads scatter it.
-            scatter = _BlockScatter(aud_all) if n * self.frame_samples * aud_all.itemsize >= (1 << 19) else None
+            scatter = _BlockScatter(aud_all) if n * self.frame_samples * aud_all.itemsize >= (1 << 18) else None
 
             def put_audio(block):
                 if scatter is not None:

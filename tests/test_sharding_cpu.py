@@ -65,6 +65,74 @@ def test_two_gloo_replicas_partition_and_gather():
     assert sum(n for _, _, _, n in res) == 37
 
 
+class _StubModel:
+    """Stands in for a per-GPU TTSModel replica: an utterance's "waveform" is a deterministic function of its token ids
+    and its own noise only, like the real path with injected noise."""
+
+    def _estimate_max_gen_len(self, n_tok):
+        import math
+        return math.ceil((n_tok / 3.0 + 2.0) * 12.5)
+
+    def generate_audio_continuous(self, model_states, token_ids, slots=256, frames_after_eos=3, noise=None, seed=0, **kw):
+        assert len(model_states) == len(token_ids) and (noise is None or len(noise) == len(token_ids))
+        return [np.asarray(t, dtype=np.float32).cumsum() * (1 + s["voice_id"]) + (0 if noise is None else float(z[0]))
+                for s, t, z in zip(model_states, token_ids, noise if noise is not None else [None] * len(token_ids))]
+
+
+def _jobs():
+    rng = np.random.Generator(np.random.PCG64(4))
+    ids = [rng.integers(0, 4000, size=int(rng.integers(3, 40))).astype(np.int32) for _ in range(23)]
+    states = [{"voice_id": j % 3, "prompt_len": 125} for j in range(23)]
+    noise = [rng.standard_normal(4).astype(np.float32) for _ in range(23)]
+    return states, ids, noise
+
+
+def _launcher_worker(rank, world, port, q):
+    sys.path.insert(0, str(REPO))
+    import torch.distributed as dist
+    from pocket_tts_mlx_b200.sharding import generate_sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    states, ids, noise = _jobs()
+    mine, local = generate_sharded(_StubModel(), states, ids, rank=rank, world_size=world, slots=4, noise=noise)
+    full = generate_sharded(_StubModel(), states, ids, rank=rank, world_size=world, slots=4, noise=noise, gather=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, mine, [np.asarray(x) for x in full]))
+
+
+def test_sharded_launcher_two_ranks_equal_one_rank():
+    """`generate_sharded` (the multi-GPU product path) with two gloo ranks: the ranks' shares are disjoint and cover the
+    set, no data crosses ranks unless a gather is asked for, and the gathered list equals the single-rank result
+    utterance by utterance and in input order."""
+    import torch.multiprocessing as mp
+    from pocket_tts_mlx_b200.sharding import generate_sharded
+    states, ids, noise = _jobs()
+    idx1, one = generate_sharded(_StubModel(), states, ids, rank=0, world_size=1, slots=4, noise=noise)
+    single = [None] * len(ids)
+    for i, w in zip(idx1, one):
+        single[i] = w
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_launcher_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    shares = [set(m) for _, m, _ in res]
+    assert shares[0].isdisjoint(shares[1]) and shares[0] | shares[1] == set(range(len(ids)))
+    for _, _, full in res:
+        assert len(full) == len(ids)
+        for a, b in zip(full, single):
+            assert np.array_equal(a, b)
+
+
 def test_bench_reference_arm_runs_on_cpu():
     """`bench.py --impl reference` is the CPU arm (oracle port on host cores); it must emit the contract line."""
     import json
