@@ -164,6 +164,8 @@ struct ptts_ctx {
 
   void* pool = nullptr;
   long long n_pages = 0, page_stride = 0, layer_stride = 0;
+  CUtensorMap kv_tmap[2];              // bf16 pool as [page][k|v][head][slot][64]: whole-page and 8-slot boxes (decode attention)
+  bool kv_tmap_ok = false;
   std::vector<int> free_pages;
   std::vector<Voice> voices;
   FlowWork prefill_work;
@@ -479,6 +481,20 @@ int finalize(Ctx& c) {
   c.layer_stride = c.n_pages * c.page_stride;
   const size_t esz = c.bf16 ? 2 : 4;
   RET(c.dalloc(&c.pool, (size_t)g.n_layers * c.layer_stride * esz));
+  // every byte of the pool is finite from the start: the tensor-core decode attention multiplies masked keys' V rows
+  // by an exact 0
+  CU(cudaMemset(c.pool, 0, (size_t)g.n_layers * c.layer_stride * esz));
+  c.kv_tmap_ok = false;
+  if (c.bf16 && gemm_tc_available()) {
+    const unsigned long long H = (unsigned long long)g.n_heads, pages = (unsigned long long)g.n_layers * (unsigned long long)c.n_pages;
+    const unsigned long long dims[5] = {(unsigned long long)kHeadDim, (unsigned long long)kPageTokens, H, 2ull, pages};
+    const unsigned long long str[4] = {(unsigned long long)kHeadDim * 2, (unsigned long long)kPageTokens * kHeadDim * 2,
+                                       H * kPageTokens * kHeadDim * 2, (unsigned long long)c.page_stride * 2};
+    const unsigned box_page[5] = {(unsigned)kHeadDim, (unsigned)kPageTokens, 1u, 2u, 1u};
+    const unsigned box_8[5] = {(unsigned)kHeadDim, 8u, 1u, 1u, 1u};
+    c.kv_tmap_ok = pages < (1ull << 31) && tc_encode_bf16(&c.kv_tmap[0], c.pool, 5, dims, str, box_page, 64) &&
+                   tc_encode_bf16(&c.kv_tmap[1], c.pool, 5, dims, str, box_8, 64);
+  }
   c.free_pages.resize(c.n_pages);
   for (long long i = 0; i < c.n_pages; ++i) c.free_pages[i] = (int)(c.n_pages - 1 - i);
   // ---- voice cloning: SEANet encoder, encoder transformer, downsample, speaker projection (fp32) ----
@@ -711,6 +727,7 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       a.layer = i; a.row_seq = row_seq; a.row_pos = row_pos; a.page_table = page_table; a.max_pages = max_pages;
       a.M = M; a.H = c.cfg.n_heads; a.freqs = c.freqs_flow; a.total_keys = total_keys;
       a.part = w.attn_part; a.splits = w.attn_part ? std::min(8, std::max(1, 296 / (M * c.cfg.n_heads))) : 1;
+      a.kv_tmap = c.kv_tmap_ok ? c.kv_tmap : nullptr;
       if (!row_seq && w.prefix_len > 0 && a.splits == 1) {
         a.prefix_len = w.prefix_len; a.prefix_pages = w.d_prefix_pages; a.prefix_part = w.prefix_part;
       }
@@ -1346,7 +1363,13 @@ void pipelined_frame(Batch& bt, int parity, bool host_io) {
   float *hn = alt ? bt.h2_noise : bt.h_noise, *hl = alt ? bt.h2_latent : bt.h_latent, *hg = alt ? bt.h2_logit : bt.h_logit,
         *ha = alt ? bt.h2_audio : bt.h_audio;
   short* hp = alt ? bt.h2_pcm : bt.h_pcm;
-  mimi_frame(bt, lat_prev, true);
+  {
+    // optional SM partition: the Mimi branch's persistent kernels take at most PTTS_MIMI_GRID SMs
+    static const int mimi_grid = [] { const char* v = getenv("PTTS_MIMI_GRID"); return v ? atoi(v) : 0; }();
+    gemm_tc_set_grid_cap(mimi_grid);
+    mimi_frame(bt, lat_prev, true);
+    gemm_tc_set_grid_cap(0);
+  }
   if (host_io) {
     if (bt.pcm16) cudaMemcpyAsync(hp, bt.d_pcm, (size_t)B * bt.frame_samples * sizeof(short), cudaMemcpyDeviceToHost, c.stream);
     else cudaMemcpyAsync(ha, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
@@ -1811,9 +1834,12 @@ static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32
   t.pipelined = false;
   t.async_staging = false;
   t.pcm16 = false;
-  if (t.graphs_pcm) {          // a recycled arena whose graphs were captured with the PCM output on
+  if (t.graphs_pcm || t.graphs_async) {
+    // a recycled arena whose graphs were captured with the PCM output on, or with odd frames going through the second
+    // staging set: both are baked into the copy nodes and this batch starts with neither
     drop_graphs(t);
     t.graphs_pcm = false;
+    t.graphs_async = false;
   }
   std::vector<int> pt((size_t)B * maxp, 0), src, dst;
   t.slot_pages.assign(B, {});

@@ -409,6 +409,7 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
 EncodeFn g_encode = nullptr;
 bool g_init_done = false;
 int g_force[4] = {0, 0, 0, 0};
+int g_grid_cap = 0;            // > 0: persistent kernels launch at most this many CTAs (SM partition between graph branches)
 
 template <int BN, int BK, int ST>
 void set_attr1() {
@@ -426,7 +427,7 @@ void set_attr() {
 
 bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
             const cuuint32_t* box, int bk) {
-  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapSwizzle sw = (bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
                         strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -442,6 +443,9 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 }
 
 }  // namespace
+
+void gemm_tc_set_grid_cap(int cap) { g_grid_cap = cap; }
+int gemm_tc_grid_cap() { return g_grid_cap; }
 
 void gemm_tc_init() {
   if (g_init_done) return;
@@ -516,9 +520,11 @@ bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a
     const int stg = (bn >= 64) ? n_bf16_out * (bn / 64) : 0;
     const double stage_bytes = 128.0 * bk * 2 + (double)bn * bk * 2;
     best_stages = 2;
+    static const int small_cap = [] { const char* v = getenv("PTTS_TC_SMALL_STAGES"); return v ? atoi(v) : 8; }();
     for (int st : {8, 6, 4}) {
       if (bk == 32) break;
       if (st == 8 && bn == 128) continue;
+      if (small_m && st > small_cap) continue;
       const double ring = st * stage_bytes;
       const double smem = (best_persist ? ring + stg * 16384.0 : std::max(ring, stg * 16384.0)) + 2048;
       // PTTS_TC_SMEM_CAP_KB: experiment knob, per-CTA shared-memory budget (co-residency of the two graph branches)
@@ -616,7 +622,9 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   per_sm = std::max(1, std::min(per_sm, std::min(2, 512 / (2 * g.bn))));
   static const bool epw16_ok = [] { const char* v = getenv("PTTS_TC_EPW16"); return !(v && v[0] == '0'); }();
   const bool epw16 = epw16_ok && g.persist && g.bn == 128 && g.bk == 64 && a.tma_store;
-  dim3 grid((unsigned)(g.persist ? std::min<long long>(tiles, 148LL * per_sm) : tiles)), block(epw16 ? 576 : kThreads);
+  long long resident = 148LL * per_sm;
+  if (g_grid_cap > 0) resident = std::min<long long>(resident, g_grid_cap);
+  dim3 grid((unsigned)(g.persist ? std::min<long long>(tiles, resident) : tiles)), block(epw16 ? 576 : kThreads);
   const double flops = 2.0 * g.nb * g.T * (double)g.N * g.taps * g.C;
   const double bytes = (double)g.N * g.taps * g.C * 2 + (double)g.nb * (g.T + g.taps - 1) * g.C * 2 +
                        (double)g.nb * g.T * g.N * ((g.e.y32 ? 4 : 0) + (g.e.y16 ? 2 : 0) + (g.e.yraw16 ? 2 : 0) +

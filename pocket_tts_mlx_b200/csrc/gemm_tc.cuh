@@ -71,6 +71,11 @@ bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a
 // shared-memory tile and cp.async.bulk.tensor stores instead of per-thread row stores.
 void gemm_tc_bind_outputs(TcGemm* g);
 void gemm_tc_launch(const TcGemm& g, cudaStream_t s);
+// SM partition between the branches of the pipelined frame graph: while cap > 0 the persistent kernels (GEMM, SEANet tail)
+// launch at most `cap` CTAs, leaving the other SMs to the kernels of the other branch.  Set around the launches of a
+// branch at capture time (single-threaded per context).
+void gemm_tc_set_grid_cap(int cap);
+int gemm_tc_grid_cap();
 // fp32-in / fp32-out debug entry used by ptts_debug_linear(path=3); returns < 0 when unsupported.
 int gemm_tc_debug(const LinearParams& p, bool bf16_storage, cudaStream_t s);
 

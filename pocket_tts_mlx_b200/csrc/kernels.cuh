@@ -99,6 +99,10 @@ struct FlowAttnParams {
   // prefill (many rows per sequence): rows of sequence s are seq_row0[s] .. seq_row0[s+1]-1 at positions
   // seq_pos0[s] + t; set by the text / voice prefill so that the tensor-core prefill kernel can be used
   const int* seq_row0; const int* seq_pos0; int n_seq, max_rows_per_seq;
+  // host pointer to two CUtensorMaps over the bf16 pool viewed as [page][k|v][head][slot][64] (128-byte swizzle):
+  // [0] box = one head's K and V slices of a whole page (8 KB), [1] box = 8 key slots of K or V (1 KB); or null.
+  // Lets the decode attention stream K/V with TMA (flow_attention_stream_kernel).
+  const void* kv_tmap;
 };
 void launch_flow_prefix_attention(const FlowAttnParams& p, cudaStream_t s);
 // causal attention of whole prefill chunks on tensor cores (bf16 KV, bf16 output); false when not applicable

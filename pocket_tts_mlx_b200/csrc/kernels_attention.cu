@@ -6,6 +6,10 @@
 // Work split: 8 lanes own one key (16-byte slices of the 64-wide head), so a warp covers 4 keys per step,
 // keeps an online-softmax state per 8-lane group and merges groups/warps at the end.
 #include "kernels.cuh"
+#include "tc_device.cuh"
+
+#include <algorithm>
+#include <cstdlib>
 
 namespace ptts {
 namespace {
@@ -635,6 +639,298 @@ __global__ void __launch_bounds__(128) flow_prefix_attention_kernel(const FlowAt
   }
 }
 
+
+// ---- decode attention as a persistent stream of TMA boxes + tensor-core math ------------------------------------
+// ncu on the per-(row, head) CUDA-core kernel above: 28.8 M warp instructions per launch, ~31 per key -- it is bound by
+// instruction issue at about half the issue peak, not by HBM (62 % of the measured bandwidth), and three dependent
+// global loads sit in front of every short-lived CTA.  Two persistent warp-specialised versions with one producer warp
+// feeding four consumer warps through a 12-stage ring were SLOWER (61-70 us vs 52): ncu showed the single producer
+// never waiting for a free stage (it was the bottleneck at ~1000 cycles of mbarrier / shuffle / TMA-issue overhead per
+// 8 KB) and the consumers meeting at a CTA barrier per item.  This version keeps the idea and removes both:
+//   * a CTA is ONE consumer warp + ONE producer warp (64 threads), 6 CTAs per SM, persistent; a CTA owns a contiguous
+//     range of (row, head) items, so nothing is ever merged across warps and there is no CTA-wide barrier;
+//   * the producer moves 64 keys per stage: each 32-token page of the head is ONE 5-D TMA box (K and V slices, 8 KB,
+//     128-byte swizzle); only the first / last page of an item, where [key_lo, n_all) cuts the page, go as 8-key
+//     boxes; two 16 KB stages per CTA, so ~100-190 KB per SM are in flight;
+//   * the consumer works on 64 keys at a time with mma.sync m16n8k16 (the query is row 0 of the 16-row A tile):
+//     S = q K^T (32 MMAs, ldmatrix on the swizzled rows), one online-softmax update on the 4 lanes that hold row 0,
+//     O += P V (32 MMAs, ldmatrix.trans): ~3 warp instructions per key;
+//   * the item's query row and meta data go through a two-slot side buffer; the cascade partial of the shared voice
+//     prefix is fetched one item ahead and merged at the end of the item.
+// Masked keys get p = 0 exactly; their V bytes are whatever the pool (or a stale stage) holds, which is why the pool
+// and the ring are zeroed once (0 x finite = 0; never-written memory could hold NaN patterns).
+constexpr int kAttnPageBytes = 2 * kPageTokens * kHeadDim * 2;    // K + V of one page and head, bf16: 8 KB
+constexpr int kAttnStageBytes = 2 * kAttnPageBytes;               // two pages = 64 keys
+constexpr int kAttnThreads = 64;
+constexpr int kAttnSmem = 2 * kAttnStageBytes + 2 * 256 + 2 * 16 + 256 + 64 + 1024;
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 6) flow_attention_stream_kernel(const __grid_constant__ CUtensorMap tm_page,
+                                                                                const __grid_constant__ CUtensorMap tm_box,
+                                                                                const FlowAttnParams p, const int items) {
+  pdl_sync();
+  extern __shared__ __align__(1024) unsigned char attn_smem[];
+  const uint32_t ring = (smem_u32(attn_smem) + 1023u) & ~1023u;
+  const uint32_t qbuf = ring + 2 * kAttnStageBytes;                 // 2 x 64 floats
+  const uint32_t metab = qbuf + 2 * 256;                            // 2 x {n_all, key_lo, pg_lo, n_pg}
+  const uint32_t obuf = metab + 2 * 16;                             // 64 floats: the item's un-normalised output row
+  const uint32_t bars = obuf + 256;
+  const uint32_t full0 = bars, empty0 = bars + 16, qfull0 = bars + 32, qempty0 = bars + 48;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = p.H, D = H * kHeadDim;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_page) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_box) : "memory");
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+      mbar_init(qfull0 + 8 * i, 1);
+      mbar_init(qempty0 + 8 * i, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // pages / boxes that are never loaded (keys outside [key_lo, n_all)) must still hold finite values
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(2 * kAttnStageBytes / 16); i += kAttnThreads)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ring + i * 16u), "r"(0) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  // contiguous, balanced item range of this CTA
+  const int it_lo = (int)(((long long)blockIdx.x * items) / gridDim.x);
+  const int it_hi = (int)(((long long)(blockIdx.x + 1) * items) / gridDim.x);
+  const int page0 = p.layer * (int)(p.layer_stride / p.page_stride);     // page coordinate of this layer's page 0
+
+  if (warp == 1) {
+    // ---------------- producer ----------------
+    uint32_t gst = 0, qcnt = 0;
+    const int pg_first = p.prefix_len / kPageTokens;
+    // lane l holds pages pg_first + l and pg_first + 32 + l of a row (2048 keys); rows beyond that reload in the loop.
+    // Entries past the row's last page are zero in the table, so the two loads do not depend on each other.
+    auto fetch = [&](int m, int& n_all, int& pa, int& pb) {
+      const int seq = p.row_seq ? p.row_seq[m] : m;
+      const int* pt = p.page_table + (long long)seq * p.max_pages;
+      n_all = p.row_pos[m] + 1;
+      pa = (pg_first + lane < p.max_pages) ? pt[pg_first + lane] : 0;
+      pb = (pg_first + 32 + lane < p.max_pages) ? pt[pg_first + 32 + lane] : 0;
+    };
+    int m_cur = -1, cur_n = 0, cur_a = 0, cur_b = 0, nx_n = 0, nx_a = 0, nx_b = 0;
+    if (it_lo < it_hi) fetch(it_lo / H, nx_n, nx_a, nx_b);
+    for (int it = it_lo; it < it_hi; ++it) {
+      const int m = it / H, h = it - m * H;
+      if (m != m_cur) {
+        m_cur = m; cur_n = nx_n; cur_a = nx_a; cur_b = nx_b;
+        if ((m + 1) * H < it_hi) fetch(m + 1, nx_n, nx_a, nx_b);     // consumed a whole row (H items) later
+      }
+      const int n_all = cur_n;
+      const int key_lo = p.prefix_len;
+      const int pg_lo = pg_first, pg_hi = (n_all - 1) / kPageTokens;
+      const int n_pg = pg_hi - pg_lo + 1;
+      const uint32_t qs = qcnt & 1, qph = (qcnt >> 1) & 1;
+      if (lane == 0) {
+        mbar_wait(qempty0 + 8 * qs, qph ^ 1);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(metab + 16 * qs), "r"(n_all), "r"(key_lo), "r"(pg_lo), "r"(n_pg) : "memory");
+        mbar_expect_tx(qfull0 + 8 * qs, 256);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 256, [%2];"
+                     ::"r"(qbuf + 256 * qs), "l"(p.q_rot + (long long)m * D + h * kHeadDim), "r"(qfull0 + 8 * qs) : "memory");
+      }
+      ++qcnt;
+      const int seq = p.row_seq ? p.row_seq[m] : m;
+      int far = 0;
+      for (int j0 = 0; j0 < n_pg; j0 += 2, ++gst) {
+        const uint32_t s = gst & 1, ph = (gst >> 1) & 1;
+        int pages[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = j0 + e;
+          if (j >= 64 && (j & 31) == 0) {     // more than 64 pages (> 2048 keys): further page ids, fetched in place
+            const int pg = pg_lo + j + lane;
+            far = (pg <= pg_hi) ? p.page_table[(long long)seq * p.max_pages + pg] : 0;
+          }
+          pages[e] = __shfl_sync(0xffffffffu, j < 32 ? cur_a : (j < 64 ? cur_b : far), j & 31);
+        }
+        if (lane == 0) {
+          uint32_t bytes = 0;
+          int blo[2], bhi[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k0 = (pg_lo + j0 + e) * kPageTokens;
+            blo[e] = (max(key_lo, k0) - k0) >> 3;                                    // 8-key boxes that hold valid keys
+            bhi[e] = (j0 + e < n_pg) ? (min(n_all, k0 + kPageTokens) - 1 - k0) >> 3 : -1;
+            if (bhi[e] >= blo[e]) bytes += (uint32_t)(bhi[e] - blo[e] + 1) * 2048u;
+          }
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, bytes);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const uint32_t dst = ring + s * kAttnStageBytes + (uint32_t)e * kAttnPageBytes;
+            const int pc = page0 + pages[e];
+            if (blo[e] == 0 && bhi[e] == 3) {
+              tma_load_5d(dst, &tm_page, full0 + 8 * s, 0, 0, h, 0, pc);             // K and V of the whole page
+            } else {
+              for (int b = blo[e]; b <= bhi[e]; ++b) {
+                tma_load_5d(dst + (uint32_t)b * 1024u, &tm_box, full0 + 8 * s, 0, 8 * b, h, 0, pc);
+                tma_load_5d(dst + 4096u + (uint32_t)b * 1024u, &tm_box, full0 + 8 * s, 0, 8 * b, h, 1, pc);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer ----------------
+  const int g = lane >> 2, t4 = lane & 3;
+  uint32_t qcnt = 0, gst = 0;
+  // cascade partial of the shared prefix: fetched one item ahead (items are consecutive (row, head) pairs);
+  // lane l holds dims 2l, 2l+1
+  const bool has_pp = p.prefix_len > 0;
+  float2 nx_a = make_float2(0.f, 0.f);
+  float nx_m = -INFINITY, nx_l = 0.f;
+  if (has_pp && it_lo < it_hi) {
+    const float* pp = p.prefix_part + (long long)it_lo * 66;
+    nx_a = *reinterpret_cast<const float2*>(pp + 2 * lane); nx_m = pp[64]; nx_l = pp[65];
+  }
+  for (int it = it_lo; it < it_hi; ++it, ++qcnt) {
+    const int m = it / H, h = it - m * H;
+    const uint32_t qs = qcnt & 1, qph = (qcnt >> 1) & 1;
+    const float2 pp_a = nx_a;
+    const float pp_m = nx_m, pp_l = nx_l;
+    if (has_pp && it + 1 < it_hi) {
+      const float* pp = p.prefix_part + (long long)(it + 1) * 66;
+      nx_a = *reinterpret_cast<const float2*>(pp + 2 * lane); nx_m = pp[64]; nx_l = pp[65];
+    }
+    mbar_wait(qfull0 + 8 * qs, qph);
+    uint32_t qa[4][2];           // A fragments of row 0 (a0, a2); rows 8..15 (a1, a3) are zero
+    int n_all, key_lo, pg_lo, n_pg;
+    {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        float2 x, y;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x.x), "=f"(x.y) : "r"(qbuf + 256 * qs + (uint32_t)(16 * ks + 2 * t4) * 4u));
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(y.x), "=f"(y.y) : "r"(qbuf + 256 * qs + (uint32_t)(16 * ks + 8 + 2 * t4) * 4u));
+        qa[ks][0] = g == 0 ? pack2_bf16(x.x * 0.125f, x.y * 0.125f) : 0u;
+        qa[ks][1] = g == 0 ? pack2_bf16(y.x * 0.125f, y.y * 0.125f) : 0u;
+      }
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(n_all), "=r"(key_lo), "=r"(pg_lo), "=r"(n_pg) : "r"(metab + 16 * qs));
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(qempty0 + 8 * qs) : "memory");
+    float oc[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f;
+    float mrun = -INFINITY, lrun = 0.f;
+    for (int j0 = 0; j0 < n_pg; j0 += 2, ++gst) {
+      const uint32_t s = gst & 1, ph = (gst >> 1) & 1;
+      const bool two = j0 + 1 < n_pg;                            // warp-uniform: the stage holds a second page
+      mbar_wait(full0 + 8 * s, ph);
+      const uint32_t st0 = ring + s * kAttnStageBytes;
+      // S = q K^T: per page 4 n-tiles of 8 keys x 4 k-steps of 16 dims
+      float sc[8][4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (e == 1 && !two) break;
+        const uint32_t Ks = st0 + (uint32_t)e * kAttnPageBytes;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          float (&acc)[4] = sc[4 * e + nt];
+          acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+          const int r = nt * 8 + (lane & 7);                     // key row this lane addresses for ldmatrix
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            uint32_t kb[4];
+            const int c = 4 * kk + (lane >> 3);                   // 16-byte chunk (8 dims) of the row
+            ldsm_x4(kb, Ks + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4));
+            const uint32_t a0[4] = {qa[2 * kk][0], 0u, qa[2 * kk][1], 0u};
+            const uint32_t a1[4] = {qa[2 * kk + 1][0], 0u, qa[2 * kk + 1][1], 0u};
+            mma_bf16_16816(acc, a0, kb[0], kb[1]);
+            mma_bf16_16816(acc, a1, kb[2], kb[3]);
+          }
+        }
+      }
+      const int k0 = (pg_lo + j0) * kPageTokens;
+      float bm = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = k0 + nt * 8 + 2 * t4 + e;
+          if (key < key_lo || key >= n_all || (nt >= 4 && !two)) sc[nt][e] = -INFINITY;
+          bm = fmaxf(bm, sc[nt][e]);
+        }
+      }
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+      const float nm = fmaxf(mrun, bm);                          // finite: every stage holds at least one valid key
+      const float corr = (mrun == -INFINITY) ? 0.f : __expf(mrun - nm);
+      mrun = nm;
+      float ssum = 0.f;
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = __expf(sc[nt][0] - nm), p1 = __expf(sc[nt][1] - nm);
+        ssum += p0 + p1;
+        pa[nt >> 1][(nt & 1) * 2] = pack2_bf16(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = 0u;                      // rows 8..15 of the A tile
+      }
+      ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+      ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+      lrun = lrun * corr + ssum;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) { oc[dt][0] *= corr; oc[dt][1] *= corr; }
+      // O += P V: per page 2 k-steps of 16 keys x 8 n-tiles of 8 dims
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (e == 1 && !two) break;
+        const uint32_t Vs = st0 + (uint32_t)e * kAttnPageBytes + 4096u;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+          for (int dp = 0; dp < 4; ++dp) {
+            uint32_t vb[4];
+            const int mid = lane >> 3;
+            const int r = 16 * jj + 8 * (mid & 1) + (lane & 7);
+            const int c = 2 * dp + (mid >> 1);
+            ldsm_x4_t(vb, Vs + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4));
+            mma_bf16_16816(oc[2 * dp], pa[2 * e + jj], vb[0], vb[1]);
+            mma_bf16_16816(oc[2 * dp + 1], pa[2 * e + jj], vb[2], vb[3]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * s) : "memory");
+    }
+    // row 0 of the tile lives in lanes 0..3: through shared memory to "lane l owns dims 2l, 2l+1"
+    if (g == 0) {
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt)
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(obuf + (uint32_t)(dt * 8 + 2 * t4) * 4u), "f"(oc[dt][0]), "f"(oc[dt][1]) : "memory");
+    }
+    const float m_own = __shfl_sync(0xffffffffu, mrun, 0), l_own = __shfl_sync(0xffffffffu, lrun, 0);
+    __syncwarp();
+    float2 o;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(obuf + (uint32_t)lane * 8u));
+    __syncwarp();
+    float l = l_own;
+    if (has_pp) {
+      const float mx = fmaxf(m_own, pp_m);
+      const float c0 = __expf(m_own - mx), c1 = __expf(pp_m - mx);
+      l = l_own * c0 + pp_l * c1;
+      o.x = o.x * c0 + pp_a.x * c1;
+      o.y = o.y * c0 + pp_a.y * c1;
+    }
+    const float inv = 1.0f / l;
+    const long long oi = (long long)m * D + h * kHeadDim + 2 * lane;
+    if (p.out16) *reinterpret_cast<__nv_bfloat162*>(p.out16 + oi) = __floats2bfloat162_rn(o.x * inv, o.y * inv);
+    else *reinterpret_cast<float2*>(p.out + oi) = make_float2(o.x * inv, o.y * inv);
+  }
+}
+
 }  // namespace
 
 // cos / sin of every row's position, shared by the 6 layers of a step: table[m] = cos[32] | sin[32]
@@ -677,12 +973,32 @@ void launch_flow_prefix_attention(const FlowAttnParams& p, cudaStream_t s) {
   ++g_launches;
 }
 
+// bf16 decode rows, enough (row, head) items to fill the machine: the persistent bulk-copy kernel
+static bool flow_attention_stream_ok(const FlowAttnParams& p) {
+  static const int mode = [] { const char* v = getenv("PTTS_ATTN_STREAM"); return v ? atoi(v) : 1; }();
+  return mode != 0 && p.kv_tmap && p.kv_bf16 && p.splits <= 1 && !p.row_seq && p.M * p.H >= 296 && p.q_rot && (p.out16 || p.out);
+}
+
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
   if (p.M <= 0) return;
   dim3 grid(p.M, p.H, p.splits > 1 ? p.splits : 1);
   const double keys = (double)p.total_keys - (double)p.M * p.prefix_len;     // keys streamed by this kernel
   ProfScope ps("flow_attention", nullptr, 4.0 * keys * p.H * 64,
                2.0 * keys * p.H * 64 * (p.kv_bf16 ? 2 : 4) + 2.0 * p.M * p.H * 64 * 4, s);
+  if (flow_attention_stream_ok(p)) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(flow_attention_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      attr_done = true;
+    }
+    const int items = p.M * p.H;
+    static const int per_sm = [] { const char* v = getenv("PTTS_ATTN_CTAS_PER_SM"); return v ? std::max(1, atoi(v)) : 6; }();
+    const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(p.kv_tmap);
+    launch_k(flow_attention_stream_kernel, dim3((unsigned)std::min(items, 148 * per_sm)), dim3(kAttnThreads), (size_t)kAttnSmem, s,
+             maps[0], maps[1], p, items);
+    ++g_launches;
+    return;
+  }
   if (p.kv_bf16) launch_k(flow_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, s, p);
   else launch_k(flow_attention_kernel<float>, dim3(grid), dim3(128), 0, s, p);
   ++g_launches;

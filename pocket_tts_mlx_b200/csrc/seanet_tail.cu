@@ -380,7 +380,7 @@ void sn_tail_launch(const SnTail& p, cudaStream_t s, bool with_fix) {
   {
     const double rows = (double)p.nb * p.T;
     ProfScope ps("sn_tail", nullptr, 2.0 * rows * (192.0 * 32 + 32.0 * 64 + 192.0), rows * (64 * 2 * 2 + 4), s);
-    launch_k(sn_tail_kernel, dim3((unsigned)std::min(a.total_tiles, 148)), dim3(kTailThreads), (size_t)kTailSmem, s,
+    launch_k(sn_tail_kernel, dim3((unsigned)std::min(a.total_tiles, gemm_tc_grid_cap() > 0 ? std::min(148, gemm_tc_grid_cap()) : 148)), dim3(kTailThreads), (size_t)kTailSmem, s,
              p.tm_a, p.tm_w1, p.tm_w2, p.tm_res, a);
     ++g_launches;
   }

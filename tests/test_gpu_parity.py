@@ -531,7 +531,7 @@ def test_continuous_batching_with_cascade_attention(model_bf16):
     """40 same-voice utterances through 32 slots (the batch size where the shared-prefix cascade kernel is on):
     admitted utterances agree with the ones decoded in a plain 32-batch to the bf16 bound (an utterance admitted on
     its own is prefilled by the fp32-activation GEMV path, the lock-step batch by the bf16-operand tcgen05 path, so
-    their KV entries differ by bf16 rounding), and a slot cannot change voice."""
+    their KV entries differ by bf16 rounding)."""
     from pocket_tts_mlx_b200 import _native
     rng = np.random.Generator(np.random.PCG64(22))
     st = model_bf16.get_state_for_audio_prompt("alba")
@@ -549,10 +549,10 @@ def test_continuous_batching_with_cascade_attention(model_bf16):
     for k, j in enumerate(sel[:8]):
         assert rel_l2(lats[j], l2[k]) < 1e-2, (j, rel_l2(lats[j], l2[k]))
         assert snr_db(waves[j], w2[k]) > 30.0
+    # a slot may switch voice: the batch then leaves the cascade path (tests/test_gpu_round2.py covers the results)
     other = model_bf16.get_state_for_audio_prompt("marius")
     batch = _native.Batch(model_bf16._ctx, [st["voice_id"]] * 32, [st["prompt_len"] + 40] * 32)
-    with pytest.raises(_native.PttsError):
-        batch.reset_seq(3, other["voice_id"], other["prompt_len"] + 30)
+    batch.reset_seq(3, other["voice_id"], other["prompt_len"] + 30)
     batch.close()
 
 

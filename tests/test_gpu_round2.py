@@ -144,6 +144,44 @@ def test_config4_batch256_async_staging_is_bit_identical(model_b256):
     assert np.array_equal(out["sync"][frames], out["async"][frames])
 
 
+def test_recycled_arena_forgets_async_staging_graphs(model_b256):
+    """A batch that ran with asynchronous staging leaves frame graphs whose odd frames copy through the second staging
+    set; the next batch recycled from its arena, stepped with the synchronous call, must not replay them (found by the
+    bench's own parity check in round 2)."""
+    from pocket_tts_mlx_b200 import _native
+    rng = np.random.Generator(np.random.PCG64(606))
+    st = model_b256.get_state_for_audio_prompt("alba")
+    n, frames = 40, 4
+    ids = [rng.integers(0, 4000, size=7).astype(np.int32) for _ in range(n)]
+    noise = rng.standard_normal((frames, n, 32)).astype(np.float32)
+
+    def make():
+        b = _native.Batch(model_b256._ctx, [st["voice_id"]] * n, [st["prompt_len"] + 7 + frames + 4] * n)
+        b.set_pipelined(True)
+        return b
+
+    first = make()
+    first.set_async_staging(True)
+    first.warmup_mimi(1)
+    first.prefill_text(ids)
+    sets = first.staging_sets()
+    for f in range(frames):
+        sets[f & 1][0][...] = noise[f]
+        first.staged_wait(first.step_staged_async())
+    first.close()
+    outs = []
+    for _ in range(2):                       # the first of these recycles the async arena
+        b = make()
+        b.warmup_mimi(1)
+        b.prefill_text(ids)
+        outs.append([tuple(a.copy() for a in b.step(noise[f])) for f in range(frames)] + [(b.flush(),)])
+        b.close()
+    for x, y in zip(*outs):
+        for a, c in zip(x, y):
+            assert np.array_equal(a, c)
+    assert np.abs(outs[0][1][0]).max() > 0 and np.isfinite(outs[0][1][0]).all()
+
+
 def test_batch256_mixed_voices_plain_attention_vs_oracle(model_b256, cfg, weights, voices):
     """256 sequences over four different voices: no shared prefix, so the per-sequence attention walks every key
     (the non-cascade path of the bench shape); sequential frame graph."""
