@@ -814,8 +814,10 @@ __global__ void __launch_bounds__(kAttnThreads, 6) flow_attention_stream_kernel(
         float2 x, y;
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x.x), "=f"(x.y) : "r"(qbuf + 256 * qs + (uint32_t)(16 * ks + 2 * t4) * 4u));
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(y.x), "=f"(y.y) : "r"(qbuf + 256 * qs + (uint32_t)(16 * ks + 8 + 2 * t4) * 4u));
-        qa[ks][0] = g == 0 ? pack2_bf16(x.x * 0.125f, x.y * 0.125f) : 0u;
-        qa[ks][1] = g == 0 ? pack2_bf16(y.x * 0.125f, y.y * 0.125f) : 0u;
+        // 1/sqrt(64) and log2(e) folded into q: scores live in the log2 domain, p = 2^(s - m)
+        constexpr float kQs = 0.125f * 1.4426950408889634f;
+        qa[ks][0] = g == 0 ? pack2_bf16(x.x * kQs, x.y * kQs) : 0u;
+        qa[ks][1] = g == 0 ? pack2_bf16(y.x * kQs, y.y * kQs) : 0u;
       }
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(n_all), "=r"(key_lo), "=r"(pg_lo), "=r"(n_pg) : "r"(metab + 16 * qs));
     }
@@ -854,26 +856,29 @@ __global__ void __launch_bounds__(kAttnThreads, 6) flow_attention_stream_kernel(
         }
       }
       const int k0 = (pg_lo + j0) * kPageTokens;
-      float bm = -INFINITY;
+      if (k0 < key_lo || k0 + 2 * kPageTokens > n_all) {        // warp-uniform: only an item's first / last stage is cut
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int key = k0 + nt * 8 + 2 * t4 + e;
-          if (key < key_lo || key >= n_all || (nt >= 4 && !two)) sc[nt][e] = -INFINITY;
-          bm = fmaxf(bm, sc[nt][e]);
+          for (int e = 0; e < 2; ++e) {
+            const int key = k0 + nt * 8 + 2 * t4 + e;
+            if (key < key_lo || key >= n_all) sc[nt][e] = -INFINITY;      // (covers the absent second page: its keys are >= n_all)
+          }
         }
       }
+      float bm = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) bm = fmaxf(bm, fmaxf(sc[nt][0], sc[nt][1]));
       bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
       bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
       const float nm = fmaxf(mrun, bm);                          // finite: every stage holds at least one valid key
-      const float corr = (mrun == -INFINITY) ? 0.f : __expf(mrun - nm);
+      const float corr = (mrun == -INFINITY) ? 0.f : exp2f(mrun - nm);
       mrun = nm;
       float ssum = 0.f;
       uint32_t pa[4][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const float p0 = __expf(sc[nt][0] - nm), p1 = __expf(sc[nt][1] - nm);
+        const float p0 = exp2f(sc[nt][0] - nm), p1 = exp2f(sc[nt][1] - nm);
         ssum += p0 + p1;
         pa[nt >> 1][(nt & 1) * 2] = pack2_bf16(p0, p1);
         pa[nt >> 1][(nt & 1) * 2 + 1] = 0u;                      // rows 8..15 of the A tile
@@ -911,7 +916,8 @@ __global__ void __launch_bounds__(kAttnThreads, 6) flow_attention_stream_kernel(
       for (int dt = 0; dt < 8; ++dt)
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(obuf + (uint32_t)(dt * 8 + 2 * t4) * 4u), "f"(oc[dt][0]), "f"(oc[dt][1]) : "memory");
     }
-    const float m_own = __shfl_sync(0xffffffffu, mrun, 0), l_own = __shfl_sync(0xffffffffu, lrun, 0);
+    const float m_own = __shfl_sync(0xffffffffu, mrun, 0) * 0.6931471805599453f;   // back to the natural-log domain
+    const float l_own = __shfl_sync(0xffffffffu, lrun, 0);
     __syncwarp();
     float2 o;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(obuf + (uint32_t)lane * 8u));
