@@ -215,6 +215,19 @@ int32_t ptts_debug_linear(ptts_ctx* ctx, int32_t path, int32_t n_b, int32_t n_t,
                           int32_t c_in, int32_t n_out, const float* a, const float* w,
                           const float* bias, float* y);
 
+/* Stand-alone run of the cluster chain kernel (one launch for a dependent chain of small-M GEMMs with fused
+ * LayerNorm; csrc/chain_tc.cu) on a miniature flow head, for kernel-level parity tests:
+ *   sy = silu(a0 W0^T + b0); ada = sy Wa^T + ba = shift | scale | gate; x1 = a1 Wi^T + bi;
+ *   h = LN(x1; lnw, lnb)(1 + scale) + shift; u = silu(h W1^T + b1); x1 += gate * (u W2^T + b2); h = LN(x1);
+ *   lat = lat_in + out_scale (h Wf^T + bf).
+ * a0 [M, K0], a1 [M, 64], W0 [D, K0], Wa [3D, D], Wi [D, 64], W1 / W2 [D, D], Wf [32, D]; operands are rounded to
+ * bf16 on upload.  Returns the cluster size used (8 or 16). */
+int32_t ptts_debug_chain(ptts_ctx* ctx, int32_t M, int32_t D, int32_t K0, const float* a0, const float* a1, const float* w0,
+                         const float* b0, const float* wa, const float* ba, const float* wi, const float* bi,
+                         const float* lnw, const float* lnb, const float* w1, const float* b1, const float* w2,
+                         const float* b2, const float* wf, const float* bf, const float* lat_in, float out_scale,
+                         float* out_x1, float* out_h, float* out_lat, float* out_ada);
+
 /* Kernel-level benchmark of the tcgen05 multi-tap GEMM on synthetic bf16 operands (L2 flushed between
  * launches): median microseconds over `reps`.  force = {N tile, ring stages, split-K, persistent} or NULL for
  * the planner's choice (returned in chosen[4]); epi = number of bf16 outputs (0: one fp32 output), +4 adds a

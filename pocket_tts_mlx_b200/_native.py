@@ -29,7 +29,7 @@ EXPORTED = [
     "ptts_has_voice_cloning", "ptts_encode_audio",
     "ptts_batch_set_async_staging", "ptts_batch_host_buffers_set", "ptts_batch_step_staged_async", "ptts_batch_staged_wait",
     "ptts_batch_host_buffers", "ptts_batch_step_staged",
-    "ptts_batch_set_pcm16", "ptts_batch_host_pcm", "ptts_unused_weights",
+    "ptts_batch_set_pcm16", "ptts_batch_host_pcm", "ptts_unused_weights", "ptts_debug_chain",
 ]
 
 
@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
         "ptts_batch_set_pcm16": (i32, [vp, i32]),
         "ptts_batch_host_pcm": (i32, [vp, i32, C.POINTER(C.POINTER(C.c_int16))]),
         "ptts_debug_gemm_bench": (i32, [vp, i32, i32, i32, i32, i32, i32, i32p, i32, f32p, i32p]),
+        "ptts_debug_chain": (i32, [vp, i32, i32, i32] + [f32p] * 17 + [C.c_float] + [f32p] * 4),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -265,6 +266,22 @@ class Context:
         f = (C.c_int32 * 4)(*force) if force is not None else None
         check(lib().ptts_debug_gemm_bench(self._h, nb, t, taps, c_in, n_out, epi, f, reps, C.byref(us), chosen))
         return float(us.value), tuple(int(x) for x in chosen)
+
+    def debug_chain(self, t: dict, out_scale: float = 1.0):
+        """Miniature flow head through the cluster chain kernel (see ptts_debug_chain); t holds the fp32 inputs
+        a0, a1, w0, b0, wa, ba, wi, bi, lnw, lnb, w1, b1, w2, b2, wf, bf, lat_in.  -> dict(x1, h, lat, ada, nc)."""
+        a0 = _f32(t["a0"])
+        m, k0 = a0.shape
+        d = t["w0"].shape[0]
+        names = ["a0", "a1", "w0", "b0", "wa", "ba", "wi", "bi", "lnw", "lnb", "w1", "b1", "w2", "b2", "wf", "bf", "lat_in"]
+        arrs = [_f32(t[k]) for k in names]
+        x1 = np.empty((m, d), np.float32)
+        h = np.empty((m, d), np.float32)
+        lat = np.empty((m, 32), np.float32)
+        ada = np.empty((m, 3 * d), np.float32)
+        nc = check(lib().ptts_debug_chain(self._h, m, d, k0, *[_fp(a) for a in arrs], C.c_float(out_scale),
+                                          _fp(x1), _fp(h), _fp(lat), _fp(ada)))
+        return {"x1": x1, "h": h, "lat": lat, "ada": ada, "nc": nc}
 
     def debug_linear(self, a, w, bias=None, taps=1, path=0):
         """a [nb, T+taps-1, C], w [N, taps*C] -> y [nb, T, N] through the chosen kernel path."""

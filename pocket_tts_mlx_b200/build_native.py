@@ -14,7 +14,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = CSRC / "build"
 LIB = PKG / "libptts_b200.so"
-SOURCES = ["engine.cu", "kernels_linear.cu", "kernels_misc.cu", "kernels_attention.cu", "gemm_tc.cu", "seanet_tail.cu"]
+SOURCES = ["engine.cu", "kernels_linear.cu", "kernels_misc.cu", "kernels_attention.cu", "gemm_tc.cu", "seanet_tail.cu",
+           "chain_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/ptts.h"
+#include "chain_tc.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
@@ -117,6 +118,11 @@ struct FlowWork {
   // set by the prefill callers around flow_layers: row ranges / start positions per sequence (device arrays), which
   // let whole chunks go through the tensor-core prefill attention instead of the per-row decode kernel
   const int* seq_row0 = nullptr; const int* seq_pos0 = nullptr; int n_seq = 0, max_rows_per_seq = 0;
+  // decode at batch <= 512: per layer ONE cluster chain launch [out-proj + LN2, ffn1 + GELU, ffn2 + next LN1, next qkv +
+  // RoPE + KV append] instead of 4 GEMM + 2 LayerNorm launches (chain_tc.cu)
+  ChainOp* d_chain = nullptr;             // [n_layers][4]
+  int chain_M = 0, chain_nc = 0;
+  const int *chain_pos = nullptr, *chain_pt = nullptr; int chain_maxp = 0;
 };
 
 }  // namespace
@@ -141,6 +147,7 @@ struct ptts_ctx {
   float *w_in = nullptr, *bos = nullptr, *emb_std = nullptr, *emb_mean = nullptr;
   float *outn_w = nullptr, *outn_b = nullptr, *eos_w = nullptr, *eos_b = nullptr;
   LinW cond, ada_all, in_proj, fin;
+  __nv_bfloat16* in_proj_pad = nullptr;     // [flow_dim][64] bf16: input_proj with K zero-padded to one 64-wide k-block (chain kernel)
   std::vector<float*> cond_bias_step;
   struct ResBlk { float *lnw, *lnb; LinW m1, m2; };
   std::vector<ResBlk> rb;
@@ -363,6 +370,15 @@ int finalize(Ctx& c) {
   const std::string fp = "flow_lm.flow_net";
   RET(load_linear(c, fp + ".cond_embed", fd, D, true, &c.cond));
   RET(load_linear(c, fp + ".input_proj", fd, L, true, &c.in_proj));
+  if (c.bf16 && L <= 64) {
+    const HostTensor* t;
+    RET(need(c, fp + ".input_proj.weight", {fd, L}, &t));
+    std::vector<uint16_t> h((size_t)fd * 64, 0);
+    for (int n = 0; n < fd; ++n)
+      for (int k = 0; k < L; ++k) h[(size_t)n * 64 + k] = f2bf(t->data[(size_t)n * L + k]);
+    RET(c.dalloc((void**)&c.in_proj_pad, h.size() * 2));
+    CU(cudaMemcpy(c.in_proj_pad, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  }
   RET(load_linear(c, fp + ".final_layer.linear", L, fd, true, &c.fin));
   c.rb.resize(g.flow_depth);
   c.n_ada = g.flow_depth * 3 * fd + 2 * fd;
@@ -630,7 +646,7 @@ bool want_tc(Ctx& c, int M) {
 
 void free_flow_work(FlowWork& w) {
   void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16, w.ws_out, w.ws_ff2, w.attn_part,
-                  w.d_prefix_pages, w.prefix_part, w.rope_cs};
+                  w.d_prefix_pages, w.prefix_part, w.rope_cs, w.d_chain};
   for (void* p : ptrs) if (p) cudaFree(p);
   w = FlowWork{};
 }
@@ -696,6 +712,55 @@ int build_flow_plans(Ctx& c, FlowWork& w, int M) {
   return 0;
 }
 
+bool chain_enabled() {
+  static const bool on = [] { const char* v = getenv("PTTS_CHAIN"); return !(v && v[0] == '0'); }();
+  return on && chain_cluster_size() > 0;
+}
+
+// (re)build the per-layer chain op lists of a decode batch; false: keep the per-GEMM launches
+bool ensure_flow_chain(Ctx& c, FlowWork& w, int M, const int* row_pos, const int* page_table, int max_pages) {
+  if (!chain_enabled() || !w.tc || M > 512) return false;
+  const int nc = chain_cluster_size();
+  if (w.d_chain && w.chain_M == M && w.chain_nc == nc && w.chain_pos == row_pos && w.chain_pt == page_table && w.chain_maxp == max_pages)
+    return true;
+  const int D = c.cfg.d_model, FF = c.cfg.ffn_dim, NL = c.cfg.n_layers;
+  if (D / nc > 128 || D % nc || chain_pick_bn(D, nc) != D / nc) return false;          // LayerNorm steps: one tile per CTA
+  std::vector<ChainOp> ops((size_t)NL * 4);
+  memset(ops.data(), 0, ops.size() * sizeof(ChainOp));
+  bool ok = true;
+  auto gemm = [&](ChainOp& o, const __nv_bfloat16* a, int K, const LinW& lw, int kind) {
+    o.K = K; o.N = lw.N; o.bn = chain_pick_bn(lw.N, nc); o.kind = kind; o.bias = lw.bias;
+    ok = ok && lw.w16 && lw.K == K && o.bn > 0 && K % 64 == 0 && chain_encode_a(&o.tm_a, a, M, K, K) &&
+         chain_encode_w(&o.tm_w, lw.w16, lw.N, K, o.bn);
+  };
+  for (int i = 0; i < NL; ++i) {
+    auto& l = c.fl[i];
+    ChainOp* o = &ops[(size_t)i * 4];
+    gemm(o[0], w.att16, D, l.out, CH_RES_LN);
+    o[0].x = w.x; o[0].x_rs = D; o[0].ln_on = 1; o[0].ln_w = l.ln2w; o[0].ln_b = l.ln2b; o[0].ln_eps = 1e-5f;
+    o[0].h16 = w.h16; o[0].h_rs = D;
+    gemm(o[1], w.h16, D, l.ff1, CH_STORE16);
+    o[1].act = ACT_GELU; o[1].y16 = w.ff16; o[1].y_rs = FF;
+    gemm(o[2], w.ff16, FF, l.ff2, CH_RES_LN);
+    o[2].x = w.x; o[2].x_rs = D; o[2].h16 = w.h16; o[2].h_rs = D;
+    if (i + 1 < NL) {
+      auto& nx = c.fl[i + 1];
+      o[2].ln_on = 1; o[2].ln_w = nx.ln1w; o[2].ln_b = nx.ln1b; o[2].ln_eps = 1e-5f;
+      gemm(o[3], w.h16, D, nx.qkv, CH_ROPE_KV);
+      o[3].rope_cs = w.rope_cs; o[3].q_rot = w.qrot;
+      o[3].kv_layer = reinterpret_cast<__nv_bfloat16*>(c.pool) + (long long)(i + 1) * c.layer_stride;
+      o[3].kv_row_pos = row_pos; o[3].kv_page_table = page_table; o[3].kv_max_pages = max_pages;
+      o[3].kv_heads = c.cfg.n_heads; o[3].kv_page_stride = c.page_stride;
+    }
+  }
+  if (!ok) return false;
+  if (!w.d_chain && cudaMalloc((void**)&w.d_chain, ops.size() * sizeof(ChainOp)) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cudaMemcpyAsync(w.d_chain, ops.data(), ops.size() * sizeof(ChainOp), cudaMemcpyHostToDevice, c.stream) != cudaSuccess) return false;
+  cudaStreamSynchronize(c.stream);         // ops is a local vector
+  w.chain_M = M; w.chain_nc = nc; w.chain_pos = row_pos; w.chain_pt = page_table; w.chain_maxp = max_pages;
+  return true;
+}
+
 // the 6 pre-LN layers over M rows that sit at (row_seq, row_pos) of their sequences
 void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_pos, const int* page_table,
                  int max_pages, long long total_keys) {
@@ -705,9 +770,12 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
     // RoPE + KV append ride in the qkv GEMM's epilogue (PTTS_NO_ROPE_FUSE=1 keeps the separate kernel)
     static const bool fuse_rope = [] { const char* v = getenv("PTTS_NO_ROPE_FUSE"); return !(v && v[0] == '1'); }();
     if (fuse_rope) launch_rope_table(row_pos, c.freqs_flow, w.rope_cs, M, 1, c.stream);
+    // decode steps: everything between two attention kernels is one cluster chain launch
+    const bool chain = fuse_rope && !row_seq && ensure_flow_chain(c, w, M, row_pos, page_table, max_pages);
     for (int i = 0; i < c.cfg.n_layers; ++i) {
       auto& l = c.fl[i];
       const TcGemm* g = &w.plans[(size_t)i * 4];
+      if (chain && i > 0) goto attention;          // LN1 + qkv of this layer ran at the end of the previous layer's chain
       rows_norm(c, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16, w.ws_ff2, pend);
       if (fuse_rope) {
         TcGemm q = g[0];
@@ -721,6 +789,7 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       } else {
         gemm_tc_launch(g[0], c.stream);
       }
+    attention:
       FlowAttnParams a{};
       a.qkv = w.qkv; a.q_rot = w.qrot; a.out16 = w.att16;
       a.pool = c.pool; a.kv_bf16 = c.bf16; a.layer_stride = c.layer_stride; a.page_stride = c.page_stride;
@@ -739,6 +808,13 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       } else {
         launch_flow_prefix_attention(a, c.stream);
         launch_flow_attention(a, c.stream);
+      }
+      if (chain) {
+        const int n_ops = (i + 1 < c.cfg.n_layers) ? 4 : 3;
+        const double fl = 2.0 * M * ((double)D * D + 2.0 * D * FF + (n_ops == 4 ? 3.0 * D * D : 0.0));
+        chain_launch(w.d_chain + (size_t)i * 4, n_ops, M, w.chain_nc, "flow.layer", fl, fl / M, c.stream);
+        pend = 0;
+        continue;
       }
       gemm_tc_launch(g[1], c.stream);
       rows_norm(c, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16, w.ws_out,
@@ -851,6 +927,11 @@ struct ptts_batch {
   __nv_bfloat16 *d_c16 = nullptr, *d_sy16 = nullptr, *d_hh16 = nullptr, *d_u16 = nullptr;
   std::vector<TcGemm> g_cond, g_m1, g_m2;
   TcGemm g_ada, g_fin;
+  // the whole flow head (all Euler steps) as ONE cluster chain launch: two op lists that differ in where the last
+  // step writes the latent (d_latent / d_latent_b, the ping-pong buffers of the pipelined frame graph)
+  ChainOp* d_head_ops[2] = {nullptr, nullptr};
+  int n_head_ops = 0, head_nc = 0;
+  __nv_bfloat16* d_x16 = nullptr;    // [B][64] bf16 copy of the head's current latent (zero beyond latent_dim)
   float* d_xm = nullptr;
   __nv_bfloat16 *d_mh16 = nullptr, *d_matt16 = nullptr, *d_mff16 = nullptr, *d_c0_16 = nullptr, *d_fin16 = nullptr;
   std::vector<TcGemm> g_mimi;
@@ -1082,6 +1163,11 @@ void flow_head_tc(Batch& bt, float* lat_out) {
   const ptts_config& g = c.cfg;
   const int B = bt.B, L = g.latent_dim, fd = g.flow_dim;
   const int n = g.lsd_decode_steps;
+  if (bt.n_head_ops > 0 && (lat_out == bt.d_latent || lat_out == bt.d_latent_b)) {
+    const double fl = 2.0 * B * n * ((double)g.d_model * fd + (double)c.n_ada * fd + 64.0 * fd + 2.0 * g.flow_depth * fd * fd + (double)fd * L);
+    chain_launch(bt.d_head_ops[lat_out == bt.d_latent ? 0 : 1], bt.n_head_ops, B, bt.head_nc, "flow.head", fl, fl / B, c.stream);
+    return;
+  }
   for (int i = 0; i < n; ++i) {
     gemm_tc_launch(bt.g_cond[i], c.stream);
     gemm_tc_launch(bt.g_ada, c.stream);
@@ -1150,6 +1236,57 @@ int build_batch_tc(Batch& t) {
     if (!ok) return fail(PTTS_ERR_CUDA, "tcgen05 plan failed for the flow head (B=%d)", B);
     for (auto& gm : t.g_cond) gemm_tc_bind_outputs(&gm);
     for (auto& gm : t.g_m1) gemm_tc_bind_outputs(&gm);
+    // ---- single-launch flow head (cluster chain kernel)
+    t.n_head_ops = 0;
+    const int nc = chain_enabled() ? chain_cluster_size() : 0;
+    if (nc > 0 && B <= 512 && L == 32 && c.in_proj_pad && fd % nc == 0 && fd / nc <= 128 && chain_pick_bn(fd, nc) == fd / nc) {
+      RET(bz(&t.d_x16, (size_t)B * 64));
+      const int nst = g.lsd_decode_steps, per = 4 + 2 * g.flow_depth;
+      std::vector<ChainOp> ops((size_t)nst * per);
+      bool cok = true;
+      auto gemm = [&](ChainOp& o, const __nv_bfloat16* a, int K, const __nv_bfloat16* w16, int N, const float* bias, int kind) {
+        o.K = K; o.N = N; o.bn = chain_pick_bn(N, nc); o.kind = kind; o.bias = bias;
+        cok = cok && w16 && o.bn > 0 && K % 64 == 0 && chain_encode_a(&o.tm_a, a, B, K, K) && chain_encode_w(&o.tm_w, w16, N, K, o.bn);
+      };
+      for (int v = 0; v < 2 && cok; ++v) {
+        memset(ops.data(), 0, ops.size() * sizeof(ChainOp));
+        for (int i = 0; i < nst; ++i) {
+          ChainOp* o = &ops[(size_t)i * per];
+          gemm(o[0], t.d_c16, D, c.cond.w16, fd, c.cond_bias_step[i], CH_STORE16);          // silu(t_emb + cond_embed(c))
+          o[0].act = ACT_SILU; o[0].y16 = t.d_sy16; o[0].y_rs = fd;
+          gemm(o[1], t.d_sy16, fd, c.ada_all.w16, c.n_ada, c.ada_all.bias, CH_STORE32);     // every AdaLN modulation at once
+          o[1].y32 = t.d_ada; o[1].y_rs = c.n_ada;
+          gemm(o[2], t.d_x16, 64, c.in_proj_pad, fd, c.in_proj.bias, CH_RES_LN);            // x1 = input_proj(x); first in_ln
+          o[2].x = t.d_x1; o[2].x_rs = fd; o[2].x_init = 1;
+          for (int r = 0; r < g.flow_depth; ++r) {
+            ChainOp& pre = (r == 0) ? o[2] : o[2 + 2 * r];                                   // the step whose epilogue normalises for block r
+            const float* ada = t.d_ada + (long long)r * 3 * fd;
+            pre.ln_on = 1; pre.ln_w = c.rb[r].lnw; pre.ln_b = c.rb[r].lnb; pre.ln_eps = 1e-6f;
+            pre.mod_shift = ada; pre.mod_scale = ada + fd; pre.mod_rs = c.n_ada; pre.h16 = t.d_hh16; pre.h_rs = fd;
+            gemm(o[3 + 2 * r], t.d_hh16, fd, c.rb[r].m1.w16, fd, c.rb[r].m1.bias, CH_STORE16);
+            o[3 + 2 * r].act = ACT_SILU; o[3 + 2 * r].y16 = t.d_u16; o[3 + 2 * r].y_rs = fd;
+            gemm(o[4 + 2 * r], t.d_u16, fd, c.rb[r].m2.w16, fd, c.rb[r].m2.bias, CH_RES_LN);
+            o[4 + 2 * r].x = t.d_x1; o[4 + 2 * r].x_rs = fd; o[4 + 2 * r].gate = ada + 2 * fd; o[4 + 2 * r].gate_rs = c.n_ada;
+          }
+          {
+            ChainOp& last = o[2 + 2 * g.flow_depth];                                         // m2 of the last block: final-layer norm
+            const float* adaf = t.d_ada + (long long)g.flow_depth * 3 * fd;
+            last.ln_on = 1; last.ln_w = nullptr; last.ln_b = nullptr; last.ln_eps = 1e-6f;
+            last.mod_shift = adaf; last.mod_scale = adaf + fd; last.mod_rs = c.n_ada; last.h16 = t.d_hh16; last.h_rs = fd;
+          }
+          ChainOp& f = o[per - 1];
+          gemm(f, t.d_hh16, fd, c.fin.w16, L, c.fin.bias, CH_FIN);                           // x += v / n
+          f.out_scale = 1.0f / (float)nst; f.lat_in = t.d_x; f.lat_rs = L;
+          f.lat_out = (i == nst - 1) ? (v == 0 ? t.d_latent : t.d_latent_b) : t.d_x;
+          f.lat16 = (i == nst - 1) ? nullptr : t.d_x16; f.lat16_rs = 64;
+        }
+        if (!cok) break;
+        if (!t.d_head_ops[v]) RET(t.dalloc((void**)&t.d_head_ops[v], ops.size() * sizeof(ChainOp)));
+        CU(cudaMemcpyAsync(t.d_head_ops[v], ops.data(), ops.size() * sizeof(ChainOp), cudaMemcpyHostToDevice, c.stream));
+        CU(cudaStreamSynchronize(c.stream));
+      }
+      if (cok) { t.n_head_ops = nst * per; t.head_nc = nc; }
+    }
   }
   if (t.tc_mimi) {
     const int T = t.T0, MD = g.mimi_d, SD = g.seanet_dim, FFm = g.mimi_ffn, k0 = g.kernel_size, rk = g.res_kernel_size;
@@ -1291,7 +1428,8 @@ void flow_step(Batch& bt, bool host_noise, int part = 0, const float* lat_in = n
   if (L <= 128) {
     launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.tc_head ? bt.d_c16 : nullptr,
                           bt.d_logit, B, D, bt.fw.ws_ff2, bt.fw.pend_n, (long long)B * D, c.stream,
-                          bt.d_noise, bt.d_x, L, sqrtf(g.temp), nclamp, host_noise ? 0 : 1, bt.d_counter);
+                          bt.d_noise, bt.d_x, L, sqrtf(g.temp), nclamp, host_noise ? 0 : 1, bt.d_counter,
+                          bt.n_head_ops > 0 ? bt.d_x16 : nullptr);
   } else {
     launch_final_norm_eos(bt.fw.x, nullptr, c.outn_w, c.outn_b, c.eos_w, c.eos_b, bt.d_c, bt.tc_head ? bt.d_c16 : nullptr,
                           bt.d_logit, B, D, bt.fw.ws_ff2, bt.fw.pend_n, (long long)B * D, c.stream);
@@ -2610,6 +2748,90 @@ int32_t ptts_debug_gemm_bench(ptts_ctx* c, int32_t nb, int32_t T, int32_t taps, 
   if (r == -1) return fail(PTTS_ERR_INVALID, "configuration not supported by the tcgen05 GEMM");
   if (r < 0) return fail(PTTS_ERR_CUDA, "gemm bench failed: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
+}
+
+// Stand-alone run of the cluster chain kernel on a miniature flow head (kernel-level parity test):
+//   sy  = silu(a0 W0^T + b0)                       CH_STORE16      [K0 -> D]
+//   ada = sy Wa^T + ba  = shift | scale | gate     CH_STORE32      [D -> 3D]
+//   x1  = a1 Wi^T + bi ; h = LN(x1; g, b)(1 + scale) + shift       CH_RES_LN (x_init)   [64 -> D]
+//   u   = silu(h W1^T + b1)                        CH_STORE16      [D -> D]
+//   x1 += gate * (u W2^T + b2) ; h = LN(x1)        CH_RES_LN       [D -> D]
+//   lat = lat_in + s (h Wf^T + bf)                 CH_FIN          [D -> 32]
+// All matrices are given in fp32 and rounded to bf16 on upload (operands) ; biases / LN / lat_in stay fp32.
+int32_t ptts_debug_chain(ptts_ctx* c, int32_t M, int32_t D, int32_t K0, const float* a0, const float* a1, const float* w0,
+                         const float* b0, const float* wa, const float* ba, const float* wi, const float* bi,
+                         const float* lnw, const float* lnb, const float* w1, const float* b1, const float* w2,
+                         const float* b2, const float* wf, const float* bf, const float* lat_in, float out_scale,
+                         float* out_x1, float* out_h, float* out_lat, float* out_ada) {
+  if (!c) return fail(PTTS_ERR_INVALID, "null ctx");
+  CU(cudaSetDevice(c->device));
+  const int nc = chain_cluster_size();
+  if (nc == 0) return fail(PTTS_ERR_STATE, "the cluster chain kernel is not available on this device");
+  std::vector<void*> tmp;
+  auto up16 = [&](const float* src, size_t n, __nv_bfloat16** dst) -> int {
+    std::vector<uint16_t> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = f2bf(src[i]);
+    CU(cudaMalloc((void**)dst, n * 2));
+    tmp.push_back(*dst);
+    CU(cudaMemcpy(*dst, h.data(), n * 2, cudaMemcpyHostToDevice));
+    return 0;
+  };
+  auto up32 = [&](const float* src, size_t n, float** dst) -> int {
+    CU(cudaMalloc((void**)dst, n * 4));
+    tmp.push_back(*dst);
+    if (src) CU(cudaMemcpy(*dst, src, n * 4, cudaMemcpyHostToDevice));
+    else CU(cudaMemset(*dst, 0, n * 4));
+    return 0;
+  };
+  auto done = [&](int rc) { for (void* p : tmp) cudaFree(p); return rc; };
+#define DC(x) do { int rc_ = (x); if (rc_ != 0) return done(rc_); } while (0)
+  __nv_bfloat16 *d_a0, *d_a1, *d_w0, *d_wa, *d_wi, *d_w1, *d_w2, *d_wf, *d_sy, *d_h, *d_u;
+  float *d_b0, *d_ba, *d_bi, *d_lnw, *d_lnb, *d_b1, *d_b2, *d_bf, *d_lat_in, *d_x1, *d_lat, *d_ada;
+  DC(up16(a0, (size_t)M * K0, &d_a0)); DC(up16(a1, (size_t)M * 64, &d_a1));
+  DC(up16(w0, (size_t)D * K0, &d_w0)); DC(up16(wa, (size_t)3 * D * D, &d_wa)); DC(up16(wi, (size_t)D * 64, &d_wi));
+  DC(up16(w1, (size_t)D * D, &d_w1)); DC(up16(w2, (size_t)D * D, &d_w2)); DC(up16(wf, (size_t)32 * D, &d_wf));
+  DC(up32(b0, D, &d_b0)); DC(up32(ba, 3 * D, &d_ba)); DC(up32(bi, D, &d_bi)); DC(up32(lnw, D, &d_lnw)); DC(up32(lnb, D, &d_lnb));
+  DC(up32(b1, D, &d_b1)); DC(up32(b2, D, &d_b2)); DC(up32(bf, 32, &d_bf)); DC(up32(lat_in, (size_t)M * 32, &d_lat_in));
+  DC(up32(nullptr, (size_t)M * D, &d_x1)); DC(up32(nullptr, (size_t)M * 32, &d_lat)); DC(up32(nullptr, (size_t)M * 3 * D, &d_ada));
+  {
+    std::vector<float> z((size_t)M * D, 0.f);
+    DC(up16(z.data(), z.size(), &d_sy)); DC(up16(z.data(), z.size(), &d_h)); DC(up16(z.data(), z.size(), &d_u));
+  }
+  std::vector<ChainOp> ops(6);
+  memset(ops.data(), 0, ops.size() * sizeof(ChainOp));
+  bool ok = true;
+  auto gemm = [&](ChainOp& o, const __nv_bfloat16* a, int K, const __nv_bfloat16* w, int N, const float* bias, int kind) {
+    o.K = K; o.N = N; o.bn = chain_pick_bn(N, nc); o.kind = kind; o.bias = bias;
+    ok = ok && o.bn > 0 && chain_encode_a(&o.tm_a, a, M, K, K) && chain_encode_w(&o.tm_w, w, N, K, o.bn);
+  };
+  gemm(ops[0], d_a0, K0, d_w0, D, d_b0, CH_STORE16); ops[0].act = ACT_SILU; ops[0].y16 = d_sy; ops[0].y_rs = D;
+  gemm(ops[1], d_sy, D, d_wa, 3 * D, d_ba, CH_STORE32); ops[1].y32 = d_ada; ops[1].y_rs = 3 * D;
+  gemm(ops[2], d_a1, 64, d_wi, D, d_bi, CH_RES_LN);
+  ops[2].x = d_x1; ops[2].x_rs = D; ops[2].x_init = 1; ops[2].ln_on = 1; ops[2].ln_w = d_lnw; ops[2].ln_b = d_lnb; ops[2].ln_eps = 1e-6f;
+  ops[2].mod_shift = d_ada; ops[2].mod_scale = d_ada + D; ops[2].mod_rs = 3 * D; ops[2].h16 = d_h; ops[2].h_rs = D;
+  gemm(ops[3], d_h, D, d_w1, D, d_b1, CH_STORE16); ops[3].act = ACT_SILU; ops[3].y16 = d_u; ops[3].y_rs = D;
+  gemm(ops[4], d_u, D, d_w2, D, d_b2, CH_RES_LN);
+  ops[4].x = d_x1; ops[4].x_rs = D; ops[4].gate = d_ada + 2 * D; ops[4].gate_rs = 3 * D; ops[4].ln_on = 1; ops[4].ln_eps = 1e-6f;
+  ops[4].h16 = d_h; ops[4].h_rs = D;
+  gemm(ops[5], d_h, D, d_wf, 32, d_bf, CH_FIN);
+  ops[5].out_scale = out_scale; ops[5].lat_in = d_lat_in; ops[5].lat_out = d_lat; ops[5].lat_rs = 32;
+  if (!ok) return done(fail(PTTS_ERR_INVALID, "chain plan failed (M=%d D=%d K0=%d nc=%d)", M, D, K0, nc));
+  ChainOp* d_ops;
+  CU(cudaMalloc((void**)&d_ops, ops.size() * sizeof(ChainOp)));
+  tmp.push_back(d_ops);
+  CU(cudaMemcpy(d_ops, ops.data(), ops.size() * sizeof(ChainOp), cudaMemcpyHostToDevice));
+  chain_launch(d_ops, (int)ops.size(), M, nc, "debug", 0, 0, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return done(fail(PTTS_ERR_CUDA, "debug_chain: %s", cudaGetErrorString(e)));
+  std::vector<uint16_t> hh((size_t)M * D);
+  CU(cudaMemcpy(hh.data(), d_h, hh.size() * 2, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < hh.size(); ++i) out_h[i] = bf2f(hh[i]);
+  CU(cudaMemcpy(out_x1, d_x1, (size_t)M * D * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out_lat, d_lat, (size_t)M * 32 * 4, cudaMemcpyDeviceToHost));
+  if (out_ada) CU(cudaMemcpy(out_ada, d_ada, (size_t)M * 3 * D * 4, cudaMemcpyDeviceToHost));
+#undef DC
+  return done(nc);
 }
 
 int32_t ptts_debug_linear(ptts_ctx* c, int32_t path, int32_t nb, int32_t T, int32_t taps, int32_t C, int32_t N,

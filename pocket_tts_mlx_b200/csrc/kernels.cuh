@@ -144,7 +144,9 @@ void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w,
                            int B, int D, const float* acc, int acc_n, long long acc_stride, cudaStream_t s,
                            // optional: the flow head's start noise of each row is prepared by the same launch
                            const float* nz = nullptr, float* x0 = nullptr, int nL = 0, float nstd = 1.f,
-                           float nclamp = -1.f, int use_philox = 0, const unsigned long long* counter = nullptr);
+                           float nclamp = -1.f, int use_philox = 0, const unsigned long long* counter = nullptr,
+                           // optional bf16 copy of x0 as rows of 64 (A operand of the chain kernel's input projection)
+                           __nv_bfloat16* x0_16 = nullptr);
 // x0 = clip(sqrt(temp) * z); z from the host buffer or a Philox4x32-10 + Box-Muller stream
 void launch_noise_prep(const float* z, float* x0, int n, float std, float clamp, int use_philox,
                        const unsigned long long* counter, cudaStream_t s);

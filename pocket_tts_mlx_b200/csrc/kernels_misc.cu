@@ -146,9 +146,9 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 // x0[i] = clamp(g_i * std): g from the host buffer z or from Philox(seed, frame counter, i)
-__device__ __forceinline__ void noise_prep_one(const float* __restrict__ z, float* __restrict__ x0, int i, float std,
-                                               float clamp, int use_philox,
-                                               const unsigned long long* __restrict__ counter) {
+__device__ __forceinline__ float noise_prep_one(const float* __restrict__ z, float* __restrict__ x0, int i, float std,
+                                                float clamp, int use_philox,
+                                                const unsigned long long* __restrict__ counter) {
   float g;
   if (use_philox) {
     const unsigned long long step = counter[0], seed = counter[1];   // {frame counter, seed} live on the device
@@ -163,6 +163,7 @@ __device__ __forceinline__ void noise_prep_one(const float* __restrict__ z, floa
   float v = g * std;
   if (clamp >= 0.f) v = fminf(fmaxf(v, -clamp), clamp);
   x0[i] = v;
+  return v;
 }
 
 __global__ void __launch_bounds__(128) final_norm_eos_kernel(const float* __restrict__ x,
@@ -179,11 +180,17 @@ __global__ void __launch_bounds__(128) final_norm_eos_kernel(const float* __rest
                                                              // flow-head start noise of the same row (x0 null: skip)
                                                              const float* __restrict__ nz, float* __restrict__ x0, int nL,
                                                              float nstd, float nclamp, int use_philox,
-                                                             const unsigned long long* __restrict__ counter) {
+                                                             const unsigned long long* __restrict__ counter,
+                                                             // bf16 copy of x0 as rows of 64 (zero beyond nL): A operand of
+                                                             // the flow head's input projection in the chain kernel
+                                                             __nv_bfloat16* __restrict__ x0_16) {
   pdl_sync();
   __shared__ float red[32];
   const int b = blockIdx.x;
-  if (x0 && (int)threadIdx.x < nL) noise_prep_one(nz, x0, b * nL + threadIdx.x, nstd, nclamp, use_philox, counter);
+  if (x0 && (int)threadIdx.x < nL) {
+    const float v0 = noise_prep_one(nz, x0, b * nL + threadIdx.x, nstd, nclamp, use_philox, counter);
+    if (x0_16) x0_16[b * 64 + threadIdx.x] = __float2bfloat16_rn(v0);
+  }
   const long long row = row_of ? row_of[b] : b;
   const float* xr = x + row * D;
   if (D == 1024 && acc_n <= 8) {
@@ -623,11 +630,12 @@ void launch_final_norm_eos(const float* x, const int* row_of, const float* ln_w,
                            const float* w_eos, const float* b_eos, float* c, __nv_bfloat16* c16, float* logit,
                            int B, int D, const float* acc, int acc_n, long long acc_stride, cudaStream_t s,
                            const float* nz, float* x0, int nL, float nstd, float nclamp, int use_philox,
-                           const unsigned long long* counter) {
+                           const unsigned long long* counter, __nv_bfloat16* x0_16) {
   ProfScope ps("final_norm_eos", nullptr, 0, 2.0 * B * D * 4, s);
   if (nL > 128) { x0 = nullptr; }
+  if (nL > 64) x0_16 = nullptr;
   launch_k(final_norm_eos_kernel, dim3(B), dim3(128), 0, s, x, row_of, ln_w, ln_b, w_eos, b_eos, c, c16, logit, D, acc, acc_n, acc_stride,
-           nz, x0, nL, nstd, nclamp, use_philox, counter);
+           nz, x0, nL, nstd, nclamp, use_philox, counter, x0_16);
   ++g_launches;
 }
 

@@ -487,3 +487,49 @@ def test_sharded_launcher_equals_single_replica(model_fp32):
             assert rel_l2(l, one[j][1]) < 1e-5, (r, j)
             assert snr_db(w, one[j][0]) > 80.0, (r, j)
     assert sorted(seen) == list(range(n_jobs))
+
+
+# ------------------------------------------------------------------------------------ cluster chain kernel
+def _bf16(x):
+    from pocket_tts_mlx_b200.safetensors_io import bf16_bits_to_f32, f32_to_bf16_bits
+    x = np.asarray(x, dtype=np.float32)
+    return bf16_bits_to_f32(f32_to_bf16_bits(x)).reshape(x.shape).astype(np.float64)
+
+
+@pytest.mark.parametrize("m", [256, 128, 37, 300])
+def test_cluster_chain_kernel_matches_numpy(model_b256, m):
+    """csrc/chain_tc.cu on a miniature flow head: six dependent GEMM steps in one cluster launch (multicast A blocks,
+    cluster-scope step barriers, LayerNorm with row statistics exchanged through distributed shared memory, AdaLN
+    modulation, gated residual, Euler update) against NumPy with bf16 rounding at the same points; M = 256 (two
+    clusters), one cluster, ragged tiles."""
+    rng = np.random.Generator(np.random.PCG64(1000 + m))
+    d, k0 = 512, 1024
+    f = lambda *s, sc=1.0: (rng.standard_normal(s) * sc).astype(np.float32)
+    t = dict(a0=f(m, k0), a1=np.concatenate([f(m, 32), np.zeros((m, 32), np.float32)], axis=1),
+             w0=f(d, k0, sc=k0 ** -0.5), b0=f(d, sc=0.1), wa=f(3 * d, d, sc=d ** -0.5), ba=f(3 * d, sc=0.1),
+             wi=f(d, 64, sc=32 ** -0.5), bi=f(d, sc=0.1), lnw=1 + f(d, sc=0.1), lnb=f(d, sc=0.1),
+             w1=f(d, d, sc=d ** -0.5), b1=f(d, sc=0.1), w2=f(d, d, sc=d ** -0.5), b2=f(d, sc=0.1),
+             wf=f(32, d, sc=d ** -0.5), bf=f(32, sc=0.1), lat_in=f(m, 32))
+    out = model_b256._ctx.debug_chain(t, out_scale=0.5)
+    assert out["nc"] in (8, 16)
+    silu = lambda x: x / (1 + np.exp(-x))
+
+    def ln(x, eps):
+        mu = x.mean(-1, keepdims=True)
+        return (x - mu) / np.sqrt(x.var(-1, keepdims=True) + eps)
+
+    sy = _bf16(silu(_bf16(t["a0"]) @ _bf16(t["w0"]).T + t["b0"]))
+    ada = sy @ _bf16(t["wa"]).T + t["ba"]
+    shift, scale, gate = ada[:, :d], ada[:, d:2 * d], ada[:, 2 * d:]
+    x1 = _bf16(t["a1"]) @ _bf16(t["wi"]).T + t["bi"]
+    h = _bf16((ln(x1, 1e-6) * t["lnw"] + t["lnb"]) * (1 + scale) + shift)
+    u = _bf16(silu(h @ _bf16(t["w1"]).T + t["b1"]))
+    x1 = x1 + gate * (u @ _bf16(t["w2"]).T + t["b2"])
+    h2 = _bf16(ln(x1, 1e-6))
+    lat = t["lat_in"] + 0.5 * (h2 @ _bf16(t["wf"]).T + t["bf"])
+    # bf16 intermediates (sy, h, u) are rounded from fp32 on the device and from fp64 here: a value that sits on a
+    # rounding boundary flips by one bf16 ulp (2^-8 relative), which is what the tolerances below leave room for
+    assert rel_l2(out["ada"], ada) < 1e-3, rel_l2(out["ada"], ada)
+    assert rel_l2(out["x1"], x1) < 2e-3, rel_l2(out["x1"], x1)
+    assert rel_l2(out["h"], h2) < 4e-3, rel_l2(out["h"], h2)
+    assert rel_l2(out["lat"], lat) < 2e-3, rel_l2(out["lat"], lat)
