@@ -562,12 +562,14 @@ def main():
         tensor = tensor_pipe_evidence(model, peaks)
         # the two branches of the pipelined frame graph (in-graph section times) against the pipelined frame itself
         br_flow = sections.get("flow_backbone", 0.0) + sections.get("eos_flow_head", 0.0)
-        br_mimi = sections.get("mimi_transformer", 0.0) + sections.get("seanet", 0.0)
+        br_mimi = sections.get("mimi_transformer_capped", sections.get("mimi_transformer", 0.0)) + \
+            sections.get("seanet_capped", sections.get("seanet", 0.0))
         frame_us = ms / args.steps / frames * 1e3
         branches = {"flow_branch_us": round(br_flow, 1), "mimi_branch_us": round(br_mimi, 1),
                     "pipelined_frame_us": round(frame_us, 1),
                     "overlap_fraction": round(max(0.0, br_flow + br_mimi - frame_us) / max(1e-9, min(br_flow, br_mimi)), 3),
-                    "note": "overlap = (flow + mimi - frame) / min(flow, mimi); frame = whole job / frames, incl. prefill"}
+                    "note": "overlap = (flow + mimi - frame) / min(flow, mimi); mimi = the branch on the SM share it gets in "
+                            "the pipelined graph (PTTS_MIMI_GRID, default 74 SMs); frame = whole job / frames, incl. prefill"}
         parity = None if args.skip_parity else parity_check(model, state, ids)
         extra3 = extra5 = None
         if world == 1 and not args.skip_latency:

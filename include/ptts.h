@@ -203,7 +203,8 @@ int64_t ptts_launch_count(ptts_ctx* ctx, int32_t reset);
  * launches, sorted by time) valid until the next call.  Advances the batch by one frame. */
 int32_t ptts_batch_profile_step(ptts_batch* batch, const char** report);
 /* In-graph timing of the frame's sections (each captured as its own CUDA graph and replayed): ms[0] FlowLM
- * backbone, ms[1] EOS + flow head, ms[2] Mimi transformer, ms[3] SEANet decoder, ms[4] whole frame.  Perturbs
+ * backbone, ms[1] EOS + flow head, ms[2] Mimi transformer, ms[3] SEANet decoder, ms[4] whole frame, ms[5] / ms[6] the
+ * two Mimi sections with their persistent kernels capped at the SM share they get in the pipelined graph.  Perturbs
  * the batch's streaming state (profiling only).  Returns the number of entries written. */
 int32_t ptts_batch_profile_sections(ptts_batch* batch, float* ms, int32_t cap);
 /* Write an L2-sized scratch buffer (flushes L2 between timed iterations). */

@@ -463,7 +463,8 @@ class Batch:
         """In-graph milliseconds per frame section (perturbs the streaming state; profiling only)."""
         ms = (C.c_float * 8)()
         n = check(lib().ptts_batch_profile_sections(self._h, ms, 8))
-        names = ["flow_backbone", "eos_flow_head", "mimi_transformer", "seanet", "whole_frame"]
+        names = ["flow_backbone", "eos_flow_head", "mimi_transformer", "seanet", "whole_frame",
+                 "mimi_transformer_capped", "seanet_capped"]
         return dict(zip(names, [float(ms[i]) for i in range(n)]))
 
     def profile_step(self):

@@ -1,15 +1,16 @@
 // Cluster chain kernel (see chain_tc.cuh): a dependent chain of small-M GEMMs with fused LayerNorm in one launch.
 //
 // One cluster of NC CTAs per 128-row tile of the batch.  Inside a CTA the roles are those of gemm_tc.cu:
-//   warp 0    : TMA producer.  Every k-block (64 columns of K) of every step is one ring stage = the [128 x 64] A
-//               block (16 KB, the same for all CTAs of the cluster: CTA g % NC loads it ONCE and multicasts it into
-//               every CTA's ring) + this CTA's own [bn x 64] W block.  W blocks of the next step are issued before
-//               the step barrier (weights do not depend on activations), A blocks after it;
-//   warp 1    : tcgen05.mma issuer (M = 128, N = bn <= 128, two TMEM accumulator stages); the commit that frees a ring
-//               stage is multicast to every CTA of the cluster, because the stage's next A block arrives by multicast
-//               from whichever CTA's turn it is;
+//   warp 0    : TMA producer.  The A operand of a step ([128 rows x K <= 512] bf16, the same for all CTAs of the cluster)
+//               is RESIDENT for the step: its eight [128 x 64] blocks are fetched once per cluster -- CTA b % NC loads
+//               block b and multicasts it into every CTA's shared memory.  This CTA's own [bn x 64] W blocks stream
+//               through a CTA-local ring; W blocks of the next step are issued before the step barrier (weights do not
+//               depend on activations), the A blocks after it.  (A first version streamed A through a cluster-synchronous
+//               ring, one cluster-wide round trip per 16 KB block: 274 us for the flow head instead of 133.)
+//   warp 1    : tcgen05.mma issuer (M = 128, N = bn <= 64, two TMEM accumulator stages); after the last MMA that reads
+//               the resident A it multicasts a commit to every CTA's "a_free" barrier;
 //   warps 2-9 : epilogue: TMEM -> registers -> bias / activation / gate / residual -> global memory (the next step's
-//               A operand, fetched through L2 by TMA), or RoPE + KV-cache append for the FlowLM qkv step.
+//               A operand, fetched through L2 by TMA).
 // Steps are separated by a cluster-scope mbarrier ("opdone": every epilogue warp of every CTA arrives on every CTA's
 // barrier after its global stores; the producers wait on it before they fetch the next step's A blocks).
 // LayerNorm needs whole rows, which are spread over the cluster: each CTA computes (mean, M2) of its slice of a row,
@@ -27,8 +28,10 @@
 namespace ptts {
 namespace {
 
-constexpr int kChStages = 6;
-constexpr uint32_t kChA = 16384, kChW = 16384, kChStage = kChA + kChW;
+constexpr int kChStages = 8;                    // CTA-local ring of W blocks
+constexpr uint32_t kChA = 16384;                // one [128 x 64] bf16 block of the resident A operand
+constexpr int kChABlocks = 8;                   // K <= 512 per chunk
+constexpr uint32_t kChW = 8192;                 // one [bn <= 64][64] W block
 constexpr int kChThreads = 320;
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -80,14 +83,19 @@ __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, flo
 }
 
 template <int NC>
-__global__ void __launch_bounds__(kChThreads, 1) chain_kernel(const ChainOp* __restrict__ ops, const int n_ops, const int M) {
+__global__ void __launch_bounds__(kChThreads, 1) chain_kernel(const ChainOp* __restrict__ ops, const int n_ops, const int M,
+                                                              long long* __restrict__ dbg) {
+  // dbg (optional): [n_ops][8] clock64 stamps of CTA 0: producer {step barrier passed, A issued}, MMA {A resident, last
+  // commit}, epilogue warp 2 {first accumulator ready, stores done, row statistics ready}
+#define CH_STAMP(slot) do { if (dbg && blockIdx.x == 0) dbg[oi * 8 + (slot)] = clock64(); } while (0)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stats = base + kChStages * kChStage;              // [NC][128] float2 (mean, M2) of every CTA's row slices
+  const uint32_t sW = base + kChABlocks * kChA;                     // W ring behind the resident A blocks
+  const uint32_t stats = sW + kChStages * kChW;                     // [NC][128] float2 (mean, M2) of every CTA's row slices
   const uint32_t hb = stats + NC * 1024u;                           // [128] float4: the other column half's partial
   const uint32_t bars = hb + 2048u;
   const uint32_t full0 = bars, empty0 = bars + 8 * kChStages, tfull0 = empty0 + 8 * kChStages, tempty0 = tfull0 + 16,
-                 opdone = tempty0 + 16, statsdone = opdone + 8, tptr = statsdone + 8;
+                 opdone = tempty0 + 16, statsdone = opdone + 8, a_full = statsdone + 8, a_free = a_full + 8, tptr = a_free + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
   const int m0 = (int)(blockIdx.x / NC) * 128;
@@ -96,8 +104,10 @@ __global__ void __launch_bounds__(kChThreads, 1) chain_kernel(const ChainOp* __r
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kChStages; ++i) {
       mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, NC);            // one multicast commit from every CTA of the cluster
+      mbar_init(empty0 + 8 * i, 1);
     }
+    mbar_init(a_full, 1);
+    mbar_init(a_free, NC);                       // one multicast commit from every CTA of the cluster
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
       mbar_init(tempty0 + 8 * i, 8);
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(kChThreads, 1) chain_kernel(const ChainOp* __r
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(128) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -120,65 +130,79 @@ __global__ void __launch_bounds__(kChThreads, 1) chain_kernel(const ChainOp* __r
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t git = 0;
+      uint32_t git = 0, cc = 0;                 // W stages issued, A chunks loaded
       for (int oi = 0; oi < n_ops; ++oi) {
         const ChainOp* op = ops + oi;
         const int bn = op->bn, nkb = op->K / 64, slice = op->N / NC;
         const int tiles = slice >= bn ? slice / bn : 1;
         const int n_base = slice >= bn ? (int)rank * slice : 0;
         const uint32_t wbytes = (uint32_t)bn * 128u;
-        const int total = tiles * nkb;
-        const int pre = total < kChStages ? total : kChStages;
-        auto issue_w = [&](int i) {
-          const uint32_t g = git + (uint32_t)i, s = g % kChStages, ph = (g / kChStages) & 1;
-          const int t = i / nkb, kb = i - t * nkb;
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
-          mbar_expect_tx(full0 + 8 * s, kChA + wbytes);
-          tma_load_2d(base + s * kChStage + kChA, &op->tm_w, full0 + 8 * s, kb * 64, n_base + t * bn);
-        };
-        auto issue_a = [&](int i) {
-          const uint32_t g = git + (uint32_t)i;
-          if (g % NC == rank) {
-            const uint32_t s = g % kChStages;
-            const int kb = i % nkb;
-            tma_load_2d_mc(base + s * kChStage, &op->tm_a, full0 + 8 * s, kb * 64, m0, kAll);
+        const int n_chunks = (nkb + kChABlocks - 1) / kChABlocks;      // > 1 only for single-tile steps (host-checked)
+        for (int ch = 0; ch < n_chunks; ++ch, ++cc) {
+          const int kb0 = ch * kChABlocks, nkc = min(kChABlocks, nkb - kb0);
+          const int total = tiles * nkc;
+          const int pre = total < kChStages ? total : kChStages;
+          auto issue_w = [&](int i) {
+            const uint32_t g = git + (uint32_t)i, s = g % kChStages, ph = (g / kChStages) & 1;
+            const int t = i / nkc, kb = kb0 + i - t * nkc;
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            mbar_expect_tx(full0 + 8 * s, wbytes);
+            tma_load_2d(sW + s * kChW, &op->tm_w, full0 + 8 * s, kb * 64, n_base + t * bn);
+          };
+          for (int i = 0; i < pre; ++i) issue_w(i);        // weights first: they do not depend on the previous step
+          if (cc > 0) mbar_wait(a_free, (cc - 1) & 1u);     // every CTA's MMAs have finished with the resident A
+          if (ch == 0 && oi > 0) {
+            mbar_wait_cluster(opdone, (uint32_t)(oi - 1) & 1u);      // the previous step's outputs are in global memory
+            asm volatile("fence.proxy.async;" ::: "memory");
           }
-        };
-        for (int i = 0; i < pre; ++i) issue_w(i);        // weights: under the previous step's epilogue
-        if (oi > 0) {
-          mbar_wait_cluster(opdone, (uint32_t)(oi - 1) & 1u);      // the previous step's outputs are in global memory
-          asm volatile("fence.proxy.async;" ::: "memory");
+          if (ch == 0) CH_STAMP(0);
+          mbar_expect_tx(a_full, (uint32_t)nkc * kChA);
+          for (int b = 0; b < nkc; ++b)
+            if ((uint32_t)b % NC == rank) tma_load_2d_mc(base + (uint32_t)b * kChA, &op->tm_a, a_full, (kb0 + b) * 64, m0, kAll);
+          if (ch == 0) CH_STAMP(1);
+          for (int i = pre; i < total; ++i) issue_w(i);
+          git += (uint32_t)total;
         }
-        for (int i = 0; i < pre; ++i) issue_a(i);
-        for (int i = pre; i < total; ++i) { issue_w(i); issue_a(i); }
-        git += (uint32_t)total;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t git = 0, tcount = 0;
+      uint32_t git = 0, tcount = 0, cc = 0;
       for (int oi = 0; oi < n_ops; ++oi) {
         const ChainOp* op = ops + oi;
         const int bn = op->bn, nkb = op->K / 64, slice = op->N / NC;
         const int tiles = slice >= bn ? slice / bn : 1;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        for (int t = 0; t < tiles; ++t, ++tcount) {
-          const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-          mbar_wait(tempty0 + 8 * as, aph ^ 1);
+        const int n_chunks = (nkb + kChABlocks - 1) / kChABlocks;
+        for (int ch = 0; ch < n_chunks; ++ch, ++cc) {
+          const int nkc = min(kChABlocks, nkb - ch * kChABlocks);
+          mbar_wait(a_full, cc & 1u);
           tc_fence_after();
-          const uint32_t tmem_acc = tmem_base + as * 128;
-          for (int kb = 0; kb < nkb; ++kb, ++git) {
-            const uint32_t s = git % kChStages, ph = (git / kChStages) & 1;
-            mbar_wait(full0 + 8 * s, ph);
-            tc_fence_after();
-            const uint64_t da = make_desc<128>(base + s * kChStage);
-            const uint64_t db = make_desc<128>(base + s * kChStage + kChA);
+          if (ch == 0) CH_STAMP(2);
+          for (int t = 0; t < tiles; ++t) {
+            const uint32_t tc_ = tcount + (n_chunks == 1 ? (uint32_t)t : 0u);
+            const uint32_t as = tc_ & 1, aph = (tc_ >> 1) & 1;
+            if (ch == 0) {
+              mbar_wait(tempty0 + 8 * as, aph ^ 1);
+              tc_fence_after();
+            }
+            const uint32_t tmem_acc = tmem_base + as * 64;
+            for (int kb = 0; kb < nkc; ++kb, ++git) {
+              const uint32_t s = git % kChStages, ph = (git / kChStages) & 1;
+              mbar_wait(full0 + 8 * s, ph);
+              tc_fence_after();
+              const uint64_t da = make_desc<128>(base + (uint32_t)kb * kChA);
+              const uint64_t db = make_desc<128>(sW + s * kChW);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            tc_commit_mc(empty0 + 8 * s, kAll);     // frees the stage in EVERY CTA's view once these MMAs have read it
+              for (int k = 0; k < 4; ++k) tc_mma(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ch | kb | k) != 0);
+              tc_commit(empty0 + 8 * s);
+            }
+            if (ch == n_chunks - 1) tc_commit(tfull0 + 8 * as);
           }
-          tc_commit(tfull0 + 8 * as);
+          tc_commit_mc(a_free, kAll);              // this CTA is done reading the resident A blocks
+          CH_STAMP(3);
         }
+        tcount += (uint32_t)tiles;
       }
     }
   } else {
@@ -198,7 +222,8 @@ __global__ void __launch_bounds__(kChThreads, 1) chain_kernel(const ChainOp* __r
         const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(tfull0 + 8 * as, aph);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + as * 128 + ((uint32_t)(quad * 32) << 16);
+        if (t == 0 && warp == 2 && lane == 0) CH_STAMP(4);
+        const uint32_t tmem_acc = tmem_base + as * 64 + ((uint32_t)(quad * 32) << 16);
         const int n_tile = n_base + t * bn;
         if (op.kind == CH_RES_LN) {
           // ---- residual stream update + LayerNorm over the whole row (one tile per CTA by construction)
@@ -280,13 +305,11 @@ __global__ void __launch_bounds__(kChThreads, 1) chain_kernel(const ChainOp* __r
               for (uint32_t c = 0; c < (uint32_t)NC; ++c)
                 asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(map_remote(mine_addr, c)), "f"(mean), "f"(m2) : "memory");
               __syncwarp();
-              if (lane == 0) {
-#pragma unroll 1
-                for (uint32_t c = 0; c < (uint32_t)NC; ++c) mbar_arrive_remote(statsdone, c);
-              }
+              if (lane < NC) mbar_arrive_remote(statsdone, (uint32_t)lane);      // lane c tells CTA c
             }
             mbar_wait_cluster(statsdone, ln_count & 1u);
             ++ln_count;
+            if (warp == 2 && lane == 0) CH_STAMP(6);
             float nt = 0.f, mt = 0.f, m2t = 0.f;
 #pragma unroll 1
             for (uint32_t c = 0; c < (uint32_t)NC; ++c) {
@@ -340,43 +363,6 @@ __global__ void __launch_bounds__(kChThreads, 1) chain_kernel(const ChainOp* __r
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          if (op.kind == CH_ROPE_KV) {
-            if (!st_ok) continue;
-            // this thread holds 32 consecutive columns = half a head (see gemm_tc.cu)
-            const int Dm = op.kv_heads * 64;
-            const int which = n / Dm, within = n - which * Dm;       // 0 q, 1 k, 2 v
-            if (which < 2) {
-              const float4* cp = reinterpret_cast<const float4*>(op.rope_cs + (long long)row * 64 + ((within & 63) >> 1));
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 c4 = cp[i], s4 = cp[8 + i];
-                const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float xr = v[8 * i + 2 * j], xi = v[8 * i + 2 * j + 1];
-                  v[8 * i + 2 * j] = xr * cc[j] - xi * ss[j];
-                  v[8 * i + 2 * j + 1] = xr * ss[j] + xi * cc[j];
-                }
-              }
-            }
-            if (which == 0) {
-              float4* qp = reinterpret_cast<float4*>(op.q_rot + (long long)row * Dm + within);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) qp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            } else {
-              const int hh = within >> 6;
-              const int pos = op.kv_row_pos[row];
-              const int page = op.kv_page_table[(long long)row * op.kv_max_pages + pos / 32];
-              __nv_bfloat16* dst = op.kv_layer + page * op.kv_page_stride + ((long long)hh * 32 + (pos & 31)) * 64 + (within & 63);
-              if (which == 2) dst += (long long)op.kv_heads * 32 * 64;
-              uint4* dp = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                dp[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                                   pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-            }
-            continue;
-          }
           if (op.bias) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -422,10 +408,8 @@ __global__ void __launch_bounds__(kChThreads, 1) chain_kernel(const ChainOp* __r
       // this warp's global stores of the step are done: tell every CTA of the cluster (their producers fetch them by TMA)
       asm volatile("fence.proxy.async;" ::: "memory");
       __syncwarp();
-      if (lane == 0 && oi + 1 < n_ops) {
-#pragma unroll 1
-        for (uint32_t c = 0; c < (uint32_t)NC; ++c) mbar_arrive_remote(opdone, c);
-      }
+      if (warp == 2 && lane == 0) CH_STAMP(5);
+      if (lane < NC && oi + 1 < n_ops) mbar_arrive_remote(opdone, (uint32_t)lane);      // lane c tells CTA c
     }
   }
   tc_fence_before();
@@ -433,13 +417,13 @@ __global__ void __launch_bounds__(kChThreads, 1) chain_kernel(const ChainOp* __r
   cluster_sync_all();            // nobody leaves while a peer may still multicast, store or arrive into this CTA
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
   }
 }
 
 template <int NC>
 constexpr size_t chain_smem() {
-  return (size_t)kChStages * kChStage + NC * 1024 + 2048 + 256 + 1024;
+  return (size_t)kChABlocks * kChA + (size_t)kChStages * kChW + NC * 1024 + 2048 + 256 + 1024;
 }
 
 int g_nc = -1;
@@ -501,9 +485,16 @@ bool chain_encode_w(CUtensorMap* tm, const __nv_bfloat16* w, int N, int K, int b
 int chain_pick_bn(int N, int nc) {
   if (N % nc) return (N % 32 == 0 && N < nc * 32) ? 32 : 0;
   const int slice = N / nc;
-  for (int bn : {128, 64, 32})
+  for (int bn : {64, 32})
     if (slice % bn == 0) return bn;
   return (N % 32 == 0 && slice < 32) ? 32 : 0;
+}
+
+bool chain_step_ok(int N, int K, int nc) {
+  const int bn = chain_pick_bn(N, nc);
+  if (bn == 0 || K % 64) return false;
+  const int slice = N / nc, tiles = slice >= bn ? slice / bn : 1;
+  return K <= 64 * kChABlocks || tiles == 1;
 }
 
 void chain_launch(const ChainOp* d_ops, int n_ops, int M, int nc, const char* tag, double flops, double bytes, cudaStream_t s) {
@@ -518,14 +509,32 @@ void chain_launch(const ChainOp* d_ops, int n_ops, int M, int nc, const char* ta
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = g_pdl_on ? 2 : 1;
+  // PTTS_CHAIN_DBG=1: per-step clock stamps of CTA 0, printed after a synchronisation (debugging / profiling only)
+  static const bool dbg_on = [] { const char* v = getenv("PTTS_CHAIN_DBG"); return v && v[0] == '1'; }();
+  static long long* d_dbg = nullptr;
+  if (dbg_on && !d_dbg) cudaMalloc((void**)&d_dbg, 64 * 8 * sizeof(long long));
+  long long* dbg = (dbg_on && n_ops <= 64) ? d_dbg : nullptr;
+  if (dbg) cudaMemsetAsync(dbg, 0, 64 * 8 * sizeof(long long), s);
   if (nc == 16) {
     cfg.dynamicSmemBytes = chain_smem<16>();
-    cudaLaunchKernelEx(&cfg, chain_kernel<16>, d_ops, n_ops, M);
+    cudaLaunchKernelEx(&cfg, chain_kernel<16>, d_ops, n_ops, M, dbg);
   } else {
     cfg.dynamicSmemBytes = chain_smem<8>();
-    cudaLaunchKernelEx(&cfg, chain_kernel<8>, d_ops, n_ops, M);
+    cudaLaunchKernelEx(&cfg, chain_kernel<8>, d_ops, n_ops, M, dbg);
   }
   ++g_launches;
+  if (dbg) {
+    long long h[64 * 8];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost);
+    const long long t0 = h[1] ? h[1] : h[0];
+    fprintf(stderr, "[chain %s] M=%d nc=%d  (cycles since the first A issue)\n  op  barrier  a_issue  a_ready  mma_done  acc_ready  stats  stored\n", tag ? tag : "?", M, nc);
+    for (int i = 0; i < n_ops; ++i) {
+      const long long* r = h + i * 8;
+      auto rel = [&](long long v) { return v ? (long long)(v - t0) : -1LL; };
+      fprintf(stderr, "  %2d %8lld %8lld %8lld %9lld %10lld %6lld %7lld\n", i, rel(r[0]), rel(r[1]), rel(r[2]), rel(r[3]), rel(r[4]), rel(r[6]), rel(r[5]));
+    }
+  }
 }
 
 }  // namespace ptts

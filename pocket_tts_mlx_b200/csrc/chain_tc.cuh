@@ -21,7 +21,6 @@ enum ChainEpi : int {
   CH_STORE32 = 1,   // y32 = acc + bias                                        (fp32: AdaLN modulation table)
   CH_RES_LN = 2,    // x = [x +] gate * (acc + bias); h16 = mod(LN(x))          (residual stream + fused LayerNorm)
   CH_FIN = 3,       // lat_out = lat_in + out_scale * (acc + bias)              (Euler update of the latent, N = latent_dim)
-  CH_ROPE_KV = 4,   // FlowLM qkv: RoPE on q / k, q -> q_rot fp32, k / v -> paged KV cache
 };
 
 struct alignas(128) ChainOp {
@@ -40,9 +39,6 @@ struct alignas(128) ChainOp {
   __nv_bfloat16* h16; long long h_rs;
   // CH_FIN
   const float* lat_in; float* lat_out; long long lat_rs; __nv_bfloat16* lat16; long long lat16_rs;
-  // CH_ROPE_KV (see TcEpilogue in gemm_tc.cuh)
-  const float* rope_cs; float* q_rot; __nv_bfloat16* kv_layer;
-  const int *kv_row_pos, *kv_page_table; int kv_max_pages, kv_heads; long long kv_page_stride;
 };
 
 bool chain_available();
@@ -50,8 +46,10 @@ bool chain_available();
 int chain_cluster_size();
 bool chain_encode_a(CUtensorMap* tm, const __nv_bfloat16* a, int M, int K, long long row_stride);
 bool chain_encode_w(CUtensorMap* tm, const __nv_bfloat16* w, int N, int K, int bn);
-// N tile for an op of width N split over nc CTAs (0: not divisible)
+// N tile (64 or 32) for a step of width N split over nc CTAs (0: not divisible).  Steps with K > 512 keep their
+// accumulator across the K chunks and must be a single tile per CTA: chain_step_ok checks both.
 int chain_pick_bn(int N, int nc);
+bool chain_step_ok(int N, int K, int nc);
 // ops: DEVICE array of n_ops ChainOp (128-byte aligned); M rows; nc = cluster size the ops were planned for
 void chain_launch(const ChainOp* d_ops, int n_ops, int M, int nc, const char* tag, double flops, double bytes, cudaStream_t s);
 

@@ -118,11 +118,6 @@ struct FlowWork {
   // set by the prefill callers around flow_layers: row ranges / start positions per sequence (device arrays), which
   // let whole chunks go through the tensor-core prefill attention instead of the per-row decode kernel
   const int* seq_row0 = nullptr; const int* seq_pos0 = nullptr; int n_seq = 0, max_rows_per_seq = 0;
-  // decode at batch <= 512: per layer ONE cluster chain launch [out-proj + LN2, ffn1 + GELU, ffn2 + next LN1, next qkv +
-  // RoPE + KV append] instead of 4 GEMM + 2 LayerNorm launches (chain_tc.cu)
-  ChainOp* d_chain = nullptr;             // [n_layers][4]
-  int chain_M = 0, chain_nc = 0;
-  const int *chain_pos = nullptr, *chain_pt = nullptr; int chain_maxp = 0;
 };
 
 }  // namespace
@@ -646,7 +641,7 @@ bool want_tc(Ctx& c, int M) {
 
 void free_flow_work(FlowWork& w) {
   void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16, w.ws_out, w.ws_ff2, w.attn_part,
-                  w.d_prefix_pages, w.prefix_part, w.rope_cs, w.d_chain};
+                  w.d_prefix_pages, w.prefix_part, w.rope_cs};
   for (void* p : ptrs) if (p) cudaFree(p);
   w = FlowWork{};
 }
@@ -712,53 +707,12 @@ int build_flow_plans(Ctx& c, FlowWork& w, int M) {
   return 0;
 }
 
+// The single-launch flow head (cluster chain kernel) is opt-in: measured at batch 256 it takes 199 us against 133 us for
+// the chain of 23 launches it replaces (per step ~10 us of cluster barrier, multicast fetch and L2-latency-bound
+// epilogue work against ~5.8 us per captured launch), see DESIGN.md.
 bool chain_enabled() {
-  static const bool on = [] { const char* v = getenv("PTTS_CHAIN"); return !(v && v[0] == '0'); }();
-  return on && chain_cluster_size() > 0;
-}
-
-// (re)build the per-layer chain op lists of a decode batch; false: keep the per-GEMM launches
-bool ensure_flow_chain(Ctx& c, FlowWork& w, int M, const int* row_pos, const int* page_table, int max_pages) {
-  if (!chain_enabled() || !w.tc || M > 512) return false;
-  const int nc = chain_cluster_size();
-  if (w.d_chain && w.chain_M == M && w.chain_nc == nc && w.chain_pos == row_pos && w.chain_pt == page_table && w.chain_maxp == max_pages)
-    return true;
-  const int D = c.cfg.d_model, FF = c.cfg.ffn_dim, NL = c.cfg.n_layers;
-  if (D / nc > 128 || D % nc || chain_pick_bn(D, nc) != D / nc) return false;          // LayerNorm steps: one tile per CTA
-  std::vector<ChainOp> ops((size_t)NL * 4);
-  memset(ops.data(), 0, ops.size() * sizeof(ChainOp));
-  bool ok = true;
-  auto gemm = [&](ChainOp& o, const __nv_bfloat16* a, int K, const LinW& lw, int kind) {
-    o.K = K; o.N = lw.N; o.bn = chain_pick_bn(lw.N, nc); o.kind = kind; o.bias = lw.bias;
-    ok = ok && lw.w16 && lw.K == K && o.bn > 0 && K % 64 == 0 && chain_encode_a(&o.tm_a, a, M, K, K) &&
-         chain_encode_w(&o.tm_w, lw.w16, lw.N, K, o.bn);
-  };
-  for (int i = 0; i < NL; ++i) {
-    auto& l = c.fl[i];
-    ChainOp* o = &ops[(size_t)i * 4];
-    gemm(o[0], w.att16, D, l.out, CH_RES_LN);
-    o[0].x = w.x; o[0].x_rs = D; o[0].ln_on = 1; o[0].ln_w = l.ln2w; o[0].ln_b = l.ln2b; o[0].ln_eps = 1e-5f;
-    o[0].h16 = w.h16; o[0].h_rs = D;
-    gemm(o[1], w.h16, D, l.ff1, CH_STORE16);
-    o[1].act = ACT_GELU; o[1].y16 = w.ff16; o[1].y_rs = FF;
-    gemm(o[2], w.ff16, FF, l.ff2, CH_RES_LN);
-    o[2].x = w.x; o[2].x_rs = D; o[2].h16 = w.h16; o[2].h_rs = D;
-    if (i + 1 < NL) {
-      auto& nx = c.fl[i + 1];
-      o[2].ln_on = 1; o[2].ln_w = nx.ln1w; o[2].ln_b = nx.ln1b; o[2].ln_eps = 1e-5f;
-      gemm(o[3], w.h16, D, nx.qkv, CH_ROPE_KV);
-      o[3].rope_cs = w.rope_cs; o[3].q_rot = w.qrot;
-      o[3].kv_layer = reinterpret_cast<__nv_bfloat16*>(c.pool) + (long long)(i + 1) * c.layer_stride;
-      o[3].kv_row_pos = row_pos; o[3].kv_page_table = page_table; o[3].kv_max_pages = max_pages;
-      o[3].kv_heads = c.cfg.n_heads; o[3].kv_page_stride = c.page_stride;
-    }
-  }
-  if (!ok) return false;
-  if (!w.d_chain && cudaMalloc((void**)&w.d_chain, ops.size() * sizeof(ChainOp)) != cudaSuccess) { cudaGetLastError(); return false; }
-  if (cudaMemcpyAsync(w.d_chain, ops.data(), ops.size() * sizeof(ChainOp), cudaMemcpyHostToDevice, c.stream) != cudaSuccess) return false;
-  cudaStreamSynchronize(c.stream);         // ops is a local vector
-  w.chain_M = M; w.chain_nc = nc; w.chain_pos = row_pos; w.chain_pt = page_table; w.chain_maxp = max_pages;
-  return true;
+  const char* v = getenv("PTTS_CHAIN");
+  return v && v[0] == '1' && chain_cluster_size() > 0;
 }
 
 // the 6 pre-LN layers over M rows that sit at (row_seq, row_pos) of their sequences
@@ -770,12 +724,9 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
     // RoPE + KV append ride in the qkv GEMM's epilogue (PTTS_NO_ROPE_FUSE=1 keeps the separate kernel)
     static const bool fuse_rope = [] { const char* v = getenv("PTTS_NO_ROPE_FUSE"); return !(v && v[0] == '1'); }();
     if (fuse_rope) launch_rope_table(row_pos, c.freqs_flow, w.rope_cs, M, 1, c.stream);
-    // decode steps: everything between two attention kernels is one cluster chain launch
-    const bool chain = fuse_rope && !row_seq && ensure_flow_chain(c, w, M, row_pos, page_table, max_pages);
     for (int i = 0; i < c.cfg.n_layers; ++i) {
       auto& l = c.fl[i];
       const TcGemm* g = &w.plans[(size_t)i * 4];
-      if (chain && i > 0) goto attention;          // LN1 + qkv of this layer ran at the end of the previous layer's chain
       rows_norm(c, w.x, M, D, l.ln1w, l.ln1b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16, w.ws_ff2, pend);
       if (fuse_rope) {
         TcGemm q = g[0];
@@ -789,7 +740,6 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       } else {
         gemm_tc_launch(g[0], c.stream);
       }
-    attention:
       FlowAttnParams a{};
       a.qkv = w.qkv; a.q_rot = w.qrot; a.out16 = w.att16;
       a.pool = c.pool; a.kv_bf16 = c.bf16; a.layer_stride = c.layer_stride; a.page_stride = c.page_stride;
@@ -808,13 +758,6 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       } else {
         launch_flow_prefix_attention(a, c.stream);
         launch_flow_attention(a, c.stream);
-      }
-      if (chain) {
-        const int n_ops = (i + 1 < c.cfg.n_layers) ? 4 : 3;
-        const double fl = 2.0 * M * ((double)D * D + 2.0 * D * FF + (n_ops == 4 ? 3.0 * D * D : 0.0));
-        chain_launch(w.d_chain + (size_t)i * 4, n_ops, M, w.chain_nc, "flow.layer", fl, fl / M, c.stream);
-        pend = 0;
-        continue;
       }
       gemm_tc_launch(g[1], c.stream);
       rows_norm(c, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16, w.ws_out,
@@ -1239,14 +1182,14 @@ int build_batch_tc(Batch& t) {
     // ---- single-launch flow head (cluster chain kernel)
     t.n_head_ops = 0;
     const int nc = chain_enabled() ? chain_cluster_size() : 0;
-    if (nc > 0 && B <= 512 && L == 32 && c.in_proj_pad && fd % nc == 0 && fd / nc <= 128 && chain_pick_bn(fd, nc) == fd / nc) {
+    if (nc > 0 && B <= 512 && L == 32 && c.in_proj_pad && fd % nc == 0 && fd / nc <= 64 && chain_pick_bn(fd, nc) == fd / nc) {
       RET(bz(&t.d_x16, (size_t)B * 64));
       const int nst = g.lsd_decode_steps, per = 4 + 2 * g.flow_depth;
       std::vector<ChainOp> ops((size_t)nst * per);
       bool cok = true;
       auto gemm = [&](ChainOp& o, const __nv_bfloat16* a, int K, const __nv_bfloat16* w16, int N, const float* bias, int kind) {
         o.K = K; o.N = N; o.bn = chain_pick_bn(N, nc); o.kind = kind; o.bias = bias;
-        cok = cok && w16 && o.bn > 0 && K % 64 == 0 && chain_encode_a(&o.tm_a, a, B, K, K) && chain_encode_w(&o.tm_w, w16, N, K, o.bn);
+        cok = cok && w16 && chain_step_ok(N, K, nc) && chain_encode_a(&o.tm_a, a, B, K, K) && chain_encode_w(&o.tm_w, w16, N, K, o.bn);
       };
       for (int v = 0; v < 2 && cok; ++v) {
         memset(ops.data(), 0, ops.size() * sizeof(ChainOp));
@@ -2692,13 +2635,14 @@ int32_t ptts_batch_profile_step(ptts_batch* bt, const char** report) {
 }
 
 int32_t ptts_batch_profile_sections(ptts_batch* bt, float* ms, int32_t cap) {
-  if (!bt || !ms || cap < 5) return fail(PTTS_ERR_INVALID, "bad arguments");
+  if (!bt || !ms || cap < 7) return fail(PTTS_ERR_INVALID, "bad arguments");
   Ctx& c = *bt->ctx;
   CU(cudaSetDevice(c.device));
   RET(check_step_ready(*bt));
   if (!bt->tc_mimi) return fail(PTTS_ERR_STATE, "section profile needs the tensor-core pipeline (batch >= 2, bf16)");
   const long long before = g_launches;
-  for (int sec = 0; sec < 5; ++sec) {
+  const int mimi_cap = [] { const char* v = getenv("PTTS_MIMI_GRID"); return v ? atoi(v) : 74; }();
+  for (int sec = 0; sec < 7; ++sec) {
     cudaGraph_t graph;
     cudaGraphExec_t exec;
     CU(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed));
@@ -2707,7 +2651,10 @@ int32_t ptts_batch_profile_sections(ptts_batch* bt, float* ms, int32_t cap) {
       case 1: flow_step(*bt, false, 2); break;                 // out-norm + EOS + flow head
       case 2: mimi_frame_tc(*bt, bt->d_latent, 1); break;      // quantizer/upsample + Mimi transformer
       case 3: mimi_frame_tc(*bt, bt->d_latent, 2); break;      // SEANet decoder
-      default: full_step(*bt, false, false); break;            // whole frame (advances the batch)
+      case 4: full_step(*bt, false, false); break;             // whole frame (advances the batch)
+      // the Mimi sections as they run in the pipelined frame graph: persistent kernels capped at PTTS_MIMI_GRID SMs
+      case 5: gemm_tc_set_grid_cap(mimi_cap); mimi_frame_tc(*bt, bt->d_latent, 1); gemm_tc_set_grid_cap(0); break;
+      default: gemm_tc_set_grid_cap(mimi_cap); mimi_frame_tc(*bt, bt->d_latent, 2); gemm_tc_set_grid_cap(0); break;
     }
     CU(cudaStreamEndCapture(c.stream, &graph));
     CU(cudaGraphInstantiate(&exec, graph, 0));
@@ -2726,7 +2673,7 @@ int32_t ptts_batch_profile_sections(ptts_batch* bt, float* ms, int32_t cap) {
   }
   g_launches = before;
   CU(cudaGetLastError());
-  return 5;
+  return 7;
 }
 
 int32_t ptts_flush_l2(ptts_ctx* c) {

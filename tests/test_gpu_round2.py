@@ -533,3 +533,44 @@ def test_cluster_chain_kernel_matches_numpy(model_b256, m):
     assert rel_l2(out["x1"], x1) < 2e-3, rel_l2(out["x1"], x1)
     assert rel_l2(out["h"], h2) < 4e-3, rel_l2(out["h"], h2)
     assert rel_l2(out["lat"], lat) < 2e-3, rel_l2(out["lat"], lat)
+
+
+@pytest.mark.parametrize("lsd", [1, 2])
+def test_single_launch_flow_head_vs_oracle(bundle, cfg, weights, voices, monkeypatch, lsd):
+    """PTTS_CHAIN=1: the whole flow head (all Euler steps: cond embedding, AdaLN table, input projection, six
+    LayerNorm-modulated residual blocks, final layer, latent update) runs as ONE cluster-chain launch; teacher-forced
+    latents and the waveform against the oracle, and against the default launch chain of the same model."""
+    from pocket_tts_mlx_b200 import TTSModel, _native
+    n, frames = 40, 4
+    rng = np.random.Generator(np.random.PCG64(3030 + lsd))
+    ids = [rng.integers(0, 4000, size=int(rng.integers(8, 20))).astype(np.int32) for _ in range(n)]
+    noise = rng.standard_normal((1 + frames, n, 32)).astype(np.float32)
+    sample = [0, 17, 39]
+    orc, st = _oracle(weights, cfg, voices("alba")[0], eos_threshold=1e30, lsd_decode_steps=lsd)
+    refs = {b: orc.generate(st, ids[b], noise[:, b, :], frames_after_eos=3, max_frames=frames) for b in sample}
+    got = {}
+    for chain in ("1", "0"):
+        monkeypatch.setenv("PTTS_CHAIN", chain)
+        m = TTSModel.load_model(str(bundle), lsd_decode_steps=lsd, eos_threshold=1e30, precision="bf16", kv_pool_tokens=32768)
+        try:
+            state = m.get_state_for_audio_prompt("alba")
+            # different reservations per mode: the arena (and its op lists) of the other mode must not be recycled
+            batch = _native.Batch(m._ctx, [state["voice_id"]] * n,
+                                  [state["prompt_len"] + len(t) + frames + (4 if chain == "1" else 40) for t in ids])
+            launches0 = m._ctx.launch_count(reset=True)
+            batch.warmup_mimi(1)
+            batch.prefill_text(ids)
+            lat, logit, aud = _teacher_forced(batch, noise, refs, frames, pipelined=False)
+            got[chain] = (lat, m._ctx.launch_count())
+            batch.close()
+        finally:
+            m.close()
+        for b in sample:
+            for f in range(frames):
+                e = rel_l2(lat[b][f], refs[b]["latents"][f])
+                assert e < 1e-2, (chain, b, f, e)
+            assert snr_db(np.concatenate(aud[b]), refs[b]["audio"]) > 30.0, (chain, b)
+    # one launch instead of 23 per Euler step and frame
+    assert got["0"][1] - got["1"][1] >= frames * (22 * lsd) - 4, (got["0"][1], got["1"][1])
+    for b in sample:
+        assert rel_l2(np.stack(got["1"][0][b]), np.stack(got["0"][0][b])) < 6e-3
