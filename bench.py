@@ -267,7 +267,7 @@ def roofline_from_profile(model, state, ids, at_frame: int, peaks):
         roof = {"bound": "tensor", "achieved": tfs, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": tfs / peaks["tf_sustained"]}
     traffic = None
-    tp = REPO / "profiles" / "r01_ncu_traffic.json"
+    tp = REPO / "profiles" / "r02_ncu_traffic.json"
     if tp.exists():
         traffic = json.loads(tp.read_text()).get(name, {}).get("dram_bytes_per_launch")
     roof.update({"kernel": name, "share_of_frame": a["ms"] / total if total else None,

@@ -365,7 +365,7 @@ class TTSModel:
             n_steps = int(lim.max()) if n else 0
             # sequence-major output arrays: step blocks are written straight into them, and a sequence's waveform /
             # latents are a contiguous slice (returned as a view, no concatenation at the end)
-            aud_all = np.empty((n, n_steps, self.frame_samples), dtype=np.int16 if pcm16 else np.float32)
+            aud_all = _alloc_output((n, n_steps, self.frame_samples), np.int16 if pcm16 else np.float32)
             lat_all = np.empty((n, n_steps, ldim), dtype=np.float32)
             counts = {"lat": 0, "audio": 0}
             thr = self.eos_threshold
@@ -615,6 +615,25 @@ class TTSModel:
     def close(self):
         self._state_cache.clear()
         self._ctx.close()
+
+
+def _alloc_output(shape, dtype) -> np.ndarray:
+    """Large result arrays are touched for the first time while the GPU is producing them: with 4 KB pages the page
+    faults of a 256-utterance job (~0.5 GB) cost about as much host time as the job itself.  Ask for transparent huge
+    pages (2 MB) when the platform offers them; otherwise this is np.empty."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if nbytes >= (64 << 20):
+        try:
+            import mmap
+            if hasattr(mmap, "MADV_HUGEPAGE"):
+                buf = mmap.mmap(-1, nbytes + (2 << 20))
+                buf.madvise(mmap.MADV_HUGEPAGE)
+                base = np.frombuffer(buf, dtype=np.uint8)
+                off = (-base.ctypes.data) % (2 << 20)
+                return base[off:off + nbytes].view(dtype).reshape(shape)
+        except (OSError, ValueError, AttributeError):
+            pass
+    return np.empty(shape, dtype=dtype)
 
 
 class _BlockScatter:
