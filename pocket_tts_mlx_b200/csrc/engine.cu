@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -118,6 +119,8 @@ struct FlowWork {
   // set by the prefill callers around flow_layers: row ranges / start positions per sequence (device arrays), which
   // let whole chunks go through the tensor-core prefill attention instead of the per-row decode kernel
   const int* seq_row0 = nullptr; const int* seq_pos0 = nullptr; int n_seq = 0, max_rows_per_seq = 0;
+  // interleaved pipelined frame: called right before / right after the attention kernels of layer i are launched
+  std::function<void(int)> pre_attn, post_attn;
 };
 
 }  // namespace
@@ -128,6 +131,7 @@ struct ptts_ctx {
   ptts_config cfg{};
   cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2 carries the Mimi branch of the pipelined frame graph
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_attn[16] = {}, ev_slice[16] = {};     // interleaved pipelined frame: attention i launched / Mimi slice i done
   bool finalized = false;
   bool bf16 = true;
   bool force_simt = false;     // PTTS_FORCE_SIMT=1: keep the CUDA-core GEMMs (A/B comparisons)
@@ -756,8 +760,10 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       if (row_seq && !no_tc_prefill && launch_flow_prefill_attention(a, c.stream)) {
         // whole prefill chunks: FlashAttention-2 style mma.sync kernel (64 query rows per CTA)
       } else {
+        if (w.pre_attn) w.pre_attn(i);
         launch_flow_prefix_attention(a, c.stream);
         launch_flow_attention(a, c.stream);
+        if (w.post_attn) w.post_attn(i);
       }
       gemm_tc_launch(g[1], c.stream);
       rows_norm(c, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, nullptr, nullptr, nullptr, 0, w.h16, w.ws_out,
@@ -927,7 +933,7 @@ namespace {
 
 using Batch = ptts_batch;
 
-void mimi_frame_tc(Batch& bt, const float* latent, int part = 0, bool advance = false);
+void mimi_frame_tc(Batch& bt, const float* latent, int part = 0, bool advance = false, int seg_lo = 0, int seg_hi = 1 << 30);
 
 // one Mimi frame for every sequence: latent [B][L] -> audio [B][frame_samples]
 // advance: also move every sequence's ring offset on by one frame (folded into the end-of-frame launch)
@@ -1035,15 +1041,21 @@ void mimi_frame(Batch& bt, const float* latent, bool advance = false) {
 
 // Mimi frame on the tensor-core path: bf16 operands everywhere, every conv / transposed conv / linear is a
 // tcgen05 GEMM whose epilogue already writes the next GEMM's (ELU'd) bf16 input, incl. the carried state rows.
-void mimi_frame_tc(Batch& bt, const float* latent, int part, bool advance) {   // part: 0 all, 1 transformer, 2 SEANet
+// seg_lo / seg_hi: only the launches with index in [seg_lo, seg_hi) are issued (the interleaved pipelined frame cuts the
+// decoder into slices that it starts behind the FlowLM attention kernels); one index per logical step, whatever the
+// configuration, see mimi_tc_launches().
+void mimi_frame_tc(Batch& bt, const float* latent, int part, bool advance, int seg_lo, int seg_hi) {   // part: 0 all, 1 transformer, 2 SEANet
   Ctx& c = *bt.ctx;
   const ptts_config& g = c.cfg;
   const int B = bt.B, T = bt.T0, MD = g.mimi_d, SD = g.seanet_dim;
+  int k = 0;
+  auto in = [&]() { const bool t = k >= seg_lo && k < seg_hi; ++k; return t; };
   if (part != 2) {
-  launch_quant_upsample(latent, c.emb_std, c.emb_mean, c.wq, c.wu, bt.d_zprev, bt.d_xm, (long long)T * SD, B,
-                        g.latent_dim, SD, g.upsample_stride, c.stream);
+  if (in())
+    launch_quant_upsample(latent, c.emb_std, c.emb_mean, c.wq, c.wu, bt.d_zprev, bt.d_xm, (long long)T * SD, B,
+                          g.latent_dim, SD, g.upsample_stride, c.stream);
   static const bool fuse_rope = [] { const char* v = getenv("PTTS_NO_ROPE_FUSE"); return !(v && v[0] == '1'); }();
-  if (fuse_rope) launch_rope_table(bt.d_mimi_off, c.freqs_mimi, bt.d_mrope_cs, B * T, T, c.stream);
+  if (in() && fuse_rope) launch_rope_table(bt.d_mimi_off, c.freqs_mimi, bt.d_mrope_cs, B * T, T, c.stream);
   for (int i = 0; i < g.mimi_layers; ++i) {
     auto& l = c.ml[i];
     const TcGemm* gm = &bt.g_mimi[(size_t)i * 4];
@@ -1051,53 +1063,70 @@ void mimi_frame_tc(Batch& bt, const float* latent, int part, bool advance) {   /
     n.X = bt.d_xm; n.x_bs = (long long)T * MD; n.x_rs = MD; n.nb = B; n.T = T; n.C = MD;
     n.w = l.ln1w; n.b = l.ln1b; n.eps = 1e-5f;
     n.Y16 = bt.d_mh16; n.y_bs = (long long)T * MD; n.y_rs = MD;
-    launch_layernorm(n, c.stream);
-    if (fuse_rope) {   // RoPE + ring write in the qkv epilogue
-      TcGemm q = gm[0];
-      auto& e = q.e;
-      e.y32 = nullptr;
-      e.rope_cs = bt.d_mrope_cs; e.q_rot = bt.d_mqrot;
-      e.kv_layer = reinterpret_cast<__nv_bfloat16*>(bt.ring) + (long long)i * bt.ring_layer_stride;
-      e.kv_row_pos = bt.d_mimi_off; e.kv_heads = g.mimi_heads;
-      e.kv_ring = g.mimi_context; e.kv_v_offset = bt.ring_kv_stride;
-      gemm_tc_launch(q, c.stream);
-    } else {
-      gemm_tc_launch(gm[0], c.stream);
+    if (in()) launch_layernorm(n, c.stream);
+    if (in()) {
+      if (fuse_rope) {   // RoPE + ring write in the qkv epilogue
+        TcGemm q = gm[0];
+        auto& e = q.e;
+        e.y32 = nullptr;
+        e.rope_cs = bt.d_mrope_cs; e.q_rot = bt.d_mqrot;
+        e.kv_layer = reinterpret_cast<__nv_bfloat16*>(bt.ring) + (long long)i * bt.ring_layer_stride;
+        e.kv_row_pos = bt.d_mimi_off; e.kv_heads = g.mimi_heads;
+        e.kv_ring = g.mimi_context; e.kv_v_offset = bt.ring_kv_stride;
+        gemm_tc_launch(q, c.stream);
+      } else {
+        gemm_tc_launch(gm[0], c.stream);
+      }
     }
-    MimiAttnParams a{};
-    a.qkv = bt.d_mqkv; a.q_rot = bt.d_mqrot; a.out16 = bt.d_matt16;
-    a.ring = bt.ring; a.kv_bf16 = c.bf16; a.layer_stride = bt.ring_layer_stride; a.kv_stride = bt.ring_kv_stride;
-    a.layer = i; a.offset = bt.d_mimi_off; a.B = B; a.T = T; a.H = g.mimi_heads; a.context = g.mimi_context;
-    a.freqs = c.freqs_mimi;
-    if (!fuse_rope) launch_mimi_rope_ring(a, c.stream);
-    launch_mimi_attention(a, c.stream);
-    gemm_tc_launch(gm[1], c.stream);
+    if (in()) {
+      MimiAttnParams a{};
+      a.qkv = bt.d_mqkv; a.q_rot = bt.d_mqrot; a.out16 = bt.d_matt16;
+      a.ring = bt.ring; a.kv_bf16 = c.bf16; a.layer_stride = bt.ring_layer_stride; a.kv_stride = bt.ring_kv_stride;
+      a.layer = i; a.offset = bt.d_mimi_off; a.B = B; a.T = T; a.H = g.mimi_heads; a.context = g.mimi_context;
+      a.freqs = c.freqs_mimi;
+      if (!fuse_rope) launch_mimi_rope_ring(a, c.stream);
+      launch_mimi_attention(a, c.stream);
+    }
+    if (in()) gemm_tc_launch(gm[1], c.stream);
     n.w = l.ln2w; n.b = l.ln2b;
-    launch_layernorm(n, c.stream);
-    gemm_tc_launch(gm[2], c.stream);
-    gemm_tc_launch(gm[3], c.stream);
+    if (in()) launch_layernorm(n, c.stream);
+    if (in()) gemm_tc_launch(gm[2], c.stream);
+    if (in()) gemm_tc_launch(gm[3], c.stream);
   }
   }
   if (part == 1) return;
-  gemm_tc_launch(bt.g_conv0, c.stream);
+  if (in()) gemm_tc_launch(bt.g_conv0, c.stream);
   for (size_t r = 0; r < bt.sb16.size(); ++r) {
     auto& sb = bt.sb16[r];
-    gemm_tc_launch(sb.ct, c.stream);
+    if (in()) gemm_tc_launch(sb.ct, c.stream);
     if (bt.sn_tail.valid && r + 1 == bt.sb16.size()) {
-      SnTail tl = bt.sn_tail;
-      tl.pcm = bt.pcm16 ? bt.d_pcm : nullptr;
-      sn_tail_launch(tl, c.stream, false);             // its boundary fix-up rides in the state-shift launch below
+      if (in()) {
+        SnTail tl = bt.sn_tail;
+        tl.pcm = bt.pcm16 ? bt.d_pcm : nullptr;
+        sn_tail_launch(tl, c.stream, false);             // its boundary fix-up rides in the state-shift launch below
+      }
       break;
     }
-    gemm_tc_launch(sb.r3, c.stream);
-    gemm_tc_launch(sb.r1, c.stream);
+    if (in()) gemm_tc_launch(sb.r3, c.stream);
+    if (in()) gemm_tc_launch(sb.r1, c.stream);
   }
-  if (!bt.sn_tail.valid)
-    launch_final_conv16(bt.d_fin16, (long long)(bt.frame_samples + c.fin_taps - 1) * c.fin_c, c.fin_w, c.fin_b,
-                        bt.d_audio, bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream,
-                        bt.pcm16 ? bt.d_pcm : nullptr);
-  launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream, bt.d_audio, bt.frame_samples, bt.sn_tail.valid ? bt.d_bnd : nullptr,
-                     bt.frame_samples / 128, advance ? bt.d_mimi_off : nullptr, bt.T0, bt.pcm16 ? bt.d_pcm : nullptr);
+  if (!bt.sn_tail.valid) {
+    if (in())
+      launch_final_conv16(bt.d_fin16, (long long)(bt.frame_samples + c.fin_taps - 1) * c.fin_c, c.fin_w, c.fin_b,
+                          bt.d_audio, bt.frame_samples, B, bt.frame_samples, c.fin_c, c.fin_taps, c.stream,
+                          bt.pcm16 ? bt.d_pcm : nullptr);
+  }
+  if (in())
+    launch_state_shift(bt.d_shift, bt.n_shift, B, c.stream, bt.d_audio, bt.frame_samples, bt.sn_tail.valid ? bt.d_bnd : nullptr,
+                       bt.frame_samples / 128, advance ? bt.d_mimi_off : nullptr, bt.T0, bt.pcm16 ? bt.d_pcm : nullptr);
+}
+
+// number of launch indices mimi_frame_tc(part = 0) walks through
+int mimi_tc_launches(Batch& bt) {
+  const ptts_config& g = bt.ctx->cfg;
+  const int R = (int)bt.sb16.size();
+  const int sn = bt.sn_tail.valid ? (1 + 3 * (R - 1) + 2) : (1 + 3 * R + 1);
+  return 2 + 7 * g.mimi_layers + sn + 1;
 }
 
 // flow head on the tensor-core path (M = B rows)
@@ -1439,29 +1468,62 @@ void pipelined_frame(Batch& bt, int parity, bool host_io) {
   cudaStream_t main = c.stream;
   cudaEventRecord(c.ev_fork, main);
   cudaStreamWaitEvent(c.stream2, c.ev_fork, 0);
-  c.stream = c.stream2;                                   // every launcher below targets the Mimi branch
   const bool alt = bt.async_staging && parity == 1;        // odd frames of an async-staged batch: second buffer set
   float *hn = alt ? bt.h2_noise : bt.h_noise, *hl = alt ? bt.h2_latent : bt.h_latent, *hg = alt ? bt.h2_logit : bt.h_logit,
         *ha = alt ? bt.h2_audio : bt.h_audio;
   short* hp = alt ? bt.h2_pcm : bt.h_pcm;
-  {
-    // SM partition between the branches: the Mimi branch's persistent kernels take at most PTTS_MIMI_GRID SMs (default
-    // 74 = one die's worth), so the latency-bound FlowLM chain always finds free SMs instead of queueing behind a
-    // 148-CTA persistent GEMM.  Measured at batch 256: 17.9 k -> 19.2 k audio-s/s (60: 19.0 k, 88: 18.7 k, 100: 18.1 k).
-    static const int mimi_grid = [] { const char* v = getenv("PTTS_MIMI_GRID"); return v ? atoi(v) : 74; }();
+  // SM partition between the branches: the Mimi branch's persistent kernels take at most PTTS_MIMI_GRID SMs (default
+  // 74 = one die's worth), so the latency-bound FlowLM chain always finds free SMs instead of queueing behind a
+  // 148-CTA persistent GEMM.  Measured at batch 256: 17.9 k -> 19.2 k audio-s/s (60: 19.0 k, 88: 18.7 k, 100: 18.1 k).
+  static const int mimi_grid = [] { const char* v = getenv("PTTS_MIMI_GRID"); return v ? atoi(v) : 74; }();
+  // PTTS_INTERLEAVE: 0 = the two branches start together and run freely; 1 = the Mimi decoder is cut into one slice per
+  // FlowLM layer and slice i starts only when the attention kernels of layer i have finished (the HBM-bound attention
+  // gets the whole machine, the decoder fills the latency-bound GEMM chains between two attentions); 2 = additionally
+  // attention i+1 waits for slice i (strict alternation)
+  static const int interleave = [] { const char* v = getenv("PTTS_INTERLEAVE"); return v ? atoi(v) : 0; }();
+  const int NL = c.cfg.n_layers;
+  auto mimi_out = [&]() {
+    if (!host_io) return;
+    if (bt.pcm16) cudaMemcpyAsync(hp, bt.d_pcm, (size_t)B * bt.frame_samples * sizeof(short), cudaMemcpyDeviceToHost, c.stream2);
+    else cudaMemcpyAsync(ha, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream2);
+  };
+  if (interleave > 0 && bt.tc_mimi && bt.fw.tc && NL <= 16) {
+    const int n_launch = mimi_tc_launches(bt);
+    std::vector<int> cut(NL + 1);
+    for (int i = 0; i <= NL; ++i) cut[i] = (int)((long long)i * n_launch / NL);
+    if (NL == 6 && n_launch == 26) { const int hand[7] = {0, 6, 11, 16, 20, 23, 26}; cut.assign(hand, hand + 7); }   // ~equal time
+    bt.fw.post_attn = [&](int i) {
+      cudaEventRecord(c.ev_attn[i], main);
+      cudaStreamWaitEvent(c.stream2, c.ev_attn[i], 0);
+      c.stream = c.stream2;
+      gemm_tc_set_grid_cap(mimi_grid);
+      mimi_frame_tc(bt, lat_prev, 0, true, cut[i], cut[i + 1]);
+      gemm_tc_set_grid_cap(0);
+      if (i == NL - 1) mimi_out();
+      c.stream = main;
+      if (interleave > 1) cudaEventRecord(c.ev_slice[i], c.stream2);
+    };
+    bt.fw.pre_attn = [&](int i) {
+      if (interleave > 1 && i > 0) cudaStreamWaitEvent(main, c.ev_slice[i - 1], 0);
+    };
+    if (host_io)
+      cudaMemcpyAsync(bt.d_noise, hn, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
+    flow_step(bt, host_io, 0, lat_prev, lat_cur);
+    bt.fw.post_attn = nullptr;
+    bt.fw.pre_attn = nullptr;
+    cudaEventRecord(c.ev_join, c.stream2);
+  } else {
+    c.stream = c.stream2;                                   // every launcher below targets the Mimi branch
     gemm_tc_set_grid_cap(mimi_grid);
     mimi_frame(bt, lat_prev, true);
     gemm_tc_set_grid_cap(0);
+    c.stream = main;
+    mimi_out();
+    cudaEventRecord(c.ev_join, c.stream2);
+    if (host_io)
+      cudaMemcpyAsync(bt.d_noise, hn, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
+    flow_step(bt, host_io, 0, lat_prev, lat_cur);
   }
-  if (host_io) {
-    if (bt.pcm16) cudaMemcpyAsync(hp, bt.d_pcm, (size_t)B * bt.frame_samples * sizeof(short), cudaMemcpyDeviceToHost, c.stream);
-    else cudaMemcpyAsync(ha, bt.d_audio, (size_t)B * bt.frame_samples * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
-  }
-  cudaEventRecord(c.ev_join, c.stream2);
-  c.stream = main;
-  if (host_io)
-    cudaMemcpyAsync(bt.d_noise, hn, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
-  flow_step(bt, host_io, 0, lat_prev, lat_cur);
   launch_advance(bt.d_len, bt.d_bos, nullptr, bt.d_counter, B, 1, 0, c.stream, bt.d_active);
   if (host_io) {
     cudaMemcpyAsync(hl, lat_cur, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
@@ -1646,6 +1708,10 @@ int32_t ptts_ctx_create(int32_t device, const ptts_config* cfg, ptts_ctx** out) 
   CU(cudaEventCreate(&c->ev1));
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  for (int i = 0; i < 16; ++i) {
+    CU(cudaEventCreateWithFlags(&c->ev_attn[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_slice[i], cudaEventDisableTiming));
+  }
   gemm_tc_init();
   *out = c.release();
   return 0;
@@ -1664,6 +1730,7 @@ void ptts_ctx_destroy(ptts_ctx* c) {
   cudaEventDestroy(c->ev1);
   cudaEventDestroy(c->ev_fork);
   cudaEventDestroy(c->ev_join);
+  for (int i = 0; i < 16; ++i) { cudaEventDestroy(c->ev_attn[i]); cudaEventDestroy(c->ev_slice[i]); }
   cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;

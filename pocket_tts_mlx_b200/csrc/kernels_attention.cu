@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(128) flow_prefix_attention_kernel(const FlowAt
 constexpr int kAttnPageBytes = 2 * kPageTokens * kHeadDim * 2;    // K + V of one page and head, bf16: 8 KB
 constexpr int kAttnStageBytes = 2 * kAttnPageBytes;               // two pages = 64 keys
 constexpr int kAttnThreads = 64;
-constexpr int kAttnSmem = 2 * kAttnStageBytes + 2 * 256 + 2 * 16 + 256 + 64 + 1024;
+constexpr int attn_smem_bytes(int stages) { return stages * kAttnStageBytes + 2 * 256 + 2 * 16 + 256 + 16 * stages + 32 + 1024; }
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -670,32 +670,35 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 6) flow_attention_stream_kernel(const __grid_constant__ CUtensorMap tm_page,
+template <int STAGES>
+__global__ void __launch_bounds__(kAttnThreads, STAGES == 2 ? 6 : 4) flow_attention_stream_kernel(const __grid_constant__ CUtensorMap tm_page,
                                                                                 const __grid_constant__ CUtensorMap tm_box,
                                                                                 const FlowAttnParams p, const int items) {
   pdl_sync();
   extern __shared__ __align__(1024) unsigned char attn_smem[];
   const uint32_t ring = (smem_u32(attn_smem) + 1023u) & ~1023u;
-  const uint32_t qbuf = ring + 2 * kAttnStageBytes;                 // 2 x 64 floats
+  const uint32_t qbuf = ring + STAGES * kAttnStageBytes;            // 2 x 64 floats
   const uint32_t metab = qbuf + 2 * 256;                            // 2 x {n_all, key_lo, pg_lo, n_pg}
   const uint32_t obuf = metab + 2 * 16;                             // 64 floats: the item's un-normalised output row
   const uint32_t bars = obuf + 256;
-  const uint32_t full0 = bars, empty0 = bars + 16, qfull0 = bars + 32, qempty0 = bars + 48;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, qfull0 = empty0 + 8 * STAGES, qempty0 = qfull0 + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, D = H * kHeadDim;
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_page) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_box) : "memory");
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       mbar_init(full0 + 8 * i, 1);
       mbar_init(empty0 + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(qfull0 + 8 * i, 1);
       mbar_init(qempty0 + 8 * i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // pages / boxes that are never loaded (keys outside [key_lo, n_all)) must still hold finite values
-  for (uint32_t i = threadIdx.x; i < (uint32_t)(2 * kAttnStageBytes / 16); i += kAttnThreads)
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(STAGES * kAttnStageBytes / 16); i += kAttnThreads)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ring + i * 16u), "r"(0) : "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -741,7 +744,7 @@ __global__ void __launch_bounds__(kAttnThreads, 6) flow_attention_stream_kernel(
       const int seq = p.row_seq ? p.row_seq[m] : m;
       int far = 0;
       for (int j0 = 0; j0 < n_pg; j0 += 2, ++gst) {
-        const uint32_t s = gst & 1, ph = (gst >> 1) & 1;
+        const uint32_t s = gst % STAGES, ph = (gst / STAGES) & 1;
         int pages[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -828,7 +831,7 @@ __global__ void __launch_bounds__(kAttnThreads, 6) flow_attention_stream_kernel(
     for (int dt = 0; dt < 8; ++dt) oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f;
     float mrun = -INFINITY, lrun = 0.f;
     for (int j0 = 0; j0 < n_pg; j0 += 2, ++gst) {
-      const uint32_t s = gst & 1, ph = (gst >> 1) & 1;
+      const uint32_t s = gst % STAGES, ph = (gst / STAGES) & 1;
       const bool two = j0 + 1 < n_pg;                            // warp-uniform: the stage holds a second page
       mbar_wait(full0 + 8 * s, ph);
       const uint32_t st0 = ring + s * kAttnStageBytes;
@@ -992,16 +995,24 @@ void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
   ProfScope ps("flow_attention", nullptr, 4.0 * keys * p.H * 64,
                2.0 * keys * p.H * 64 * (p.kv_bf16 ? 2 : 4) + 2.0 * p.M * p.H * 64 * 4, s);
   if (flow_attention_stream_ok(p)) {
+    // ring depth x CTAs per SM: 2 x 6 (default), or 3 x 4 (PTTS_ATTN_STAGES=3)
+    static const int stages = [] { const char* v = getenv("PTTS_ATTN_STAGES"); return (v && atoi(v) == 3) ? 3 : 2; }();
     static bool attr_done = false;
     if (!attr_done) {
-      cudaFuncSetAttribute(flow_attention_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      cudaFuncSetAttribute(flow_attention_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(2));
+      cudaFuncSetAttribute(flow_attention_stream_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(3));
       attr_done = true;
     }
     const int items = p.M * p.H;
-    static const int per_sm = [] { const char* v = getenv("PTTS_ATTN_CTAS_PER_SM"); return v ? std::max(1, atoi(v)) : 6; }();
+    static const int per_sm = [] { const char* v = getenv("PTTS_ATTN_CTAS_PER_SM"); return v ? std::max(1, atoi(v)) : 0; }();
+    const int ctas = per_sm > 0 ? per_sm : (stages == 2 ? 6 : 4);
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(p.kv_tmap);
-    launch_k(flow_attention_stream_kernel, dim3((unsigned)std::min(items, 148 * per_sm)), dim3(kAttnThreads), (size_t)kAttnSmem, s,
-             maps[0], maps[1], p, items);
+    if (stages == 3)
+      launch_k(flow_attention_stream_kernel<3>, dim3((unsigned)std::min(items, 148 * ctas)), dim3(kAttnThreads), (size_t)attn_smem_bytes(3), s,
+               maps[0], maps[1], p, items);
+    else
+      launch_k(flow_attention_stream_kernel<2>, dim3((unsigned)std::min(items, 148 * ctas)), dim3(kAttnThreads), (size_t)attn_smem_bytes(2), s,
+               maps[0], maps[1], p, items);
     ++g_launches;
     return;
   }
