@@ -159,8 +159,10 @@ int32_t ptts_batch_step_device(ptts_batch* batch);
  * one right after ptts_batch_warmup_mimi (= init_states + _warmup_mimi_decoder, models/tts_model.py:378-383,464-476).
  * Follow it with ptts_batch_prefill_text where every other sequence has an empty token range.
  * ptts_batch_set_active(slot, 0) parks a slot: it is still computed with the batch but stops growing its KV cache
- * (stream-ordered, allowed in every mode).  ptts_batch_reset_seq(s) is refused in pipelined mode (flush and leave it
- * first).  A batch whose sequences all share one voice attends the shared prefix once (cascade attention); the first
+ * (stream-ordered, allowed in every mode).  In pipelined mode the frame graph launched after ptts_batch_reset_seq(s)
+ * still decodes the PREVIOUS utterance's last latent for the slot (that frame's audio for the slot is to be ignored)
+ * and the slot's Mimi state is restored right after it; the new utterance's audio starts one step later, as always in
+ * pipelined mode.  A batch whose sequences all share one voice attends the shared prefix once (cascade attention); the first
  * slot that switches to another voice turns that off for the batch (the frame graphs are re-captured). */
 int32_t ptts_batch_reset_seq(ptts_batch* batch, int32_t slot, int32_t voice_id, int32_t max_len);
 /* the same for n slots with one stream synchronisation */

@@ -913,6 +913,9 @@ struct ptts_batch {
   // pipelined mode: frame graph = { FlowLM step t } || { Mimi decode of latent t-1 } on two streams.
   // Latents ping-pong between d_latent (even frames) and d_latent_b (odd frames); index = parity*2 + host_io.
   bool pipelined = false;
+  // slots re-initialised while the batch is in pipelined mode: the frame graph launched next still decodes the OLD
+  // utterance's last latent for them, so their Mimi streaming state is restored right AFTER that graph
+  std::vector<int> pending_mimi_reset;
   int cascade_len = 0;              // prefix length the captured graphs were built for
   long long frame_idx = 0;          // frames stepped since the last (re)initialisation
   float* d_latent_b = nullptr;
@@ -1532,6 +1535,8 @@ void pipelined_frame(Batch& bt, int parity, bool host_io) {
   cudaStreamWaitEvent(main, c.ev_join, 0);
 }
 
+int restore_mimi_slot(Batch& t, int slot);
+
 int run_pipelined_step(Batch& bt, bool host_io) {
   Ctx& c = *bt.ctx;
   const int B = bt.B, L = c.cfg.latent_dim;
@@ -1567,6 +1572,12 @@ int run_pipelined_step(Batch& bt, bool host_io) {
     }
     CU(cudaGraphLaunch(bt.pipe_graph[idx], c.stream));
     g_launches += bt.pipe_graph_launches[idx];
+  }
+  if (!bt.pending_mimi_reset.empty()) {
+    // slots re-initialised since the previous frame: this frame's Mimi branch has just consumed the old utterance's last
+    // latent with the old state; the NEXT frame decodes the new utterance's first latent and needs the fresh state
+    for (int slot : bt.pending_mimi_reset) RET(restore_mimi_slot(bt, slot));
+    bt.pending_mimi_reset.clear();
   }
   bt.frame_idx += 1;
   for (int b = 0; b < bt.B; ++b) bt.h_len[b] += bt.h_active[b];
@@ -1636,6 +1647,20 @@ std::vector<StatePiece> mimi_state_pieces(Batch& t) {
     v.push_back({(char*)e.buf, (size_t)e.bs * e.esz, (size_t)e.rows * e.C * e.esz});
   if (t.d_bnd) v.push_back({(char*)t.d_bnd, (size_t)(t.frame_samples / 128 + 1) * 16, 16});
   return v;
+}
+
+// per-slot Mimi streaming state back to the post-warm-up template (or zero), stream-ordered
+int restore_mimi_slot(Batch& t, int slot) {
+  Ctx& c = *t.ctx;
+  auto pieces = mimi_state_pieces(t);
+  size_t off = 0;
+  for (auto& p : pieces) {
+    char* dst = p.base + (size_t)slot * p.stride;
+    if (t.has_tpl) CU(cudaMemcpyAsync(dst, (char*)t.mimi_tpl + off, p.bytes, cudaMemcpyDeviceToDevice, c.stream));
+    else CU(cudaMemsetAsync(dst, 0, p.bytes, c.stream));
+    off += (p.bytes + 15) & ~(size_t)15;
+  }
+  return 0;
 }
 
 // captured frame graphs bake pointers and modes in (staging sets, cascade prefix length, PCM output): drop them all
@@ -1984,6 +2009,7 @@ static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32
   t.pipelined = false;
   t.async_staging = false;
   t.pcm16 = false;
+  t.pending_mimi_reset.clear();
   if (t.graphs_pcm || t.graphs_async) {
     // a recycled arena whose graphs were captured with the PCM output on, or with odd frames going through the second
     // staging set: both are baked into the copy nodes and this batch starts with neither
@@ -2303,7 +2329,6 @@ static int reset_seq_impl(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_
   Ctx& c = *bt->ctx;
   Batch& t = *bt;
   if (slot < 0 || slot >= t.B) return fail(PTTS_ERR_INVALID, "slot %d out of range", slot);
-  if (t.pipelined) return fail(PTTS_ERR_STATE, "slots of a pipelined batch cannot be re-used (flush and leave pipelined mode first)");
   if (voice_id < 0 || voice_id >= (int)c.voices.size() || !c.voices[voice_id].alive)
     return fail(PTTS_ERR_INVALID, "unknown voice id %d", voice_id);
   const Voice& v = c.voices[voice_id];
@@ -2357,17 +2382,10 @@ static int reset_seq_impl(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_
   CU(cudaMemcpyAsync(t.d_len + slot, &t.h_len[slot], 4, cudaMemcpyHostToDevice, c.stream));
   CU(cudaMemcpyAsync(t.d_bos + slot, &one, 4, cudaMemcpyHostToDevice, c.stream));
   CU(cudaMemcpyAsync(t.d_active + slot, &one, 4, cudaMemcpyHostToDevice, c.stream));
-  // Mimi: back to the post-warm-up state (or to the zero state when the batch was never warmed up)
-  {
-    auto pieces = mimi_state_pieces(t);
-    size_t off = 0;
-    for (auto& p : pieces) {
-      char* dst = p.base + (size_t)slot * p.stride;
-      if (t.has_tpl) CU(cudaMemcpyAsync(dst, (char*)t.mimi_tpl + off, p.bytes, cudaMemcpyDeviceToDevice, c.stream));
-      else CU(cudaMemsetAsync(dst, 0, p.bytes, c.stream));
-      off += (p.bytes + 15) & ~(size_t)15;
-    }
-  }
+  // Mimi: back to the post-warm-up state (or to the zero state when the batch was never warmed up).  In pipelined
+  // mode the next frame graph still decodes the previous utterance's last latent for this slot: restore after it.
+  if (t.pipelined && t.frame_idx > 0) t.pending_mimi_reset.push_back(slot);
+  else RET(restore_mimi_slot(t, slot));
   return 0;
 }
 

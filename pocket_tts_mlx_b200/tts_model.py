@@ -454,13 +454,15 @@ class TTSModel:
                                   slots: int = 256, frames_after_eos: Union[int, Sequence[int]] = 3,
                                   warmup_frames: int = _MIMI_WARMUP_FRAMES, max_frames: Optional[int] = None,
                                   noise: Optional[Sequence[np.ndarray]] = None, seed: int = 0,
-                                  return_latents: bool = False, min_admit: Optional[int] = None):
+                                  return_latents: bool = False, min_admit: Optional[int] = None, pipelined: bool = True):
         """Continuous batching over `slots` lock-step sequences: when an utterance ends (EOS rule or frame limit of
         the reference, tts_model.py:404-426) its slot is parked and later re-initialised for the next queued
         utterance while the others keep decoding, so the batch stays full.  Admissions are
         grouped: freed slots wait until `min_admit` of them (default slots/16) can be prefilled together, which turns
         the text prefill into one dense GEMM pass instead of one GEMV pass per utterance.  Results per utterance are
-        the same as decoding it in a batch of its own.
+        the same as decoding it in a batch of its own.  pipelined=True uses the two-branch frame graph (FlowLM step t next
+        to the Mimi decode of frame t-1): the audio of a frame then arrives one step after its latent, also across the
+        re-use of a slot.
 
         noise: optional per-utterance arrays [1 + frames, latent_dim] (row 0 = the unused prefill draw, like the
         reference); without it the host draws one N(0,1) block per step from `seed`.
@@ -487,7 +489,7 @@ class TTSModel:
                     model_states[lo:hi], token_ids[lo:hi], slots=slots, frames_after_eos=fae[lo:hi],
                     warmup_frames=warmup_frames, max_frames=max_frames,
                     noise=None if noise is None else noise[lo:hi], seed=seed + lo, return_latents=True,
-                    min_admit=min_admit)
+                    min_admit=min_admit, pipelined=pipelined)
                 waves_all += r[0]
                 lats_all += r[1]
             return (waves_all, lats_all) if return_latents else waves_all
@@ -499,8 +501,11 @@ class TTSModel:
         rng = np.random.Generator(np.random.PCG64(seed))
         try:
             batch.seed(seed)
+            if pipelined:
+                batch.set_pipelined(True)
             batch.set_async_staging(True)                 # frame t+1 is enqueued before frame t is read back
             sets = batch.staging_sets()
+            lag = 1 if pipelined else 0                   # audio block that holds the frame whose latent is in block t: t + lag
             batch.warmup_mimi(warmup_frames)
             batch.prefill_text([token_ids[j] for j in range(n_slots)])
             # Whole-array bookkeeping.  Per slot: the utterance it holds (-1 = parked), the frame index its next
@@ -518,7 +523,7 @@ class TTSModel:
             slot_of[:n_slots] = np.arange(n_slots)
             free: List[int] = []                          # parked slots waiting for the next admission round
             next_job = n_slots
-            est_steps = int(np.ceil(lim_all.sum() / n_slots * 1.25)) + int(lim_all.max()) + 8
+            est_steps = int(np.ceil(lim_all.sum() / n_slots * 1.25)) + int(lim_all.max()) + 8 + lag
             # slot-major, so that an utterance's waveform is one contiguous slice (returned as a view, no final gather)
             aud = np.empty((n_slots, est_steps, self.frame_samples), dtype=np.float32)   # pages are touched on write
             lat_b = np.empty((n_slots, est_steps, ldim), dtype=np.float32)
@@ -590,10 +595,16 @@ class TTSModel:
                         toks[s_] = token_ids[j]
                     batch.prefill_text(toks)
                     state["live"] += len(take)
+            if pipelined and state["done_blocks"] > 0:
+                # the frames whose latents came with the last step are still to be decoded
+                t = state["done_blocks"]
+                if t >= aud.shape[1]:
+                    aud = np.concatenate([aud, np.empty((n_slots, 1, self.frame_samples), dtype=aud.dtype)], axis=1)
+                aud[:, t] = batch.flush()
             waves, lats = [], []
             for j in range(n_jobs):
                 s_, t0, k = int(slot_of[j]), int(t0_of[j]), int(n_of[j])
-                waves.append(aud[s_, t0:t0 + k].reshape(-1))
+                waves.append(aud[s_, t0 + lag:t0 + lag + k].reshape(-1))
                 lats.append(lat_b[s_, t0:t0 + k])
             if return_latents:
                 return waves, lats
