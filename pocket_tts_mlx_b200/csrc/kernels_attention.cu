@@ -660,9 +660,8 @@ __global__ void __launch_bounds__(128) flow_prefix_attention_kernel(const FlowAt
 // Masked keys get p = 0 exactly; their V bytes are whatever the pool (or a stale stage) holds, which is why the pool
 // and the ring are zeroed once (0 x finite = 0; never-written memory could hold NaN patterns).
 constexpr int kAttnPageBytes = 2 * kPageTokens * kHeadDim * 2;    // K + V of one page and head, bf16: 8 KB
-constexpr int kAttnStageBytes = 2 * kAttnPageBytes;               // two pages = 64 keys
 constexpr int kAttnThreads = 64;
-constexpr int attn_smem_bytes(int stages) { return stages * kAttnStageBytes + 2 * 256 + 2 * 16 + 256 + 16 * stages + 32 + 1024; }
+constexpr int attn_smem_bytes(int stages, int pg) { return stages * pg * kAttnPageBytes + 2 * 256 + 2 * 16 + 256 + 16 * stages + 32 + 1024; }
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -670,12 +669,14 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
-template <int STAGES>
-__global__ void __launch_bounds__(kAttnThreads, STAGES == 2 ? 6 : 4) flow_attention_stream_kernel(const __grid_constant__ CUtensorMap tm_page,
+// PG = pages (32 keys) per stage; CTAs per SM follow the stage size: 2 x 2 pages -> 6, 3 x 2 -> 4, 2 x 1 -> 9
+template <int STAGES, int PG>
+__global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 : 4)) flow_attention_stream_kernel(const __grid_constant__ CUtensorMap tm_page,
                                                                                 const __grid_constant__ CUtensorMap tm_box,
                                                                                 const FlowAttnParams p, const int items) {
   pdl_sync();
   extern __shared__ __align__(1024) unsigned char attn_smem[];
+  constexpr int kAttnStageBytes = PG * kAttnPageBytes;
   const uint32_t ring = (smem_u32(attn_smem) + 1023u) & ~1023u;
   const uint32_t qbuf = ring + STAGES * kAttnStageBytes;            // 2 x 64 floats
   const uint32_t metab = qbuf + 2 * 256;                            // 2 x {n_all, key_lo, pg_lo, n_pg}
@@ -743,11 +744,11 @@ __global__ void __launch_bounds__(kAttnThreads, STAGES == 2 ? 6 : 4) flow_attent
       ++qcnt;
       const int seq = p.row_seq ? p.row_seq[m] : m;
       int far = 0;
-      for (int j0 = 0; j0 < n_pg; j0 += 2, ++gst) {
+      for (int j0 = 0; j0 < n_pg; j0 += PG, ++gst) {
         const uint32_t s = gst % STAGES, ph = (gst / STAGES) & 1;
-        int pages[2];
+        int pages[PG];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
+        for (int e = 0; e < PG; ++e) {
           const int j = j0 + e;
           if (j >= 64 && (j & 31) == 0) {     // more than 64 pages (> 2048 keys): further page ids, fetched in place
             const int pg = pg_lo + j + lane;
@@ -757,9 +758,9 @@ __global__ void __launch_bounds__(kAttnThreads, STAGES == 2 ? 6 : 4) flow_attent
         }
         if (lane == 0) {
           uint32_t bytes = 0;
-          int blo[2], bhi[2];
+          int blo[PG], bhi[PG];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
+          for (int e = 0; e < PG; ++e) {
             const int k0 = (pg_lo + j0 + e) * kPageTokens;
             blo[e] = (max(key_lo, k0) - k0) >> 3;                                    // 8-key boxes that hold valid keys
             bhi[e] = (j0 + e < n_pg) ? (min(n_all, k0 + kPageTokens) - 1 - k0) >> 3 : -1;
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(kAttnThreads, STAGES == 2 ? 6 : 4) flow_attent
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           mbar_expect_tx(full0 + 8 * s, bytes);
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
+          for (int e = 0; e < PG; ++e) {
             const uint32_t dst = ring + s * kAttnStageBytes + (uint32_t)e * kAttnPageBytes;
             const int pc = page0 + pages[e];
             if (blo[e] == 0 && bhi[e] == 3) {
@@ -830,15 +831,15 @@ __global__ void __launch_bounds__(kAttnThreads, STAGES == 2 ? 6 : 4) flow_attent
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f;
     float mrun = -INFINITY, lrun = 0.f;
-    for (int j0 = 0; j0 < n_pg; j0 += 2, ++gst) {
+    for (int j0 = 0; j0 < n_pg; j0 += PG, ++gst) {
       const uint32_t s = gst % STAGES, ph = (gst / STAGES) & 1;
-      const bool two = j0 + 1 < n_pg;                            // warp-uniform: the stage holds a second page
+      const bool two = PG == 2 && j0 + 1 < n_pg;                 // warp-uniform: the stage holds a second page
       mbar_wait(full0 + 8 * s, ph);
       const uint32_t st0 = ring + s * kAttnStageBytes;
       // S = q K^T: per page 4 n-tiles of 8 keys x 4 k-steps of 16 dims
-      float sc[8][4];
+      float sc[4 * PG][4];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
+      for (int e = 0; e < PG; ++e) {
         if (e == 1 && !two) break;
         const uint32_t Ks = st0 + (uint32_t)e * kAttnPageBytes;
 #pragma unroll
@@ -859,9 +860,9 @@ __global__ void __launch_bounds__(kAttnThreads, STAGES == 2 ? 6 : 4) flow_attent
         }
       }
       const int k0 = (pg_lo + j0) * kPageTokens;
-      if (k0 < key_lo || k0 + 2 * kPageTokens > n_all) {        // warp-uniform: only an item's first / last stage is cut
+      if (k0 < key_lo || k0 + PG * kPageTokens > n_all) {        // warp-uniform: only an item's first / last stage is cut
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < 4 * PG; ++nt) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int key = k0 + nt * 8 + 2 * t4 + e;
@@ -871,16 +872,16 @@ __global__ void __launch_bounds__(kAttnThreads, STAGES == 2 ? 6 : 4) flow_attent
       }
       float bm = -INFINITY;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) bm = fmaxf(bm, fmaxf(sc[nt][0], sc[nt][1]));
+      for (int nt = 0; nt < 4 * PG; ++nt) bm = fmaxf(bm, fmaxf(sc[nt][0], sc[nt][1]));
       bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
       bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
       const float nm = fmaxf(mrun, bm);                          // finite: every stage holds at least one valid key
       const float corr = (mrun == -INFINITY) ? 0.f : exp2f(mrun - nm);
       mrun = nm;
       float ssum = 0.f;
-      uint32_t pa[4][4];
+      uint32_t pa[2 * PG][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 4 * PG; ++nt) {
         const float p0 = exp2f(sc[nt][0] - nm), p1 = exp2f(sc[nt][1] - nm);
         ssum += p0 + p1;
         pa[nt >> 1][(nt & 1) * 2] = pack2_bf16(p0, p1);
@@ -893,7 +894,7 @@ __global__ void __launch_bounds__(kAttnThreads, STAGES == 2 ? 6 : 4) flow_attent
       for (int dt = 0; dt < 8; ++dt) { oc[dt][0] *= corr; oc[dt][1] *= corr; }
       // O += P V: per page 2 k-steps of 16 keys x 8 n-tiles of 8 dims
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
+      for (int e = 0; e < PG; ++e) {
         if (e == 1 && !two) break;
         const uint32_t Vs = st0 + (uint32_t)e * kAttnPageBytes + 4096u;
 #pragma unroll
@@ -995,24 +996,27 @@ void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
   ProfScope ps("flow_attention", nullptr, 4.0 * keys * p.H * 64,
                2.0 * keys * p.H * 64 * (p.kv_bf16 ? 2 : 4) + 2.0 * p.M * p.H * 64 * 4, s);
   if (flow_attention_stream_ok(p)) {
-    // ring depth x CTAs per SM: 2 x 6 (default), or 3 x 4 (PTTS_ATTN_STAGES=3)
+    // stage geometry: PTTS_ATTN_STAGES (2 | 3 ring stages) x PTTS_ATTN_PAGES (2 | 1 pages of 32 keys per stage)
     static const int stages = [] { const char* v = getenv("PTTS_ATTN_STAGES"); return (v && atoi(v) == 3) ? 3 : 2; }();
+    static const int pg = [] { const char* v = getenv("PTTS_ATTN_PAGES"); return (v && atoi(v) == 1) ? 1 : 2; }();
     static bool attr_done = false;
     if (!attr_done) {
-      cudaFuncSetAttribute(flow_attention_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(2));
-      cudaFuncSetAttribute(flow_attention_stream_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(3));
+      cudaFuncSetAttribute(flow_attention_stream_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(2, 2));
+      cudaFuncSetAttribute(flow_attention_stream_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(3, 2));
+      cudaFuncSetAttribute(flow_attention_stream_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(2, 1));
+      cudaFuncSetAttribute(flow_attention_stream_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(3, 1));
       attr_done = true;
     }
     const int items = p.M * p.H;
     static const int per_sm = [] { const char* v = getenv("PTTS_ATTN_CTAS_PER_SM"); return v ? std::max(1, atoi(v)) : 0; }();
-    const int ctas = per_sm > 0 ? per_sm : (stages == 2 ? 6 : 4);
+    const int ctas = per_sm > 0 ? per_sm : (pg == 1 ? 9 : (stages == 2 ? 6 : 4));
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(p.kv_tmap);
-    if (stages == 3)
-      launch_k(flow_attention_stream_kernel<3>, dim3((unsigned)std::min(items, 148 * ctas)), dim3(kAttnThreads), (size_t)attn_smem_bytes(3), s,
-               maps[0], maps[1], p, items);
-    else
-      launch_k(flow_attention_stream_kernel<2>, dim3((unsigned)std::min(items, 148 * ctas)), dim3(kAttnThreads), (size_t)attn_smem_bytes(2), s,
-               maps[0], maps[1], p, items);
+    const dim3 grid((unsigned)std::min(items, 148 * ctas)), block(kAttnThreads);
+    const size_t smem = (size_t)attn_smem_bytes(stages, pg);
+    if (stages == 3 && pg == 2) launch_k(flow_attention_stream_kernel<3, 2>, grid, block, smem, s, maps[0], maps[1], p, items);
+    else if (stages == 2 && pg == 1) launch_k(flow_attention_stream_kernel<2, 1>, grid, block, smem, s, maps[0], maps[1], p, items);
+    else if (stages == 3 && pg == 1) launch_k(flow_attention_stream_kernel<3, 1>, grid, block, smem, s, maps[0], maps[1], p, items);
+    else launch_k(flow_attention_stream_kernel<2, 2>, grid, block, smem, s, maps[0], maps[1], p, items);
     ++g_launches;
     return;
   }
