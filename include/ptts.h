@@ -218,6 +218,12 @@ int32_t ptts_debug_linear(ptts_ctx* ctx, int32_t path, int32_t n_b, int32_t n_t,
                           int32_t c_in, int32_t n_out, const float* a, const float* w,
                           const float* bias, float* y);
 
+/* Debugging aid (PTTS_ATTN_DBG=1 in the environment): {earliest CTA start, latest CTA end} in globaltimer nanoseconds of
+ * the decode-attention launch of every FlowLM layer since the previous call (the stamps are reset by the call), i.e.
+ * how long the HBM-bound attention really takes INSIDE a pipelined frame graph, next to the Mimi branch.  out holds
+ * 2 * max_layers values; returns the number of layers written, 0 when the switch is off. */
+int32_t ptts_debug_attention_stamps(ptts_ctx* ctx, uint64_t* out, int32_t max_layers);
+
 /* Stand-alone run of the cluster chain kernel (one launch for a dependent chain of small-M GEMMs with fused
  * LayerNorm; csrc/chain_tc.cu) on a miniature flow head, for kernel-level parity tests:
  *   sy = silu(a0 W0^T + b0); ada = sy Wa^T + ba = shift | scale | gate; x1 = a1 Wi^T + bi;

@@ -29,7 +29,7 @@ EXPORTED = [
     "ptts_has_voice_cloning", "ptts_encode_audio",
     "ptts_batch_set_async_staging", "ptts_batch_host_buffers_set", "ptts_batch_step_staged_async", "ptts_batch_staged_wait",
     "ptts_batch_host_buffers", "ptts_batch_step_staged",
-    "ptts_batch_set_pcm16", "ptts_batch_host_pcm", "ptts_unused_weights", "ptts_debug_chain",
+    "ptts_batch_set_pcm16", "ptts_batch_host_pcm", "ptts_unused_weights", "ptts_debug_chain", "ptts_debug_attention_stamps",
 ]
 
 
@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
         "ptts_batch_set_pcm16": (i32, [vp, i32]),
         "ptts_batch_host_pcm": (i32, [vp, i32, C.POINTER(C.POINTER(C.c_int16))]),
         "ptts_debug_gemm_bench": (i32, [vp, i32, i32, i32, i32, i32, i32, i32p, i32, f32p, i32p]),
+        "ptts_debug_attention_stamps": (i32, [vp, C.POINTER(C.c_uint64), i32]),
         "ptts_debug_chain": (i32, [vp, i32, i32, i32] + [f32p] * 17 + [C.c_float] + [f32p] * 4),
     }
     for name, (res, args) in sig.items():
@@ -266,6 +267,12 @@ class Context:
         f = (C.c_int32 * 4)(*force) if force is not None else None
         check(lib().ptts_debug_gemm_bench(self._h, nb, t, taps, c_in, n_out, epi, f, reps, C.byref(us), chosen))
         return float(us.value), tuple(int(x) for x in chosen)
+
+    def attention_stamps(self, max_layers: int = 16) -> np.ndarray:
+        """PTTS_ATTN_DBG=1: [layers, 2] {earliest CTA start, latest CTA end} in ns of the last decode-attention launches."""
+        out = np.zeros((max_layers, 2), dtype=np.uint64)
+        n = check(lib().ptts_debug_attention_stamps(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), max_layers))
+        return out[:n]
 
     def debug_chain(self, t: dict, out_scale: float = 1.0):
         """Miniature flow head through the cluster chain kernel (see ptts_debug_chain); t holds the fp32 inputs

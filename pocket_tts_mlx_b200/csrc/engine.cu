@@ -751,6 +751,7 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       a.M = M; a.H = c.cfg.n_heads; a.freqs = c.freqs_flow; a.total_keys = total_keys;
       a.part = w.attn_part; a.splits = w.attn_part ? std::min(8, std::max(1, 296 / (M * c.cfg.n_heads))) : 1;
       a.kv_tmap = c.kv_tmap_ok ? c.kv_tmap : nullptr;
+      a.tstamp = (!row_seq && i < 32) ? flow_attention_dbg_buffer() : nullptr;
       if (!row_seq && w.prefix_len > 0 && a.splits == 1) {
         a.prefix_len = w.prefix_len; a.prefix_pages = w.d_prefix_pages; a.prefix_part = w.prefix_part;
       }
@@ -2864,6 +2865,22 @@ int32_t ptts_debug_chain(ptts_ctx* c, int32_t M, int32_t D, int32_t K0, const fl
   if (out_ada) CU(cudaMemcpy(out_ada, d_ada, (size_t)M * 3 * D * 4, cudaMemcpyDeviceToHost));
 #undef DC
   return done(nc);
+}
+
+// PTTS_ATTN_DBG=1: per FlowLM layer {earliest CTA start, latest CTA end} (globaltimer ns) of the decode attention
+// launches since the last call; resets the stamps.  Returns the number of layers written (0 when the switch is off).
+int32_t ptts_debug_attention_stamps(ptts_ctx* c, uint64_t* out, int32_t max_layers) {
+  if (!c || !out) return fail(PTTS_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(c->device));
+  unsigned long long* buf = flow_attention_dbg_buffer();
+  if (!buf) return 0;
+  const int n = std::min(max_layers, std::min(32, c->cfg.n_layers));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(out, buf, (size_t)n * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  std::vector<unsigned long long> init(64 * 2);
+  for (int i = 0; i < 64; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+  CU(cudaMemcpy(buf, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  return n;
 }
 
 int32_t ptts_debug_linear(ptts_ctx* c, int32_t path, int32_t nb, int32_t T, int32_t taps, int32_t C, int32_t N,

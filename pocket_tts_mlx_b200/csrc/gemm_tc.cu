@@ -49,7 +49,11 @@ template <int BN, int BK, int STAGES, int ACC, int EPW = 8>   // ACC = TMEM accu
 // The persistent 8-warp variant is compiled for 2 CTAs per SM (96 registers): it never runs two of its own CTAs on an
 // SM (shared memory), but the smaller register footprint lets CTAs of the other branch of the pipelined frame graph
 // (FlowLM attention next to Mimi GEMMs) co-reside: sequential frame +3 us, pipelined job -1.2 ms.
-__global__ void __launch_bounds__(64 + 32 * EPW, (EPW == 8 && ACC == 2) ? 2 : 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
+// The one-tile-per-CTA variants with N tiles <= 64 are the small-M GEMMs of the FlowLM decode chain (96-128 CTAs each):
+// compiled for 2 CTAs per SM as well, so that with a 4-stage ring (96 KB) a whole GEMM fits on the ~74 SMs the Mimi
+// branch leaves free in the pipelined graph instead of running in two waves (tools/attn_in_graph.py: the chain between
+// two attention kernels took 78-120 us in the pipelined graph against 50 us alone).
+__global__ void __launch_bounds__(64 + 32 * EPW, (EPW == 8 && (ACC == 2 || BN <= 64)) ? 2 : 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                               const __grid_constant__ CUtensorMap tm_b,
                                                               const __grid_constant__ CUtensorMap tm_y16,
                                                               const __grid_constant__ CUtensorMap tm_yraw16,
@@ -520,7 +524,9 @@ bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a
     const int stg = (bn >= 64) ? n_bf16_out * (bn / 64) : 0;
     const double stage_bytes = 128.0 * bk * 2 + (double)bn * bk * 2;
     best_stages = 2;
-    static const int small_cap = [] { const char* v = getenv("PTTS_TC_SMALL_STAGES"); return v ? atoi(v) : 8; }();
+    // small-M GEMMs: 4 stages (96 KB at N tile 64) so that two CTAs share an SM (see the launch bounds of the kernel);
+    // batch 256: 19.2 k -> 20.3 k audio-s/s in the pipelined graph, and 8 stages bought nothing standalone (564 vs 562 us)
+    static const int small_cap = [] { const char* v = getenv("PTTS_TC_SMALL_STAGES"); return v ? atoi(v) : 4; }();
     for (int st : {8, 6, 4}) {
       if (bk == 32) break;
       if (st == 8 && bn == 128) continue;
@@ -617,14 +623,15 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   const size_t ring = (size_t)g.stages * (128 * g.bk * 2 + g.bn * g.bk * 2);
   const size_t stg_b = (size_t)g.stg_tiles * 16384;
   const size_t res_b = (g.res_tma && g.tma_store && g.splits == 1) ? (size_t)2 * (g.bn / 64) * 16384 : 0;
-  const size_t smem = (g.persist ? ring + stg_b : std::max(ring, stg_b)) + res_b + 1024 + 16 * g.stages + 128;
+  const bool persist = g.persist != 0;
+  const size_t smem = (persist ? ring + stg_b : std::max(ring, stg_b)) + res_b + 1024 + 16 * g.stages + 128;
   int per_sm = (int)((227 * 1024) / smem);
   per_sm = std::max(1, std::min(per_sm, std::min(2, 512 / (2 * g.bn))));
   static const bool epw16_ok = [] { const char* v = getenv("PTTS_TC_EPW16"); return !(v && v[0] == '0'); }();
-  const bool epw16 = epw16_ok && g.persist && g.bn == 128 && g.bk == 64 && a.tma_store;
+  const bool epw16 = epw16_ok && persist && g.bn == 128 && g.bk == 64 && a.tma_store;
   long long resident = 148LL * per_sm;
   if (g_grid_cap > 0) resident = std::min<long long>(resident, g_grid_cap);
-  dim3 grid((unsigned)(g.persist ? std::min<long long>(tiles, resident) : tiles)), block(epw16 ? 576 : kThreads);
+  dim3 grid((unsigned)(persist ? std::min<long long>(tiles, resident) : tiles)), block(epw16 ? 576 : kThreads);
   const double flops = 2.0 * g.nb * g.T * (double)g.N * g.taps * g.C;
   const double bytes = (double)g.N * g.taps * g.C * 2 + (double)g.nb * (g.T + g.taps - 1) * g.C * 2 +
                        (double)g.nb * g.T * g.N * ((g.e.y32 ? 4 : 0) + (g.e.y16 ? 2 : 0) + (g.e.yraw16 ? 2 : 0) +
@@ -632,9 +639,9 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   ProfScope ps("gemm_tc", g.tag, flops, bytes, s);
 #define PTTS_TC1(BN_, BK_, ST_)                                                                                  \
   do {                                                                                                           \
-    if (g.persist && epw16 && BN_ == 128 && BK_ == 64)                                                            \
+    if (persist && epw16 && BN_ == 128 && BK_ == 64)                                                              \
       launch_k(gemm_tc_kernel<128, 64, ST_, 2, 16>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, g.tm_res, a);        \
-    else if (g.persist) launch_k(gemm_tc_kernel<BN_, BK_, ST_, 2>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, g.tm_res, a); \
+    else if (persist) launch_k(gemm_tc_kernel<BN_, BK_, ST_, 2>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, g.tm_res, a); \
     else launch_k(gemm_tc_kernel<BN_, BK_, ST_, 1>, grid, block, smem, s, g.tm_a, g.tm_b, g.tm_y16, g.tm_yraw16, g.tm_res, a);           \
   } while (0)
 #define PTTS_TC(BN_, BK_)                                                                                        \

@@ -103,6 +103,8 @@ struct FlowAttnParams {
   // [0] box = one head's K and V slices of a whole page (8 KB), [1] box = 8 key slots of K or V (1 KB); or null.
   // Lets the decode attention stream K/V with TMA (flow_attention_stream_kernel).
   const void* kv_tmap;
+  // debugging (PTTS_ATTN_DBG=1): [layer][2] {earliest CTA start, latest CTA end} in globaltimer nanoseconds, or null
+  unsigned long long* tstamp;
 };
 void launch_flow_prefix_attention(const FlowAttnParams& p, cudaStream_t s);
 // causal attention of whole prefill chunks on tensor cores (bf16 KV, bf16 output); false when not applicable
@@ -114,6 +116,8 @@ void launch_replicate_row(float* dst, const float* src, int n, int C, cudaStream
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s);
 void launch_rope_table(const int* row_pos, const float* freqs, float* table, int M, int T, cudaStream_t s);
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s);
+// device buffer [64][2] of the attention time stamps (allocated on first use), or null when PTTS_ATTN_DBG is off
+unsigned long long* flow_attention_dbg_buffer();
 
 // ---- Mimi ring-buffer attention --------------------------------------------------------------------
 // Ring layout: [layer][k|v][seq][head][slot(context)][64].

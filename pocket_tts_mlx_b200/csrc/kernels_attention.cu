@@ -675,6 +675,11 @@ __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 :
                                                                                 const __grid_constant__ CUtensorMap tm_box,
                                                                                 const FlowAttnParams p, const int items) {
   pdl_sync();
+  if (p.tstamp && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(p.tstamp + 2 * p.layer, t);
+  }
   extern __shared__ __align__(1024) unsigned char attn_smem[];
   constexpr int kAttnStageBytes = PG * kAttnPageBytes;
   const uint32_t ring = (smem_u32(attn_smem) + 1023u) & ~1023u;
@@ -939,6 +944,11 @@ __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 :
     if (p.out16) *reinterpret_cast<__nv_bfloat162*>(p.out16 + oi) = __floats2bfloat162_rn(o.x * inv, o.y * inv);
     else *reinterpret_cast<float2*>(p.out + oi) = make_float2(o.x * inv, o.y * inv);
   }
+  if (p.tstamp && lane == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(p.tstamp + 2 * p.layer + 1, t);
+  }
 }
 
 }  // namespace
@@ -981,6 +991,13 @@ void launch_flow_prefix_attention(const FlowAttnParams& p, cudaStream_t s) {
                2.0 * p.H * p.prefix_len * 64 * 2 + (double)p.M * p.H * (64 * 4 + 66 * 4), s);
   launch_k(flow_prefix_attention_kernel, dim3((p.M + 63) / 64, p.H), dim3(128), smem, s, p);
   ++g_launches;
+}
+
+unsigned long long* flow_attention_dbg_buffer() {
+  static const bool on = [] { const char* v = getenv("PTTS_ATTN_DBG"); return v && v[0] == '1'; }();
+  static unsigned long long* buf = nullptr;
+  if (on && !buf) cudaMalloc((void**)&buf, 64 * 2 * sizeof(unsigned long long));
+  return on ? buf : nullptr;
 }
 
 // bf16 decode rows, enough (row, head) items to fill the machine: the persistent bulk-copy kernel
