@@ -1728,8 +1728,21 @@ int32_t ptts_ctx_create(int32_t device, const ptts_config* cfg, ptts_ctx** out) 
     const char* np = getenv("PTTS_PDL");
     g_pdl_on = np && np[0] == '1';
   }
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  {
+    // PTTS_PRIO=1: the main stream (FlowLM branch of the pipelined graph: a chain of short latency-bound kernels) gets the
+    // highest priority and the Mimi branch the lowest, so that the block scheduler dispatches a waiting FlowLM grid before
+    // the remaining CTAs of a large Mimi grid (captured kernel nodes inherit the priority of their stream)
+    const char* pv = getenv("PTTS_PRIO");
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    if (pv && pv[0] == '1') {
+      CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+      CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, lo));
+    } else {
+      CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    }
+  }
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
