@@ -114,6 +114,7 @@ struct FlowWork {
   float* attn_part = nullptr;                   // split-KV attention partials [M][H][8][66] (decode at small batch)
   // cascade attention (decode of a batch whose sequences all share one voice prefix)
   int prefix_len = 0; int* d_prefix_pages = nullptr; float* prefix_part = nullptr;
+  int* pflags = nullptr; int pflags_stride = 0;     // folded cascade: [n_layers][1 + tiles] claim counter + tile flags
   int pend_n = 0;             // planes of the last ffn2 still to be added to x (consumed by the next norm)
   float* rope_cs = nullptr;   // [M][64] cos | sin of each row's position (fused RoPE epilogue of the qkv GEMM)
   // set by the prefill callers around flow_layers: row ranges / start positions per sequence (device arrays), which
@@ -645,7 +646,7 @@ bool want_tc(Ctx& c, int M) {
 
 void free_flow_work(FlowWork& w) {
   void* ptrs[] = {w.x, w.h, w.qkv, w.qrot, w.att, w.ff, w.h16, w.att16, w.ff16, w.ws_out, w.ws_ff2, w.attn_part,
-                  w.d_prefix_pages, w.prefix_part, w.rope_cs};
+                  w.d_prefix_pages, w.prefix_part, w.pflags, w.rope_cs};
   for (void* p : ptrs) if (p) cudaFree(p);
   w = FlowWork{};
 }
@@ -755,6 +756,7 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       if (!row_seq && w.prefix_len > 0 && a.splits == 1) {
         a.prefix_len = w.prefix_len; a.prefix_pages = w.d_prefix_pages; a.prefix_part = w.prefix_part;
       }
+      bool folded = false;
       if (!fuse_rope) launch_flow_rope_append(a, c.stream);
       a.seq_row0 = w.seq_row0; a.seq_pos0 = w.seq_pos0; a.n_seq = w.n_seq; a.max_rows_per_seq = w.max_rows_per_seq;
       static const bool no_tc_prefill = [] { const char* v = getenv("PTTS_NO_TC_PREFILL_ATTN"); return v && v[0] == '1'; }();
@@ -762,7 +764,16 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
         // whole prefill chunks: FlashAttention-2 style mma.sync kernel (64 query rows per CTA)
       } else {
         if (w.pre_attn) w.pre_attn(i);
-        launch_flow_prefix_attention(a, c.stream);
+        // cascade: the shared-prefix partials come from the stream kernel itself when it runs (no launch of their own)
+        // (opt-in, PTTS_FOLD=1, read when the step is recorded: it saves the launch but its tiles unbalance the CTAs'
+        // item ranges, measured +0.6 % frame throughput with the attention launch 6 us longer -- DESIGN.md section 4b)
+        const char* fold_env = getenv("PTTS_FOLD");
+        if (a.prefix_len > 0 && w.pflags && fold_env && fold_env[0] == '1' && c.cfg.n_layers >= 2 && flow_attention_streams(a)) {
+          a.pflags = w.pflags + (long long)i * w.pflags_stride;
+          a.pflags_next = w.pflags + (long long)((i + 1) % c.cfg.n_layers) * w.pflags_stride;
+          folded = true;
+        }
+        if (!folded) launch_flow_prefix_attention(a, c.stream);
         launch_flow_attention(a, c.stream);
         if (w.post_attn) w.post_attn(i);
       }
@@ -2072,7 +2083,10 @@ static int batch_init_state(ptts_batch& t, const int32_t* voice_ids, const int32
       if (!t.fw.d_prefix_pages) {
         CU(cudaMalloc((void**)&t.fw.d_prefix_pages, 8 * sizeof(int)));
         CU(cudaMalloc((void**)&t.fw.prefix_part, (size_t)B * c->cfg.n_heads * 66 * sizeof(float)));
+        t.fw.pflags_stride = 1 + ((B + 15) / 16) * c->cfg.n_heads;
+        CU(cudaMalloc((void**)&t.fw.pflags, (size_t)c->cfg.n_layers * t.fw.pflags_stride * sizeof(int)));
       }
+      CU(cudaMemsetAsync(t.fw.pflags, 0, (size_t)c->cfg.n_layers * t.fw.pflags_stride * sizeof(int), c->stream));
       CU(cudaMemcpyAsync(t.fw.d_prefix_pages, v0.pages.data(), v0.pages.size() * sizeof(int), cudaMemcpyHostToDevice,
                          c->stream));
       t.fw.prefix_len = v0.len;

@@ -105,6 +105,10 @@ struct FlowAttnParams {
   const void* kv_tmap;
   // debugging (PTTS_ATTN_DBG=1): [layer][2] {earliest CTA start, latest CTA end} in globaltimer nanoseconds, or null
   unsigned long long* tstamp;
+  // folded cascade (stream kernel only): this layer's {claim counter, flag per (16 rows, head) tile} block, zero when the
+  // launch starts, and the block of the layer launched next (zeroed by this launch).  Null: the prefix partial comes
+  // from flow_prefix_attention_kernel (its own launch).
+  int* pflags; int* pflags_next;
 };
 void launch_flow_prefix_attention(const FlowAttnParams& p, cudaStream_t s);
 // causal attention of whole prefill chunks on tensor cores (bf16 KV, bf16 output); false when not applicable
@@ -116,6 +120,8 @@ void launch_replicate_row(float* dst, const float* src, int n, int C, cudaStream
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s);
 void launch_rope_table(const int* row_pos, const float* freqs, float* table, int M, int T, cudaStream_t s);
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s);
+// true when launch_flow_attention(p) would run the persistent TMA-stream kernel (which can fold the cascade prefix in)
+bool flow_attention_streams(const FlowAttnParams& p);
 // device buffer [64][2] of the attention time stamps (allocated on first use), or null when PTTS_ATTN_DBG is off
 unsigned long long* flow_attention_dbg_buffer();
 

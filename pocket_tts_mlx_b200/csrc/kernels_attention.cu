@@ -669,6 +669,116 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
+// One ring stage (PG pages = 32 * PG keys of one head) against the query tile: S = Q K^T, online softmax in the log2
+// domain, O += P V.  TWO = false: the tile holds ONE query (row 0: lanes 0..3 carry it, a1 / a3 are zero, element [1] of
+// mrun / lrun is unused); TWO = true: 16 queries (rows g and g + 8 of every lane), used for the shared voice prefix.
+template <int PG, bool TWO>
+__device__ __forceinline__ void attn_stage(uint32_t st0, bool two_pages, const uint32_t (&qa)[4][4], int k0, int key_lo, int n_all,
+                                           float (&oc)[8][4], float (&mrun)[2], float (&lrun)[2], int lane) {
+  const int t4 = lane & 3;
+  float sc[4 * PG][4];
+#pragma unroll
+  for (int e = 0; e < PG; ++e) {
+    if (e == 1 && !two_pages) break;
+    const uint32_t Ks = st0 + (uint32_t)e * kAttnPageBytes;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float (&acc)[4] = sc[4 * e + nt];
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+      const int r = nt * 8 + (lane & 7);                     // key row this lane addresses for ldmatrix
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        uint32_t kb[4];
+        const int c = 4 * kk + (lane >> 3);                   // 16-byte chunk (8 dims) of the row
+        ldsm_x4(kb, Ks + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4));
+        mma_bf16_16816(acc, qa[2 * kk], kb[0], kb[1]);
+        mma_bf16_16816(acc, qa[2 * kk + 1], kb[2], kb[3]);
+      }
+    }
+  }
+  if (k0 < key_lo || k0 + PG * kPageTokens > n_all) {        // warp-uniform: only an item's first / last stage is cut
+#pragma unroll
+    for (int nt = 0; nt < 4 * PG; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = k0 + nt * 8 + 2 * t4 + e;
+        if (key < key_lo || key >= n_all) {                   // (covers an absent second page: its keys are >= n_all)
+          sc[nt][e] = -INFINITY;
+          if (TWO) sc[nt][2 + e] = -INFINITY;
+        }
+      }
+    }
+  }
+  float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 4 * PG; ++nt) {
+    bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
+    if (TWO) bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+  }
+  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+  if (TWO) {
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+  }
+  const float nm0 = fmaxf(mrun[0], bm0);                       // finite: every stage holds at least one valid key
+  const float corr0 = (mrun[0] == -INFINITY) ? 0.f : exp2f(mrun[0] - nm0);
+  mrun[0] = nm0;
+  float nm1 = 0.f, corr1 = 0.f;
+  if (TWO) {
+    nm1 = fmaxf(mrun[1], bm1);
+    corr1 = (mrun[1] == -INFINITY) ? 0.f : exp2f(mrun[1] - nm1);
+    mrun[1] = nm1;
+  }
+  float s0 = 0.f, s1 = 0.f;
+  uint32_t pa[2 * PG][4];
+#pragma unroll
+  for (int nt = 0; nt < 4 * PG; ++nt) {
+    const float p0 = exp2f(sc[nt][0] - nm0), p1 = exp2f(sc[nt][1] - nm0);
+    s0 += p0 + p1;
+    pa[nt >> 1][(nt & 1) * 2] = pack2_bf16(p0, p1);
+    if (TWO) {
+      const float q0 = exp2f(sc[nt][2] - nm1), q1 = exp2f(sc[nt][3] - nm1);
+      s1 += q0 + q1;
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(q0, q1);
+    } else {
+      pa[nt >> 1][(nt & 1) * 2 + 1] = 0u;                      // rows 8..15 of the A tile
+    }
+  }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  lrun[0] = lrun[0] * corr0 + s0;
+  if (TWO) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    lrun[1] = lrun[1] * corr1 + s1;
+  }
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) {
+    oc[dt][0] *= corr0; oc[dt][1] *= corr0;
+    if (TWO) { oc[dt][2] *= corr1; oc[dt][3] *= corr1; }
+  }
+  // O += P V: per page 2 k-steps of 16 keys x 8 n-tiles of 8 dims
+#pragma unroll
+  for (int e = 0; e < PG; ++e) {
+    if (e == 1 && !two_pages) break;
+    const uint32_t Vs = st0 + (uint32_t)e * kAttnPageBytes + 4096u;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t vb[4];
+        const int mid = lane >> 3;
+        const int r = 16 * jj + 8 * (mid & 1) + (lane & 7);
+        const int c = 2 * dp + (mid >> 1);
+        ldsm_x4_t(vb, Vs + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4));
+        mma_bf16_16816(oc[2 * dp], pa[2 * e + jj], vb[0], vb[1]);
+        mma_bf16_16816(oc[2 * dp + 1], pa[2 * e + jj], vb[2], vb[3]);
+      }
+    }
+  }
+}
+
 // PG = pages (32 keys) per stage; CTAs per SM follow the stage size: 2 x 2 pages -> 6, 3 x 2 -> 4, 2 x 1 -> 9
 template <int STAGES, int PG>
 __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 : 4)) flow_attention_stream_kernel(const __grid_constant__ CUtensorMap tm_page,
@@ -712,10 +822,72 @@ __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 :
   const int it_lo = (int)(((long long)blockIdx.x * items) / gridDim.x);
   const int it_hi = (int)(((long long)(blockIdx.x + 1) * items) / gridDim.x);
   const int page0 = p.layer * (int)(p.layer_stride / p.page_stride);     // page coordinate of this layer's page 0
+  // folded cascade (p.pflags): the shared-prefix partials are computed by this kernel too, as (16 rows, head) tiles with
+  // real 16-row MMAs.  Tiles are CLAIMED (atomic counter p.pflags[0]) by whichever CTAs are running, so a tile always
+  // belongs to a resident CTA and the per-sequence items that later wait for its flag (p.pflags[1 + tile]) cannot
+  // deadlock on a CTA that has not been scheduled.  This launch also zeroes the NEXT layer's counter and flags (the
+  // last layer those of layer 0, for the next frame): launches of one batch are ordered on its stream.
+  const bool fold = p.pflags != nullptr && p.prefix_len > 0;
+  const int n_pitems = fold ? ((p.M + 15) / 16) * H : 0;
+  if (fold && blockIdx.x == 0)
+    for (int i = threadIdx.x; i <= n_pitems; i += kAttnThreads) p.pflags_next[i] = 0;
 
   if (warp == 1) {
     // ---------------- producer ----------------
     uint32_t gst = 0, qcnt = 0;
+    // folded cascade: (16 rows, head) tiles against the shared voice prefix first (pages of the voice itself, L2-resident);
+    // the claimed tile id travels to the consumer through the query ring's metadata slot, -1 ends the phase
+    if (fold) {
+      const int n_ppg = (p.prefix_len + kPageTokens - 1) / kPageTokens;
+      const int my_page = lane < n_ppg ? p.prefix_pages[lane] : 0;             // <= 4 pages (prefix <= 128 keys)
+      for (;;) {
+        int pi = 0;
+        if (lane == 0) pi = atomicAdd(p.pflags, 1);
+        pi = __shfl_sync(0xffffffffu, pi, 0);
+        const bool end = pi >= n_pitems;
+        const uint32_t qs = qcnt & 1, qph = (qcnt >> 1) & 1;
+        if (lane == 0) {
+          mbar_wait(qempty0 + 8 * qs, qph ^ 1);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(metab + 16 * qs), "r"(end ? -1 : pi), "r"(-1), "r"(0), "r"(n_ppg) : "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(qfull0 + 8 * qs) : "memory");
+        }
+        ++qcnt;
+        if (end) break;
+        const int h = pi % H;
+        for (int j0 = 0; j0 < n_ppg; j0 += PG, ++gst) {
+          const uint32_t s = gst % STAGES, ph = (gst / STAGES) & 1;
+          int pages[PG];
+#pragma unroll
+          for (int e = 0; e < PG; ++e) pages[e] = __shfl_sync(0xffffffffu, my_page, (j0 + e) & 31);
+          if (lane == 0) {
+            uint32_t bytes = 0;
+            int bhi[PG];
+#pragma unroll
+            for (int e = 0; e < PG; ++e) {
+              const int k0 = (j0 + e) * kPageTokens;
+              bhi[e] = (j0 + e < n_ppg) ? (min(p.prefix_len, k0 + kPageTokens) - 1 - k0) >> 3 : -1;
+              bytes += (uint32_t)(bhi[e] + 1) * 2048u;
+            }
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            mbar_expect_tx(full0 + 8 * s, bytes);
+#pragma unroll
+            for (int e = 0; e < PG; ++e) {
+              const uint32_t dst = ring + s * kAttnStageBytes + (uint32_t)e * kAttnPageBytes;
+              const int pc = page0 + pages[e];
+              if (bhi[e] == 3) {
+                tma_load_5d(dst, &tm_page, full0 + 8 * s, 0, 0, h, 0, pc);
+              } else {
+                for (int b = 0; b <= bhi[e]; ++b) {
+                  tma_load_5d(dst + (uint32_t)b * 1024u, &tm_box, full0 + 8 * s, 0, 8 * b, h, 0, pc);
+                  tma_load_5d(dst + 4096u + (uint32_t)b * 1024u, &tm_box, full0 + 8 * s, 0, 8 * b, h, 1, pc);
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
     const int pg_first = p.prefix_len / kPageTokens;
     // lane l holds pages pg_first + l and pg_first + 32 + l of a row (2048 keys); rows beyond that reload in the loop.
     // Entries past the row's last page are zero in the table, so the two loads do not depend on each other.
@@ -796,26 +968,94 @@ __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 :
   // ---------------- consumer ----------------
   const int g = lane >> 2, t4 = lane & 3;
   uint32_t qcnt = 0, gst = 0;
-  // cascade partial of the shared prefix: fetched one item ahead (items are consecutive (row, head) pairs);
-  // lane l holds dims 2l, 2l+1
+  constexpr float kQs = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) and log2(e) folded into q: scores in the log2 domain
+  if (fold) {
+    const int n_ppg = (p.prefix_len + kPageTokens - 1) / kPageTokens;
+    for (;;) {
+      const uint32_t qs = qcnt & 1, qph = (qcnt >> 1) & 1;
+      mbar_wait(qfull0 + 8 * qs, qph);
+      int pi;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pi) : "r"(metab + 16 * qs));
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(qempty0 + 8 * qs) : "memory");
+      ++qcnt;
+      if (pi < 0) break;
+      const int rg = pi / H, h = pi - rg * H;
+      const int m0 = rg * 16 + g, m1 = m0 + 8;
+      const bool r0 = m0 < p.M, r1 = m1 < p.M;
+      uint32_t qa[4][4];
+      {
+        const float* q0 = p.q_rot + (long long)(r0 ? m0 : 0) * D + h * kHeadDim;
+        const float* q1 = p.q_rot + (long long)(r1 ? m1 : 0) * D + h * kHeadDim;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const int c = 16 * ks + 2 * t4;
+          const float2 a0 = *reinterpret_cast<const float2*>(q0 + c), a2 = *reinterpret_cast<const float2*>(q0 + c + 8);
+          const float2 a1 = *reinterpret_cast<const float2*>(q1 + c), a3 = *reinterpret_cast<const float2*>(q1 + c + 8);
+          qa[ks][0] = r0 ? pack2_bf16(a0.x * kQs, a0.y * kQs) : 0u;
+          qa[ks][1] = r1 ? pack2_bf16(a1.x * kQs, a1.y * kQs) : 0u;
+          qa[ks][2] = r0 ? pack2_bf16(a2.x * kQs, a2.y * kQs) : 0u;
+          qa[ks][3] = r1 ? pack2_bf16(a3.x * kQs, a3.y * kQs) : 0u;
+        }
+      }
+      float oc[8][4];
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f;
+      float mrun[2] = {-INFINITY, -INFINITY}, lrun[2] = {0.f, 0.f};
+      for (int j0 = 0; j0 < n_ppg; j0 += PG, ++gst) {
+        const uint32_t s = gst % STAGES, ph = (gst / STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        attn_stage<PG, true>(ring + s * kAttnStageBytes, PG == 2 && j0 + 1 < n_ppg, qa, j0 * kPageTokens, 0, p.prefix_len, oc, mrun,
+                             lrun, lane);
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * s) : "memory");
+      }
+      // un-normalised partial {O[64], max (natural log domain), sum} per (row, head), as flow_prefix_attention_kernel writes it
+      if (r0) {
+        float* o = p.prefix_part + ((long long)m0 * H + h) * 66;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<float2*>(o + dt * 8 + 2 * t4) = make_float2(oc[dt][0], oc[dt][1]);
+        if (t4 == 0) { o[64] = mrun[0] * 0.6931471805599453f; o[65] = lrun[0]; }
+      }
+      if (r1) {
+        float* o = p.prefix_part + ((long long)m1 * H + h) * 66;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<float2*>(o + dt * 8 + 2 * t4) = make_float2(oc[dt][2], oc[dt][3]);
+        if (t4 == 0) { o[64] = mrun[1] * 0.6931471805599453f; o[65] = lrun[1]; }
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p.pflags + 1 + pi), "r"(1) : "memory");
+    }
+  }
   const bool has_pp = p.prefix_len > 0;
+  // not folded: the partial comes from flow_prefix_attention_kernel (an earlier launch) and is fetched one item ahead
   float2 nx_a = make_float2(0.f, 0.f);
   float nx_m = -INFINITY, nx_l = 0.f;
-  if (has_pp && it_lo < it_hi) {
+  if (has_pp && !fold && it_lo < it_hi) {
     const float* pp = p.prefix_part + (long long)it_lo * 66;
     nx_a = *reinterpret_cast<const float2*>(pp + 2 * lane); nx_m = pp[64]; nx_l = pp[65];
   }
   for (int it = it_lo; it < it_hi; ++it, ++qcnt) {
     const int m = it / H, h = it - m * H;
     const uint32_t qs = qcnt & 1, qph = (qcnt >> 1) & 1;
-    const float2 pp_a = nx_a;
-    const float pp_m = nx_m, pp_l = nx_l;
-    if (has_pp && it + 1 < it_hi) {
+    float2 pp_a = nx_a;
+    float pp_m = nx_m, pp_l = nx_l;
+    bool pp_ready = has_pp && !fold;
+    const float* ppc = p.prefix_part + (long long)it * 66;
+    const int* my_flag = fold ? p.pflags + 1 + (m >> 4) * H + h : nullptr;
+    if (fold) {
+      // published already (the usual case after the first microseconds)?  then its loads ride under this item
+      int f;
+      asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(f) : "l"(my_flag) : "memory");
+      pp_ready = f != 0;
+      if (pp_ready) { pp_a = __ldcg(reinterpret_cast<const float2*>(ppc + 2 * lane)); pp_m = __ldcg(ppc + 64); pp_l = __ldcg(ppc + 65); }
+    } else if (has_pp && it + 1 < it_hi) {
       const float* pp = p.prefix_part + (long long)(it + 1) * 66;
       nx_a = *reinterpret_cast<const float2*>(pp + 2 * lane); nx_m = pp[64]; nx_l = pp[65];
     }
     mbar_wait(qfull0 + 8 * qs, qph);
-    uint32_t qa[4][2];           // A fragments of row 0 (a0, a2); rows 8..15 (a1, a3) are zero
+    uint32_t qa[4][4];           // A fragments of row 0 (a0, a2); rows 8..15 (a1, a3) are zero
     int n_all, key_lo, pg_lo, n_pg;
     {
 #pragma unroll
@@ -823,10 +1063,10 @@ __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 :
         float2 x, y;
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x.x), "=f"(x.y) : "r"(qbuf + 256 * qs + (uint32_t)(16 * ks + 2 * t4) * 4u));
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(y.x), "=f"(y.y) : "r"(qbuf + 256 * qs + (uint32_t)(16 * ks + 8 + 2 * t4) * 4u));
-        // 1/sqrt(64) and log2(e) folded into q: scores live in the log2 domain, p = 2^(s - m)
-        constexpr float kQs = 0.125f * 1.4426950408889634f;
         qa[ks][0] = g == 0 ? pack2_bf16(x.x * kQs, x.y * kQs) : 0u;
-        qa[ks][1] = g == 0 ? pack2_bf16(y.x * kQs, y.y * kQs) : 0u;
+        qa[ks][1] = 0u;
+        qa[ks][2] = g == 0 ? pack2_bf16(y.x * kQs, y.y * kQs) : 0u;
+        qa[ks][3] = 0u;
       }
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(n_all), "=r"(key_lo), "=r"(pg_lo), "=r"(n_pg) : "r"(metab + 16 * qs));
     }
@@ -835,87 +1075,12 @@ __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 :
     float oc[8][4];
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f;
-    float mrun = -INFINITY, lrun = 0.f;
+    float mrun[2] = {-INFINITY, -INFINITY}, lrun[2] = {0.f, 0.f};
     for (int j0 = 0; j0 < n_pg; j0 += PG, ++gst) {
       const uint32_t s = gst % STAGES, ph = (gst / STAGES) & 1;
-      const bool two = PG == 2 && j0 + 1 < n_pg;                 // warp-uniform: the stage holds a second page
       mbar_wait(full0 + 8 * s, ph);
-      const uint32_t st0 = ring + s * kAttnStageBytes;
-      // S = q K^T: per page 4 n-tiles of 8 keys x 4 k-steps of 16 dims
-      float sc[4 * PG][4];
-#pragma unroll
-      for (int e = 0; e < PG; ++e) {
-        if (e == 1 && !two) break;
-        const uint32_t Ks = st0 + (uint32_t)e * kAttnPageBytes;
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          float (&acc)[4] = sc[4 * e + nt];
-          acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-          const int r = nt * 8 + (lane & 7);                     // key row this lane addresses for ldmatrix
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            uint32_t kb[4];
-            const int c = 4 * kk + (lane >> 3);                   // 16-byte chunk (8 dims) of the row
-            ldsm_x4(kb, Ks + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4));
-            const uint32_t a0[4] = {qa[2 * kk][0], 0u, qa[2 * kk][1], 0u};
-            const uint32_t a1[4] = {qa[2 * kk + 1][0], 0u, qa[2 * kk + 1][1], 0u};
-            mma_bf16_16816(acc, a0, kb[0], kb[1]);
-            mma_bf16_16816(acc, a1, kb[2], kb[3]);
-          }
-        }
-      }
-      const int k0 = (pg_lo + j0) * kPageTokens;
-      if (k0 < key_lo || k0 + PG * kPageTokens > n_all) {        // warp-uniform: only an item's first / last stage is cut
-#pragma unroll
-        for (int nt = 0; nt < 4 * PG; ++nt) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int key = k0 + nt * 8 + 2 * t4 + e;
-            if (key < key_lo || key >= n_all) sc[nt][e] = -INFINITY;      // (covers the absent second page: its keys are >= n_all)
-          }
-        }
-      }
-      float bm = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 4 * PG; ++nt) bm = fmaxf(bm, fmaxf(sc[nt][0], sc[nt][1]));
-      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
-      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
-      const float nm = fmaxf(mrun, bm);                          // finite: every stage holds at least one valid key
-      const float corr = (mrun == -INFINITY) ? 0.f : exp2f(mrun - nm);
-      mrun = nm;
-      float ssum = 0.f;
-      uint32_t pa[2 * PG][4];
-#pragma unroll
-      for (int nt = 0; nt < 4 * PG; ++nt) {
-        const float p0 = exp2f(sc[nt][0] - nm), p1 = exp2f(sc[nt][1] - nm);
-        ssum += p0 + p1;
-        pa[nt >> 1][(nt & 1) * 2] = pack2_bf16(p0, p1);
-        pa[nt >> 1][(nt & 1) * 2 + 1] = 0u;                      // rows 8..15 of the A tile
-      }
-      ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
-      ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
-      lrun = lrun * corr + ssum;
-#pragma unroll
-      for (int dt = 0; dt < 8; ++dt) { oc[dt][0] *= corr; oc[dt][1] *= corr; }
-      // O += P V: per page 2 k-steps of 16 keys x 8 n-tiles of 8 dims
-#pragma unroll
-      for (int e = 0; e < PG; ++e) {
-        if (e == 1 && !two) break;
-        const uint32_t Vs = st0 + (uint32_t)e * kAttnPageBytes + 4096u;
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-#pragma unroll
-          for (int dp = 0; dp < 4; ++dp) {
-            uint32_t vb[4];
-            const int mid = lane >> 3;
-            const int r = 16 * jj + 8 * (mid & 1) + (lane & 7);
-            const int c = 2 * dp + (mid >> 1);
-            ldsm_x4_t(vb, Vs + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4));
-            mma_bf16_16816(oc[2 * dp], pa[2 * e + jj], vb[0], vb[1]);
-            mma_bf16_16816(oc[2 * dp + 1], pa[2 * e + jj], vb[2], vb[3]);
-          }
-        }
-      }
+      attn_stage<PG, false>(ring + s * kAttnStageBytes, PG == 2 && j0 + 1 < n_pg, qa, (pg_lo + j0) * kPageTokens, key_lo, n_all, oc,
+                            mrun, lrun, lane);
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * s) : "memory");
     }
@@ -925,14 +1090,21 @@ __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 :
       for (int dt = 0; dt < 8; ++dt)
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(obuf + (uint32_t)(dt * 8 + 2 * t4) * 4u), "f"(oc[dt][0]), "f"(oc[dt][1]) : "memory");
     }
-    const float m_own = __shfl_sync(0xffffffffu, mrun, 0) * 0.6931471805599453f;   // back to the natural-log domain
-    const float l_own = __shfl_sync(0xffffffffu, lrun, 0);
+    const float m_own = __shfl_sync(0xffffffffu, mrun[0], 0) * 0.6931471805599453f;   // back to the natural-log domain
+    const float l_own = __shfl_sync(0xffffffffu, lrun[0], 0);
     __syncwarp();
     float2 o;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(obuf + (uint32_t)lane * 8u));
     __syncwarp();
     float l = l_own;
     if (has_pp) {
+      if (!pp_ready) {           // folded cascade, tile not published when this item started: wait for it now
+        int f;
+        do {
+          asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(f) : "l"(my_flag) : "memory");
+        } while (f == 0);
+        pp_a = __ldcg(reinterpret_cast<const float2*>(ppc + 2 * lane)); pp_m = __ldcg(ppc + 64); pp_l = __ldcg(ppc + 65);
+      }
       const float mx = fmaxf(m_own, pp_m);
       const float c0 = __expf(m_own - mx), c1 = __expf(pp_m - mx);
       l = l_own * c0 + pp_l * c1;
@@ -1005,6 +1177,8 @@ static bool flow_attention_stream_ok(const FlowAttnParams& p) {
   static const int mode = [] { const char* v = getenv("PTTS_ATTN_STREAM"); return v ? atoi(v) : 1; }();
   return mode != 0 && p.kv_tmap && p.kv_bf16 && p.splits <= 1 && !p.row_seq && p.M * p.H >= 296 && p.q_rot && (p.out16 || p.out);
 }
+
+bool flow_attention_streams(const FlowAttnParams& p) { return flow_attention_stream_ok(p); }
 
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
   if (p.M <= 0) return;

@@ -98,6 +98,37 @@ def test_config4_batch256_shared_voice_vs_oracle(model_b256, cfg, weights, voice
         assert s > 30.0, (b, s)
 
 
+def test_config4_folded_prefix_attention_matches_separate_launch(model_b256):
+    """PTTS_FOLD=1 (read when a batch records its step graph): the shared-voice prefix partials are computed inside the
+    persistent stream-attention kernel -- (16 rows, head) tiles claimed through an atomic counter, published through
+    per-tile flags -- instead of by flow_prefix_attention_kernel.  Same math on the same bf16 keys: the generated
+    latents agree with the two-launch path to accumulation-order noise over 6 free-running frames."""
+    import os
+    from pocket_tts_mlx_b200 import _native
+    from pocket_tts_mlx_b200.synthetic import synthetic_token_ids
+    n, frames = 256, 6
+    ids = list(synthetic_token_ids(5, n, 60))
+    rng = np.random.Generator(np.random.PCG64(99))
+    noise = rng.standard_normal((frames, n, 32)).astype(np.float32)
+    state = model_b256.get_state_for_audio_prompt("alba")
+    out = {}
+    for fold in ("0", "1"):
+        os.environ["PTTS_FOLD"] = fold
+        try:
+            batch = _native.Batch(model_b256._ctx, [state["voice_id"]] * n, [state["prompt_len"] + 60 + frames + 4] * n)
+            batch.set_pipelined(True)
+            batch.warmup_mimi(1)
+            batch.prefill_text(ids)
+            out[fold] = [tuple(a.copy() for a in batch.step(noise[f])) for f in range(frames)]
+            batch.close()
+        finally:
+            os.environ.pop("PTTS_FOLD", None)
+    for f in range(frames):
+        e = rel_l2(out["1"][f][0], out["0"][f][0])
+        assert e < 5e-3, (f, e)
+        assert np.max(np.abs(out["1"][f][1] - out["0"][f][1])) < 5e-2, f
+
+
 def test_config4_batch256_async_staging_is_bit_identical(model_b256):
     """The exact call pattern of the bench's e2e leg (pipelined graph + asynchronous double-buffered staged steps)
     returns bit for bit what synchronous pipelined host steps return at batch 256."""
