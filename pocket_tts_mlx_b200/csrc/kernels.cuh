@@ -120,7 +120,8 @@ void launch_replicate_row(float* dst, const float* src, int n, int C, cudaStream
 void launch_flow_rope_append(const FlowAttnParams& p, cudaStream_t s);
 void launch_rope_table(const int* row_pos, const float* freqs, float* table, int M, int T, cudaStream_t s);
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s);
-// true when launch_flow_attention(p) would run the persistent TMA-stream kernel (which can fold the cascade prefix in)
+// true when launch_flow_attention(p) would run the persistent TMA-stream kernel in the geometry that can fold the
+// cascade prefix in (p.pflags)
 bool flow_attention_streams(const FlowAttnParams& p);
 // device buffer [64][2] of the attention time stamps (allocated on first use), or null when PTTS_ATTN_DBG is off
 unsigned long long* flow_attention_dbg_buffer();

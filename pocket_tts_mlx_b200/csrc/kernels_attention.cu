@@ -780,7 +780,7 @@ __device__ __forceinline__ void attn_stage(uint32_t st0, bool two_pages, const u
 }
 
 // PG = pages (32 keys) per stage; CTAs per SM follow the stage size: 2 x 2 pages -> 6, 3 x 2 -> 4, 2 x 1 -> 9
-template <int STAGES, int PG>
+template <int STAGES, int PG, bool FOLD>
 __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 : 4)) flow_attention_stream_kernel(const __grid_constant__ CUtensorMap tm_page,
                                                                                 const __grid_constant__ CUtensorMap tm_box,
                                                                                 const FlowAttnParams p, const int items) {
@@ -827,7 +827,7 @@ __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 :
   // belongs to a resident CTA and the per-sequence items that later wait for its flag (p.pflags[1 + tile]) cannot
   // deadlock on a CTA that has not been scheduled.  This launch also zeroes the NEXT layer's counter and flags (the
   // last layer those of layer 0, for the next frame): launches of one batch are ordered on its stream.
-  const bool fold = p.pflags != nullptr && p.prefix_len > 0;
+  const bool fold = FOLD && p.pflags != nullptr && p.prefix_len > 0;     // (compiled out of the default instantiation)
   const int n_pitems = fold ? ((p.M + 15) / 16) * H : 0;
   if (fold && blockIdx.x == 0)
     for (int i = threadIdx.x; i <= n_pitems; i += kAttnThreads) p.pflags_next[i] = 0;
@@ -1178,7 +1178,12 @@ static bool flow_attention_stream_ok(const FlowAttnParams& p) {
   return mode != 0 && p.kv_tmap && p.kv_bf16 && p.splits <= 1 && !p.row_seq && p.M * p.H >= 296 && p.q_rot && (p.out16 || p.out);
 }
 
-bool flow_attention_streams(const FlowAttnParams& p) { return flow_attention_stream_ok(p); }
+// the folded-cascade instantiation exists for the default stage geometry only
+bool flow_attention_streams(const FlowAttnParams& p) {
+  const char* st = getenv("PTTS_ATTN_STAGES");
+  const char* pg = getenv("PTTS_ATTN_PAGES");
+  return flow_attention_stream_ok(p) && !(st && atoi(st) == 3) && !(pg && atoi(pg) == 1);
+}
 
 void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
   if (p.M <= 0) return;
@@ -1192,10 +1197,11 @@ void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
     static const int pg = [] { const char* v = getenv("PTTS_ATTN_PAGES"); return (v && atoi(v) == 1) ? 1 : 2; }();
     static bool attr_done = false;
     if (!attr_done) {
-      cudaFuncSetAttribute(flow_attention_stream_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(2, 2));
-      cudaFuncSetAttribute(flow_attention_stream_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(3, 2));
-      cudaFuncSetAttribute(flow_attention_stream_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(2, 1));
-      cudaFuncSetAttribute(flow_attention_stream_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(3, 1));
+      cudaFuncSetAttribute(flow_attention_stream_kernel<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(2, 2));
+      cudaFuncSetAttribute(flow_attention_stream_kernel<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(2, 2));
+      cudaFuncSetAttribute(flow_attention_stream_kernel<3, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(3, 2));
+      cudaFuncSetAttribute(flow_attention_stream_kernel<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(2, 1));
+      cudaFuncSetAttribute(flow_attention_stream_kernel<3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(3, 1));
       attr_done = true;
     }
     const int items = p.M * p.H;
@@ -1204,10 +1210,12 @@ void launch_flow_attention(const FlowAttnParams& p, cudaStream_t s) {
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(p.kv_tmap);
     const dim3 grid((unsigned)std::min(items, 148 * ctas)), block(kAttnThreads);
     const size_t smem = (size_t)attn_smem_bytes(stages, pg);
-    if (stages == 3 && pg == 2) launch_k(flow_attention_stream_kernel<3, 2>, grid, block, smem, s, maps[0], maps[1], p, items);
-    else if (stages == 2 && pg == 1) launch_k(flow_attention_stream_kernel<2, 1>, grid, block, smem, s, maps[0], maps[1], p, items);
-    else if (stages == 3 && pg == 1) launch_k(flow_attention_stream_kernel<3, 1>, grid, block, smem, s, maps[0], maps[1], p, items);
-    else launch_k(flow_attention_stream_kernel<2, 2>, grid, block, smem, s, maps[0], maps[1], p, items);
+    const bool fold = p.pflags != nullptr && p.prefix_len > 0;       // only with the default stage geometry
+    if (fold && stages == 2 && pg == 2) launch_k(flow_attention_stream_kernel<2, 2, true>, grid, block, smem, s, maps[0], maps[1], p, items);
+    else if (stages == 3 && pg == 2) launch_k(flow_attention_stream_kernel<3, 2, false>, grid, block, smem, s, maps[0], maps[1], p, items);
+    else if (stages == 2 && pg == 1) launch_k(flow_attention_stream_kernel<2, 1, false>, grid, block, smem, s, maps[0], maps[1], p, items);
+    else if (stages == 3 && pg == 1) launch_k(flow_attention_stream_kernel<3, 1, false>, grid, block, smem, s, maps[0], maps[1], p, items);
+    else launch_k(flow_attention_stream_kernel<2, 2, false>, grid, block, smem, s, maps[0], maps[1], p, items);
     ++g_launches;
     return;
   }
