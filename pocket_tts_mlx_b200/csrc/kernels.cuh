@@ -199,6 +199,7 @@ extern std::atomic<long long> g_launches;   // process-wide: contexts may be dri
 extern bool g_prof_on;
 struct ProfScope {
   int slot = -1;
+  bool nvtx = false;      // PTTS_NVTX=1: an NVTX range "kernel:tag" around the launch (ncu --nvtx --nvtx-include, Nsight Systems)
   cudaStream_t s;
   ProfScope(const char* kernel, const char* tag, double flops, double bytes, cudaStream_t stream);
   ~ProfScope();

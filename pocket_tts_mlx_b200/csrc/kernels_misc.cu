@@ -1,5 +1,6 @@
 // Row-wise normalisation and the small fused ops around the GEMMs (LayerNorm,
 // Embedding, NaN->BOS, noise, quantizer + upsample, last SEANet conv, carried conv state).
+#include <nvtx3/nvToolsExt.h>
 #include "kernels.cuh"
 
 namespace ptts {
@@ -764,6 +765,13 @@ cudaEvent_t get_event() {
 }  // namespace
 
 ProfScope::ProfScope(const char* kernel, const char* tag, double flops, double bytes, cudaStream_t stream) : s(stream) {
+  static const bool nvtx_on = [] { const char* v = getenv("PTTS_NVTX"); return v && v[0] == '1'; }();
+  if (nvtx_on) {
+    char name[96];
+    snprintf(name, sizeof name, tag ? "%s:%s" : "%s", kernel, tag);
+    nvtxRangePushA(name);
+    nvtx = true;
+  }
   if (!g_prof_on) return;
   Rec r;
   r.name = kernel;
@@ -775,6 +783,7 @@ ProfScope::ProfScope(const char* kernel, const char* tag, double flops, double b
 }
 ProfScope::~ProfScope() {
   if (slot >= 0) cudaEventRecord(g_recs[slot].e1, s);
+  if (nvtx) nvtxRangePop();
 }
 void prof_start() { g_recs.clear(); g_prof_on = true; }
 const char* prof_report() {
