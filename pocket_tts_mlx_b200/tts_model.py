@@ -482,6 +482,7 @@ class TTSModel:
         bytes_per_frame = 4.0 * (self.frame_samples + self._ctx.config.latent_dim)
         if n_jobs > int(slots) and sum(limits) * bytes_per_frame * 1.3 > max_host_gb * 2 ** 30:
             per_run = max(int(slots), int(n_jobs * max_host_gb * 2 ** 30 / (sum(limits) * bytes_per_frame * 1.3)))
+            per_run -= per_run % int(slots)              # whole waves of the slots: a run does not end with a few stragglers
             waves_all, lats_all = [], []
             for lo in range(0, n_jobs, per_run):
                 hi = min(n_jobs, lo + per_run)
