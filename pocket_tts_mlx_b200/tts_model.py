@@ -454,7 +454,8 @@ class TTSModel:
                                   slots: int = 256, frames_after_eos: Union[int, Sequence[int]] = 3,
                                   warmup_frames: int = _MIMI_WARMUP_FRAMES, max_frames: Optional[int] = None,
                                   noise: Optional[Sequence[np.ndarray]] = None, seed: int = 0,
-                                  return_latents: bool = False, min_admit: Optional[int] = None, pipelined: bool = True):
+                                  return_latents: bool = False, min_admit: Optional[int] = None, pipelined: bool = True,
+                                  _scheduled: bool = False):
         """Continuous batching over `slots` lock-step sequences: when an utterance ends (EOS rule or frame limit of
         the reference, tts_model.py:404-426) its slot is parked and later re-initialised for the next queued
         utterance while the others keep decoding, so the batch stays full.  Admissions are
@@ -466,7 +467,8 @@ class TTSModel:
 
         noise: optional per-utterance arrays [1 + frames, latent_dim] (row 0 = the unused prefill draw, like the
         reference); without it the host draws one N(0,1) block per step from `seed`.
-        Returns the waveforms in input order (and the per-utterance latents when asked)."""
+        Utterances are started longest frame budget first (shortest tail); the waveforms (and the per-utterance
+        latents when asked) come back in input order."""
         n_jobs = len(model_states)
         if n_jobs == 0:
             return ([], []) if return_latents else []
@@ -475,6 +477,21 @@ class TTSModel:
         limits = [self._estimate_max_gen_len(k) for k in n_tok]
         if max_frames is not None:
             limits = [min(l, max_frames) for l in limits]
+        if not _scheduled and n_jobs > int(slots) and min(limits) != max(limits):
+            # longest budget first: the run then ends with the SHORT utterances, so the tail in which the queue is
+            # empty and the slots drain one by one is as short as it can be; results go back in submission order
+            order = sorted(range(n_jobs), key=lambda j: -limits[j])
+            r = self.generate_audio_continuous(
+                [model_states[j] for j in order], [token_ids[j] for j in order], slots=slots,
+                frames_after_eos=[fae[j] for j in order], warmup_frames=warmup_frames, max_frames=max_frames,
+                noise=None if noise is None else [noise[j] for j in order], seed=seed, return_latents=return_latents,
+                min_admit=min_admit, pipelined=pipelined, _scheduled=True)
+            inv = [0] * n_jobs
+            for pos, j in enumerate(order):
+                inv[j] = pos
+            if return_latents:
+                return [r[0][inv[j]] for j in range(n_jobs)], [r[1][inv[j]] for j in range(n_jobs)]
+            return [r[inv[j]] for j in range(n_jobs)]
         need = [int(s["prompt_len"]) + k + l for s, k, l in zip(model_states, n_tok, limits)]
         # host memory: the frames of all utterances of one run are kept in one slot-major array (waveforms are views
         # into it); very long job lists are cut into runs of at most ~max_host_gb of output each
@@ -490,7 +507,7 @@ class TTSModel:
                     model_states[lo:hi], token_ids[lo:hi], slots=slots, frames_after_eos=fae[lo:hi],
                     warmup_frames=warmup_frames, max_frames=max_frames,
                     noise=None if noise is None else noise[lo:hi], seed=seed + lo, return_latents=True,
-                    min_admit=min_admit, pipelined=pipelined)
+                    min_admit=min_admit, pipelined=pipelined, _scheduled=True)
                 waves_all += r[0]
                 lats_all += r[1]
             return (waves_all, lats_all) if return_latents else waves_all

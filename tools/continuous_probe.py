@@ -1,4 +1,5 @@
-"""Continuous batching vs lock-step waves on ragged utterance lengths (python tools/continuous_probe.py [n_jobs] [slots])."""
+"""Continuous batching vs lock-step waves on ragged utterance lengths
+(python tools/continuous_probe.py [n_jobs] [slots] [min_admit,min_admit,...])."""
 import sys, time
 from pathlib import Path
 import numpy as np
@@ -16,12 +17,16 @@ frames = [model._estimate_max_gen_len(int(k)) for k in n_tok]
 audio_s = 0.08 * sum(frames)
 print(f"{n_jobs} utterances, {min(frames)}..{max(frames)} frames, {audio_s:.0f} audio-seconds in total")
 
-for rep in range(2):
-    t0 = time.perf_counter()
-    waves = model.generate_audio_continuous([state] * n_jobs, ids, slots=slots, seed=1)
-    dt = time.perf_counter() - t0
-    assert [len(w) // 1920 for w in waves] == frames
-    print(f"continuous, {slots} slots: {dt:.2f} s -> {audio_s / dt:.0f} audio-s/s")
+admits = [int(a) for a in sys.argv[3].split(",")] if len(sys.argv) > 3 else [None]
+for ma in admits:
+    for rep in range(2):
+        t0 = time.perf_counter()
+        waves = model.generate_audio_continuous([state] * n_jobs, ids, slots=slots, seed=1, min_admit=ma)
+        dt = time.perf_counter() - t0
+        assert [len(w) // 1920 for w in waves] == frames
+        print(f"continuous, {slots} slots, min_admit {ma}: {dt:.2f} s -> {audio_s / dt:.0f} audio-s/s")
+if len(sys.argv) > 3:
+    sys.exit(0)
 
 for pipelined in (True, True, False):
     t0 = time.perf_counter()
