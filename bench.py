@@ -452,11 +452,19 @@ def _blas_threads():
         return os.cpu_count() or 1
 
 
+def config4(n_seq: int, frames: int) -> dict:
+    """The workload both arms are quoted on (BASELINE config 4)."""
+    return {"workload": f"config 4: {n_seq} x {N_TOK}-token utterances, shared {VOICE_FRAMES}-frame voice prefix, "
+                        f"{frames} frames each, random-init b6369a24 weights",
+            "per_gpu_batch": n_seq, "frames": frames,
+            "l2": "inputs larger than L2 (per-frame KV + activations > 126 MB)"}
+
+
 def run_reference(args, world, rank):
     _use_all_host_threads()
     if rank != 0:
         return
-    frames = 100
+    frames = args.frames          # one whole utterance of the workload per step (275 frames: about 6 s of CPU work)
     for _ in range(args.warmup):
         cpu_baseline(4)
     t_all, audio = 0.0, 0.0
@@ -470,8 +478,9 @@ def run_reference(args, world, rank):
         "impl": "reference", "metric": "audio_seconds_per_second", "value": v, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config 4 (256 x 60-token utterances, 125-frame voice prefix, 275 frames)",
-                   "note": "reference is batch-1 only: each step = 1 utterance x 100 frames incl. text prefill"},
+        "config": dict(config4(args.batch, frames), storage="fp32 (NumPy port of the reference)",
+                       note=f"reference is batch-1 only: each step = 1 utterance of the workload ({frames} frames incl. text "
+                            "prefill), the job's utterances would run one after the other at this rate"),
         "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} x (1 utterance, 60 tokens, {frames} frames), NumPy/OpenBLAS fp32; "
                                    "MLX itself is not installable here"},
@@ -612,11 +621,7 @@ def main():
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"config 4: {n_seq} x {N_TOK}-token utterances, shared {VOICE_FRAMES}-frame voice prefix, "
-                                   f"{frames} frames each, random-init b6369a24 weights",
-                       "per_gpu_batch": n_seq, "frames": frames,
-                       "l2": "inputs larger than L2 (per-frame KV + activations > 126 MB)",
-                       "storage": "bf16 weights + bf16 paged KV, fp32 accumulate"},
+            "config": dict(config4(n_seq, frames), storage="bf16 weights + bf16 paged KV, fp32 accumulate"),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d // e2e_steps,
                     "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps},
