@@ -862,6 +862,7 @@ struct ptts_batch {
   std::vector<ShiftEntry> h_shift;              // host copy of the streaming-conv state map
   void* mimi_tpl = nullptr;                     // Mimi state of one sequence right after the warm-up frames
   bool has_tpl = false;
+  StatePieceDev* d_state_pieces = nullptr; int n_state_pieces = 0; int* d_restore_slots = nullptr;   // restore_mimi_slots
   std::vector<void*> allocs;
   std::vector<std::pair<void*, size_t>> zero_list;   // streaming state + scratch that a fresh batch starts zeroed
   int *d_cp_src = nullptr, *d_cp_dst = nullptr;
@@ -1548,6 +1549,7 @@ void pipelined_frame(Batch& bt, int parity, bool host_io) {
 }
 
 int restore_mimi_slot(Batch& t, int slot);
+int restore_mimi_slots(Batch& t, const std::vector<int>& slots);
 
 int run_pipelined_step(Batch& bt, bool host_io) {
   Ctx& c = *bt.ctx;
@@ -1588,7 +1590,7 @@ int run_pipelined_step(Batch& bt, bool host_io) {
   if (!bt.pending_mimi_reset.empty()) {
     // slots re-initialised since the previous frame: this frame's Mimi branch has just consumed the old utterance's last
     // latent with the old state; the NEXT frame decodes the new utterance's first latent and needs the fresh state
-    for (int slot : bt.pending_mimi_reset) RET(restore_mimi_slot(bt, slot));
+    RET(restore_mimi_slots(bt, bt.pending_mimi_reset));
     bt.pending_mimi_reset.clear();
   }
   bt.frame_idx += 1;
@@ -1661,19 +1663,33 @@ std::vector<StatePiece> mimi_state_pieces(Batch& t) {
   return v;
 }
 
-// per-slot Mimi streaming state back to the post-warm-up template (or zero), stream-ordered
-int restore_mimi_slot(Batch& t, int slot) {
+// Mimi streaming state of the given slots back to the post-warm-up template (or zero), stream-ordered, ONE launch for
+// all pieces and slots (an admission round of the continuous scheduler re-initialises ~16 slots x ~25 buffers)
+int restore_mimi_slots(Batch& t, const std::vector<int>& slots) {
   Ctx& c = *t.ctx;
-  auto pieces = mimi_state_pieces(t);
-  size_t off = 0;
-  for (auto& p : pieces) {
-    char* dst = p.base + (size_t)slot * p.stride;
-    if (t.has_tpl) CU(cudaMemcpyAsync(dst, (char*)t.mimi_tpl + off, p.bytes, cudaMemcpyDeviceToDevice, c.stream));
-    else CU(cudaMemsetAsync(dst, 0, p.bytes, c.stream));
-    off += (p.bytes + 15) & ~(size_t)15;
+  if (slots.empty()) return 0;
+  if (!t.d_state_pieces) {
+    auto pieces = mimi_state_pieces(t);
+    std::vector<StatePieceDev> dev;
+    size_t off = 0;
+    for (auto& p : pieces) {
+      if ((p.bytes & 3) || (p.stride & 3)) return fail(PTTS_ERR_STATE, "state piece of %zu bytes is not a multiple of 4", p.bytes);
+      dev.push_back({p.base, (unsigned long long)p.stride, (unsigned long long)p.bytes, (unsigned long long)off});
+      off += (p.bytes + 15) & ~(size_t)15;
+    }
+    t.n_state_pieces = (int)dev.size();
+    RET(t.dalloc((void**)&t.d_state_pieces, dev.size() * sizeof(StatePieceDev)));
+    RET(t.dalloc((void**)&t.d_restore_slots, (size_t)t.B * sizeof(int)));
+    CU(cudaMemcpyAsync(t.d_state_pieces, dev.data(), dev.size() * sizeof(StatePieceDev), cudaMemcpyHostToDevice, c.stream));
+    CU(cudaStreamSynchronize(c.stream));     // dev is a local
   }
+  // (a pageable host -> device copy of a few bytes has been staged by the time cudaMemcpyAsync returns)
+  CU(cudaMemcpyAsync(t.d_restore_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+  launch_restore_state(t.d_state_pieces, t.n_state_pieces, t.d_restore_slots, (int)slots.size(),
+                       t.has_tpl ? (const char*)t.mimi_tpl : nullptr, c.stream);
   return 0;
 }
+int restore_mimi_slot(Batch& t, int slot) { return restore_mimi_slots(t, std::vector<int>{slot}); }
 
 // captured frame graphs bake pointers and modes in (staging sets, cascade prefix length, PCM output): drop them all
 void drop_graphs(Batch& t) {
@@ -2353,7 +2369,7 @@ int32_t ptts_batch_warmup_mimi(ptts_batch* bt, int32_t n_frames) {
   return 0;
 }
 
-static int reset_seq_impl(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_t max_len) {
+static int reset_seq_impl(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_t max_len, std::vector<int>* restore_now = nullptr) {
   Ctx& c = *bt->ctx;
   Batch& t = *bt;
   if (slot < 0 || slot >= t.B) return fail(PTTS_ERR_INVALID, "slot %d out of range", slot);
@@ -2413,6 +2429,7 @@ static int reset_seq_impl(ptts_batch* bt, int32_t slot, int32_t voice_id, int32_
   // Mimi: back to the post-warm-up state (or to the zero state when the batch was never warmed up).  In pipelined
   // mode the next frame graph still decodes the previous utterance's last latent for this slot: restore after it.
   if (t.pipelined && t.frame_idx > 0) t.pending_mimi_reset.push_back(slot);
+  else if (restore_now) restore_now->push_back(slot);
   else RET(restore_mimi_slot(t, slot));
   return 0;
 }
@@ -2423,7 +2440,9 @@ int32_t ptts_batch_reset_seqs(ptts_batch* bt, int32_t n, const int32_t* slots, c
   Ctx& c = *bt->ctx;
   CU(cudaSetDevice(c.device));
   CU(cudaStreamSynchronize(c.stream));
-  for (int i = 0; i < n; ++i) RET(reset_seq_impl(bt, slots[i], voice_ids[i], max_lens[i]));
+  std::vector<int> restore_now;          // the slots' Mimi state goes back to the template in one launch
+  for (int i = 0; i < n; ++i) RET(reset_seq_impl(bt, slots[i], voice_ids[i], max_lens[i], &restore_now));
+  RET(restore_mimi_slots(*bt, restore_now));
   CU(cudaStreamSynchronize(c.stream));
   CU(cudaGetLastError());
   return 0;

@@ -186,6 +186,11 @@ void launch_axpy(const float* x, float* y, float a, int n, cudaStream_t s);
 void launch_copy_pages(void* pool, int kv_bf16, long long layer_stride, long long page_stride, int n_layers,
                        const int* src_pages, const int* dst_pages, int n_pairs, cudaStream_t s);
 void launch_fill_u32(unsigned int* dst, unsigned int v, long long n, cudaStream_t s);
+// continuous batching: the streaming state of n_slots sequences back to a template (or to zero when tpl is null) in one
+// launch.  A piece is one state buffer: sequence b's part is bytes long at base + b * stride, its image in the template
+// at tpl + tpl_off (bytes and addresses are multiples of 4).
+struct StatePieceDev { char* base; unsigned long long stride, bytes, tpl_off; };
+void launch_restore_state(const StatePieceDev* pieces, int n_pieces, const int* slots, int n_slots, const char* tpl, cudaStream_t s);
 void launch_gather_frame(const float* lat_all, float* lat, int B, int F, int L, const int* frame_idx,
                          cudaStream_t s);
 void launch_scatter_audio(const float* audio, float* audio_all, int B, int F, int n, const int* frame_idx,

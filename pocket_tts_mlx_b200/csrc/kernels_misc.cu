@@ -689,6 +689,34 @@ void launch_state_shift(const ShiftEntry* entries_dev, int n_entries, int B, cud
   ++g_launches;
 }
 
+// grid (pieces, slots, 8 chunks of a piece)
+__global__ void __launch_bounds__(256) restore_state_kernel(const StatePieceDev* __restrict__ pieces, const int* __restrict__ slots,
+                                                            const char* __restrict__ tpl) {
+  pdl_sync();
+  const StatePieceDev p = pieces[blockIdx.x];
+  char* dst = p.base + (unsigned long long)slots[blockIdx.y] * p.stride;
+  const char* src = tpl ? tpl + p.tpl_off : nullptr;
+  const bool wide = (p.bytes & 15) == 0 && (reinterpret_cast<unsigned long long>(dst) & 15) == 0 &&
+                    (!src || (reinterpret_cast<unsigned long long>(src) & 15) == 0);
+  if (wide) {
+    const long long n = (long long)(p.bytes >> 4);
+    const long long per = (n + gridDim.z - 1) / gridDim.z, lo = per * blockIdx.z, hi = min(n, lo + per);
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x)
+      reinterpret_cast<uint4*>(dst)[i] = src ? __ldg(reinterpret_cast<const uint4*>(src) + i) : make_uint4(0, 0, 0, 0);
+  } else if (blockIdx.z == 0) {
+    const long long n = (long long)(p.bytes >> 2);
+    for (long long i = threadIdx.x; i < n; i += blockDim.x)
+      reinterpret_cast<unsigned*>(dst)[i] = src ? __ldg(reinterpret_cast<const unsigned*>(src) + i) : 0u;
+  }
+}
+
+void launch_restore_state(const StatePieceDev* pieces, int n_pieces, const int* slots, int n_slots, const char* tpl, cudaStream_t s) {
+  if (n_pieces <= 0 || n_slots <= 0) return;
+  ProfScope ps("restore_state", nullptr, 0, 0, s);
+  launch_k(restore_state_kernel, dim3(n_pieces, n_slots, 8), dim3(256), 0, s, pieces, slots, tpl);
+  ++g_launches;
+}
+
 void launch_advance(int* seq_len, int* bos_flag, int* mimi_offset, unsigned long long* counter, int B,
                     int inc_len, int inc_mimi, cudaStream_t s, const int* active) {
   ProfScope ps("advance", nullptr, 0, 0, s);
