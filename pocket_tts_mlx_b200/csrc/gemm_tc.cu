@@ -495,7 +495,7 @@ bool gemm_tc_plan(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a
   const int tiles_b = (nb + box_b - 1) / box_b;
   const long long m_tiles = (long long)tiles_t * tiles_b;
   // Tile / split / ring-depth / persistence rules distilled from the measured sweep in
-  // profiles/r01_gemm_tune_b256.txt (tools/gemm_tune.py, kernel-level, L2 flushed):
+  // profiles/r01_gemm_tune_b256.json (tools/gemm_tune.py, kernel-level, L2 flushed):
   //  * persistent CTAs with the deepest ring that fits win whenever there is more than one tile per SM, even
   //    for shallow K (the ring then prefetches across tiles);
   //  * a weight-streaming GEMM with at most two M tiles wants many small CTAs: N tile 64 and, where the consumer
