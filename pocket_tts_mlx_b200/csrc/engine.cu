@@ -180,6 +180,7 @@ struct ptts_ctx {
   void* l2_scratch = nullptr;
   size_t l2_bytes = 0;
   std::string prof_names;
+  int prio_hi = 0, prio_lo = 0;
 
   int dalloc(void** p, size_t bytes) {
     CU(cudaMalloc(p, bytes ? bytes : 16));
@@ -1531,6 +1532,7 @@ void pipelined_frame(Batch& bt, int parity, bool host_io) {
   } else {
     c.stream = c.stream2;                                   // every launcher below targets the Mimi branch
     gemm_tc_set_grid_cap(mimi_grid);
+    g_launch_prio = c.prio_lo;
     mimi_frame(bt, lat_prev, true);
     gemm_tc_set_grid_cap(0);
     c.stream = main;
@@ -1538,7 +1540,9 @@ void pipelined_frame(Batch& bt, int parity, bool host_io) {
     cudaEventRecord(c.ev_join, c.stream2);
     if (host_io)
       cudaMemcpyAsync(bt.d_noise, hn, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, c.stream);
+    g_launch_prio = c.prio_hi;
     flow_step(bt, host_io, 0, lat_prev, lat_cur);
+    g_launch_prio = 0;
   }
   launch_advance(bt.d_len, bt.d_bos, nullptr, bt.d_counter, B, 1, 0, c.stream, bt.d_active);
   if (host_io) {
@@ -1762,6 +1766,8 @@ int32_t ptts_ctx_create(int32_t device, const ptts_config* cfg, ptts_ctx** out) 
     const char* pv = getenv("PTTS_PRIO");
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    c->prio_hi = hi; c->prio_lo = lo;
+    if (pv && pv[0] == '2') g_launch_prio_on = true;     // per-launch priorities, set around the two branches in pipelined_frame
     if (pv && pv[0] == '1') {
       CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
       CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, lo));

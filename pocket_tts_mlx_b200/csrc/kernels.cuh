@@ -219,6 +219,8 @@ const char* prof_report();
 // successor be scheduled early) and pdl_wait() before the first access to global memory that the predecessor
 // may have written (griddepcontrol.wait returns once the predecessor grid has completed and flushed).
 extern std::atomic<bool> g_pdl_on;   // PTTS_NO_PDL=1 turns the launch attribute off (the device calls are then no-ops)
+extern std::atomic<bool> g_launch_prio_on;
+extern thread_local int g_launch_prio;
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
@@ -227,10 +229,19 @@ template <typename... KP, typename... Args>
 inline void launch_k(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = g_pdl_on ? 1 : 0;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (g_pdl_on) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (g_launch_prio_on) {          // PTTS_PRIO=2: explicit per-launch priority (kept by a captured kernel node)
+    at[n].id = cudaLaunchAttributePriority;
+    at[n].val.priority = g_launch_prio;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KP>(args)...);
 }
 

@@ -10,6 +10,8 @@ namespace ptts {
 
 std::atomic<long long> g_launches{0};
 std::atomic<bool> g_pdl_on{false};
+std::atomic<bool> g_launch_prio_on{false};
+thread_local int g_launch_prio = 0;
 
 namespace {
 
