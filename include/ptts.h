@@ -189,7 +189,8 @@ int32_t ptts_batch_lengths(ptts_batch* batch, int32_t* out_len);
 
 /* Mimi decode only (models/mimi.py:70-75 driven frame by frame as in tts_model.py:415-419):
  * latents [n_seq, n_frames, latent_dim] -> audio [n_seq, n_frames*1920], continuing the batch's
- * Mimi streaming state.  audio may be NULL (device-resident timing). */
+ * Mimi streaming state.  audio may be NULL (device-resident timing).  With audio set, the waveforms are copied out in
+ * chunks of 16 frames while later frames are still being decoded (any host memory; no extra pass at the end). */
 int32_t ptts_batch_mimi_decode(ptts_batch* batch, const float* latents, int32_t n_frames, float* audio);
 
 /* ---- timing + introspection -------------------------------------------------------------- */

@@ -938,6 +938,7 @@ struct ptts_batch {
   std::map<int, std::pair<cudaGraphExec_t, long long>> mimi_graphs;   // keyed by n_frames
   float *d_lat_all = nullptr, *d_audio_all = nullptr;
   long long lat_all_cap = 0;
+  float* h_chunk[2] = {nullptr, nullptr};       // pinned staging of ptts_batch_mimi_decode's chunked read-back
 
   int dalloc(void** p, size_t bytes) {
     CU(cudaMalloc(p, bytes ? bytes : 16));
@@ -2267,6 +2268,7 @@ static void batch_free(ptts_batch* bt) {
   if (bt->d_audio_all) cudaFree(bt->d_audio_all);
   cudaFreeHost(bt->h_noise); cudaFreeHost(bt->h_latent); cudaFreeHost(bt->h_logit); cudaFreeHost(bt->h_audio);
   if (bt->h2_noise) { cudaFreeHost(bt->h2_noise); cudaFreeHost(bt->h2_latent); cudaFreeHost(bt->h2_logit); cudaFreeHost(bt->h2_audio); }
+  if (bt->h_chunk[0]) { cudaFreeHost(bt->h_chunk[0]); cudaFreeHost(bt->h_chunk[1]); }
   if (bt->h_pcm) cudaFreeHost(bt->h_pcm);
   if (bt->h2_pcm) cudaFreeHost(bt->h2_pcm);
   for (auto& e : bt->ev_set) if (e) cudaEventDestroy(e);
@@ -2716,12 +2718,47 @@ int32_t ptts_batch_mimi_decode(ptts_batch* bt, const float* latents, int32_t F, 
     CU(cudaGraphDestroy(graph));
     it = bt->mimi_graphs.emplace(F, std::make_pair(exec, cnt)).first;
   }
-  for (int f = 0; f < F; ++f) {
-    CU(cudaGraphLaunch(it->second.first, c.stream));
-    g_launches += it->second.second;
+  if (!audio) {
+    for (int f = 0; f < F; ++f) {
+      CU(cudaGraphLaunch(it->second.first, c.stream));
+      g_launches += it->second.second;
+    }
+    CU(cudaStreamSynchronize(c.stream));
+    CU(cudaGetLastError());
+    return 0;
   }
-  if (audio)
-    CU(cudaMemcpyAsync(audio, bt->d_audio_all, (size_t)B * F * n * 4, cudaMemcpyDeviceToHost, c.stream));
+  // Waveforms to the host while the decoder keeps running: frames go out in chunks of kChunk through two pinned staging
+  // buffers (strided device -> host copy on the second stream), and this thread moves a finished chunk into the
+  // caller's (pageable) array while the GPU decodes the next one.
+  constexpr int kChunk = 16;
+  const size_t row = (size_t)n * 4;
+  if (!bt->h_chunk[0]) {
+    CU(cudaHostAlloc((void**)&bt->h_chunk[0], (size_t)B * kChunk * row, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&bt->h_chunk[1], (size_t)B * kChunk * row, cudaHostAllocDefault));
+  }
+  auto drain = [&](int k) -> int {                       // chunk k: staging buffer -> audio[b][f0 .. f0 + nf)
+    const int f0 = k * kChunk, nf = std::min(kChunk, F - f0);
+    CU(cudaEventSynchronize(c.ev_slice[k & 1]));
+    const char* src = reinterpret_cast<const char*>(bt->h_chunk[k & 1]);
+    for (int b = 0; b < B; ++b)
+      memcpy(reinterpret_cast<char*>(audio) + ((size_t)b * F + f0) * row, src + (size_t)b * nf * row, (size_t)nf * row);
+    return 0;
+  };
+  const int n_chunks = (F + kChunk - 1) / kChunk;
+  for (int k = 0; k < n_chunks; ++k) {
+    const int f0 = k * kChunk, nf = std::min(kChunk, F - f0);
+    for (int f = 0; f < nf; ++f) {
+      CU(cudaGraphLaunch(it->second.first, c.stream));
+      g_launches += it->second.second;
+    }
+    CU(cudaEventRecord(c.ev_attn[k & 1], c.stream));
+    CU(cudaStreamWaitEvent(c.stream2, c.ev_attn[k & 1], 0));
+    CU(cudaMemcpy2DAsync(bt->h_chunk[k & 1], (size_t)nf * row, bt->d_audio_all + (size_t)f0 * n, (size_t)F * row, (size_t)nf * row, B,
+                         cudaMemcpyDeviceToHost, c.stream2));
+    CU(cudaEventRecord(c.ev_slice[k & 1], c.stream2));
+    if (k >= 1) RET(drain(k - 1));
+  }
+  RET(drain(n_chunks - 1));
   CU(cudaStreamSynchronize(c.stream));
   CU(cudaGetLastError());
   return 0;

@@ -646,23 +646,7 @@ class TTSModel:
         self._ctx.close()
 
 
-def _alloc_output(shape, dtype) -> np.ndarray:
-    """Large result arrays are touched for the first time while the GPU is producing them: with 4 KB pages the page
-    faults of a 256-utterance job (~0.5 GB) cost about as much host time as the job itself.  Ask for transparent huge
-    pages (2 MB) when the platform offers them; otherwise this is np.empty."""
-    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-    if nbytes >= (64 << 20):
-        try:
-            import mmap
-            if hasattr(mmap, "MADV_HUGEPAGE"):
-                buf = mmap.mmap(-1, nbytes + (2 << 20))
-                buf.madvise(mmap.MADV_HUGEPAGE)
-                base = np.frombuffer(buf, dtype=np.uint8)
-                off = (-base.ctypes.data) % (2 << 20)
-                return base[off:off + nbytes].view(dtype).reshape(shape)
-        except (OSError, ValueError, AttributeError):
-            pass
-    return np.empty(shape, dtype=dtype)
+_alloc_output = _native._big_empty
 
 
 class _BlockScatter:

@@ -471,6 +471,36 @@ def test_real_checkpoint_key_map(tmp_path):
         m.close()
 
 
+def test_mimi_decode_chunked_readback_and_reused_buffer(model_fp32, cfg, weights):
+    """BASELINE config 3 path (`ptts_batch_mimi_decode`, models/mimi.py:70-75): the waveforms leave the device in chunks
+    of 16 frames while the decoder keeps running; 37 frames = two whole chunks and a short one, read into a caller-owned
+    array that held garbage, against the oracle frame by frame."""
+    from oracle.ptts_oracle import Oracle
+    from pocket_tts_mlx_b200 import _native
+    n, frames = 3, 37
+    rng = np.random.Generator(np.random.PCG64(41))
+    lat = rng.standard_normal((n, frames, 32)).astype(np.float32)
+    vid = model_fp32.get_state_for_audio_prompt("alba")
+    batch = _native.Batch(model_fp32._ctx, [vid["voice_id"]] * n, [vid["prompt_len"] + 8] * n)
+    batch.warmup_mimi(1)
+    out = np.full((n, frames * 1920), np.nan, dtype=np.float32)
+    got = batch.mimi_decode(lat, out=out)
+    batch.close()
+    assert got is out and np.isfinite(out).all()
+    with pytest.raises(ValueError):
+        batch2 = _native.Batch(model_fp32._ctx, [vid["voice_id"]] * n, [vid["prompt_len"] + 8] * n)
+        try:
+            batch2.mimi_decode(lat, out=np.empty((n, 5), np.float32))
+        finally:
+            batch2.close()
+    orc = Oracle(weights, cfg, dtype=np.float32)
+    for b in range(n):
+        ms = orc.new_mimi_state()
+        orc.warmup_mimi(ms, 1)
+        ref = np.concatenate([orc.mimi_decode_frame(ms, lat[b, f]) for f in range(frames)])
+        assert snr_db(out[b], ref) > 60.0, b
+
+
 # ------------------------------------------------------------------------------------ continuous batching / sharding
 def test_continuous_batching_mixed_voices_with_cascade_start(model_b256):
     """40 jobs through 32 slots where the first 32 share one voice (so the batch starts with cascade
