@@ -679,11 +679,37 @@ int alloc_flow_work(Ctx& c, FlowWork& w, int M) {
   return 0;
 }
 
+// L2 policy of a GEMM's operand loads by call site.  PTTS_L2_W / PTTS_L2_A: comma-separated "prefix=policy" (policy 0
+// default, 1 evict-first, 2 evict-last), e.g. PTTS_L2_W="flow.=1,head.=2".
+int l2_policy_for(const char* env, const char* dflt, const char* tag) {
+  const char* v = getenv(env);
+  std::string spec = v ? v : dflt;
+  int best = 0; size_t best_len = 0;
+  size_t pos = 0;
+  while (pos < spec.size()) {
+    size_t end = spec.find(',', pos);
+    if (end == std::string::npos) end = spec.size();
+    const std::string item = spec.substr(pos, end - pos);
+    const size_t eq = item.find('=');
+    if (eq != std::string::npos) {
+      const std::string pre = item.substr(0, eq);
+      if (tag && strncmp(tag, pre.c_str(), pre.size()) == 0 && pre.size() >= best_len) { best = atoi(item.c_str() + eq + 1); best_len = pre.size(); }
+    }
+    pos = end + 1;
+  }
+  return best;
+}
+
 bool plan_tc(TcGemm* g, const __nv_bfloat16* a, long long a_bs, long long a_rs, int nb, int T, int taps, int C,
              const LinW& w, const char* tag, int max_splits = 1, int n_bf16_out = 0) {
   if (!w.w16 || w.K != taps * C) return false;
   if (!gemm_tc_plan(g, a, a_bs, a_rs, nb, T, taps, C, w.w16, w.N, tag, max_splits, n_bf16_out)) return false;
   g->e.bias = w.bias;
+  // defaults: the FlowLM layer weights of a decode step (144 MB, read once per frame) and the big Mimi / SEANet
+  // activations (read once by their consumer) are evict-first
+  g->w_policy = l2_policy_for("PTTS_L2_W", "flow.=1", tag);
+  g->a_policy = l2_policy_for("PTTS_L2_A", "sn.=1,mimi.=1", tag);
+  if ((long long)nb * T > 2048 && g->w_policy == 1) g->w_policy = 0;      // prefill: the weights are re-read by every M tile
   return true;
 }
 
@@ -754,6 +780,7 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
       a.part = w.attn_part; a.splits = w.attn_part ? std::min(8, std::max(1, 296 / (M * c.cfg.n_heads))) : 1;
       a.kv_tmap = c.kv_tmap_ok ? c.kv_tmap : nullptr;
       a.tstamp = (!row_seq && i < 32) ? flow_attention_dbg_buffer() : nullptr;
+      { static const int kvp = [] { const char* v = getenv("PTTS_KV_EVICT_FIRST"); return v ? atoi(v) : 1; }(); a.kv_evict_first = kvp; }
       if (!row_seq && w.prefix_len > 0 && a.splits == 1) {
         a.prefix_len = w.prefix_len; a.prefix_pages = w.d_prefix_pages; a.prefix_part = w.prefix_part;
       }
@@ -790,9 +817,15 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
   }
   w.pend_n = 0;
   static const bool fuse_rope_gemv = [] { const char* v = getenv("PTTS_NO_ROPE_FUSE"); return !(v && v[0] == '1'); }();
+  // The 144 MB of layer weights pass through once per frame and do not fit L2 next to anything else: they are loaded with
+  // the streaming (evict-first) hint, which leaves the flow head's and the Mimi decoder's weights (40 MB) resident from
+  // frame to frame: batch-1 frame 0.488 -> 0.400 ms.  Keeping the first layer or two resident as well is slower (0.418 /
+  // 0.479), and so is asking L2 for the next launch's weights ahead of time (0.454).  PTTS_W_STREAM=0: plain loads.
+  static const int w_stream = [] { const char* v = getenv("PTTS_W_STREAM"); return (v && v[0] == '0') ? 0 : 1; }();
   for (int i = 0; i < c.cfg.n_layers; ++i) {
     auto& l = c.fl[i];
     LinearParams q = rows_linear(w.h, M, D, w.qkv, 3 * D, "flow.qkv");
+    q.w_stream = w_stream;
     bool roped = false;
     {
       // batch <= 4 (the latency path): RoPE + KV append ride in the GEMV epilogue, one launch less per layer
@@ -816,13 +849,13 @@ void flow_layers(Ctx& c, FlowWork& w, int M, const int* row_seq, const int* row_
     if (!roped) launch_flow_rope_append(a, c.stream);
     launch_flow_attention(a, c.stream);
     LinearParams o = rows_linear(w.att, M, D, w.x, D, "flow.out");
-    o.res = w.x; o.res_bs = 0; o.res_rs = D;
+    o.res = w.x; o.res_bs = 0; o.res_rs = D; o.w_stream = w_stream;
     run_linear(c, l.out, o);
     LinearParams f1 = rows_linear(w.h, M, D, w.ff, FF, "flow.ff1");
-    f1.act = ACT_GELU;
+    f1.act = ACT_GELU; f1.w_stream = w_stream;
     run_norm_linear(c, l.ff1, w.x, M, D, l.ln2w, l.ln2b, 1e-5f, nullptr, nullptr, 0, w.h, f1);
     LinearParams f2 = rows_linear(w.ff, M, FF, w.x, D, "flow.ff2");
-    f2.res = w.x; f2.res_bs = 0; f2.res_rs = D;
+    f2.res = w.x; f2.res_bs = 0; f2.res_rs = D; f2.w_stream = w_stream;
     run_linear(c, l.ff2, f2);
   }
 }

@@ -32,6 +32,7 @@ struct KArgs {
   int splits;                   // gridDim.z; split z covers k-iterations [z*ips, (z+1)*ips)
   long long split_stride;       // elements between the partial planes of split_ws
   float* split_ws;
+  int a_policy, w_policy;       // L2Policy of the operand loads
   TcEpilogue e;
 };
 
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(64 + 32 * EPW, (EPW == 8 && (ACC == 2 || BN <=
   if (warp == 0) {
     if (lane == 0) {
       uint32_t git = 0, rcount = 0;
+      const unsigned long long pol_a = l2_policy(g.a_policy), pol_w = l2_policy(g.w_policy);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % n_nt, mt = (tile / n_nt) % g.m_tiles, z = tile / (n_nt * g.m_tiles);
         const int n0 = nt * BN;
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(64 + 32 * EPW, (EPW == 8 && (ACC == 2 || BN <=
           mbar_expect_tx(rfull0 + 8 * rb, RES_BYTES);
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j)
-            tma_load_3d(resb + rb * RES_BYTES + (uint32_t)j * 16384u, &tm_res, rfull0 + 8 * rb, n0 + 64 * j, t0, b0);
+            tma_load_3d(resb + rb * RES_BYTES + (uint32_t)j * 16384u, &tm_res, rfull0 + 8 * rb, n0 + 64 * j, t0, b0, pol_a);   // (read once, like A)
           ++rcount;
         }
         for (int it = 0; it < ips; ++it, ++git) {
@@ -132,8 +134,8 @@ __global__ void __launch_bounds__(64 + 32 * EPW, (EPW == 8 && (ACC == 2 || BN <=
           const int tap = kit / kc_per_tap, kc = kit - tap * kc_per_tap;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
-          tma_load_3d(sA + s * A_BYTES, &tm_a, full0 + 8 * s, kc * BK, t0 + tap, b0);
-          tma_load_2d(sB + s * B_BYTES, &tm_b, full0 + 8 * s, tap * g.C + kc * BK, n0);
+          tma_load_3d(sA + s * A_BYTES, &tm_a, full0 + 8 * s, kc * BK, t0 + tap, b0, pol_a);
+          tma_load_2d(sB + s * B_BYTES, &tm_b, full0 + 8 * s, tap * g.C + kc * BK, n0, pol_w);
         }
       }
     }
@@ -619,6 +621,7 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   a.stg_tiles = g.stg_tiles;
   a.res_tma = (g.res_tma && a.tma_store) ? 1 : 0;
   a.splits = g.splits; a.split_ws = g.split_ws; a.split_stride = (long long)g.nb * g.T * g.N;
+  a.a_policy = g.a_policy; a.w_policy = g.w_policy;
   const long long tiles = (long long)(g.N / g.bn) * a.m_tiles * g.splits;
   const size_t ring = (size_t)g.stages * (128 * g.bk * 2 + g.bn * g.bk * 2);
   const size_t stg_b = (size_t)g.stg_tiles * 16384;

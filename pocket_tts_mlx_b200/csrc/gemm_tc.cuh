@@ -56,6 +56,7 @@ struct TcGemm {
   int persist;                // 1: persistent CTAs with two TMEM accumulator stages; 0: one tile per CTA
   int splits;                 // split-K factor; > 1: raw fp32 partials go to split_ws[z][nb*T][N], epilogue skipped
   float* split_ws;
+  int a_policy = 0, w_policy = 0;   // L2Policy (tc_device.cuh) of the A / W operand loads, set by the engine per call site
   TcEpilogue e;
   const char* tag;
   bool valid = false;

@@ -34,6 +34,9 @@ struct LinearParams {
   const float* res; long long res_bs, res_rs; // null or residual with Y's row indexing
   float* Y; long long y_bs, y_rs;
   const char* tag;                            // call-site label for the profiler (may be null)
+  // GEMV path only: the weights are read once per frame and are too many to stay in L2 (FlowLM layers at batch 1): load
+  // them with the streaming (evict-first) hint so that they do not evict the flow head's and the Mimi decoder's
+  int w_stream;
   // GEMV path only: LayerNorm (optionally AdaLN-modulated) fused into the row staging -- every CTA holds the full
   // input rows in shared memory anyway, so the separate norm launch disappears from the batch-1 chain
   int ln_on; const float* ln_w; const float* ln_b; float ln_eps;
@@ -109,6 +112,7 @@ struct FlowAttnParams {
   // launch starts, and the block of the layer launched next (zeroed by this launch).  Null: the prefix partial comes
   // from flow_prefix_attention_kernel (its own launch).
   int* pflags; int* pflags_next;
+  int kv_evict_first;      // stream kernel: the private K/V boxes carry an L2 evict-first policy
 };
 void launch_flow_prefix_attention(const FlowAttnParams& p, cudaStream_t s);
 // causal attention of whole prefill chunks on tensor cores (bf16 KV, bf16 output); false when not applicable

@@ -379,6 +379,9 @@ __global__ void __launch_bounds__(128) mimi_attention_mma_kernel(const MimiAttnP
   // ---- stage this warp's 64 slots of K and V (16-byte chunks, fully coalesced) ----
   // cp.async (16 B, L1-bypassing) straight into shared memory: all 32 copies of a lane are in flight at once and
   // no registers are spent on staging; slots beyond the ring are zero-filled (src-size 0)
+  // (the ring is read once per frame and layer: L2 evict-first, see tc_device.cuh)
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int idx = lane + 32 * i;
@@ -386,10 +389,10 @@ __global__ void __launch_bounds__(128) mimi_attention_mma_kernel(const MimiAttnP
     const int slot = slot0 + row;
     const int sz = slot < cap ? 16 : 0;
     const long long off = (long long)(slot < cap ? slot : 0) * kHeadDim + ch * 8;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(Ks + row * kMimiLd + ch * 8)),
-                 "l"(kbase + off), "r"(sz) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(Vs + row * kMimiLd + ch * 8)),
-                 "l"(vbase + off), "r"(sz) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"((uint32_t)__cvta_generic_to_shared(Ks + row * kMimiLd + ch * 8)),
+                 "l"(kbase + off), "r"(sz), "l"(pol) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"((uint32_t)__cvta_generic_to_shared(Vs + row * kMimiLd + ch * 8)),
+                 "l"(vbase + off), "r"(sz), "l"(pol) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   // ---- Q fragments (rows g and g+8 of the chunk), pre-scaled by 1/sqrt(64) ----
@@ -663,10 +666,19 @@ constexpr int kAttnPageBytes = 2 * kPageTokens * kHeadDim * 2;    // K + V of on
 constexpr int kAttnThreads = 64;
 constexpr int attn_smem_bytes(int stages, int pg) { return stages * pg * kAttnPageBytes + 2 * 256 + 2 * 16 + 256 + 16 * stages + 32 + 1024; }
 
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+// The private keys / values of a sequence are read once per frame and layer and never again before ~1.5 GB of other
+// keys have gone by: the boxes carry an L2 evict-first policy so that they do not flush the weights and activations
+// that the GEMMs around the attention re-read every frame (FlowAttnParams::kv_evict_first).
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4,
+                                            unsigned long long policy = 0ull) {
+  if (policy)
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
 // One ring stage (PG pages = 32 * PG keys of one head) against the query tile: S = Q K^T, online softmax in the log2
@@ -888,6 +900,8 @@ __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 :
         }
       }
     }
+    unsigned long long kv_policy = 0ull;
+    if (p.kv_evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(kv_policy));
     const int pg_first = p.prefix_len / kPageTokens;
     // lane l holds pages pg_first + l and pg_first + 32 + l of a row (2048 keys); rows beyond that reload in the loop.
     // Entries past the row's last page are zero in the table, so the two loads do not depend on each other.
@@ -950,11 +964,11 @@ __global__ void __launch_bounds__(kAttnThreads, PG == 1 ? 9 : (STAGES == 2 ? 6 :
             const uint32_t dst = ring + s * kAttnStageBytes + (uint32_t)e * kAttnPageBytes;
             const int pc = page0 + pages[e];
             if (blo[e] == 0 && bhi[e] == 3) {
-              tma_load_5d(dst, &tm_page, full0 + 8 * s, 0, 0, h, 0, pc);             // K and V of the whole page
+              tma_load_5d(dst, &tm_page, full0 + 8 * s, 0, 0, h, 0, pc, kv_policy);  // K and V of the whole page
             } else {
               for (int b = blo[e]; b <= bhi[e]; ++b) {
-                tma_load_5d(dst + (uint32_t)b * 1024u, &tm_box, full0 + 8 * s, 0, 8 * b, h, 0, pc);
-                tma_load_5d(dst + 4096u + (uint32_t)b * 1024u, &tm_box, full0 + 8 * s, 0, 8 * b, h, 1, pc);
+                tma_load_5d(dst + (uint32_t)b * 1024u, &tm_box, full0 + 8 * s, 0, 8 * b, h, 0, pc, kv_policy);
+                tma_load_5d(dst + 4096u + (uint32_t)b * 1024u, &tm_box, full0 + 8 * s, 0, 8 * b, h, 1, pc, kv_policy);
               }
             }
           }

@@ -141,7 +141,9 @@ template <> struct WVec<float> {
 template <typename WT> struct WRaw;
 template <> struct WRaw<__nv_bfloat16> {
   uint4 v;
-  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void load(const __nv_bfloat16* p, bool stream = false) {
+    v = stream ? __ldcs(reinterpret_cast<const uint4*>(p)) : __ldg(reinterpret_cast<const uint4*>(p));
+  }
   __device__ __forceinline__ void unpack(float (&o)[8]) const {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
@@ -153,7 +155,7 @@ template <> struct WRaw<__nv_bfloat16> {
 };
 template <> struct WRaw<float> {
   float4 a, b;
-  __device__ __forceinline__ void load(const float* p) {
+  __device__ __forceinline__ void load(const float* p, bool = false) {
     a = __ldg(reinterpret_cast<const float4*>(p));
     b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   }
@@ -183,13 +185,14 @@ __global__ void __launch_bounds__(256) linear_gemv_kernel(const LinearParams p) 
   for (int r = 0; r < R; ++r) wrow[r] = W + (long long)min(n_base + r, p.N - 1) * K;
 
   WRaw<WT> wq[R][U];
+  const bool w_stream = p.w_stream != 0;
   auto issue = [&](int k0) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int k = k0 + 256 * u;
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (k < K) wq[r][u].load(wrow[r] + k);
+        if (k < K) wq[r][u].load(wrow[r] + k, w_stream);
     }
   };
   issue(lane * 8);                                  // weights do not depend on the activations: fetch first

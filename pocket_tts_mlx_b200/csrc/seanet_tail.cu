@@ -46,6 +46,7 @@ struct TailArgs {
   long long audio_bs;
   float* bnd;
   short* pcm;            // optional 16-bit PCM copy of the samples (samples 0, 1 of a tile are finished by the fix-up)
+  int stream_loads;      // L2 evict-first on the last reads of the input tensors
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -128,6 +129,9 @@ __global__ void __launch_bounds__(kTailThreads, 1) sn_tail_kernel(const __grid_c
       for (int tap = 0; tap < 3; ++tap) tma_load_2d(sW1 + tap * 4096u, &tm_w1, wfull, tap * 64, 0);
       tma_load_2d(sW2, &tm_w2, wfull, 0, 0);
       uint32_t git = 0;
+      // the [491 520 x 64] tensors are read here for the last time: the third (last) tap box of a tile and the residual
+      // box go in as L2 evict-first
+      const unsigned long long pol = l2_policy(g.stream_loads ? L2_EVICT_FIRST : L2_DEFAULT);
       for (int i = 0; i < n_my; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
         const int b = tile / g.tiles_t, t0 = (tile % g.tiles_t) * 128;
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) sn_tail_kernel(const __grid_c
           const uint32_t s = git % kTailStages, ph = (git / kTailStages) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           mbar_expect_tx(full0 + 8 * s, kABytes);
-          tma_load_3d(sA + s * kABytes, &tm_a, full0 + 8 * s, 0, t0 + tap, b);
+          tma_load_3d(sA + s * kABytes, &tm_a, full0 + 8 * s, 0, t0 + tap, b, tap == 2 ? pol : 0ull);
         }
       }
     }
@@ -182,12 +186,13 @@ __global__ void __launch_bounds__(kTailThreads, 1) sn_tail_kernel(const __grid_c
     // residual tiles (raw x) on their own producer, so the operand ring never waits for the last epilogue
     if (lane == 0) {
       uint32_t rb = 0, rph = 0;                          // buffer / phase kept as explicit counters (see note in group B)
+      const unsigned long long pol = l2_policy(g.stream_loads ? L2_EVICT_FIRST : L2_DEFAULT);
       for (int i = 0; i < n_my; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
         const int b = tile / g.tiles_t, t0 = (tile % g.tiles_t) * 128;
         mbar_wait(re + 8 * rb, rph ^ 1);
         mbar_expect_tx(rf + 8 * rb, kResBytes);
-        tma_load_3d(sRes + rb * kResBytes, &tm_res, rf + 8 * rb, 0, t0, b);
+        tma_load_3d(sRes + rb * kResBytes, &tm_res, rf + 8 * rb, 0, t0, b, pol);
         if (++rb == kResBufs) { rb = 0; rph ^= 1; }
       }
     }
@@ -377,6 +382,7 @@ void sn_tail_launch(const SnTail& p, cudaStream_t s, bool with_fix) {
   a.nb = p.nb; a.T = p.T; a.tiles_t = p.T / 128; a.total_tiles = p.nb * a.tiles_t;
   a.b1 = p.b1; a.b2 = p.b2; a.wf = p.wf; a.bf = p.bf;
   a.audio = p.audio; a.audio_bs = p.audio_bs; a.bnd = p.bnd; a.pcm = p.pcm;
+  { static const int sl = [] { const char* v = getenv("PTTS_SN_STREAM"); return (v && v[0] == '0') ? 0 : 1; }(); a.stream_loads = sl; }
   {
     const double rows = (double)p.nb * p.T;
     ProfScope ps("sn_tail", nullptr, 2.0 * rows * (192.0 * 32 + 32.0 * 64 + 192.0), rows * (64 * 2 * 2 + 4), s);
