@@ -1619,7 +1619,8 @@ int run_pipelined_step(Batch& bt, bool host_io) {
       CU(cudaStreamEndCapture(c.stream, &graph));
       bt.pipe_graph_launches[idx] = g_launches - before;
       g_launches = before;
-      CU(cudaGraphInstantiate(&bt.pipe_graph[idx], graph, 0));
+      // (per-node launch priorities only count when the graph is instantiated with this flag)
+      CU(cudaGraphInstantiate(&bt.pipe_graph[idx], graph, g_launch_prio_on ? cudaGraphInstantiateFlagUseNodePriority : 0));
       CU(cudaGraphDestroy(graph));
     }
     CU(cudaGraphLaunch(bt.pipe_graph[idx], c.stream));
