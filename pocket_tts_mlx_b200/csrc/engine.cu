@@ -735,6 +735,19 @@ int build_flow_plans(Ctx& c, FlowWork& w, int M) {
     g[3].split_ws = w.ws_ff2;
     gemm_tc_bind_outputs(&g[2]);
   }
+  // decode steps: every GEMM of the chain asks L2 for the weights of the next one (PTTS_TC_PREFETCH=0: off)
+  static const bool tc_pf = [] { const char* v = getenv("PTTS_TC_PREFETCH"); return !(v && v[0] == '0'); }();
+  if (tc_pf && M <= 2048) {
+    auto wbytes = [](const LinW& l) { return (long long)l.N * l.K * 2; };
+    for (int i = 0; i < c.cfg.n_layers; ++i) {
+      auto& l = c.fl[i];
+      TcGemm* g = &w.plans[(size_t)i * 4];
+      g[0].pf_ptr = l.out.w16; g[0].pf_bytes = wbytes(l.out);
+      g[1].pf_ptr = l.ff1.w16; g[1].pf_bytes = wbytes(l.ff1);
+      g[2].pf_ptr = l.ff2.w16; g[2].pf_bytes = wbytes(l.ff2);
+      if (i + 1 < c.cfg.n_layers) { g[3].pf_ptr = c.fl[i + 1].qkv.w16; g[3].pf_bytes = wbytes(c.fl[i + 1].qkv); }
+    }
+  }
   w.plan_M = M;
   return 0;
 }

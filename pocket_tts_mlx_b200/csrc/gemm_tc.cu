@@ -33,6 +33,7 @@ struct KArgs {
   long long split_stride;       // elements between the partial planes of split_ws
   float* split_ws;
   int a_policy, w_policy;       // L2Policy of the operand loads
+  const void* pf_ptr; long long pf_bytes;    // weights of the NEXT GEMM of the chain: every CTA asks L2 for a slice
   TcEpilogue e;
 };
 
@@ -114,6 +115,15 @@ __global__ void __launch_bounds__(64 + 32 * EPW, (EPW == 8 && (ACC == 2 || BN <=
     if (lane == 0) {
       uint32_t git = 0, rcount = 0;
       const unsigned long long pol_a = l2_policy(g.a_policy), pol_w = l2_policy(g.w_policy);
+      if (g.pf_ptr) {
+        // The decode-step GEMMs wait on HBM latency, not bandwidth (a 4-stage ring, 16-64 k-blocks, weights read with
+        // the evict-first policy so never resident): the next GEMM's weights are requested now, so that its ring is fed
+        // from L2.  One bulk prefetch per CTA, 16-byte granularity.
+        const long long per = ((g.pf_bytes + gridDim.x - 1) / gridDim.x + 15) & ~15ll;
+        const long long lo = per * blockIdx.x, n = min(per, g.pf_bytes - lo) & ~15ll;
+        if (n > 0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(g.pf_ptr) + lo), "r"((unsigned)n) : "memory");
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % n_nt, mt = (tile / n_nt) % g.m_tiles, z = tile / (n_nt * g.m_tiles);
         const int n0 = nt * BN;
@@ -622,6 +632,7 @@ void gemm_tc_launch(const TcGemm& g, cudaStream_t s) {
   a.res_tma = (g.res_tma && a.tma_store) ? 1 : 0;
   a.splits = g.splits; a.split_ws = g.split_ws; a.split_stride = (long long)g.nb * g.T * g.N;
   a.a_policy = g.a_policy; a.w_policy = g.w_policy;
+  a.pf_ptr = g.pf_ptr; a.pf_bytes = g.pf_bytes;
   const long long tiles = (long long)(g.N / g.bn) * a.m_tiles * g.splits;
   const size_t ring = (size_t)g.stages * (128 * g.bk * 2 + g.bn * g.bk * 2);
   const size_t stg_b = (size_t)g.stg_tiles * 16384;

@@ -57,6 +57,7 @@ struct TcGemm {
   int splits;                 // split-K factor; > 1: raw fp32 partials go to split_ws[z][nb*T][N], epilogue skipped
   float* split_ws;
   int a_policy = 0, w_policy = 0;   // L2Policy (tc_device.cuh) of the A / W operand loads, set by the engine per call site
+  const void* pf_ptr = nullptr; long long pf_bytes = 0;   // weights of the next GEMM of a latency-bound chain (L2 prefetch), or null
   TcEpilogue e;
   const char* tag;
   bool valid = false;
